@@ -1,0 +1,166 @@
+/*
+ * scab200.h -- C ABI of libscab200.so: the B200-native batched collision-avoidance step.
+ *
+ * The reference (wuuya1/SCA, pure Python) has no FFI; its boundary is the duck-typed
+ * policy/kd-tree interface MACAEnv drives once per step:
+ *     mamp/envs/mampenv.py:28   self.kdTree.buildAgentTree()
+ *     mamp/envs/mampenv.py:40   agent.policy.find_next_action(dict_comm, agent, self.kdTree)
+ *     mamp/envs/mampenv.py:43   update_velocitie(agent, all_actions[i, :])
+ *     mamp/envs/mampenv.py:46   self.check_agent_state(agent)
+ *     mamp/envs/mampenv.py:24   self.is_done(NEAR_GOAL_THRESHOLD)
+ * Each entry point below names the reference code it replaces.  sca_b200/mamp_compat.py is the
+ * Python-side binding that plugs these into an unmodified MACAEnv.
+ *
+ * Conventions: every function returns 0 on success or a negative scab_status; the message of the last
+ * failure is available from scab_last_error().  No C++ types, no exceptions cross the boundary.  All
+ * kernels are launched asynchronously on the caller's stream (pass the cudaStream_t as void*; NULL =
+ * legacy default stream).  One handle per device; a handle is not thread-safe; distinct handles are
+ * independent.  State arrays are CALLER-OWNED device memory (PyTorch tensors in this repo): the library
+ * never allocates, frees or keeps them alive -- the caller must keep them alive until scab_destroy or
+ * the next scab_bind_state.
+ */
+#ifndef SCAB200_H
+#define SCAB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCAB_MAX_NEIGHBORS 16 /* mamp/agents/agent.py:32 maxNeighbors */
+
+typedef struct scab_handle scab_handle;
+
+typedef enum {
+    SCAB_OK = 0,
+    SCAB_ERR_INVALID = -1,   /* bad argument / state not bound */
+    SCAB_ERR_CUDA = -2,      /* CUDA runtime error (message in scab_last_error) */
+    SCAB_ERR_CAPACITY = -3,  /* n exceeds the capacity given to scab_create */
+    SCAB_ERR_NOMEM = -4
+} scab_status;
+
+/* Policy selector: one per reference policy class. */
+typedef enum {
+    SCAB_POLICY_SCA = 0,          /* mamp/policies/sca/scaPolicy.py:18 SCAPolicy */
+    SCAB_POLICY_SRVO3D = 1,       /* mamp/policies/srvo3dPolicy.py:15 SRVO3DPolicy */
+    SCAB_POLICY_RVO3D = 2,        /* mamp/policies/rvo3dPolicy.py:15 RVO3DPolicy */
+    SCAB_POLICY_RVO3D_DUBINS = 3, /* mamp/policies/sca/rvo3dDubinsPolicy.py:18 RVO3dDubinsPolicy */
+    SCAB_POLICY_ORCA_SAMPLED = 4, /* mamp/policies/orca3dPolicy.py:27 ORCA3DPolicy (run_orca.py imports this) */
+    SCAB_POLICY_ORCA_LP = 5       /* mamp/policies/orca3dPolicyOfficial.py:27 ORCA3DPolicy (linearProgram3/4) */
+} scab_policy;
+
+/* Neighbour semantics. */
+typedef enum {
+    SCAB_NBR_KNN = 0,        /* true 16 nearest by (distSq, obstacles first, id): what RVO2-3D computes */
+    SCAB_NBR_REF_COMPAT = 1  /* bit-exact replay of the reference: kdTree.py:127-156 traversal order +
+                                agent.py:79-124 insertion with the by-value rangeSq (never shrinks) */
+} scab_nbr_mode;
+
+/* Status bits (mamp/agents/agent.py:70-73 flags). */
+#define SCAB_ST_AT_GOAL 1
+#define SCAB_ST_COLLISION 2
+#define SCAB_ST_TIMEOUT 4
+#define SCAB_ST_RUN_DONE 8
+#define SCAB_ST_ZAXIS 16      /* static: start->goal is vertical (scaPolicy.py:188-190 -> 2x128 candidates) */
+
+/* Branch tags written to state.tag (which path produced the velocity). */
+#define SCAB_TAG_FIRST 1      /* zero-velocity shortcut vA_post = 0.3 v_pref (scaPolicy.py:34-40) */
+#define SCAB_TAG_SUITABLE 2   /* sampled policies: a suitable candidate existed (scaPolicy.py:218) */
+#define SCAB_TAG_FALLBACK 4   /* sampled policies: compute_without_suitV path (scaPolicy.py:224-238) */
+#define SCAB_TAG_LP3_OK 8     /* ORCA-LP: linearProgram3 satisfied every plane (orca3dPolicyOfficial.py:108) */
+#define SCAB_TAG_LP4 16       /* ORCA-LP: linearProgram4 fallback ran (orca3dPolicyOfficial.py:110-111) */
+
+/* Constants of mamp/agents/agent.py:23-42 and mamp/configs/config.py:1-4 plus the cell-list geometry. */
+typedef struct {
+    double neighbor_dist;  /* 10.0  agent.py:33 */
+    double time_step;      /* 0.1   config.py:2 */
+    double time_horizon;   /* 10.0  agent.py:35 */
+    double max_speed;      /* 1.0   agent.py:36 */
+    double near_goal;      /* 0.5   config.py:3 */
+    double grid_origin[3]; /* lower corner of the uniform grid (agents outside are clamped into the border cells) */
+    double cell_size;      /* >= neighbor_dist */
+    int32_t grid_dim[3];   /* cells per axis */
+    int32_t reserved;
+} scab_params;
+
+/* Device pointers to the caller-owned structure-of-arrays state (replaces the per-object attributes
+ * of mamp/agents/agent.py:13-36,56-74).  n rows each.  Optional pointers may be NULL. */
+typedef struct {
+    double *pos;           /* [n,3] pos_global_frame (f64)                          in/out */
+    float *vel;            /* [n,3] vel_global_frame (f32, as after mampenv.py:104) in/out */
+    double *heading;       /* [n,3] heading_global_frame (yaw, pitch, roll)         in/out */
+    const double *goal;    /* [n,3] goal_global_frame                               in */
+    const double *radius;  /* [n]                                                   in */
+    const double *pref_speed;   /* [n]                                              in */
+    int32_t *status;       /* [n] SCAB_ST_* bits                                    in/out */
+    double *total_dist;    /* [n]                                                   in/out */
+    int32_t *step_num;     /* [n]                                                   in/out */
+    const double *max_run_dist; /* [n] 3*|start-goal| (agent.py:74)                 in */
+    const double *vpref_ext;    /* [n,3] optional: externally supplied V_des (e.g. the Dubins provider of
+                                   scaPolicy.py:264-338); NULL -> straight-line v_pref (rvo3dPolicy.py:182-196) */
+    double *vpref_out;     /* [n,3] optional: agent.v_pref as stored by compute_v_pref  out */
+    float *action;         /* [n,7] vx vy vz speed d_yaw d_pitch d_roll (mampenv.py:31) out */
+    /* observability (optional) */
+    int32_t *nbr_cnt;      /* [n]    len(agent.neighbors), -1 if computeNeighbors did not run  out */
+    int32_t *nbr_ids;      /* [n,16] agent id, or n + obstacle id; -1 padding                  out */
+    double *nbr_dsq;       /* [n,16] the sort key (agent.py:81,106)                            out */
+    int32_t *tag;          /* [n] SCAB_TAG_* bits                                              out */
+    int32_t *n_suit;       /* [n] sampled policies: number of suitable candidates              out */
+    int32_t *plane_fail;   /* [n] ORCA-LP: linearProgram3's return value                       out */
+    int32_t *n_planes;     /* [n] ORCA-LP: len(orcaPlanes)                                     out */
+    int32_t *lp4_proj;     /* [n] ORCA-LP: number of inner dir-opt LP3 solves in LP4           out */
+} scab_state_ptrs;
+
+/* Step counters, read back with scab_read_counters (device->host copy of 4 x int64). */
+typedef struct {
+    int64_t n_active;      /* agents that ran the policy this step (not at_goal/collision/timeout) */
+    int64_t n_not_done;    /* agents without RUN_DONE after the step; 0 <=> MACAEnv.is_done() is True */
+    int64_t n_collision;   /* agents with the collision flag after the step */
+    int64_t n_recheck;     /* fp32 guard-band hits re-evaluated in fp64 (diagnostic) */
+} scab_counters;
+
+const char *scab_version(void);
+void scab_default_params(scab_params *p);
+
+/* Handle life cycle.  `capacity` bounds n (library-owned scratch is sized from it). */
+int scab_create(scab_handle **out, const scab_params *p, int device, int64_t capacity);
+int scab_destroy(scab_handle *h);
+const char *scab_last_error(const scab_handle *h);
+
+/* Replace the grid geometry (e.g. after the swarm's bounding box changed). */
+int scab_set_grid(scab_handle *h, const double origin[3], double cell_size, const int32_t dim[3]);
+
+/* Bind the SoA state (replaces Agent attribute storage, agent.py:13-74). */
+int scab_bind_state(scab_handle *h, const scab_state_ptrs *s, int64_t n);
+
+/* Static obstacles: HOST array [m,4] = x y z r (mamp/agents/obstacle.py:10-33).  Builds the static
+ * obstacle cell list and the reference's obstacle kd-tree (kdTree.py:158-227; mampenv.py:20). */
+int scab_set_obstacles(scab_handle *h, const double *xyzr_host, int32_t m);
+
+/* REF_COMPAT only: rebuild the reference's agent kd-tree from HOST positions [n,3] (kdTree.py:56-122,
+ * including its persistent agentIDs permutation) and upload it.  Replaces KDTree.buildAgentTree(). */
+int scab_kdtree_build(scab_handle *h, const double *pos_host, int64_t n);
+/* Copy the current agentIDs permutation to `out_host` [n] (test hook). */
+int scab_kdtree_get_perm(scab_handle *h, int32_t *out_host, int64_t n);
+
+/* Stage 1: uniform-grid cell list over all agents (replaces the per-step kd-tree rebuild, mampenv.py:28). */
+int scab_build_grid(scab_handle *h, void *stream);
+/* Stage 2: neighbour query for every active agent (replaces computeNeighbors, scaPolicy.py:107-116 ->
+ * kdTree.py:124-156,229-262 -> agent.py:79-124). */
+int scab_neighbors(scab_handle *h, int mode, void *stream);
+/* Stage 3: v_pref, constraint construction, velocity selection, action, kinematic update
+ * (replaces Policy.find_next_action + update_velocitie, mampenv.py:83-105). */
+int scab_policy_step(scab_handle *h, int policy, void *stream);
+/* Stage 4: collision / timeout / goal flags and the done reduction (mampenv.py:51-80). */
+int scab_status_step(scab_handle *h, void *stream);
+/* Stages 1-4 back to back: one MACAEnv.step (mampenv.py:22-25). */
+int scab_step(scab_handle *h, int policy, int nbr_mode, void *stream);
+
+/* Blocking read of the counters written by the last scab_status_step on `stream`. */
+int scab_read_counters(scab_handle *h, scab_counters *out_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCAB200_H */

@@ -1,0 +1,159 @@
+"""ctypes binding of libscab200.so (include/scab200.h).
+
+There is no CPU fallback: if the CUDA library is missing this module raises at load time, and every
+entry point raises ScabError on a non-zero status.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libscab200.so')
+
+POLICIES = {'sca': 0, 'srvo3d': 1, 'rvo3d': 2, 'rvo3d_dubins': 3, 'orca_sampled': 4, 'orca_lp': 5}
+NBR_KNN, NBR_REF_COMPAT = 0, 1
+K = 16
+
+ST_AT_GOAL, ST_COLLISION, ST_TIMEOUT, ST_RUN_DONE, ST_ZAXIS = 1, 2, 4, 8, 16
+TAG_FIRST, TAG_SUITABLE, TAG_FALLBACK, TAG_LP3_OK, TAG_LP4 = 1, 2, 4, 8, 16
+
+# every symbol include/scab200.h declares (tests/test_capi_symbols.py checks the header against this)
+SYMBOLS = ['scab_version', 'scab_default_params', 'scab_create', 'scab_destroy', 'scab_last_error', 'scab_set_grid',
+           'scab_bind_state', 'scab_set_obstacles', 'scab_kdtree_build', 'scab_kdtree_get_perm', 'scab_build_grid',
+           'scab_neighbors', 'scab_policy_step', 'scab_status_step', 'scab_step', 'scab_read_counters']
+
+
+class ScabError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [('neighbor_dist', C.c_double), ('time_step', C.c_double), ('time_horizon', C.c_double),
+                ('max_speed', C.c_double), ('near_goal', C.c_double), ('grid_origin', C.c_double * 3),
+                ('cell_size', C.c_double), ('grid_dim', C.c_int32 * 3), ('reserved', C.c_int32)]
+
+
+STATE_FIELDS = ['pos', 'vel', 'heading', 'goal', 'radius', 'pref_speed', 'status', 'total_dist', 'step_num',
+                'max_run_dist', 'vpref_ext', 'vpref_out', 'action', 'nbr_cnt', 'nbr_ids', 'nbr_dsq', 'tag', 'n_suit',
+                'plane_fail', 'n_planes', 'lp4_proj']
+
+
+class StatePtrs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in STATE_FIELDS]
+
+
+class Counters(C.Structure):
+    _fields_ = [('n_active', C.c_int64), ('n_not_done', C.c_int64), ('n_collision', C.c_int64),
+                ('n_recheck', C.c_int64)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libscab200.so (built in-tree by sca_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ScabError('libscab200.so is missing (%s): run `python -m sca_b200.build`; there is no CPU fallback'
+                        % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.scab_version.restype = C.c_char_p
+    L.scab_last_error.restype = C.c_char_p
+    L.scab_last_error.argtypes = [vp]
+    L.scab_default_params.restype = None
+    L.scab_default_params.argtypes = [C.POINTER(Params)]
+    L.scab_create.argtypes = [C.POINTER(vp), C.POINTER(Params), C.c_int, i64]
+    L.scab_destroy.argtypes = [vp]
+    L.scab_set_grid.argtypes = [vp, C.POINTER(C.c_double), C.c_double, C.POINTER(i32)]
+    L.scab_bind_state.argtypes = [vp, C.POINTER(StatePtrs), i64]
+    L.scab_set_obstacles.argtypes = [vp, vp, i32]
+    L.scab_kdtree_build.argtypes = [vp, vp, i64]
+    L.scab_kdtree_get_perm.argtypes = [vp, vp, i64]
+    L.scab_build_grid.argtypes = [vp, vp]
+    L.scab_neighbors.argtypes = [vp, C.c_int, vp]
+    L.scab_policy_step.argtypes = [vp, C.c_int, vp]
+    L.scab_status_step.argtypes = [vp, vp]
+    L.scab_step.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.scab_read_counters.argtypes = [vp, C.POINTER(Counters), vp]
+    _lib = L
+    return L
+
+
+def default_params():
+    p = Params()
+    lib().scab_default_params(C.byref(p))
+    return p
+
+
+class Handle:
+    """RAII wrapper of scab_handle."""
+
+    def __init__(self, params, device, capacity):
+        self._h = C.c_void_p()
+        self._L = lib()
+        rc = self._L.scab_create(C.byref(self._h), C.byref(params), int(device), int(capacity))
+        if rc != 0:
+            raise ScabError('scab_create failed with status %d' % rc)
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._L.scab_last_error(self._h)
+            raise ScabError('libscab200 status %d: %s' % (rc, msg.decode() if msg else '?'))
+
+    def close(self):
+        if self._h:
+            self._L.scab_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_grid(self, origin, cell_size, dim):
+        o = (C.c_double * 3)(*[float(x) for x in origin])
+        d = (C.c_int32 * 3)(*[int(x) for x in dim])
+        self._ck(self._L.scab_set_grid(self._h, o, float(cell_size), d))
+
+    def bind_state(self, ptrs, n):
+        self._ck(self._L.scab_bind_state(self._h, C.byref(ptrs), int(n)))
+
+    def set_obstacles(self, xyzr_host):
+        import numpy as np
+        a = np.ascontiguousarray(xyzr_host, dtype='float64').reshape(-1, 4)
+        self._ck(self._L.scab_set_obstacles(self._h, a.ctypes.data if len(a) else None, len(a)))
+
+    def kdtree_build(self, pos_host):
+        import numpy as np
+        a = np.ascontiguousarray(pos_host, dtype='float64')
+        self._ck(self._L.scab_kdtree_build(self._h, a.ctypes.data, a.shape[0]))
+
+    def kdtree_perm(self, n):
+        import numpy as np
+        out = np.zeros(n, np.int32)
+        self._ck(self._L.scab_kdtree_get_perm(self._h, out.ctypes.data, n))
+        return out
+
+    def build_grid(self, stream=0):
+        self._ck(self._L.scab_build_grid(self._h, stream))
+
+    def neighbors(self, mode, stream=0):
+        self._ck(self._L.scab_neighbors(self._h, mode, stream))
+
+    def policy_step(self, policy, stream=0):
+        self._ck(self._L.scab_policy_step(self._h, policy, stream))
+
+    def status_step(self, stream=0):
+        self._ck(self._L.scab_status_step(self._h, stream))
+
+    def step(self, policy, nbr_mode, stream=0):
+        self._ck(self._L.scab_step(self._h, policy, nbr_mode, stream))
+
+    def read_counters(self, stream=0):
+        c = Counters()
+        self._ck(self._L.scab_read_counters(self._h, C.byref(c), stream))
+        return {'n_active': c.n_active, 'n_not_done': c.n_not_done, 'n_collision': c.n_collision,
+                'n_recheck': c.n_recheck}

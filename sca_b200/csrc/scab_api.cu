@@ -1,0 +1,402 @@
+// scab_api.cu -- the C ABI of libscab200.so (include/scab200.h): handle, library-owned scratch,
+// static obstacle structures, the host-side replay of the reference's kd-tree build (REF_COMPAT), and
+// the stage launchers.  No torch types, no exceptions across the boundary.
+#include "scab_common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+struct scab_handle {
+    int device = 0;
+    int64_t capacity = 0;
+    scab_params p{};
+    StepArgs A{};
+    bool bound = false;
+    std::string err;
+    // library-owned device scratch
+    void *d_block = nullptr;
+    int32_t *d_cell_count = nullptr, *d_cell_start = nullptr;
+    int64_t cell_cap = 0;
+    double *d_dir256 = nullptr, *d_dir128 = nullptr;
+    float4 *d_dir256f = nullptr, *d_dir128f = nullptr;
+    unsigned long long *d_counters = nullptr;
+    // obstacles
+    int32_t m = 0;
+    double4 *d_o_posr = nullptr, *d_o_posr_by_id = nullptr;
+    int32_t *d_o_id = nullptr, *d_o_cell_start = nullptr, *d_kd_obst_perm = nullptr;
+    KdNodeDev *d_kd_obst = nullptr;
+    // reference kd-tree over agents (REF_COMPAT)
+    std::vector<int32_t> kd_perm;          // persistent agentIDs (kdTree.py:43-45)
+    std::vector<KdNodeDev> kd_nodes;
+    KdNodeDev *d_kd_agent = nullptr;
+    int32_t *d_kd_agent_perm = nullptr;
+    bool kd_valid = false;
+};
+
+static int fail(scab_handle *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(h, SCAB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+    } while (0)
+
+extern "C" const char *scab_version(void) { return "scab200 0.1 (sm_100a)"; }
+
+extern "C" void scab_default_params(scab_params *p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->neighbor_dist = 10.0;   // agent.py:33
+    p->time_step = 0.1;        // config.py:2
+    p->time_horizon = 10.0;    // agent.py:35
+    p->max_speed = 1.0;        // agent.py:36
+    p->near_goal = 0.5;        // config.py:3
+    p->grid_origin[0] = p->grid_origin[1] = p->grid_origin[2] = 0.0;
+    p->cell_size = 10.0;
+    p->grid_dim[0] = p->grid_dim[1] = p->grid_dim[2] = 1;
+}
+
+extern "C" const char *scab_last_error(const scab_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+// Fibonacci-sphere unit directions (scaPolicy.py:196-199), evaluated with the host libm exactly as the
+// reference does (math.sqrt / math.cos / math.sin), then uploaded.
+static void make_dirs(int N, std::vector<double> &d64, std::vector<float4> &d32)
+{
+    const double pi = 3.141592653589793;
+    const double param_phi = (sqrt(5.0) - 1.0) / 2.0;
+    d64.resize(3 * (size_t)N);
+    d32.resize(N);
+    for (int n = 1; n <= N; n++) {
+        volatile double zq = (double)(2 * n - 1) / N;
+        double z = zq - 1;
+        volatile double z2 = z * z;
+        double sq = sqrt(1 - z2);
+        volatile double a1 = 2 * pi;
+        volatile double a2 = a1 * n;
+        double ang = a2 * param_phi;
+        volatile double x = sq * cos(ang);
+        volatile double y = sq * sin(ang);
+        d64[3 * (n - 1)] = x; d64[3 * (n - 1) + 1] = y; d64[3 * (n - 1) + 2] = z;
+        d32[n - 1] = make_float4((float)x, (float)y, (float)z, 0.f);
+    }
+}
+
+static void set_geom(GridGeom &g, const double origin[3], double cs, const int32_t dim[3])
+{
+    g.ox = origin[0]; g.oy = origin[1]; g.oz = origin[2];
+    g.inv_cs = 1.0 / cs;
+    g.nx = std::max(1, dim[0]); g.ny = std::max(1, dim[1]); g.nz = std::max(1, dim[2]);
+    g.ncell = g.nx * g.ny * g.nz;
+}
+
+static int ensure_cells(scab_handle *h, int64_t ncell)
+{
+    if (ncell <= h->cell_cap) return SCAB_OK;
+    if (h->d_cell_count) cudaFree(h->d_cell_count);
+    if (h->d_cell_start) cudaFree(h->d_cell_start);
+    h->d_cell_count = h->d_cell_start = nullptr;
+    h->cell_cap = 0;
+    CK(cudaMalloc(&h->d_cell_count, sizeof(int32_t) * (size_t)ncell));
+    CK(cudaMalloc(&h->d_cell_start, sizeof(int32_t) * (size_t)(ncell + 1)));
+    h->cell_cap = ncell;
+    h->A.cell_count = h->d_cell_count;
+    h->A.cell_start = h->d_cell_start;
+    return SCAB_OK;
+}
+
+extern "C" int scab_set_grid(scab_handle *h, const double origin[3], double cell_size, const int32_t dim[3])
+{
+    if (!h || !origin || !dim) return fail(h, SCAB_ERR_INVALID, "scab_set_grid: null argument");
+    if (!(cell_size >= h->p.neighbor_dist)) return fail(h, SCAB_ERR_INVALID, "scab_set_grid: cell_size < neighbor_dist");
+    int64_t nc = (int64_t)std::max(1, dim[0]) * std::max(1, dim[1]) * std::max(1, dim[2]);
+    if (nc > (int64_t)1 << 28) return fail(h, SCAB_ERR_INVALID, "scab_set_grid: too many cells");
+    CK(cudaSetDevice(h->device));
+    set_geom(h->A.g, origin, cell_size, dim);
+    for (int d = 0; d < 3; d++) { h->p.grid_origin[d] = origin[d]; h->p.grid_dim[d] = dim[d]; }
+    h->p.cell_size = cell_size;
+    return ensure_cells(h, nc);
+}
+
+extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, int64_t capacity)
+{
+    if (!out || !p || capacity <= 0) return SCAB_ERR_INVALID;
+    *out = nullptr;
+    scab_handle *h = new (std::nothrow) scab_handle();
+    if (!h) return SCAB_ERR_NOMEM;
+    h->device = device;
+    h->capacity = capacity;
+    h->p = *p;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete h; return SCAB_ERR_CUDA; }
+    StepArgs &A = h->A;
+    A.nbr_dist_sq = p->neighbor_dist * p->neighbor_dist;   // agent.neighborDist ** 2 (scaPolicy.py:112)
+    A.time_step = p->time_step;
+    A.inv_time_horizon = 1.0 / p->time_horizon;
+    A.inv_time_step = 1.0 / p->time_step;
+    A.max_speed = p->max_speed;
+    A.near_goal = p->near_goal;
+    // one block for all per-agent scratch
+    const size_t cap = (size_t)capacity;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_posr = carve(cap * sizeof(double4)), o_newpos = carve(cap * sizeof(double4)),
+                 o_vel = carve(cap * sizeof(float4)), o_id = carve(cap * 4), o_rank = carve(cap * 4),
+                 o_cid = carve(cap * 4), o_cloc = carve(cap * 4), o_nbr = carve(cap * 4 * KNBR),
+                 o_ncnt = carve(cap * 4), o_qc = carve(cap * 4), o_kdp = carve(cap * 4),
+                 o_kdn = carve((2 * cap) * sizeof(KdNodeDev));
+    e = cudaMalloc(&h->d_block, off);
+    if (e != cudaSuccess) { delete h; return SCAB_ERR_NOMEM; }
+    char *b = (char *)h->d_block;
+    A.s_posr = (double4 *)(b + o_posr); A.s_newpos = (double4 *)(b + o_newpos); A.s_vel = (float4 *)(b + o_vel);
+    A.s_id = (int32_t *)(b + o_id); A.rank = (int32_t *)(b + o_rank);
+    A.cell_id = (int32_t *)(b + o_cid); A.cell_local = (int32_t *)(b + o_cloc);
+    A.s_nbr = (int32_t *)(b + o_nbr); A.s_nbr_cnt = (int32_t *)(b + o_ncnt); A.s_qcoll = (int32_t *)(b + o_qc);
+    h->d_kd_agent_perm = (int32_t *)(b + o_kdp); h->d_kd_agent = (KdNodeDev *)(b + o_kdn);
+    A.kd_agent = h->d_kd_agent; A.kd_agent_perm = h->d_kd_agent_perm;
+    // candidate tables
+    std::vector<double> d64; std::vector<float4> d32;
+    bool ok = true;
+    make_dirs(256, d64, d32);
+    ok &= cudaMalloc(&h->d_dir256, d64.size() * 8) == cudaSuccess && cudaMalloc(&h->d_dir256f, d32.size() * 16) == cudaSuccess;
+    if (ok) { cudaMemcpy(h->d_dir256, d64.data(), d64.size() * 8, cudaMemcpyHostToDevice); cudaMemcpy(h->d_dir256f, d32.data(), d32.size() * 16, cudaMemcpyHostToDevice); }
+    make_dirs(128, d64, d32);
+    ok &= cudaMalloc(&h->d_dir128, d64.size() * 8) == cudaSuccess && cudaMalloc(&h->d_dir128f, d32.size() * 16) == cudaSuccess;
+    if (ok) { cudaMemcpy(h->d_dir128, d64.data(), d64.size() * 8, cudaMemcpyHostToDevice); cudaMemcpy(h->d_dir128f, d32.data(), d32.size() * 16, cudaMemcpyHostToDevice); }
+    ok &= cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)) == cudaSuccess;
+    if (!ok) { scab_destroy(h); return SCAB_ERR_NOMEM; }
+    cudaMemset(h->d_counters, 0, 4 * sizeof(unsigned long long));
+    A.dir256 = h->d_dir256; A.dir128 = h->d_dir128; A.dir256f = h->d_dir256f; A.dir128f = h->d_dir128f;
+    A.counters = h->d_counters;
+    set_geom(A.g, p->grid_origin, p->cell_size, p->grid_dim);
+    int32_t one[3] = {1, 1, 1};
+    double zero[3] = {0, 0, 0};
+    set_geom(A.og, zero, p->cell_size, one);
+    int rc = ensure_cells(h, A.g.ncell);
+    if (rc != SCAB_OK) { scab_destroy(h); return rc; }
+    *out = h;
+    return SCAB_OK;
+}
+
+extern "C" int scab_destroy(scab_handle *h)
+{
+    if (!h) return SCAB_ERR_INVALID;
+    cudaSetDevice(h->device);
+    void *ptrs[] = {h->d_block, h->d_cell_count, h->d_cell_start, h->d_dir256, h->d_dir128, h->d_dir256f, h->d_dir128f,
+                    h->d_counters, h->d_o_posr, h->d_o_posr_by_id, h->d_o_id, h->d_o_cell_start, h->d_kd_obst_perm, h->d_kd_obst};
+    for (void *q : ptrs) if (q) cudaFree(q);
+    delete h;
+    return SCAB_OK;
+}
+
+extern "C" int scab_bind_state(scab_handle *h, const scab_state_ptrs *s, int64_t n)
+{
+    if (!h || !s) return fail(h, SCAB_ERR_INVALID, "scab_bind_state: null argument");
+    if (n < 0 || n > h->capacity) return fail(h, SCAB_ERR_CAPACITY, "scab_bind_state: n exceeds capacity");
+    if (!s->pos || !s->vel || !s->heading || !s->goal || !s->radius || !s->pref_speed || !s->status || !s->total_dist ||
+        !s->step_num || !s->max_run_dist || !s->action)
+        return fail(h, SCAB_ERR_INVALID, "scab_bind_state: a required state pointer is NULL");
+    h->A.st = *s;
+    h->A.n = (int)n;
+    h->bound = true;
+    h->kd_valid = false;
+    if ((int64_t)h->kd_perm.size() != n) {   // KDTree.__init__: agentIDs = [0..n) (kdTree.py:43-45)
+        h->kd_perm.resize((size_t)n);
+        for (int64_t i = 0; i < n; i++) h->kd_perm[(size_t)i] = (int32_t)i;
+    }
+    return SCAB_OK;
+}
+
+// ------------------------------------------------------------------ reference kd-tree (host replay)
+// kdTree.py:60-122 buildAgentTreeRecursive / :162-227 buildObstacleTreeRecursive
+static void kd_build(const double *pos, int stride, int32_t *ids, KdNodeDev *nodes, int begin, int end, int node)
+{
+    KdNodeDev &nd = nodes[node];
+    nd.begin = begin; nd.end = end; nd.left = nd.right = 0;
+    for (int c = 0; c < 3; c++) nd.mn[c] = nd.mx[c] = pos[(size_t)stride * ids[begin] + c];
+    for (int i = begin + 1; i < end; i++)
+        for (int c = 0; c < 3; c++) {
+            const double v = pos[(size_t)stride * ids[i] + c];
+            nd.mx[c] = std::max(nd.mx[c], v);
+            nd.mn[c] = std::min(nd.mn[c], v);
+        }
+    if (end - begin > 10) {   // max_leaf_size, kdTree.py:53
+        const double d0 = nd.mx[0] - nd.mn[0], d1 = nd.mx[1] - nd.mn[1], d2 = nd.mx[2] - nd.mn[2];
+        const int coord = (d0 > d1 && d0 > d2) ? 0 : (d1 > d2 ? 1 : 2);
+        const double split = 0.5 * (nd.mx[coord] + nd.mn[coord]);
+        int left = begin, right = end;
+        while (left < right) {
+            while (left < right && pos[(size_t)stride * ids[left] + coord] < split) left++;
+            while (right > left && pos[(size_t)stride * ids[right - 1] + coord] >= split) right--;
+            if (left < right) {
+                std::swap(ids[left], ids[right - 1]);
+                left++;
+                right--;
+            }
+        }
+        int leftSize = left - begin;
+        if (leftSize == 0) { leftSize++; left++; right++; }
+        nd.left = node + 1;
+        nd.right = node + 2 * leftSize;
+        kd_build(pos, stride, ids, nodes, begin, left, nd.left);
+        kd_build(pos, stride, ids, nodes, left, end, nd.right);
+    }
+}
+
+extern "C" int scab_kdtree_build(scab_handle *h, const double *pos_host, int64_t n)
+{
+    if (!h || !pos_host) return fail(h, SCAB_ERR_INVALID, "scab_kdtree_build: null argument");
+    if (!h->bound || n != h->A.n) return fail(h, SCAB_ERR_INVALID, "scab_kdtree_build: n does not match the bound state");
+    if (n == 0) return SCAB_OK;
+    CK(cudaSetDevice(h->device));
+    h->kd_nodes.assign((size_t)(2 * n), KdNodeDev{});
+    kd_build(pos_host, 3, h->kd_perm.data(), h->kd_nodes.data(), 0, (int)n, 0);
+    CK(cudaMemcpy(h->d_kd_agent, h->kd_nodes.data(), sizeof(KdNodeDev) * (size_t)(2 * n - 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_kd_agent_perm, h->kd_perm.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
+    h->kd_valid = true;
+    return SCAB_OK;
+}
+
+extern "C" int scab_kdtree_get_perm(scab_handle *h, int32_t *out_host, int64_t n)
+{
+    if (!h || !out_host || n != (int64_t)h->kd_perm.size()) return fail(h, SCAB_ERR_INVALID, "scab_kdtree_get_perm: bad argument");
+    memcpy(out_host, h->kd_perm.data(), sizeof(int32_t) * (size_t)n);
+    return SCAB_OK;
+}
+
+extern "C" int scab_set_obstacles(scab_handle *h, const double *xyzr, int32_t m)
+{
+    if (!h || m < 0 || (m > 0 && !xyzr)) return fail(h, SCAB_ERR_INVALID, "scab_set_obstacles: bad argument");
+    CK(cudaSetDevice(h->device));
+    void *old[] = {h->d_o_posr, h->d_o_posr_by_id, h->d_o_id, h->d_o_cell_start, h->d_kd_obst_perm, h->d_kd_obst};
+    for (void *q : old) if (q) cudaFree(q);
+    h->d_o_posr = h->d_o_posr_by_id = nullptr; h->d_o_id = h->d_o_cell_start = h->d_kd_obst_perm = nullptr; h->d_kd_obst = nullptr;
+    h->m = m;
+    StepArgs &A = h->A;
+    A.m = m;
+    A.o_posr = A.o_posr_by_id = nullptr; A.o_id = A.o_cell_start = A.kd_obst_perm = nullptr; A.kd_obst = nullptr;
+    if (m == 0) return SCAB_OK;
+    // static obstacle cell list: cell >= neighbor_dist + r_max so that (|pA-pO| - r_O)^2 < D^2 stays
+    // inside the 27-cell neighbourhood (agent.py:106)
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300}, rmax = 0.0;
+    for (int i = 0; i < m; i++) {
+        for (int c = 0; c < 3; c++) { mn[c] = std::min(mn[c], xyzr[4 * i + c]); mx[c] = std::max(mx[c], xyzr[4 * i + c]); }
+        rmax = std::max(rmax, xyzr[4 * i + 3]);
+    }
+    const double cs = h->p.neighbor_dist + rmax + 1e-6;
+    int32_t dim[3];
+    for (int c = 0; c < 3; c++) dim[c] = std::max(1, std::min(1024, (int)std::floor((mx[c] - mn[c]) / cs) + 1));
+    set_geom(A.og, mn, cs, dim);
+    std::vector<int32_t> cell(m), start((size_t)A.og.ncell + 1, 0), order(m);
+    for (int i = 0; i < m; i++) {
+        int cx = std::min(std::max((int)std::floor((xyzr[4 * i] - A.og.ox) * A.og.inv_cs), 0), A.og.nx - 1);
+        int cy = std::min(std::max((int)std::floor((xyzr[4 * i + 1] - A.og.oy) * A.og.inv_cs), 0), A.og.ny - 1);
+        int cz = std::min(std::max((int)std::floor((xyzr[4 * i + 2] - A.og.oz) * A.og.inv_cs), 0), A.og.nz - 1);
+        cell[i] = (cz * A.og.ny + cy) * A.og.nx + cx;
+        start[(size_t)cell[i] + 1]++;
+    }
+    for (int c = 0; c < A.og.ncell; c++) start[(size_t)c + 1] += start[c];
+    std::vector<int32_t> fill(start.begin(), start.end() - 1);
+    for (int i = 0; i < m; i++) order[fill[cell[i]]++] = i;   // stable: id order inside a cell
+    std::vector<double4> sorted(m), byid(m);
+    std::vector<int32_t> oid(m);
+    for (int i = 0; i < m; i++) byid[i] = make_double4(xyzr[4 * i], xyzr[4 * i + 1], xyzr[4 * i + 2], xyzr[4 * i + 3]);
+    for (int k = 0; k < m; k++) { sorted[k] = byid[order[k]]; oid[k] = order[k]; }
+    // reference obstacle kd-tree (built once: mampenv.py:20)
+    std::vector<int32_t> perm(m);
+    for (int i = 0; i < m; i++) perm[i] = i;
+    std::vector<KdNodeDev> nodes((size_t)2 * m);
+    kd_build(xyzr, 4, perm.data(), nodes.data(), 0, m, 0);
+    CK(cudaMalloc(&h->d_o_posr, sizeof(double4) * m));
+    CK(cudaMalloc(&h->d_o_posr_by_id, sizeof(double4) * m));
+    CK(cudaMalloc(&h->d_o_id, 4 * (size_t)m));
+    CK(cudaMalloc(&h->d_o_cell_start, 4 * start.size()));
+    CK(cudaMalloc(&h->d_kd_obst_perm, 4 * (size_t)m));
+    CK(cudaMalloc(&h->d_kd_obst, sizeof(KdNodeDev) * nodes.size()));
+    CK(cudaMemcpy(h->d_o_posr, sorted.data(), sizeof(double4) * m, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_o_posr_by_id, byid.data(), sizeof(double4) * m, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_o_id, oid.data(), 4 * (size_t)m, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_o_cell_start, start.data(), 4 * start.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_kd_obst_perm, perm.data(), 4 * (size_t)m, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_kd_obst, nodes.data(), sizeof(KdNodeDev) * nodes.size(), cudaMemcpyHostToDevice));
+    A.o_posr = h->d_o_posr; A.o_posr_by_id = h->d_o_posr_by_id; A.o_id = h->d_o_id; A.o_cell_start = h->d_o_cell_start;
+    A.kd_obst_perm = h->d_kd_obst_perm; A.kd_obst = h->d_kd_obst;
+    return SCAB_OK;
+}
+
+// ------------------------------------------------------------------ stages
+static int check_ready(scab_handle *h, const char *who)
+{
+    if (!h) return SCAB_ERR_INVALID;
+    if (!h->bound) return fail(h, SCAB_ERR_INVALID, std::string(who) + ": no state bound");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail(h, SCAB_ERR_CUDA, cudaGetErrorString(e));
+    return SCAB_OK;
+}
+
+extern "C" int scab_build_grid(scab_handle *h, void *stream)
+{
+    int rc = check_ready(h, "scab_build_grid");
+    if (rc) return rc;
+    CK(launch_grid_build(h->A, (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int scab_neighbors(scab_handle *h, int mode, void *stream)
+{
+    int rc = check_ready(h, "scab_neighbors");
+    if (rc) return rc;
+    if (mode != SCAB_NBR_KNN && mode != SCAB_NBR_REF_COMPAT) return fail(h, SCAB_ERR_INVALID, "scab_neighbors: bad mode");
+    if (mode == SCAB_NBR_REF_COMPAT && !h->kd_valid && h->A.n > 0)
+        return fail(h, SCAB_ERR_INVALID, "scab_neighbors: REF_COMPAT needs scab_kdtree_build first");
+    CK(launch_neighbors(h->A, mode, (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int scab_policy_step(scab_handle *h, int policy, void *stream)
+{
+    int rc = check_ready(h, "scab_policy_step");
+    if (rc) return rc;
+    if (policy < SCAB_POLICY_SCA || policy > SCAB_POLICY_ORCA_LP) return fail(h, SCAB_ERR_INVALID, "scab_policy_step: bad policy");
+    if (policy == SCAB_POLICY_ORCA_LP) CK(launch_policy_lp(h->A, (cudaStream_t)stream));
+    else CK(launch_policy_sampled(h->A, policy, (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int scab_status_step(scab_handle *h, void *stream)
+{
+    int rc = check_ready(h, "scab_status_step");
+    if (rc) return rc;
+    CK(launch_status(h->A, (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int scab_step(scab_handle *h, int policy, int nbr_mode, void *stream)
+{
+    int rc = scab_build_grid(h, stream);
+    if (rc) return rc;
+    rc = scab_neighbors(h, nbr_mode, stream);
+    if (rc) return rc;
+    rc = scab_policy_step(h, policy, stream);
+    if (rc) return rc;
+    return scab_status_step(h, stream);
+}
+
+extern "C" int scab_read_counters(scab_handle *h, scab_counters *out, void *stream)
+{
+    if (!h || !out) return fail(h, SCAB_ERR_INVALID, "scab_read_counters: null argument");
+    CK(cudaSetDevice(h->device));
+    unsigned long long v[4];
+    CK(cudaMemcpyAsync(v, h->d_counters, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    out->n_active = (int64_t)v[0]; out->n_not_done = (int64_t)v[1]; out->n_collision = (int64_t)v[2]; out->n_recheck = (int64_t)v[3];
+    return SCAB_OK;
+}

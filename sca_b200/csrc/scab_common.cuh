@@ -1,0 +1,201 @@
+// scab_common.cuh -- shared declarations of libscab200 (sm_100a only).
+//
+// Numerics contract (DESIGN.md "Numerics"): every decision scalar of the reference is evaluated in
+// fp64 with the reference's own decimal-rounding conventions (mamp/util.py:100-106,140-150); the
+// library is compiled with -fmad=false so the only fused multiply-adds are the explicit ones that
+// reproduce NumPy's 3-element dot (x0*y0 followed by two FMAs).  Bulk candidate tests run in fp32
+// with an error-bounded guard band; hits inside the band are re-evaluated in fp64.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/scab200.h"
+
+#define KNBR SCAB_MAX_NEIGHBORS
+#define SCAB_PI 3.141592653589793
+#define RVO_EPS 1e-5  // mamp/configs/config.py:4
+
+// internal flag bits carried in the snapshot's vel.w (low bits == SCAB_ST_*)
+#define FL_INACTIVE (SCAB_ST_AT_GOAL | SCAB_ST_COLLISION | SCAB_ST_TIMEOUT)
+
+struct GridGeom {
+    double ox, oy, oz, inv_cs;
+    int nx, ny, nz, ncell;
+};
+
+// kd-tree node of the reference (kdTree.py:14-21), REF_COMPAT mode only
+struct KdNodeDev {
+    int32_t begin, end, left, right;
+    double mn[3], mx[3];
+};
+
+// Everything a kernel needs; passed by value.
+struct StepArgs {
+    scab_state_ptrs st;
+    int n;           // owned agents
+    int m;           // obstacles
+    GridGeom g;      // agent grid
+    GridGeom og;     // obstacle grid (static)
+    // constants
+    double nbr_dist_sq, time_step, inv_time_horizon, inv_time_step, max_speed, near_goal;
+    // snapshot, sorted by cell
+    double4 *s_posr;    // x y z r
+    float4 *s_vel;      // vx vy vz, w = status bits
+    int32_t *s_id;      // sorted idx -> agent id
+    int32_t *rank;      // agent id -> sorted idx
+    double4 *s_newpos;  // position after the kinematic update (sorted order)
+    int32_t *cell_id, *cell_local, *cell_count, *cell_start;  // [n], [n], [ncell], [ncell+1]
+    int32_t *s_nbr;     // [n,16] sorted idx, or n + sorted obstacle idx
+    int32_t *s_nbr_cnt; // [n]
+    int32_t *s_qcoll;   // [n] collision flag raised by the neighbour query (agent.py:83-85)
+    // obstacles (sorted by obstacle cell) + reference kd-trees
+    const double4 *o_posr;
+    const int32_t *o_id, *o_cell_start;
+    const KdNodeDev *kd_agent, *kd_obst;
+    const int32_t *kd_agent_perm, *kd_obst_perm;
+    const double4 *o_posr_by_id;  // unsorted (id order), for the kd-tree replay
+    // candidate direction tables (host libm, uploaded once): unit Fibonacci-sphere directions
+    const double *dir256, *dir128;   // [N,3] f64
+    const float4 *dir256f, *dir128f; // [N] f32 (x y z 0)
+    unsigned long long *counters;    // scab_counters
+};
+
+// ------------------------------------------------------------------ rounding conventions
+__device__ __forceinline__ double np_round5(double x)
+{  // round(np.float64, 5): NumPy scalar __round__ -> rint(x*1e5)/1e5 (util.py:100 l3normsq)
+    return __ddiv_rn(rint(__dmul_rn(x, 1e5)), 1e5);
+}
+__device__ __forceinline__ double py_round5_units(double x)
+{  // CPython float.__round__(x,5) numerator: round-half-even on the EXACT value of x*1e5
+    double p = __dmul_rn(x, 1e5);
+    double e = __fma_rn(x, 1e5, -p);
+    double r = rint(p);
+    if (fabs(p - r) == 0.5 && e != 0.0) r = (e > 0.0) ? ceil(p) : floor(p);
+    return r;
+}
+__device__ __forceinline__ double py_round5(double x)
+{
+    if (!isfinite(x)) return x;
+    return __ddiv_rn(py_round5_units(x), 1e5);
+}
+__device__ __forceinline__ double trunc5(double x)
+{  // int(x*1e5)/1e5 ; python ints have no -0
+    return __ddiv_rn(__dadd_rn(trunc(__dmul_rn(x, 1e5)), 0.0), 1e5);
+}
+__device__ __forceinline__ double dot3(double a0, double a1, double a2, double b0, double b1, double b2)
+{  // np.dot on 3-vectors (OpenBLAS ddot tail): product then two FMAs
+    return __fma_rn(a2, b2, __fma_rn(a1, b1, __dmul_rn(a0, b0)));
+}
+__device__ __forceinline__ double sumsq3(double d0, double d1, double d2)
+{  // python: d0**2 + d1**2 + d2**2, each op rounded
+    return __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+}
+__device__ __forceinline__ double l3norm_d(double ax, double ay, double az, double bx, double by, double bz)
+{  // util.py:103-105
+    return py_round5(__dsqrt_rn(sumsq3(__dsub_rn(ax, bx), __dsub_rn(ay, by), __dsub_rn(az, bz))));
+}
+__device__ __forceinline__ double l3normsq_d(double ax, double ay, double az, double bx, double by, double bz)
+{  // util.py:99-100
+    return np_round5(sumsq3(__dsub_rn(ax, bx), __dsub_rn(ay, by), __dsub_rn(az, bz)));
+}
+__device__ __forceinline__ double sumsq_f32(float x, float y, float z)
+{  // l3norm(vA,[0,0,0]) with float32 vA: squares and sums stay float32
+    return (double)__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+__device__ __forceinline__ float norm3f_np(float x, float y, float z)
+{  // np.linalg.norm(float32[3]): f32 products accumulated in double (OpenBLAS sdot), f32 sqrt
+    double d = (double)__fmul_rn(x, x);
+    d = __dadd_rn(d, (double)__fmul_rn(y, y));
+    d = __dadd_rn(d, (double)__fmul_rn(z, z));
+    return __fsqrt_rn((float)d);
+}
+__device__ __forceinline__ double pi_2_pi(double angle)
+{  // util.py:108-109 with NumPy's floored remainder
+    double a = __dadd_rn(angle, SCAB_PI);
+    const double b = 2 * SCAB_PI;
+    double m = fmod(a, b);
+    if (m != 0.0) {
+        if (m < 0) m = __dadd_rn(m, b);
+    } else {
+        m = 0.0;
+    }
+    return __dsub_rn(m, SCAB_PI);
+}
+
+__device__ __forceinline__ int cell_of(const GridGeom &g, double x, double y, double z, int &cx, int &cy, int &cz)
+{
+    cx = (int)floor((x - g.ox) * g.inv_cs);
+    cy = (int)floor((y - g.oy) * g.inv_cs);
+    cz = (int)floor((z - g.oz) * g.inv_cs);
+    cx = min(max(cx, 0), g.nx - 1);
+    cy = min(max(cy, 0), g.ny - 1);
+    cz = min(max(cz, 0), g.nz - 1);
+    return (cz * g.ny + cy) * g.nx + cx;
+}
+
+// ------------------------------------------------------------------ shared device routines
+struct Action7 { float a[7]; };
+
+// util.py:44-55 (use_distance=false) / orca3dPolicyOfficial.py:331-342 (use_distance=true)
+__device__ __forceinline__ Action7 cartesian2spherical(double vx, double vy, double vz, double yaw, double pitch,
+                                                       bool use_distance)
+{
+    double nrm = __dsqrt_rn(sumsq3(vx, vy, vz));
+    double speed = use_distance ? py_round5(__dadd_rn(nrm, 1e-5)) : py_round5(nrm);
+    double alpha = 0.0, beta = 0.0;
+    if (!(speed < 0.001)) {
+        alpha = __dsub_rn(atan2(vy, vx), yaw);
+        beta = __dsub_rn(atan2(vz, __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)))), pitch);
+    }
+    Action7 r;
+    r.a[0] = (float)vx; r.a[1] = (float)vy; r.a[2] = (float)vz; r.a[3] = (float)speed;
+    r.a[4] = (float)alpha; r.a[5] = (float)beta; r.a[6] = 0.f;
+    return r;
+}
+
+// rvo3dPolicy.py:182-196 (use_distance=false) / orca3dPolicy*.py:345-359 (use_distance=true)
+__device__ __forceinline__ void v_pref_straight(const double *g, double px, double py, double pz, double pref,
+                                                bool use_distance, double *v_store, double *v_des)
+{
+    double dx = __dsub_rn(g[0], px), dy = __dsub_rn(g[1], py), dz = __dsub_rn(g[2], pz);
+    double nr = __dsqrt_rn(sumsq3(dx, dy, dz));
+    double nrm = use_distance ? py_round5(__dadd_rn(nr, 1e-5)) : py_round5(nr);
+    nrm = trunc5(nrm);
+    v_store[0] = __ddiv_rn(__dmul_rn(dx, pref), nrm);
+    v_store[1] = __ddiv_rn(__dmul_rn(dy, pref), nrm);
+    v_store[2] = __ddiv_rn(__dmul_rn(dz, pref), nrm);
+    if (py_round5(nr) < 0.2) { v_store[0] = 0.0; v_store[1] = 0.0; v_store[2] = 0.0; }  // reached(), util.py:23
+    v_des[0] = trunc5(v_store[0]); v_des[1] = trunc5(v_store[1]); v_des[2] = trunc5(v_store[2]);
+}
+
+// mampenv.py:83-105 update_velocitie; writes the agent's state in place and returns the new position
+__device__ __forceinline__ void kinematic_update(const StepArgs &A, int id, const Action7 &act, double px, double py,
+                                                 double pz, double *npx, double *npy, double *npz)
+{
+    double speed = (double)act.a[3];
+    double al = pi_2_pi(__dadd_rn(A.st.heading[3 * id + 0], (double)act.a[4]));
+    double be = pi_2_pi(__dadd_rn(A.st.heading[3 * id + 1], (double)act.a[5]));
+    double ga = pi_2_pi(__dadd_rn(A.st.heading[3 * id + 2], (double)act.a[6]));
+    double sb, cb, sa, ca;
+    sincos(be, &sb, &cb);
+    sincos(al, &sa, &ca);
+    double t = __dmul_rn(speed, cb);
+    double dx = __dmul_rn(__dmul_rn(t, ca), A.time_step);
+    double dy = __dmul_rn(__dmul_rn(t, sa), A.time_step);
+    double dz = __dmul_rn(__dmul_rn(speed, sb), A.time_step);
+    double len = __dsqrt_rn(sumsq3(dx, dy, dz));
+    A.st.total_dist[id] = __dadd_rn(A.st.total_dist[id], len);
+    *npx = __dadd_rn(px, dx); *npy = __dadd_rn(py, dy); *npz = __dadd_rn(pz, dz);
+    A.st.pos[3 * id + 0] = *npx; A.st.pos[3 * id + 1] = *npy; A.st.pos[3 * id + 2] = *npz;
+    A.st.heading[3 * id + 0] = al; A.st.heading[3 * id + 1] = be; A.st.heading[3 * id + 2] = ga;
+    A.st.vel[3 * id + 0] = act.a[0]; A.st.vel[3 * id + 1] = act.a[1]; A.st.vel[3 * id + 2] = act.a[2];
+#pragma unroll
+    for (int k = 0; k < 7; k++) A.st.action[7 * id + k] = act.a[k];
+}
+
+// kernels' host-side launchers (one translation unit per stage)
+cudaError_t launch_grid_build(const StepArgs &A, cudaStream_t s);
+cudaError_t launch_neighbors(const StepArgs &A, int mode, cudaStream_t s);
+cudaError_t launch_policy_sampled(const StepArgs &A, int policy, cudaStream_t s);
+cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s);
+cudaError_t launch_status(const StepArgs &A, cudaStream_t s);

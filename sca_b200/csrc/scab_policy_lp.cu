@@ -1,0 +1,322 @@
+// scab_policy_lp.cu -- stage 3 for ORCA3D with the linear programs, one thread per agent, fp64:
+//   planes        mamp/policies/orca3dPolicyOfficial.py:56-106
+//   linearProgram1 :126-181, linearProgram2 :183-237, linearProgram3 :239-259, linearProgram4 :261-300
+// fused with cartesian2spherical (:331-342, the `distance` variant) and the kinematic update
+// (mamp/envs/mampenv.py:83-105).
+//
+// The reference's deviations from RVO2-3D are reproduced on purpose: the LP4 entry
+// test at :264 is np.dot(normal, (point - v) > 0.0) -- a dot with a BOOLEAN vector -- and LP4 keeps no
+// running distance.  Plane order == neighbour order, which is why the neighbour stage is order-exact.
+// Planes live in shared memory (16 x 48 B per agent, transposed so that lanes hit distinct banks).
+#include "scab_common.cuh"
+
+#define LP_THREADS 64
+
+struct Planes {
+    // [component][plane][thread] : consecutive threads -> consecutive 8-byte words (conflict-free)
+    double v[6][KNBR][LP_THREADS];
+};
+
+struct PlaneView {
+    double *base;  // &P.v[0][0][tid] (shared, stride LP_THREADS) or a thread-local array (stride 1)
+    int stride;
+    __device__ __forceinline__ double &at(int comp, int k) const { return base[(comp * KNBR + k) * stride]; }
+    __device__ __forceinline__ double px(int k) const { return at(0, k); }
+    __device__ __forceinline__ double py(int k) const { return at(1, k); }
+    __device__ __forceinline__ double pz(int k) const { return at(2, k); }
+    __device__ __forceinline__ double nx(int k) const { return at(3, k); }
+    __device__ __forceinline__ double ny(int k) const { return at(4, k); }
+    __device__ __forceinline__ double nz(int k) const { return at(5, k); }
+};
+
+struct Vec3 { double x, y, z; };
+
+__device__ __forceinline__ double dotv(const Vec3 &a, const Vec3 &b) { return dot3(a.x, a.y, a.z, b.x, b.y, b.z); }
+__device__ __forceinline__ Vec3 crossv(const Vec3 &a, const Vec3 &b)
+{   // np.cross: products and differences rounded separately
+    Vec3 c;
+    c.x = __dsub_rn(__dmul_rn(a.y, b.z), __dmul_rn(a.z, b.y));
+    c.y = __dsub_rn(__dmul_rn(a.z, b.x), __dmul_rn(a.x, b.z));
+    c.z = __dsub_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x));
+    return c;
+}
+__device__ __forceinline__ Vec3 P_point(const PlaneView &P, int k) { return Vec3{P.px(k), P.py(k), P.pz(k)}; }
+__device__ __forceinline__ Vec3 P_normal(const PlaneView &P, int k) { return Vec3{P.nx(k), P.ny(k), P.nz(k)}; }
+__device__ __forceinline__ Vec3 subv(const Vec3 &a, const Vec3 &b) { return Vec3{__dsub_rn(a.x, b.x), __dsub_rn(a.y, b.y), __dsub_rn(a.z, b.z)}; }
+__device__ __forceinline__ Vec3 axpy(double s, const Vec3 &d, const Vec3 &p)
+{   // p + s * d with the product rounded first (NumPy ufunc order)
+    return Vec3{__dadd_rn(p.x, __dmul_rn(s, d.x)), __dadd_rn(p.y, __dmul_rn(s, d.y)), __dadd_rn(p.z, __dmul_rn(s, d.z))};
+}
+
+// orca3dPolicyOfficial.py:126-181
+__device__ bool lp1(const PlaneView &P, int planeNo, const Vec3 &lpoint, const Vec3 &ldir, double maxSpeed,
+                    const Vec3 &vel_pref, bool dir_opt, Vec3 &res)
+{
+    const double dp = dotv(lpoint, ldir);
+    const double disc = __dsub_rn(__dadd_rn(__dmul_rn(dp, dp), __dmul_rn(maxSpeed, maxSpeed)), dotv(lpoint, lpoint));
+    if (disc < 0.0) return false;
+    const double sq = __dsqrt_rn(disc);
+    double tLeft = __dsub_rn(-dp, sq), tRight = __dadd_rn(-dp, sq);
+    for (int i = 0; i < planeNo; i++) {
+        const Vec3 n = P_normal(P, i);
+        const double num = dotv(subv(P_point(P, i), lpoint), n);
+        const double den = dotv(ldir, n);
+        if (__dmul_rn(den, den) <= RVO_EPS) {
+            if (num > 0.0) return false;
+            continue;
+        }
+        const double t = __ddiv_rn(num, den);
+        if (den >= 0.0) tLeft = fmax(tLeft, t);
+        else tRight = fmin(tRight, t);
+        if (tLeft > tRight) return false;
+    }
+    double tt;
+    if (dir_opt) {
+        tt = (dotv(vel_pref, ldir) > 0.0) ? tRight : tLeft;
+    } else {
+        const double t = dotv(ldir, subv(vel_pref, lpoint));
+        tt = (t < tLeft) ? tLeft : (t > tRight ? tRight : t);
+    }
+    res = axpy(tt, ldir, lpoint);
+    return true;
+}
+
+// orca3dPolicyOfficial.py:183-237
+__device__ bool lp2(const PlaneView &P, int planeNo, double maxSpeed, const Vec3 &vel_pref, bool dir_opt, Vec3 &res)
+{
+    const Vec3 pn = P_normal(P, planeNo), pp = P_point(P, planeNo);
+    const double planeDist = dotv(pp, pn);
+    const double planeDistSq = __dmul_rn(planeDist, planeDist);
+    const double radiusSq = __dmul_rn(maxSpeed, maxSpeed);
+    if (planeDistSq > radiusSq) return false;
+    const double planeRadiusSq = __dsub_rn(radiusSq, planeDistSq);
+    const Vec3 center{__dmul_rn(planeDist, pn.x), __dmul_rn(planeDist, pn.y), __dmul_rn(planeDist, pn.z)};
+    if (dir_opt) {
+        const double dn = dotv(vel_pref, pn);
+        const Vec3 pov{__dsub_rn(vel_pref.x, __dmul_rn(dn, pn.x)), __dsub_rn(vel_pref.y, __dmul_rn(dn, pn.y)),
+                       __dsub_rn(vel_pref.z, __dmul_rn(dn, pn.z))};
+        const double povSq = dotv(pov, pov);
+        if (povSq <= RVO_EPS) res = center;
+        else res = axpy(__dsqrt_rn(__ddiv_rn(planeRadiusSq, povSq)), pov, center);
+    } else {
+        const double dpn = dotv(subv(pp, vel_pref), pn);
+        res = axpy(dpn, pn, vel_pref);
+        if (dotv(res, res) > radiusSq) {
+            const Vec3 pr = subv(res, center);
+            const double prSq = dotv(pr, pr);
+            res = axpy(__dsqrt_rn(__ddiv_rn(planeRadiusSq, prSq)), pr, center);
+        }
+    }
+    for (int i = 0; i < planeNo; i++) {
+        const Vec3 ni = P_normal(P, i), pi = P_point(P, i);
+        if (dotv(ni, subv(pi, res)) > 0.0) {
+            const Vec3 cp = crossv(ni, pn);
+            const double cpSq = dotv(cp, cp);
+            if (cpSq <= RVO_EPS) return false;
+            const double ncp = __dsqrt_rn(cpSq);
+            const Vec3 ldir{__ddiv_rn(cp.x, ncp), __ddiv_rn(cp.y, ncp), __ddiv_rn(cp.z, ncp)};
+            const Vec3 lnormal = crossv(ldir, pn);
+            const double dp1 = dotv(subv(pi, pp), ni);
+            const double dp2 = dotv(lnormal, ni);
+            const Vec3 lpoint = axpy(__ddiv_rn(dp1, dp2), lnormal, pp);
+            if (!lp1(P, i, lpoint, ldir, maxSpeed, vel_pref, dir_opt, res)) return false;
+        }
+    }
+    return true;
+}
+
+// orca3dPolicyOfficial.py:239-259
+__device__ int lp3(const PlaneView &P, int np, double maxSpeed, const Vec3 &vel_pref, bool dir_opt, Vec3 &res)
+{
+    if (dir_opt) {
+        res = Vec3{__dmul_rn(vel_pref.x, maxSpeed), __dmul_rn(vel_pref.y, maxSpeed), __dmul_rn(vel_pref.z, maxSpeed)};
+    } else if (dotv(vel_pref, vel_pref) > __dmul_rn(maxSpeed, maxSpeed)) {
+        const double nv = __dsqrt_rn(dotv(vel_pref, vel_pref));
+        res = Vec3{__dmul_rn(__ddiv_rn(vel_pref.x, nv), maxSpeed), __dmul_rn(__ddiv_rn(vel_pref.y, nv), maxSpeed),
+                   __dmul_rn(__ddiv_rn(vel_pref.z, nv), maxSpeed)};
+    } else {
+        res = vel_pref;
+    }
+    for (int i = 0; i < np; i++) {
+        if (dotv(P_normal(P, i), subv(P_point(P, i), res)) > 0.0) {
+            const Vec3 temp = res;
+            if (!lp2(P, i, maxSpeed, vel_pref, dir_opt, res)) {
+                res = temp;
+                return i;
+            }
+        }
+    }
+    return np;
+}
+
+// orca3dPolicyOfficial.py:261-300.  `Q` is a second plane set (the projected planes).
+__device__ void lp4(const PlaneView &P, const PlaneView &Q, int np, int beginPlane, double radius, Vec3 &res, int &n_proj)
+{
+    for (int i = beginPlane; i < np; i++) {
+        const Vec3 ni = P_normal(P, i), pi = P_point(P, i);
+        // :264 np.dot(normal, (point - v) > 0.0): dot with a boolean vector, truthy iff != 0
+        const double bsum = dot3(ni.x, ni.y, ni.z, (__dsub_rn(pi.x, res.x) > 0.0) ? 1.0 : 0.0,
+                                 (__dsub_rn(pi.y, res.y) > 0.0) ? 1.0 : 0.0, (__dsub_rn(pi.z, res.z) > 0.0) ? 1.0 : 0.0);
+        if (bsum != 0.0) {
+            int nq = 0;
+            for (int j = 0; j < i; j++) {
+                const Vec3 nj = P_normal(P, j), pj = P_point(P, j);
+                const Vec3 cp = crossv(nj, ni);
+                Vec3 pt;
+                if (dotv(cp, cp) <= RVO_EPS) {
+                    if (dotv(ni, nj) > 0.0) continue;
+                    pt = Vec3{__dmul_rn(0.5, __dadd_rn(pi.x, pj.x)), __dmul_rn(0.5, __dadd_rn(pi.y, pj.y)),
+                              __dmul_rn(0.5, __dadd_rn(pi.z, pj.z))};
+                } else {
+                    const Vec3 ln = crossv(cp, ni);
+                    const double dp1 = dotv(subv(pj, pi), nj);
+                    const double dp2 = dotv(ln, nj);
+                    pt = axpy(__ddiv_rn(dp1, dp2), ln, pi);
+                }
+                const Vec3 dn = subv(nj, ni);
+                const double nn = __dsqrt_rn(dotv(dn, dn));
+                Q.at(0, nq) = pt.x; Q.at(1, nq) = pt.y; Q.at(2, nq) = pt.z;
+                Q.at(3, nq) = __ddiv_rn(dn.x, nn); Q.at(4, nq) = __ddiv_rn(dn.y, nn); Q.at(5, nq) = __ddiv_rn(dn.z, nn);
+                nq++;
+            }
+            const Vec3 temp = res;
+            n_proj++;
+            if (lp3(Q, nq, radius, ni, true, res) < nq) res = temp;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LP_THREADS) k_policy_lp(StepArgs A)
+{
+    extern __shared__ double lp_smem[];
+    Planes *PS = reinterpret_cast<Planes *>(lp_smem);
+    const int tid = threadIdx.x;
+    double qloc[6 * KNBR];   // projected planes of linearProgram4: rare path, thread-local
+    PlaneView P{&PS[0].v[0][0][tid], LP_THREADS}, Q{qloc, 1};
+    const int s = blockIdx.x * blockDim.x + tid;
+    unsigned long long ran = 0;
+    if (s < A.n) {
+        const int id = A.s_id[s];
+        const double4 me = A.s_posr[s];
+        const float4 mv = A.s_vel[s];
+        const int flags = __float_as_int(mv.w);
+        Action7 act;
+        double npx, npy, npz;
+        if (flags & FL_INACTIVE) {
+#pragma unroll
+            for (int k = 0; k < 7; k++) act.a[k] = 0.f;
+            kinematic_update(A, id, act, me.x, me.y, me.z, &npx, &npy, &npz);
+            A.s_newpos[s] = make_double4(npx, npy, npz, 0.0);
+            if (A.st.tag) A.st.tag[id] = 0;
+            if (A.st.plane_fail) A.st.plane_fail[id] = -1;
+            if (A.st.n_planes) A.st.n_planes[id] = -1;
+            if (A.st.lp4_proj) A.st.lp4_proj[id] = 0;
+        } else {
+            ran = 1;
+            double v_store[3], v_des[3];
+            v_pref_straight(&A.st.goal[3 * id], me.x, me.y, me.z, A.st.pref_speed[id], true, v_store, v_des);
+            const double nv32 = __dsqrt_rn(sumsq_f32(mv.x, mv.y, mv.z));
+            const bool first = py_round5(__dadd_rn(nv32, 1e-5)) <= 1e-5;   // :52 distance(vel, 0) <= 1e-5
+            int tag = 0, plane_fail = -1, n_planes = -1, n_proj = 0;
+            Vec3 res;
+            if (first) {
+                tag = SCAB_TAG_FIRST;
+                res = Vec3{__dmul_rn(0.3, v_des[0]), __dmul_rn(0.3, v_des[1]), __dmul_rn(0.3, v_des[2])};
+            } else {
+                const int nc = A.s_nbr_cnt[s];
+                for (int k = 0; k < nc; k++) {
+                    const int e = A.s_nbr[(size_t)s * KNBR + k];
+                    double4 o;
+                    float ox = 0.f, oy = 0.f, oz = 0.f;
+                    if (e < A.n) {
+                        o = A.s_posr[e];
+                        const float4 ov = A.s_vel[e];
+                        ox = ov.x; oy = ov.y; oz = ov.z;
+                    } else if (e < A.n + A.m) o = A.o_posr[e - A.n];
+                    else o = A.o_posr_by_id[e - A.n - A.m];
+                    // :58-105
+                    const Vec3 rp{__dsub_rn(o.x, me.x), __dsub_rn(o.y, me.y), __dsub_rn(o.z, me.z)};
+                    const Vec3 rv{(double)__fsub_rn(mv.x, ox), (double)__fsub_rn(mv.y, oy), (double)__fsub_rn(mv.z, oz)};
+                    const double distSq = dotv(rp, rp);
+                    const double R = __dadd_rn(__dadd_rn(me.w, 0.05), __dadd_rn(o.w, 0.05));
+                    const double RSq = __dmul_rn(R, R);
+                    Vec3 n, u;
+                    if (distSq > RSq) {
+                        const double invT = A.inv_time_horizon;
+                        const Vec3 w{__dsub_rn(rv.x, __dmul_rn(invT, rp.x)), __dsub_rn(rv.y, __dmul_rn(invT, rp.y)),
+                                     __dsub_rn(rv.z, __dmul_rn(invT, rp.z))};
+                        const double wl2 = dotv(w, w);
+                        const double dp = dotv(w, rp);
+                        if (dp < 0.0 && __dmul_rn(dp, dp) > __dmul_rn(RSq, wl2)) {
+                            const double wl = __dsqrt_rn(wl2);
+                            n = Vec3{__ddiv_rn(w.x, wl), __ddiv_rn(w.y, wl), __ddiv_rn(w.z, wl)};
+                            const double sc = __dsub_rn(__dmul_rn(R, invT), wl);
+                            u = Vec3{__dmul_rn(sc, n.x), __dmul_rn(sc, n.y), __dmul_rn(sc, n.z)};
+                        } else {
+                            const double difSq = __dsub_rn(distSq, RSq);
+                            const double dpr = dotv(rp, rv);
+                            const Vec3 cr = crossv(rp, rv);
+                            const double wwSq = __ddiv_rn(dotv(cr, cr), difSq);
+                            const double pl = __dsqrt_rn(distSq);
+                            const double t = __ddiv_rn(__dadd_rn(__ddiv_rn(dpr, pl), __dmul_rn(__dsqrt_rn(wwSq), __ddiv_rn(R, pl))), pl);
+                            const Vec3 ww{__dsub_rn(rv.x, __dmul_rn(t, rp.x)), __dsub_rn(rv.y, __dmul_rn(t, rp.y)),
+                                          __dsub_rn(rv.z, __dmul_rn(t, rp.z))};
+                            const double wl = __dsqrt_rn(dotv(ww, ww));
+                            n = Vec3{__ddiv_rn(ww.x, wl), __ddiv_rn(ww.y, wl), __ddiv_rn(ww.z, wl)};
+                            const double sc = __dsub_rn(__dmul_rn(R, t), wl);
+                            u = Vec3{__dmul_rn(sc, n.x), __dmul_rn(sc, n.y), __dmul_rn(sc, n.z)};
+                        }
+                    } else {
+                        const double invDt = A.inv_time_step;
+                        const Vec3 w{__dsub_rn(rv.x, __dmul_rn(invDt, rp.x)), __dsub_rn(rv.y, __dmul_rn(invDt, rp.y)),
+                                     __dsub_rn(rv.z, __dmul_rn(invDt, rp.z))};
+                        const double wl = __dsqrt_rn(dotv(w, w));
+                        n = Vec3{__ddiv_rn(w.x, wl), __ddiv_rn(w.y, wl), __ddiv_rn(w.z, wl)};
+                        const double sc = __dsub_rn(__dmul_rn(R, invDt), wl);
+                        u = Vec3{__dmul_rn(sc, n.x), __dmul_rn(sc, n.y), __dmul_rn(sc, n.z)};
+                    }
+                    P.at(0, k) = __dadd_rn((double)mv.x, __dmul_rn(0.5, u.x));
+                    P.at(1, k) = __dadd_rn((double)mv.y, __dmul_rn(0.5, u.y));
+                    P.at(2, k) = __dadd_rn((double)mv.z, __dmul_rn(0.5, u.z));
+                    P.at(3, k) = n.x; P.at(4, k) = n.y; P.at(5, k) = n.z;
+                }
+                const Vec3 vp{v_des[0], v_des[1], v_des[2]};
+                plane_fail = lp3(P, nc, A.max_speed, vp, false, res);   // :108
+                n_planes = nc;
+                if (plane_fail == nc) tag |= SCAB_TAG_LP3_OK;
+                if (plane_fail < nc) {                                   // :110-111
+                    tag |= SCAB_TAG_LP4;
+                    lp4(P, Q, nc, plane_fail, A.max_speed, res, n_proj);
+                }
+            }
+            act = cartesian2spherical(res.x, res.y, res.z, A.st.heading[3 * id], A.st.heading[3 * id + 1], true);
+            kinematic_update(A, id, act, me.x, me.y, me.z, &npx, &npy, &npz);
+            A.s_newpos[s] = make_double4(npx, npy, npz, 0.0);
+            if (A.s_qcoll[s]) A.st.status[id] = flags | SCAB_ST_COLLISION;   // agent.py:83-85
+            if (A.st.vpref_out) { A.st.vpref_out[3 * id] = v_store[0]; A.st.vpref_out[3 * id + 1] = v_store[1]; A.st.vpref_out[3 * id + 2] = v_store[2]; }
+            if (A.st.tag) A.st.tag[id] = tag;
+            if (A.st.plane_fail) A.st.plane_fail[id] = plane_fail;
+            if (A.st.n_planes) A.st.n_planes[id] = n_planes;
+            if (A.st.lp4_proj) A.st.lp4_proj[id] = n_proj;
+            if (A.st.n_suit) A.st.n_suit[id] = 0;
+        }
+    }
+    // one counter update per warp
+    const unsigned act_mask = __ballot_sync(0xffffffffu, ran != 0);
+    if ((threadIdx.x & 31) == 0 && act_mask) atomicAdd(&A.counters[0], (unsigned long long)__popc(act_mask));
+}
+
+cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
+{
+    if (A.n <= 0) return cudaSuccess;
+    static bool attr_set = false;
+    const size_t smem = sizeof(Planes);   // 6*16*64*8 = 49152 B
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_policy_lp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int nb = (A.n + LP_THREADS - 1) / LP_THREADS;
+    k_policy_lp<<<nb, LP_THREADS, smem, s>>>(A);
+    return cudaGetLastError();
+}

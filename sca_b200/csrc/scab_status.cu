@@ -1,0 +1,107 @@
+// scab_status.cu -- stage 4: collision / timeout / goal flags and the done reduction.
+// Replaces the second loop of MACAEnv._take_action (mamp/envs/mampenv.py:42-46 -> check_agent_state
+// :61-80) and MACAEnv.is_done (:51-59).
+//
+// The reference's check is O(N^2) and SEQUENTIAL: agent i is tested right after its own move against
+// every other agent, of which j < i have already moved and j > i have not.  For a pair lo < hi this is
+//     collide(lo, hi)  <=>  l3norm(new_lo, old_hi) <= R   or   l3norm(new_lo, new_hi) <= R
+// (the first test happens when lo is processed, the second when hi is), with R = r_lo + r_hi; either
+// hit flags both agents unless the flagged one is already at its goal.  That pair rule is evaluated here
+// in parallel over the cell list built from the OLD positions: a step moves an agent by <= max_speed*dt
+// << cell size, so every possible partner is inside the 27-cell neighbourhood.
+#include "scab_common.cuh"
+
+__global__ void __launch_bounds__(128) k_status(StepArgs A)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    bool not_done = false, collided = false;
+    if (s < A.n) {
+        const int id = A.s_id[s];
+        const double4 oldp = A.s_posr[s];
+        const double4 newp = A.s_newpos[s];
+        const int snap_flags = __float_as_int(A.s_vel[s].w);
+        const bool was_goal = (snap_flags & SCAB_ST_AT_GOAL) != 0;
+        int st = A.st.status[id];   // includes the collision bit a neighbour query may have raised this step
+        if (!was_goal) A.st.step_num[id] += 1;   // mampenv.py:44-45
+
+        bool coll_obst = false, coll_agent = false;
+        // obstacles (mampenv.py:63-66): flag regardless of at_goal
+        if (A.m > 0) {
+            int cx, cy, cz;
+            cell_of(A.og, newp.x, newp.y, newp.z, cx, cy, cz);
+            for (int dz = -1; dz <= 1; dz++) {
+                int z = cz + dz;
+                if (z < 0 || z >= A.og.nz) continue;
+                for (int dy = -1; dy <= 1; dy++) {
+                    int y = cy + dy;
+                    if (y < 0 || y >= A.og.ny) continue;
+                    int row = (z * A.og.ny + y) * A.og.nx;
+                    int beg = A.o_cell_start[row + max(cx - 1, 0)];
+                    int end = A.o_cell_start[row + min(cx + 1, A.og.nx - 1) + 1];
+                    for (int j = beg; j < end; j++) {
+                        const double4 o = A.o_posr[j];
+                        if (l3norm_d(newp.x, newp.y, newp.z, o.x, o.y, o.z) <= __dadd_rn(oldp.w, o.w)) coll_obst = true;
+                    }
+                }
+            }
+        }
+        // agents (mampenv.py:68-75) through the pair rule
+        {
+            int cx, cy, cz;
+            cell_of(A.g, oldp.x, oldp.y, oldp.z, cx, cy, cz);
+            for (int dz = -1; dz <= 1; dz++) {
+                int z = cz + dz;
+                if (z < 0 || z >= A.g.nz) continue;
+                for (int dy = -1; dy <= 1; dy++) {
+                    int y = cy + dy;
+                    if (y < 0 || y >= A.g.ny) continue;
+                    int row = (z * A.g.ny + y) * A.g.nx;
+                    int beg = A.cell_start[row + max(cx - 1, 0)];
+                    int end = A.cell_start[row + min(cx + 1, A.g.nx - 1) + 1];
+                    for (int j = beg; j < end; j++) {
+                        if (j == s) continue;
+                        const double4 oo = A.s_posr[j];
+                        // cheap reject on the old positions: both agents move < 1 m per step
+                        const double ex = oo.x - oldp.x, ey = oo.y - oldp.y, ez = oo.z - oldp.z;
+                        const double R = __dadd_rn(oldp.w, oo.w);
+                        const double lim = R + 2.5;
+                        if (ex * ex + ey * ey + ez * ez > lim * lim) continue;
+                        const double4 on = A.s_newpos[j];
+                        const int jid = A.s_id[j];
+                        bool hit;
+                        if (id < jid)
+                            hit = l3norm_d(newp.x, newp.y, newp.z, oo.x, oo.y, oo.z) <= R ||
+                                  l3norm_d(newp.x, newp.y, newp.z, on.x, on.y, on.z) <= R;
+                        else
+                            hit = l3norm_d(on.x, on.y, on.z, oldp.x, oldp.y, oldp.z) <= R ||
+                                  l3norm_d(on.x, on.y, on.z, newp.x, newp.y, newp.z) <= R;
+                        coll_agent |= hit;
+                    }
+                }
+            }
+        }
+        if (coll_obst) st |= SCAB_ST_COLLISION;
+        if (coll_agent && !was_goal) st |= SCAB_ST_COLLISION;
+        if (A.st.total_dist[id] > A.st.max_run_dist[id]) st |= SCAB_ST_TIMEOUT;   // :77-80
+        // is_done (:51-59)
+        const double *g = &A.st.goal[3 * id];
+        if (l3norm_d(newp.x, newp.y, newp.z, g[0], g[1], g[2]) <= A.near_goal) st |= SCAB_ST_AT_GOAL;
+        if (st & (SCAB_ST_AT_GOAL | SCAB_ST_COLLISION | SCAB_ST_TIMEOUT)) st |= SCAB_ST_RUN_DONE;
+        A.st.status[id] = st;
+        not_done = !(st & SCAB_ST_RUN_DONE);
+        collided = (st & SCAB_ST_COLLISION) != 0;
+    }
+    const unsigned m1 = __ballot_sync(0xffffffffu, not_done), m2 = __ballot_sync(0xffffffffu, collided);
+    if ((threadIdx.x & 31) == 0) {
+        if (m1) atomicAdd(&A.counters[1], (unsigned long long)__popc(m1));
+        if (m2) atomicAdd(&A.counters[2], (unsigned long long)__popc(m2));
+    }
+}
+
+cudaError_t launch_status(const StepArgs &A, cudaStream_t s)
+{
+    if (A.n <= 0) return cudaSuccess;
+    int nb = (A.n + 127) / 128;
+    k_status<<<nb, 128, 0, s>>>(A);
+    return cudaGetLastError();
+}

@@ -1,0 +1,189 @@
+"""Device-resident swarm state (structure of arrays, owned through PyTorch) + the batched step.
+
+Replaces the array-of-objects state of mamp/agents/agent.py:13-74 and the per-agent loop of
+MACAEnv._take_action (mamp/envs/mampenv.py:27-49).  PyTorch is plumbing here (device memory, streams,
+pinned host staging); all compute is libscab200's CUDA kernels, reached through the C ABI.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi
+
+_F8, _F4, _I4 = torch.float64, torch.float32, torch.int32
+
+# name -> (dtype, trailing shape, optional/debug?)
+_FIELDS = {
+    'pos': (_F8, (3,), False), 'vel': (_F4, (3,), False), 'heading': (_F8, (3,), False), 'goal': (_F8, (3,), False),
+    'radius': (_F8, (), False), 'pref_speed': (_F8, (), False), 'status': (_I4, (), False),
+    'total_dist': (_F8, (), False), 'step_num': (_I4, (), False), 'max_run_dist': (_F8, (), False),
+    'vpref_ext': (_F8, (3,), True), 'vpref_out': (_F8, (3,), False), 'action': (_F4, (7,), False),
+    'nbr_cnt': (_I4, (), True), 'nbr_ids': (_I4, (capi.K,), True), 'nbr_dsq': (_F8, (capi.K,), True),
+    'tag': (_I4, (), True), 'n_suit': (_I4, (), True), 'plane_fail': (_I4, (), True), 'n_planes': (_I4, (), True),
+    'lp4_proj': (_I4, (), True),
+}
+_DEBUG = ('nbr_cnt', 'nbr_ids', 'nbr_dsq', 'tag', 'n_suit', 'plane_fail', 'n_planes', 'lp4_proj')
+_UPLOAD = ('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')
+
+
+class Swarm:
+    """N agents resident in HBM.  `debug=True` also allocates the observability outputs
+    (ordered neighbour lists, branch tags, plane counts) the parity tests read back."""
+
+    def __init__(self, n, device='cuda:0', debug=False, params=None, capacity=None):
+        if not torch.cuda.is_available():
+            raise capi.ScabError('sca_b200.Swarm needs a CUDA device; there is no CPU fallback')
+        self.n = int(n)
+        self.device = torch.device(device)
+        self.debug = bool(debug)
+        self.params = params if params is not None else capi.default_params()
+        self.t = {}
+        for k, (dt, shp, opt) in _FIELDS.items():
+            if k == 'vpref_ext' or (k in _DEBUG and not self.debug):
+                continue
+            self.t[k] = torch.zeros((self.n,) + shp, dtype=dt, device=self.device)
+        self.h = capi.Handle(self.params, self.device.index or 0, int(capacity or max(self.n, 1)))
+        self.m = 0
+        self._pinned = {}
+        self._bind()
+
+    # ------------------------------------------------------------------ binding
+    def _bind(self):
+        p = capi.StatePtrs()
+        for k in capi.STATE_FIELDS:
+            tns = self.t.get(k)
+            setattr(p, k, tns.data_ptr() if tns is not None else None)
+        self.h.bind_state(p, self.n)
+
+    def __getattr__(self, k):
+        t = self.__dict__.get('t')
+        if t is not None and k in t:
+            return t[k]
+        raise AttributeError(k)
+
+    def set_external_vpref(self, v):
+        """Supply V_des from an upstream provider (SCA's Dubins tracker, scaPolicy.py:264-338); None ->
+        straight-line v_pref computed on the device (rvo3dPolicy.py:182-196)."""
+        if v is None:
+            if 'vpref_ext' in self.t:
+                del self.t['vpref_ext']
+                self._bind()
+            return
+        v = torch.as_tensor(np.ascontiguousarray(v, dtype='float64')) if not torch.is_tensor(v) else v
+        if 'vpref_ext' not in self.t:
+            self.t['vpref_ext'] = torch.zeros((self.n, 3), dtype=_F8, device=self.device)
+            self._bind()
+        self.t['vpref_ext'].copy_(v.to(self.device, _F8))
+
+    # ------------------------------------------------------------------ state in / out
+    def set_state(self, pos, goal, heading=None, vel=None, radius=0.5, pref_speed=1.0, status=None,
+                  total_dist=None, step_num=None, max_run_dist=None, initial_pos=None, goal_pos=None):
+        n = self.n
+        f8 = lambda a, shp: np.ascontiguousarray(np.broadcast_to(np.asarray(a, 'float64'), shp))
+        pos, goal = f8(pos, (n, 3)), f8(goal, (n, 3))
+        start = pos if initial_pos is None else np.asarray(initial_pos, 'float64')[:, :3]
+        gl = goal if goal_pos is None else np.asarray(goal_pos, 'float64')[:, :3]
+        if max_run_dist is None:   # agent.py:74
+            max_run_dist = 3.0 * np.round(np.sqrt(((start - gl) ** 2).sum(1)), 5)
+        dd = gl - start            # scaPolicy.py:188-189 is_zAxis
+        zaxis = ((np.abs(dd[:, 0]) <= 1e-5) & (np.abs(dd[:, 1]) <= 1e-5)).astype(np.int32) * capi.ST_ZAXIS
+        st = np.zeros(n, np.int32) if status is None else (np.asarray(status, np.int32) & 15)
+        host = {
+            'pos': pos, 'goal': goal, 'heading': f8(np.zeros((n, 3)) if heading is None else heading, (n, 3)),
+            'vel': np.zeros((n, 3), np.float32) if vel is None else np.ascontiguousarray(vel, np.float32),
+            'radius': f8(radius, (n,)), 'pref_speed': f8(pref_speed, (n,)), 'status': st | zaxis,
+            'total_dist': f8(0.0 if total_dist is None else total_dist, (n,)),
+            'step_num': np.zeros(n, np.int32) if step_num is None else np.ascontiguousarray(step_num, np.int32),
+            'max_run_dist': f8(max_run_dist, (n,)),
+        }
+        self._zaxis = torch.as_tensor(zaxis).to(self.device)
+        for k, a in host.items():
+            self.t[k].copy_(torch.from_numpy(np.array(a, copy=True)))
+        return self
+
+    def set_obstacles(self, xyzr):
+        xyzr = np.zeros((0, 4)) if xyzr is None else np.asarray(xyzr, 'float64').reshape(-1, 4)
+        self.m = len(xyzr)
+        self.h.set_obstacles(xyzr)
+
+    def fit_grid(self, lo=None, hi=None, margin=5.0, cell=None):
+        """Size the uniform grid from a bounding box (default: current positions and goals)."""
+        cell = float(cell or max(self.params.cell_size, self.params.neighbor_dist))
+        if lo is None or hi is None:
+            both = torch.cat([self.t['pos'], self.t['goal']])
+            lo = (both.min(0).values - margin).cpu().numpy()
+            hi = (both.max(0).values + margin).cpu().numpy()
+        lo, hi = np.asarray(lo, 'float64'), np.asarray(hi, 'float64')
+        dim = np.maximum(1, np.ceil((hi - lo) / cell).astype(np.int64))
+        while int(dim.prod()) > (1 << 24):     # keep the cell table modest; border cells absorb the rest
+            cell *= 1.26
+            dim = np.maximum(1, np.ceil((hi - lo) / cell).astype(np.int64))
+        self.h.set_grid(lo, cell, dim)
+        self.grid = (lo, cell, dim)
+        return self
+
+    def upload(self, host, stream=None):
+        """Pinned-host -> device copy of the per-step inputs (pos, vel, heading, status, ...)."""
+        nbytes = 0
+        for k in _UPLOAD + (('vpref_ext',) if 'vpref_ext' in host else ()):
+            if k not in host:
+                continue
+            src = host[k]
+            if k == 'status':
+                src = src  # caller supplies SCAB_ST_* bits; the static ZAXIS bit is OR-ed below
+            self.t[k].copy_(src, non_blocking=True)
+            nbytes += src.numel() * src.element_size()
+        if 'status' in host:
+            self.t['status'].bitwise_or_(self._zaxis)
+        return nbytes
+
+    def download(self, keys=('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num', 'action')):
+        return {k: self.t[k].cpu().numpy() for k in keys if k in self.t}
+
+    # ------------------------------------------------------------------ the step
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def step(self, policy, nbr_mode=capi.NBR_KNN):
+        """One MACAEnv.step (mampenv.py:22-25) for every agent, asynchronously on the current stream."""
+        pol = capi.POLICIES[policy] if isinstance(policy, str) else int(policy)
+        if nbr_mode == capi.NBR_REF_COMPAT:
+            self.h.kdtree_build(self.t['pos'].cpu().numpy())
+        self.h.step(pol, nbr_mode, self._stream())
+
+    def stage_grid(self):
+        self.h.build_grid(self._stream())
+
+    def stage_neighbors(self, nbr_mode=capi.NBR_KNN, pos_host=None):
+        if nbr_mode == capi.NBR_REF_COMPAT:
+            self.h.kdtree_build(self.t['pos'].cpu().numpy() if pos_host is None else pos_host)
+        self.h.neighbors(nbr_mode, self._stream())
+
+    def stage_policy(self, policy):
+        self.h.policy_step(capi.POLICIES[policy] if isinstance(policy, str) else int(policy), self._stream())
+
+    def stage_status(self):
+        self.h.status_step(self._stream())
+
+    def counters(self):
+        return self.h.read_counters(self._stream())
+
+    def is_done(self):
+        return self.counters()['n_not_done'] == 0
+
+    def metrics(self, straight_len=None, desire_steps=None, dt=0.1):
+        """Rollout metrics of run_example/run_sca.py:228-250 from the device counters."""
+        st = self.t['status'].cpu().numpy()
+        ok = ((st & (capi.ST_COLLISION | capi.ST_TIMEOUT)) == 0)
+        td = self.t['total_dist'].cpu().numpy()
+        sn = self.t['step_num'].cpu().numpy()
+        ns = int(ok.sum())
+        out = {'SuccessRate': ns / max(self.n, 1), 'successful_num': ns}
+        if straight_len is not None and desire_steps is not None and ns:
+            out['ExtraTime'] = float(((sn[ok].sum() - np.asarray(desire_steps)[ok].sum()) * dt) / ns)
+            out['ExtraDistance'] = float((td[ok].sum() - np.asarray(straight_len)[ok].sum()) / ns)
+        if ns and sn[ok].sum():
+            out['AverageSpeed'] = float(td[ok].sum() / sn[ok].sum() / dt)
+        return out
