@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the batched collision-avoidance step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--agents A] [--policy P]
+
+Workload (config.workload): BASELINE.json configs[4], "SCA synthetic uniform-random swarm, 1,000,000 UAVs"
+(pos/goal ~ U(0, 560 m)^3, >= 1.1 m initial separation, r = 0.5, pref_speed = 1, straight-line v_pref --
+the Dubins provider is upstream of the path).  It fits one B200, so N = 1 runs all 10^6
+agents on one GPU; N > 1 shards the SAME 10^6 agents into spatial slabs with a halo exchange (strong scaling).
+
+A "step" is one full MACAEnv.step for every agent: cell list -> 16-NN -> SCA candidate search ->
+kinematic update -> collision/goal status.  value = agent-steps/s with state resident in HBM;
+e2e = the same through host buffers (pinned H2D of the step's inputs + D2H of its results inside the timed
+region), which is what a mamp/envs drop-in pays per step.
+`--impl reference` times the CPU oracle port of the reference (the reference is ~40 agent-steps/s of
+single-threaded Python and cannot run this workload) on a bounded sample with every host thread.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+DENSITY = 1.0e6 / 560.0 ** 3          # agents per m^3 of BASELINE config 5
+ALGO_BYTES = {'grid': 168, 'neighbors': 116, 'policy': 660, 'status': 144}   # SURVEY.md 8(d), per agent-step
+KERNELS_PER_STEP = 8                  # k_cell_count, k_cell_scan, k_reorder, k_neighbors_knn, k_vpref, k_select, k_integrate, k_status
+METRIC = 'agent-steps/sec (SCA, 1M UAVs)'
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '50',
+                                       '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        time.sleep(0.12)
+        self.p.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.1] or [r for (_, r) in self.rows[-3:]]
+        for r in rows:
+            f = [x.strip() for x in r.split(',')]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+                for nm, v in zip(names, f[3:7]):
+                    if v == 'Active':
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def make_swarm(n_total, rank, world, device, seed=0):
+    from sca_b200 import scenarios
+    from sca_b200.swarm import Swarm
+    pos, goal, _ = scenarios.uniform_box_torch(n_total, DENSITY, seed=seed, device=device)
+    L = (n_total / DENSITY) ** (1.0 / 3.0)
+    lo, hi = np.array([-15.0, -15.0, 5.0]), np.array([L + 15.0, L + 15.0, L + 35.0])
+    if world == 1:
+        sw = Swarm(n_total, device=device, debug=False)
+        sw.set_state(pos[:, :3], goal[:, :3], heading=pos[:, 3:])
+        sw.fit_grid(lo, hi)
+        return sw
+    from sca_b200.sharding import ShardedSwarm
+    return ShardedSwarm(pos, goal, rank, world, device, lo, hi)
+
+
+def run_ours(args):
+    import torch
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    device = 'cuda:%d' % local
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device(device))
+    from sca_b200 import capi
+    n_total = args.agents
+    sw = make_swarm(n_total, rank, world, device)
+    policy = args.policy
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        sw.step(policy, capi.NBR_KNN)
+    barrier()
+    c0 = sw.counters()['n_active_total']
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        sw.step(policy, capi.NBR_KNN)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    agent_steps = sw.counters()['n_active_total'] - c0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    if world > 1:
+        t = torch.tensor([ms, float(agent_steps)], dtype=torch.float64, device=device)
+        tmax = t.clone()
+        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+        ms, agent_steps = float(tmax[0]), float(t[1])
+    value = agent_steps / (ms * 1e-3)
+
+    # ---- per-stage device times (1 GPU): which kernel dominates, and its roofline fraction
+    stage_ms, roof = None, None
+    if world == 1:
+        names = ['grid', 'neighbors', 'policy', 'status']
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+        act0 = sw.counters()['n_active_total']
+        for k in range(args.steps):
+            evs[k][0].record(); sw.stage_grid()
+            evs[k][1].record(); sw.stage_neighbors(capi.NBR_KNN)
+            evs[k][2].record(); sw.stage_policy(policy)
+            evs[k][3].record(); sw.stage_status()
+            evs[k][4].record()
+        torch.cuda.synchronize()
+        act = (sw.counters()['n_active_total'] - act0) / args.steps
+        stage_ms = {nm: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)]))
+                    for i, nm in enumerate(names)}
+        dom = max(stage_ms, key=stage_ms.get)
+        peak, how = measured_peak()
+        units = n_total if dom in ('grid', 'status') else act     # grid/status touch every agent, the others the active ones
+        achieved = ALGO_BYTES[dom] * units / (stage_ms[dom] * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'dram_traffic.json')) as f:
+                traffic = json.load(f).get(dom)
+        except Exception:
+            pass
+        roof = {'bound': 'hbm', 'kernel': {'grid': 'k_reorder+k_cell_count+k_cell_scan', 'neighbors': 'k_neighbors_knn',
+                                           'policy': 'k_vpref+k_select<SCA>+k_integrate', 'status': 'k_status'}[dom],
+                'achieved': round(achieved, 2), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 5),
+                'traffic': traffic, 'peak_source': how, 'algorithmic_bytes_per_agent_step': ALGO_BYTES[dom],
+                'units_per_launch': int(units), 'stage_ms': {k: round(v, 4) for k, v in stage_ms.items()},
+                'note': 'SCA candidate search is fp32/fp64-ALU-bound (SURVEY.md 8d): HBM fraction is reported as asked, '
+                        'stage_ms shows where the step goes'}
+
+    # ---- end to end through host buffers (pinned H2D of the inputs, D2H of the results, every step)
+    e2e = None
+    if world == 1:
+        keys_in = ('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')
+        keys_out = ('action', 'status', 'pos', 'heading', 'total_dist', 'step_num')
+        host_in = {k: sw.t[k].cpu().pin_memory() for k in keys_in}
+        host_in['status'] &= 15
+        host_out = {k: torch.empty_like(sw.t[k], device='cpu').pin_memory() for k in keys_out}
+        h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+        d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+        steps_e = max(3, min(args.steps, 20))
+
+        def one():
+            sw.upload(host_in)
+            sw.step(policy, capi.NBR_KNN)
+            for k in keys_out:
+                host_out[k].copy_(sw.t[k], non_blocking=True)
+            torch.cuda.synchronize()          # the caller needs the results on the host before the next step
+            for k in keys_in:                 # next step's inputs = this step's results (host-resident state)
+                if k in host_out:
+                    host_in[k].copy_(host_out[k])
+            host_in['vel'].copy_(host_out['action'][:, :3])
+            host_in['status'] &= 15
+        one()
+        a0 = sw.counters()['n_active_total']
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps_e):
+            one()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {'value': (sw.counters()['n_active_total'] - a0) / dt, 'unit': 'agent-steps/s',
+               'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'steps': steps_e,
+               'ms_per_step': round(dt / steps_e * 1e3, 3)}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args.cpu_agents, 1, policy, budget_s=12.0)
+
+    if rank == 0:
+        out = {'metric': METRIC, 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': args.steps,
+               'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+               'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32 candidate tests + f64 decision scalars',
+               'data': 'synthetic',
+               'config': {'workload': 'BASELINE configs[4]: SCA synthetic uniform-random swarm, %d UAVs, density 1e6/(560 m)^3, '
+                                      'straight-line v_pref, KNN neighbour mode' % n_total,
+                          'policy': policy, 'agents': n_total, 'l2': 'per-step working set (~%d MB) exceeds the 126 MB L2'
+                                                                     % (n_total * 420 // 1000000),
+                          'parallelism': 'spatial slabs x%d + halo exchange' % world if world > 1 else 'single GPU'},
+               'gpu_launches': KERNELS_PER_STEP * args.steps, 'clocks': clocks}
+        if roof:
+            out['roofline'] = roof
+        if e2e:
+            out['e2e'] = e2e
+        if cpu:
+            out['cpu_baseline'] = cpu
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def cpu_baseline(n_agents, threads, policy, budget_s=15.0, steps=None):
+    """The CPU oracle port of the reference (oracle/sca_oracle.c) on a bounded sample of the same workload:
+    the same density and policy, n_agents agents.  Returns the cpu_baseline object of the bench contract."""
+    from oracle import oracle as orc
+    from sca_b200 import scenarios
+    orc.set_threads(threads)
+    pos, goal, _ = scenarios.uniform_box_numpy(n_agents, DENSITY, seed=1)
+    w = orc.World(pos[:, :3], goal[:, :3], heading=pos[:, 3:])
+    for _ in range(2):                      # leave the zero-velocity shortcut (step 0)
+        w.step(policy, orc.NBR_KNN, fast=True)
+    done_steps, agent_steps = 0, 0
+    t0 = time.perf_counter()
+    while True:
+        w.step(policy, orc.NBR_KNN, fast=True)
+        agent_steps += int(w.ran.sum())
+        done_steps += 1
+        el = time.perf_counter() - t0
+        if (steps and done_steps >= steps) or (not steps and (el > budget_s or done_steps >= 200)):
+            break
+    return {'value': agent_steps / el, 'unit': 'agent-steps/s', 'cores': threads, 'kind': 'port',
+            'sample': '%d agents at the workload density, %d steps, %s policy, KNN neighbour mode, %.1f s' % (
+                n_agents, done_steps, policy, el), 'ms_per_step': el / done_steps * 1e3, 'steps': done_steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = []
+    total_agent_steps, total_t = 0, 0.0
+    # each "step" of this arm is one oracle step over the bounded sample
+    from oracle import oracle as orc
+    from sca_b200 import scenarios
+    orc.set_threads(threads)
+    n = args.cpu_agents
+    pos, goal, _ = scenarios.uniform_box_numpy(n, DENSITY, seed=1)
+    w = orc.World(pos[:, :3], goal[:, :3], heading=pos[:, 3:])
+    for _ in range(max(args.warmup, 2)):
+        w.step(args.policy, orc.NBR_KNN, fast=True)
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        w.step(args.policy, orc.NBR_KNN, fast=True)
+        dt = time.perf_counter() - t0
+        per_step.append(dt)
+        total_agent_steps += int(w.ran.sum())
+        total_t += dt
+    value = total_agent_steps / total_t
+    sample = '%d agents at the workload density per step (bounded sample of the 1M workload), %s policy' % (n, args.policy)
+    out = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'agent-steps/s',
+           'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': args.steps, 'warmup': max(args.warmup, 2),
+           'ms_per_step': total_t / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+           'dtype': 'f64', 'data': 'synthetic',
+           'config': {'workload': 'BASELINE configs[4]: SCA synthetic uniform-random swarm (bounded sample: %d UAVs at the '
+                                  '1M-UAV density), straight-line v_pref, KNN neighbour mode' % n,
+                      'policy': args.policy, 'agents': n,
+                      'note': 'the Python reference runs ~40 agent-steps/s single-threaded (BASELINE.md); this arm times its C '
+                              'restatement (oracle/sca_oracle.c), which is pinned to the reference by the golden fixtures'},
+           'cpu_baseline': {'value': value, 'unit': 'agent-steps/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+           'e2e': {'value': value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+           'gpu_launches': 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--agents', type=int, default=1000000)
+    ap.add_argument('--policy', default='sca')
+    ap.add_argument('--cpu-agents', type=int, default=20000)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

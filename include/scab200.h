@@ -112,12 +112,14 @@ typedef struct {
     int32_t *lp4_proj;     /* [n] ORCA-LP: number of inner dir-opt LP3 solves in LP4           out */
 } scab_state_ptrs;
 
-/* Step counters, read back with scab_read_counters (device->host copy of 4 x int64). */
+/* Step counters, read back with scab_read_counters (device->host copy of 8 x int64). */
 typedef struct {
     int64_t n_active;      /* agents that ran the policy this step (not at_goal/collision/timeout) */
     int64_t n_not_done;    /* agents without RUN_DONE after the step; 0 <=> MACAEnv.is_done() is True */
     int64_t n_collision;   /* agents with the collision flag after the step */
     int64_t n_recheck;     /* fp32 guard-band hits re-evaluated in fp64 (diagnostic) */
+    int64_t n_active_total;/* cumulative n_active since scab_create / scab_reset_counters (agent-steps) */
+    int64_t reserved[3];
 } scab_counters;
 
 const char *scab_version(void);
@@ -159,6 +161,8 @@ int scab_step(scab_handle *h, int policy, int nbr_mode, void *stream);
 
 /* Blocking read of the counters written by the last scab_status_step on `stream`. */
 int scab_read_counters(scab_handle *h, scab_counters *out_host, void *stream);
+/* Zero the cumulative counters (asynchronously on `stream`). */
+int scab_reset_counters(scab_handle *h, void *stream);
 
 #ifdef __cplusplus
 }

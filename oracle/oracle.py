@@ -54,6 +54,7 @@ def lib():
         _lib.orc_py_round5_slow.restype = C.c_double
         _lib.orc_py_round5_slow.argtypes = [C.c_double]
         _lib.orc_gen_candidates.argtypes = [C.c_int, C.c_double, _P]
+        _lib.orc_set_threads.argtypes = [C.c_int]
         assert _lib.orc_sizeof_world() == C.sizeof(OrcWorld)
         assert _lib.orc_sizeof_kdnode() == C.sizeof(KdNode)
     return _lib
@@ -140,6 +141,11 @@ class World:
     def step(self, policy, nbr_mode=NBR_REF_COMPAT, fast=False):
         self.policy_step(policy, nbr_mode)
         return self.env_update(fast)
+
+
+def set_threads(t):
+    """Threads the oracle's policy loop may use (the reference itself is single-threaded)."""
+    lib().orc_set_threads(int(t))
 
 
 def gen_candidates(num_n=256, pref_speed=1.0):

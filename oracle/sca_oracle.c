@@ -359,61 +359,112 @@ static void query_obstacle_tree(const OrcWorld *w, int self, double rangeSq, int
 }
 
 /* True-KNN variant (documented deviation): what the reference would compute if
- * rangeSq shrank (RVO2-3D semantics) with ties broken by (distSq, obstacles-before-agents, id).
- * Candidates: every obstacle then every agent in id order; same collision-mode rule.  */
-static void knn_insert(NbrList *L, int32_t id, double dsq)
+ * rangeSq shrank (RVO2-3D semantics): the 16 smallest by (distSq, obstacles-before-agents, id), with the
+ * same collision-mode rule.  Candidates come from a uniform grid (cell = neighborDist) rebuilt by
+ * orc_policy_step; the result does not depend on the visiting order. */
+typedef struct {
+    double o[3], inv;
+    int nx, ny, nz;
+    int32_t *start, *items;   /* [ncell+1], [n] */
+} KnnGrid;
+static KnnGrid g_grid = { {0, 0, 0}, 0, 0, 0, 0, NULL, NULL };
+
+static int grid_cell(const KnnGrid *g, const double *p, int *cx, int *cy, int *cz)
 {
-    /* keep the 16 smallest by (dsq, insertion order); candidates arrive in canonical order */
+    *cx = (int)floor((p[0] - g->o[0]) * g->inv);
+    *cy = (int)floor((p[1] - g->o[1]) * g->inv);
+    *cz = (int)floor((p[2] - g->o[2]) * g->inv);
+    if (*cx < 0) *cx = 0; if (*cx >= g->nx) *cx = g->nx - 1;
+    if (*cy < 0) *cy = 0; if (*cy >= g->ny) *cy = g->ny - 1;
+    if (*cz < 0) *cz = 0; if (*cz >= g->nz) *cz = g->nz - 1;
+    return (*cz * g->ny + *cy) * g->nx + *cx;
+}
+static void grid_build(const OrcWorld *w)
+{
+    KnnGrid *g = &g_grid;
+    free(g->start); free(g->items);
+    double mn[3] = { 1e300, 1e300, 1e300 }, mx[3] = { -1e300, -1e300, -1e300 };
+    for (int i = 0; i < w->n; i++)
+        for (int c = 0; c < 3; c++) {
+            if (w->pos[3 * i + c] < mn[c]) mn[c] = w->pos[3 * i + c];
+            if (w->pos[3 * i + c] > mx[c]) mx[c] = w->pos[3 * i + c];
+        }
+    double cs = NEIGHBOR_DIST;
+    for (;;) {
+        g->nx = (int)floor((mx[0] - mn[0]) / cs) + 1; g->ny = (int)floor((mx[1] - mn[1]) / cs) + 1; g->nz = (int)floor((mx[2] - mn[2]) / cs) + 1;
+        if ((double)g->nx * g->ny * g->nz <= 4.0e6 + 8.0 * w->n) break;
+        cs *= 1.5;
+    }
+    g->inv = 1.0 / cs;
+    for (int c = 0; c < 3; c++) g->o[c] = mn[c];
+    int ncell = g->nx * g->ny * g->nz;
+    g->start = (int32_t *)calloc((size_t)ncell + 1, sizeof(int32_t));
+    g->items = (int32_t *)malloc(sizeof(int32_t) * (size_t)(w->n > 0 ? w->n : 1));
+    int cx, cy, cz;
+    for (int i = 0; i < w->n; i++) g->start[grid_cell(g, &w->pos[3 * i], &cx, &cy, &cz) + 1]++;
+    for (int c = 0; c < ncell; c++) g->start[c + 1] += g->start[c];
+    int32_t *fill = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ncell > 0 ? ncell : 1));
+    memcpy(fill, g->start, sizeof(int32_t) * (size_t)ncell);
+    for (int i = 0; i < w->n; i++) g->items[fill[grid_cell(g, &w->pos[3 * i], &cx, &cy, &cz)]++] = i;
+    free(fill);
+}
+
+static void knn_insert(NbrList *L, int32_t uid, double dsq)
+{   /* uid: obstacles n + o, agents id -- ordered (dsq, obstacle-first, id) */
+#define UKEY(x, n_) ((x) >= (n_) ? (long long)(x) - (n_) : (long long)(x) + (1LL << 40))
+    extern int g_knn_n;
+    long long ku = UKEY(uid, g_knn_n);
     if (L->cnt == K_MAX) {
-        if (!(dsq < L->dsq[K_MAX - 1])) return;
+        double dl = L->dsq[K_MAX - 1];
+        long long kl = UKEY(L->id[K_MAX - 1], g_knn_n);
+        if (!(dsq < dl || (dsq == dl && ku < kl))) return;
         L->cnt--;
     }
     int k = L->cnt;
-    while (k > 0 && L->dsq[k - 1] > dsq) {
+    while (k > 0 && (L->dsq[k - 1] > dsq || (L->dsq[k - 1] == dsq && UKEY(L->id[k - 1], g_knn_n) > ku))) {
         L->dsq[k] = L->dsq[k - 1];
         L->id[k] = L->id[k - 1];
         k--;
     }
     L->dsq[k] = dsq;
-    L->id[k] = id;
+    L->id[k] = uid;
     L->cnt++;
+#undef UKEY
 }
+int g_knn_n = 0;
+
 static void knn_neighbors(const OrcWorld *w, int self, NbrList *L)
 {
     const double rangeSq = NEIGHBOR_DIST * NEIGHBOR_DIST;
-    /* pass 1: is there any collider? */
-    int coll = 0;
-    for (int o = 0; o < w->m && !coll; o++) {
-        const double *po = &w->obs[4 * o];
-        double d1 = l3normsq(&w->pos[3 * self], po);
-        double t = l3norm(&w->pos[3 * self], po) - po[3];
-        if (d1 < sqr(w->radius[self] + po[3]) && t * t < rangeSq) coll = 1;
-    }
-    for (int j = 0; j < w->n && !coll; j++) {
-        if (j == self) continue;
-        /* cheap reject */
-        double dx = w->pos[3 * self] - w->pos[3 * j];
-        if (dx > 10.5 || dx < -10.5) continue;
-        double d = l3normsq(&w->pos[3 * self], &w->pos[3 * j]);
-        if (d < sqr(w->radius[self] + w->radius[j]) && d < rangeSq) coll = 1;
-    }
-    L->is_collision = coll;
-    L->cnt = 0;
-    for (int o = 0; o < w->m; o++) {
-        const double *po = &w->obs[4 * o];
-        double d1 = l3normsq(&w->pos[3 * self], po);
-        double t = l3norm(&w->pos[3 * self], po) - po[3];
-        double d = t * t;
-        int is_c = d1 < sqr(w->radius[self] + po[3]) && d < rangeSq;
-        if (coll ? is_c : (d < rangeSq)) knn_insert(L, w->n + o, d);
-    }
-    for (int j = 0; j < w->n; j++) {
-        if (j == self) continue;
-        double dx = w->pos[3 * self] - w->pos[3 * j];
-        if (dx > 10.5 || dx < -10.5) continue;
-        double d = l3normsq(&w->pos[3 * self], &w->pos[3 * j]);
-        int is_c = d < sqr(w->radius[self] + w->radius[j]) && d < rangeSq;
-        if (coll ? is_c : (d < rangeSq)) knn_insert(L, j, d);
+    const KnnGrid *g = &g_grid;
+    int cx, cy, cz;
+    grid_cell(g, &w->pos[3 * self], &cx, &cy, &cz);
+    for (int pass = 0; pass < 2; pass++) {
+        /* pass 0: is there any collider?  pass 1: collect */
+        int coll = L->is_collision;
+        if (pass == 1) L->cnt = 0;
+        for (int o = 0; o < w->m; o++) {
+            const double *po = &w->obs[4 * o];
+            double d1 = l3normsq(&w->pos[3 * self], po);
+            double t = l3norm(&w->pos[3 * self], po) - po[3];
+            double d = t * t;
+            int is_c = d1 < sqr(w->radius[self] + po[3]) && d < rangeSq;
+            if (pass == 0) { if (is_c) L->is_collision = 1; }
+            else if (coll ? is_c : (d < rangeSq)) knn_insert(L, w->n + o, d);
+        }
+        for (int z = (cz > 0 ? cz - 1 : 0); z <= cz + 1 && z < g->nz; z++)
+            for (int y = (cy > 0 ? cy - 1 : 0); y <= cy + 1 && y < g->ny; y++)
+                for (int x = (cx > 0 ? cx - 1 : 0); x <= cx + 1 && x < g->nx; x++) {
+                    int c = (z * g->ny + y) * g->nx + x;
+                    for (int q = g->start[c]; q < g->start[c + 1]; q++) {
+                        int j = g->items[q];
+                        if (j == self) continue;
+                        double d = l3normsq(&w->pos[3 * self], &w->pos[3 * j]);
+                        int is_c = d < sqr(w->radius[self] + w->radius[j]) && d < rangeSq;
+                        if (pass == 0) { if (is_c) L->is_collision = 1; }
+                        else if (coll ? is_c : (d < rangeSq)) knn_insert(L, j, d);
+                    }
+                }
     }
 }
 
@@ -1017,17 +1068,45 @@ static void policy_one(OrcWorld *w, int a, int policy, int nbr_mode)
     }
 }
 
+/* The reference is single-threaded; agents are independent inside the policy loop, so the CPU baseline
+ * may use every host thread (orc_set_threads).  Results do not depend on the thread count. */
+#include <pthread.h>
+static int g_threads = 1;
+void orc_set_threads(int t) { g_threads = t < 1 ? 1 : (t > 256 ? 256 : t); }
+typedef struct { OrcWorld *w; int policy, nbr_mode; volatile int *next; } PJob;
+static void *policy_worker(void *arg)
+{
+    PJob *J = (PJob *)arg;
+    for (;;) {
+        int a0 = __sync_fetch_and_add(J->next, 64);
+        if (a0 >= J->w->n) break;
+        int a1 = a0 + 64 < J->w->n ? a0 + 64 : J->w->n;
+        for (int a = a0; a < a1; a++) {
+            if (J->w->status[a] & (ST_AT_GOAL | ST_COLLISION | ST_TIMEOUT)) continue;
+            policy_one(J->w, a, J->policy, J->nbr_mode);
+        }
+    }
+    return NULL;
+}
+static void parallel_policy(OrcWorld *w, int policy, int nbr_mode)
+{
+    volatile int next = 0;
+    PJob J = { w, policy, nbr_mode, &next };
+    if (g_threads <= 1) { policy_worker(&J); return; }
+    pthread_t th[256];
+    int nt = g_threads;
+    for (int t = 0; t < nt; t++) pthread_create(&th[t], NULL, policy_worker, &J);
+    for (int t = 0; t < nt; t++) pthread_join(th[t], NULL);
+}
+
 /* mampenv.py:27-40: kd-tree rebuild + policy loop over active agents */
 void orc_policy_step(OrcWorld *w, int policy, int nbr_mode)
 {
     if (nbr_mode == NBR_REF_COMPAT) orc_kdtree_build_agents(w);
     for (int i = 0; i < w->n * 7; i++) { w->action[i] = 0.f; w->action64[i] = 0.0; }
     for (int a = 0; a < w->n; a++) { w->ran[a] = 0; w->coll_query[a] = 0; w->tag[a] = 0; w->n_suit[a] = 0; w->nbr_cnt[a] = -1; }
-#pragma omp parallel for schedule(dynamic, 8)
-    for (int a = 0; a < w->n; a++) {
-        if (w->status[a] & (ST_AT_GOAL | ST_COLLISION | ST_TIMEOUT)) continue;
-        policy_one(w, a, policy, nbr_mode);
-    }
+    if (nbr_mode == NBR_KNN) { g_knn_n = w->n; grid_build(w); }
+    parallel_policy(w, policy, nbr_mode);
     /* insertAgentNeighbor sets agent.is_collision on the querying agent itself (agent.py:83-84) */
     for (int a = 0; a < w->n; a++)
         if (w->ran[a] && w->coll_query[a]) w->status[a] |= ST_COLLISION;

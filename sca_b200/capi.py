@@ -19,7 +19,8 @@ TAG_FIRST, TAG_SUITABLE, TAG_FALLBACK, TAG_LP3_OK, TAG_LP4 = 1, 2, 4, 8, 16
 # every symbol include/scab200.h declares (tests/test_capi_symbols.py checks the header against this)
 SYMBOLS = ['scab_version', 'scab_default_params', 'scab_create', 'scab_destroy', 'scab_last_error', 'scab_set_grid',
            'scab_bind_state', 'scab_set_obstacles', 'scab_kdtree_build', 'scab_kdtree_get_perm', 'scab_build_grid',
-           'scab_neighbors', 'scab_policy_step', 'scab_status_step', 'scab_step', 'scab_read_counters']
+           'scab_neighbors', 'scab_policy_step', 'scab_status_step', 'scab_step', 'scab_read_counters',
+           'scab_reset_counters']
 
 
 class ScabError(RuntimeError):
@@ -43,7 +44,7 @@ class StatePtrs(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [('n_active', C.c_int64), ('n_not_done', C.c_int64), ('n_collision', C.c_int64),
-                ('n_recheck', C.c_int64)]
+                ('n_recheck', C.c_int64), ('n_active_total', C.c_int64), ('reserved', C.c_int64 * 3)]
 
 
 _lib = None
@@ -77,6 +78,7 @@ def lib():
     L.scab_status_step.argtypes = [vp, vp]
     L.scab_step.argtypes = [vp, C.c_int, C.c_int, vp]
     L.scab_read_counters.argtypes = [vp, C.POINTER(Counters), vp]
+    L.scab_reset_counters.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -156,4 +158,7 @@ class Handle:
         c = Counters()
         self._ck(self._L.scab_read_counters(self._h, C.byref(c), stream))
         return {'n_active': c.n_active, 'n_not_done': c.n_not_done, 'n_collision': c.n_collision,
-                'n_recheck': c.n_recheck}
+                'n_recheck': c.n_recheck, 'n_active_total': c.n_active_total}
+
+    def reset_counters(self, stream=0):
+        self._ck(self._L.scab_reset_counters(self._h, stream))

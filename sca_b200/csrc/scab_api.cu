@@ -149,6 +149,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_posr = carve(cap * sizeof(double4)), o_newpos = carve(cap * sizeof(double4)),
+                 o_vdes = carve(cap * sizeof(double4)), o_vpost = carve(cap * sizeof(double4)),
                  o_vel = carve(cap * sizeof(float4)), o_id = carve(cap * 4), o_rank = carve(cap * 4),
                  o_cid = carve(cap * 4), o_cloc = carve(cap * 4), o_nbr = carve(cap * 4 * KNBR),
                  o_ncnt = carve(cap * 4), o_qc = carve(cap * 4), o_kdp = carve(cap * 4),
@@ -157,6 +158,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     if (e != cudaSuccess) { delete h; return SCAB_ERR_NOMEM; }
     char *b = (char *)h->d_block;
     A.s_posr = (double4 *)(b + o_posr); A.s_newpos = (double4 *)(b + o_newpos); A.s_vel = (float4 *)(b + o_vel);
+    A.s_vdes = (double4 *)(b + o_vdes); A.s_vpost = (double4 *)(b + o_vpost);
     A.s_id = (int32_t *)(b + o_id); A.rank = (int32_t *)(b + o_rank);
     A.cell_id = (int32_t *)(b + o_cid); A.cell_local = (int32_t *)(b + o_cloc);
     A.s_nbr = (int32_t *)(b + o_nbr); A.s_nbr_cnt = (int32_t *)(b + o_ncnt); A.s_qcoll = (int32_t *)(b + o_qc);
@@ -171,9 +173,9 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     make_dirs(128, d64, d32);
     ok &= cudaMalloc(&h->d_dir128, d64.size() * 8) == cudaSuccess && cudaMalloc(&h->d_dir128f, d32.size() * 16) == cudaSuccess;
     if (ok) { cudaMemcpy(h->d_dir128, d64.data(), d64.size() * 8, cudaMemcpyHostToDevice); cudaMemcpy(h->d_dir128f, d32.data(), d32.size() * 16, cudaMemcpyHostToDevice); }
-    ok &= cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)) == cudaSuccess;
+    ok &= cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) { scab_destroy(h); return SCAB_ERR_NOMEM; }
-    cudaMemset(h->d_counters, 0, 4 * sizeof(unsigned long long));
+    cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned long long));
     A.dir256 = h->d_dir256; A.dir128 = h->d_dir128; A.dir256f = h->d_dir256f; A.dir128f = h->d_dir128f;
     A.counters = h->d_counters;
     set_geom(A.g, p->grid_origin, p->cell_size, p->grid_dim);
@@ -394,9 +396,19 @@ extern "C" int scab_read_counters(scab_handle *h, scab_counters *out, void *stre
 {
     if (!h || !out) return fail(h, SCAB_ERR_INVALID, "scab_read_counters: null argument");
     CK(cudaSetDevice(h->device));
-    unsigned long long v[4];
+    unsigned long long v[8];
     CK(cudaMemcpyAsync(v, h->d_counters, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
+    memset(out, 0, sizeof(*out));
     out->n_active = (int64_t)v[0]; out->n_not_done = (int64_t)v[1]; out->n_collision = (int64_t)v[2]; out->n_recheck = (int64_t)v[3];
+    out->n_active_total = (int64_t)v[4];
+    return SCAB_OK;
+}
+
+extern "C" int scab_reset_counters(scab_handle *h, void *stream)
+{
+    if (!h) return SCAB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), (cudaStream_t)stream));
     return SCAB_OK;
 }

@@ -44,6 +44,8 @@ struct StepArgs {
     int32_t *s_id;      // sorted idx -> agent id
     int32_t *rank;      // agent id -> sorted idx
     double4 *s_newpos;  // position after the kinematic update (sorted order)
+    double4 *s_vdes;    // V_des (x y z) + zero-velocity-gate flag (w)        [k_vpref -> k_select]
+    double4 *s_vpost;   // vA_post (x y z) + packed tag | n_suit << 8 (w)     [k_select -> k_integrate]
     int32_t *cell_id, *cell_local, *cell_count, *cell_start;  // [n], [n], [ncell], [ncell+1]
     int32_t *s_nbr;     // [n,16] sorted idx, or n + sorted obstacle idx
     int32_t *s_nbr_cnt; // [n]

@@ -132,7 +132,9 @@ __global__ void __launch_bounds__(128) k_neighbors_knn(StepArgs A)
                 for (int j = beg; j < end; j++) {
                     if (j == s) continue;
                     const double4 o = A.s_posr[j];
-                    double dsq = l3normsq_d(me.x, me.y, me.z, o.x, o.y, o.z);   // agent.py:81
+                    const double ss = sumsq3(__dsub_rn(me.x, o.x), __dsub_rn(me.y, o.y), __dsub_rn(me.z, o.z));
+                    if (ss > rangeSq + 1e-4) continue;     // the 5-decimal rounding cannot bring it back in range
+                    double dsq = np_round5(ss);             // agent.py:81 l3normsq
                     if (!(dsq < rangeSq)) continue;
                     double rr = __dadd_rn(me.w, o.w);
                     bool is_c = dsq < __dmul_rn(rr, rr);

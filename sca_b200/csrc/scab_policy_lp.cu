@@ -303,7 +303,10 @@ __global__ void __launch_bounds__(LP_THREADS) k_policy_lp(StepArgs A)
     }
     // one counter update per warp
     const unsigned act_mask = __ballot_sync(0xffffffffu, ran != 0);
-    if ((threadIdx.x & 31) == 0 && act_mask) atomicAdd(&A.counters[0], (unsigned long long)__popc(act_mask));
+    if ((threadIdx.x & 31) == 0 && act_mask) {
+        atomicAdd(&A.counters[0], (unsigned long long)__popc(act_mask));
+        atomicAdd(&A.counters[4], (unsigned long long)__popc(act_mask));
+    }
 }
 
 cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)

@@ -1,25 +1,29 @@
-// scab_policy_sampled.cu -- stage 3 for the five sampled-velocity policies, one warp per agent:
+// scab_policy_sampled.cu -- stage 3 for the five sampled-velocity policies:
 //   SCA            mamp/policies/sca/scaPolicy.py:26-73, 119-240
 //   S-RVO3D        mamp/policies/srvo3dPolicy.py:23-69, 100-231
 //   RVO3D          mamp/policies/rvo3dPolicy.py:23-69, 102-196
 //   RVO3D+Dubins   mamp/policies/sca/rvo3dDubinsPolicy.py:26-71, 119-194
 //   ORCA sampled   mamp/policies/orca3dPolicy.py:38-120, 328-439
-// followed, fused in the same kernel, by cartesian2spherical (mamp/util.py:44-55) and the kinematic
-// update (mamp/envs/mampenv.py:83-105).
+// as a chain of three kernels on the caller's stream:
+//   k_vpref      thread/agent  v_pref (rvo3dPolicy.py:182-196) + the zero-velocity gate (scaPolicy.py:34)
+//   k_select     WARP/agent    constraints + the 513-candidate search (the hot kernel)
+//   k_integrate  thread/agent  cartesian2spherical (util.py:44-55) + kinematic update (mampenv.py:83-105)
 //
-// Candidate set (scaPolicy.py:190-211): two Fibonacci-sphere shells {0.5, pref_speed} x N directions
-// (N = 256, or 128 for SCA when start->goal is vertical) + v_pref last.  Per warp:
-//   A  posture test per candidate in fp64 (util.py:6-20), ballot-compacted into shared memory: only
-//      ~15 % of the sphere lies within pi/4 of the current velocity, so the cone tests run on that list;
+// Candidate set (scaPolicy.py:190-211): two Fibonacci-sphere shells {0.5, pref_speed} x N unit directions
+// (N = 256, or 128 for SCA when start->goal is vertical) + v_pref last.  k_select per warp:
+//   A  posture test (util.py:6-20).  cos(angle(vA, rad*u)) does not depend on the shell radius, so one
+//      fp32 dot per DIRECTION decides both shells; directions inside a 1e-6 guard band are re-evaluated
+//      with the reference's fp64 expression.  Survivors (~15 % of the sphere) are ballot-compacted.
 //   B  cone / half-space tests in fp32 with an error-bounded guard band; hits inside the band are
-//      re-evaluated in fp64 with the reference's asin/acos form (util.py:30-41);
+//      re-evaluated in fp64 with the reference's asin/acos form (util.py:30-41).
 //   C  selection without sorting: the stable sort + prefix walk of shunted_strategy
-//      (scaPolicy.py:119-145) is three lexicographic warp reductions;
+//      (scaPolicy.py:119-145) is three lexicographic warp reductions over keys computed once in fp64
+//      with the reference's decimal rounding (the keys are integers in units of 1e-5).
 //   D  the "no suitable velocity" path (scaPolicy.py:148-165, 224-238) entirely in fp64.
 #include "scab_common.cuh"
 #include <limits.h>
 
-#define WARPS_PER_CTA 8
+#define WARPS_PER_CTA 4
 #define MAX_CAND 513
 #define FULL 0xffffffffu
 
@@ -36,7 +40,9 @@ struct WarpSmem {
     // ORCA-sampled fallback needs relpos / the v_dif offset too
     double rpx[KNBR], rpy[KNBR], rpz[KNBR];
     double ofx[KNBR], ofy[KNBR], ofz[KNBR];
-    unsigned short list[MAX_CAND + 7];    // compacted candidate indices; bit 15 = suitable
+    unsigned long long key[MAX_CAND + 7];   // per live slot: sort key (suitable: units of 1e-5; fallback: fp64 bits)
+    unsigned int dvu[MAX_CAND + 7];         // per live slot: l3norm(v, vA) in units of 1e-5 (shunting)
+    unsigned short list[MAX_CAND + 7];      // candidate index per slot; bit 15 = live (suitable)
 };
 
 struct Agent {
@@ -60,7 +66,7 @@ __device__ __forceinline__ void cand64(const Agent &a, int c, double &x, double 
 }
 
 // util.py:6-20 satisfied_constraint; acos(c) <= pi/4 evaluated as c >= cos(pi/4)
-__device__ __forceinline__ bool posture_ok(const Agent &a, double time_step, double x, double y, double z)
+__device__ __noinline__ bool posture_ok(const Agent &a, double time_step, double x, double y, double z)
 {
     double next_z = __dadd_rn(a.pz, __dmul_rn(time_step, z));
     double den = __dmul_rn(a.nvA, __dsqrt_rn(dot3(x, y, z, x, y, z)));
@@ -94,37 +100,57 @@ __device__ __forceinline__ bool lex_less(unsigned long long a, unsigned b, unsig
     return a < a2 || (a == a2 && b < b2);
 }
 
+// ------------------------------------------------------------------ k_vpref (thread per agent)
+template <bool USE_DISTANCE, bool ALLOW_EXT>
+__global__ void __launch_bounds__(256) k_vpref(StepArgs A)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= A.n) return;
+    const float4 mv = A.s_vel[s];
+    if (__float_as_int(mv.w) & FL_INACTIVE) return;
+    const int id = A.s_id[s];
+    const double4 me = A.s_posr[s];
+    double v_store[3], v_des[3];
+    if (ALLOW_EXT && A.st.vpref_ext != nullptr) {
+        for (int d = 0; d < 3; d++) v_des[d] = v_store[d] = A.st.vpref_ext[3 * id + d];
+    } else {
+        v_pref_straight(&A.st.goal[3 * id], me.x, me.y, me.z, A.st.pref_speed[id], USE_DISTANCE, v_store, v_des);
+    }
+    // first-step gate: l3norm(vA,0) <= 1e-5 (scaPolicy.py:34) / distance(vA,0) <= 1e-5 (orca3dPolicy.py:52)
+    const double nv32 = __dsqrt_rn(sumsq_f32(mv.x, mv.y, mv.z));
+    const bool first = USE_DISTANCE ? (py_round5(__dadd_rn(nv32, 1e-5)) <= 1e-5) : (py_round5(nv32) <= 1e-5);
+    A.s_vdes[s] = make_double4(v_des[0], v_des[1], v_des[2], first ? 1.0 : 0.0);
+    if (A.st.vpref_out) {
+        A.st.vpref_out[3 * id] = v_store[0]; A.st.vpref_out[3 * id + 1] = v_store[1]; A.st.vpref_out[3 * id + 2] = v_store[2];
+    }
+}
+
+// ------------------------------------------------------------------ k_select (warp per agent)
 template <int POLICY>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_policy_sampled(StepArgs A)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select(StepArgs A)
 {
     constexpr bool IS_ORCA = (POLICY == SCAB_POLICY_ORCA_SAMPLED);
     constexpr bool SHUNT = (POLICY == SCAB_POLICY_SCA || POLICY == SCAB_POLICY_SRVO3D);
-    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSmem *smem = reinterpret_cast<WarpSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpSmem &W = smem[wid];
     const int warps_total = gridDim.x * WARPS_PER_CTA;
-    unsigned long long n_recheck = 0, n_ran = 0;
+    unsigned long long n_recheck = 0;
 
     for (int s = blockIdx.x * WARPS_PER_CTA + wid; s < A.n; s += warps_total) {
-        const int id = A.s_id[s];
-        const double4 me = A.s_posr[s];
         const float4 mv = A.s_vel[s];
         const int flags = __float_as_int(mv.w);
-        Action7 act;
-        int tag = 0, n_suit = 0;
-        double npx, npy, npz;
-        if (flags & FL_INACTIVE) {
-            // mampenv.py:35-36: skipped agents keep the zero action row
-#pragma unroll
-            for (int k = 0; k < 7; k++) act.a[k] = 0.f;
-            if (lane == 0) {
-                kinematic_update(A, id, act, me.x, me.y, me.z, &npx, &npy, &npz);
-                A.s_newpos[s] = make_double4(npx, npy, npz, 0.0);
-                if (A.st.tag) A.st.tag[id] = 0;
-                if (A.st.n_suit) A.st.n_suit[id] = 0;
-            }
+        if (flags & FL_INACTIVE) continue;
+        const double4 vd = A.s_vdes[s];
+        if (vd.w != 0.0) {   // zero-velocity shortcut: vA_post = 0.3 v_pref (scaPolicy.py:38)
+            if (lane == 0)
+                A.s_vpost[s] = make_double4(__dmul_rn(0.3, vd.x), __dmul_rn(0.3, vd.y), __dmul_rn(0.3, vd.z),
+                                            __longlong_as_double((long long)SCAB_TAG_FIRST));
             continue;
         }
+        const int id = A.s_id[s];
+        const double4 me = A.s_posr[s];
         Agent a;
         a.px = me.x; a.py = me.y; a.pz = me.z; a.r = me.w;
         a.vx = mv.x; a.vy = mv.y; a.vz = mv.z;
@@ -139,217 +165,228 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_policy_sampled(StepArgs 
             double second = __dadd_rn(0.5, stepv);
             a.shell1 = __dadd_rn(0.5, __dsub_rn(second, 0.5));
         }
-        double v_store[3], v_des[3];
-        const bool ext = (POLICY == SCAB_POLICY_SCA || POLICY == SCAB_POLICY_RVO3D_DUBINS) && A.st.vpref_ext != nullptr;
-        if (ext) {
-            for (int d = 0; d < 3; d++) v_des[d] = v_store[d] = A.st.vpref_ext[3 * id + d];
-        } else {
-            v_pref_straight(&A.st.goal[3 * id], a.px, a.py, a.pz, a.pref, IS_ORCA, v_store, v_des);
-        }
-        a.vdx = v_des[0]; a.vdy = v_des[1]; a.vdz = v_des[2];
+        a.vdx = vd.x; a.vdy = vd.y; a.vdz = vd.z;
         const int C = 2 * a.N + 1;
+        int tag = 0, n_suit = 0;
+        const int nc = A.s_nbr_cnt[s];
 
-        // first-step gate: l3norm(vA,0) <= 1e-5 (scaPolicy.py:34) / distance(vA,0) <= 1e-5 (orca3dPolicy.py:52)
-        const double nv32 = __dsqrt_rn(sumsq_f32(a.vx, a.vy, a.vz));
-        const bool first = IS_ORCA ? (py_round5(__dadd_rn(nv32, 1e-5)) <= 1e-5) : (py_round5(nv32) <= 1e-5);
-        const int qcoll = A.s_qcoll[s];
-        bool apply_qcoll = IS_ORCA || !first;    // RVO family: computeNeighbors is not called on the shortcut
-        double vpx, vpy, vpz;                     // vA_post
-        int nc = 0;
-        if (first) {
-            tag = SCAB_TAG_FIRST;
-            vpx = __dmul_rn(0.3, v_des[0]); vpy = __dmul_rn(0.3, v_des[1]); vpz = __dmul_rn(0.3, v_des[2]);
-        } else {
-            nc = A.s_nbr_cnt[s];
-            // ---------------------------------------------------------------- constraints (lane k)
-            if (lane < nc) {
-                const int e = A.s_nbr[(size_t)s * KNBR + lane];
-                double4 o;
-                float ox = 0.f, oy = 0.f, oz = 0.f;
-                bool at_goal = true, is_obst = true;
-                if (e < A.n) {
-                    o = A.s_posr[e];
-                    float4 ov = A.s_vel[e];
-                    ox = ov.x; oy = ov.y; oz = ov.z;
-                    at_goal = (__float_as_int(ov.w) & SCAB_ST_AT_GOAL) != 0;
-                    is_obst = false;
-                } else if (e < A.n + A.m) {
-                    o = A.o_posr[e - A.n];
-                } else {
-                    o = A.o_posr_by_id[e - A.n - A.m];
+        // ---------------------------------------------------------------- constraints (lane k)
+        if (lane < nc) {
+            const int e = A.s_nbr[(size_t)s * KNBR + lane];
+            double4 o;
+            float ox = 0.f, oy = 0.f, oz = 0.f;
+            bool at_goal = true, is_obst = true;
+            if (e < A.n) {
+                o = A.s_posr[e];
+                float4 ov = A.s_vel[e];
+                ox = ov.x; oy = ov.y; oz = ov.z;
+                at_goal = (__float_as_int(ov.w) & SCAB_ST_AT_GOAL) != 0;
+                is_obst = false;
+            } else if (e < A.n + A.m) {
+                o = A.o_posr[e - A.n];
+            } else {
+                o = A.o_posr_by_id[e - A.n - A.m];
+            }
+            const double R = IS_ORCA ? __dadd_rn(__dadd_rn(a.r, 0.05), __dadd_rn(o.w, 0.05))
+                                     : __dadd_rn(__dadd_rn(o.w, 0.05), __dadd_rn(a.r, 0.05));
+            const double rx = __dsub_rn(o.x, a.px), ry = __dsub_rn(o.y, a.py), rz = __dsub_rn(o.z, a.pz);
+            W.dR[lane] = R;
+            if (!IS_ORCA) {
+                // scaPolicy.py:47-60: apex p0 = pA (static / at goal) else pA + 0.5 (vB + vA) in float32
+                float hx = 0.f, hy = 0.f, hz = 0.f;
+                if (!at_goal) {
+                    hx = __fmul_rn(0.5f, __fadd_rn(ox, a.vx));
+                    hy = __fmul_rn(0.5f, __fadd_rn(oy, a.vy));
+                    hz = __fmul_rn(0.5f, __fadd_rn(oz, a.vz));
                 }
-                const double R = IS_ORCA ? __dadd_rn(__dadd_rn(a.r, 0.05), __dadd_rn(o.w, 0.05))
-                                         : __dadd_rn(__dadd_rn(o.w, 0.05), __dadd_rn(a.r, 0.05));
-                const double rx = __dsub_rn(o.x, a.px), ry = __dsub_rn(o.y, a.py), rz = __dsub_rn(o.z, a.pz);
-                W.dR[lane] = R;
-                if (!IS_ORCA) {
-                    // scaPolicy.py:47-60: apex p0 = pA (static / at goal) else pA + 0.5 (vB + vA) in float32
-                    float hx = 0.f, hy = 0.f, hz = 0.f;
-                    if (!at_goal) {
-                        hx = __fmul_rn(0.5f, __fadd_rn(ox, a.vx));
-                        hy = __fmul_rn(0.5f, __fadd_rn(oy, a.vy));
-                        hz = __fmul_rn(0.5f, __fadd_rn(oz, a.vz));
-                    }
-                    W.dpx[lane] = o.x; W.dpy[lane] = o.y; W.dpz[lane] = o.z;
-                    W.dhx[lane] = at_goal ? a.px : __dadd_rn(a.px, (double)hx);
-                    W.dhy[lane] = at_goal ? a.py : __dadd_rn(a.py, (double)hy);
-                    W.dhz[lane] = at_goal ? a.pz : __dadd_rn(a.pz, (double)hz);
-                    const double pp = dot3(rx, ry, rz, rx, ry, rz);
-                    const float fpx = (float)rx, fpy = (float)ry, fpz = (float)rz;
-                    W.px[lane] = fpx; W.py[lane] = fpy; W.pz[lane] = fpz;
-                    W.hx[lane] = hx; W.hy[lane] = hy; W.hz[lane] = hz;
-                    W.c2[lane] = (float)fmax(pp - R * R, 0.0);
-                    W.ph[lane] = fmaf(fpz, hz, fmaf(fpy, hy, fpx * hx));
-                    W.hh[lane] = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
-                    W.pp[lane] = (float)pp;
-                    W.hn[lane] = sqrtf(W.hh[lane]);
-                } else {
-                    // orca3dPolicy.py:57-107 (== orca3dPolicyOfficial.py:56-106)
-                    const double vrx = (double)__fsub_rn(a.vx, ox), vry = (double)__fsub_rn(a.vy, oy),
-                                 vrz = (double)__fsub_rn(a.vz, oz);
-                    const double distSq = dot3(rx, ry, rz, rx, ry, rz);
-                    const double RSq = __dmul_rn(R, R);
-                    double nx, ny, nz, ux, uy, uz;
-                    if (distSq > RSq) {
-                        const double invT = A.inv_time_horizon;
-                        double wx = __dsub_rn(vrx, __dmul_rn(invT, rx)), wy = __dsub_rn(vry, __dmul_rn(invT, ry)),
-                               wz = __dsub_rn(vrz, __dmul_rn(invT, rz));
-                        double wl2 = dot3(wx, wy, wz, wx, wy, wz);
-                        double dp = dot3(wx, wy, wz, rx, ry, rz);
-                        if (dp < 0.0 && __dmul_rn(dp, dp) > __dmul_rn(RSq, wl2)) {
-                            double wl = __dsqrt_rn(wl2);
-                            nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
-                            double sc = __dsub_rn(__dmul_rn(R, invT), wl);
-                            ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
-                        } else {
-                            double difSq = __dsub_rn(distSq, RSq);
-                            double dpr = dot3(rx, ry, rz, vrx, vry, vrz);
-                            double cx = __dsub_rn(__dmul_rn(ry, vrz), __dmul_rn(rz, vry));
-                            double cy = __dsub_rn(__dmul_rn(rz, vrx), __dmul_rn(rx, vrz));
-                            double cz = __dsub_rn(__dmul_rn(rx, vry), __dmul_rn(ry, vrx));
-                            double wwSq = __ddiv_rn(dot3(cx, cy, cz, cx, cy, cz), difSq);
-                            double pl = __dsqrt_rn(distSq);
-                            double t = __ddiv_rn(__dadd_rn(__ddiv_rn(dpr, pl), __dmul_rn(__dsqrt_rn(wwSq), __ddiv_rn(R, pl))), pl);
-                            double wx = __dsub_rn(vrx, __dmul_rn(t, rx)), wy = __dsub_rn(vry, __dmul_rn(t, ry)),
-                                   wz = __dsub_rn(vrz, __dmul_rn(t, rz));
-                            double wl = __dsqrt_rn(dot3(wx, wy, wz, wx, wy, wz));
-                            nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
-                            double sc = __dsub_rn(__dmul_rn(R, t), wl);
-                            ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
-                        }
+                W.dpx[lane] = o.x; W.dpy[lane] = o.y; W.dpz[lane] = o.z;
+                W.dhx[lane] = at_goal ? a.px : __dadd_rn(a.px, (double)hx);
+                W.dhy[lane] = at_goal ? a.py : __dadd_rn(a.py, (double)hy);
+                W.dhz[lane] = at_goal ? a.pz : __dadd_rn(a.pz, (double)hz);
+                const double pp = dot3(rx, ry, rz, rx, ry, rz);
+                const float fpx = (float)rx, fpy = (float)ry, fpz = (float)rz;
+                W.px[lane] = fpx; W.py[lane] = fpy; W.pz[lane] = fpz;
+                W.hx[lane] = hx; W.hy[lane] = hy; W.hz[lane] = hz;
+                W.c2[lane] = (float)fmax(pp - R * R, 0.0);
+                W.ph[lane] = fmaf(fpz, hz, fmaf(fpy, hy, fpx * hx));
+                W.hh[lane] = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
+                W.pp[lane] = (float)pp;
+                W.hn[lane] = sqrtf(W.hh[lane]);
+            } else {
+                // orca3dPolicy.py:57-107 (== orca3dPolicyOfficial.py:56-106)
+                const double vrx = (double)__fsub_rn(a.vx, ox), vry = (double)__fsub_rn(a.vy, oy),
+                             vrz = (double)__fsub_rn(a.vz, oz);
+                const double distSq = dot3(rx, ry, rz, rx, ry, rz);
+                const double RSq = __dmul_rn(R, R);
+                double nx, ny, nz, ux, uy, uz;
+                if (distSq > RSq) {
+                    const double invT = A.inv_time_horizon;
+                    double wx = __dsub_rn(vrx, __dmul_rn(invT, rx)), wy = __dsub_rn(vry, __dmul_rn(invT, ry)),
+                           wz = __dsub_rn(vrz, __dmul_rn(invT, rz));
+                    double wl2 = dot3(wx, wy, wz, wx, wy, wz);
+                    double dp = dot3(wx, wy, wz, rx, ry, rz);
+                    if (dp < 0.0 && __dmul_rn(dp, dp) > __dmul_rn(RSq, wl2)) {
+                        double wl = __dsqrt_rn(wl2);
+                        nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
+                        double sc = __dsub_rn(__dmul_rn(R, invT), wl);
+                        ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
                     } else {
-                        const double invDt = A.inv_time_step;
-                        double wx = __dsub_rn(vrx, __dmul_rn(invDt, rx)), wy = __dsub_rn(vry, __dmul_rn(invDt, ry)),
-                               wz = __dsub_rn(vrz, __dmul_rn(invDt, rz));
+                        double difSq = __dsub_rn(distSq, RSq);
+                        double dpr = dot3(rx, ry, rz, vrx, vry, vrz);
+                        double cx = __dsub_rn(__dmul_rn(ry, vrz), __dmul_rn(rz, vry));
+                        double cy = __dsub_rn(__dmul_rn(rz, vrx), __dmul_rn(rx, vrz));
+                        double cz = __dsub_rn(__dmul_rn(rx, vry), __dmul_rn(ry, vrx));
+                        double wwSq = __ddiv_rn(dot3(cx, cy, cz, cx, cy, cz), difSq);
+                        double pl = __dsqrt_rn(distSq);
+                        double t = __ddiv_rn(__dadd_rn(__ddiv_rn(dpr, pl), __dmul_rn(__dsqrt_rn(wwSq), __ddiv_rn(R, pl))), pl);
+                        double wx = __dsub_rn(vrx, __dmul_rn(t, rx)), wy = __dsub_rn(vry, __dmul_rn(t, ry)),
+                               wz = __dsub_rn(vrz, __dmul_rn(t, rz));
                         double wl = __dsqrt_rn(dot3(wx, wy, wz, wx, wy, wz));
                         nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
-                        double sc = __dsub_rn(__dmul_rn(R, invDt), wl);
+                        double sc = __dsub_rn(__dmul_rn(R, t), wl);
                         ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
                     }
-                    const double qx = __dadd_rn((double)a.vx, __dmul_rn(0.5, ux)), qy = __dadd_rn((double)a.vy, __dmul_rn(0.5, uy)),
-                                 qz = __dadd_rn((double)a.vz, __dmul_rn(0.5, uz));
-                    W.dpx[lane] = qx; W.dpy[lane] = qy; W.dpz[lane] = qz;
-                    W.dhx[lane] = nx; W.dhy[lane] = ny; W.dhz[lane] = nz;
-                    W.px[lane] = (float)nx; W.py[lane] = (float)ny; W.pz[lane] = (float)nz;
-                    W.c2[lane] = (float)(nx * qx + ny * qy + nz * qz);
-                    W.pp[lane] = (float)sqrt(qx * qx + qy * qy + qz * qz);
-                    W.rpx[lane] = rx; W.rpy[lane] = ry; W.rpz[lane] = rz;
-                    // orca3dPolicy.py:387: v_dif = v - 0.5 (vA + vB) if |vB| > 1e-5 else v
-                    const double nvB = is_obst ? 0.0 : (double)norm3f_np(ox, oy, oz);
-                    const bool mov = nvB > 1e-5;
-                    W.ofx[lane] = mov ? (double)__fmul_rn(0.5f, __fadd_rn(a.vx, ox)) : 0.0;
-                    W.ofy[lane] = mov ? (double)__fmul_rn(0.5f, __fadd_rn(a.vy, oy)) : 0.0;
-                    W.ofz[lane] = mov ? (double)__fmul_rn(0.5f, __fadd_rn(a.vz, oz)) : 0.0;
+                } else {
+                    const double invDt = A.inv_time_step;
+                    double wx = __dsub_rn(vrx, __dmul_rn(invDt, rx)), wy = __dsub_rn(vry, __dmul_rn(invDt, ry)),
+                           wz = __dsub_rn(vrz, __dmul_rn(invDt, rz));
+                    double wl = __dsqrt_rn(dot3(wx, wy, wz, wx, wy, wz));
+                    nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
+                    double sc = __dsub_rn(__dmul_rn(R, invDt), wl);
+                    ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
                 }
+                const double qx = __dadd_rn((double)a.vx, __dmul_rn(0.5, ux)), qy = __dadd_rn((double)a.vy, __dmul_rn(0.5, uy)),
+                             qz = __dadd_rn((double)a.vz, __dmul_rn(0.5, uz));
+                W.dpx[lane] = qx; W.dpy[lane] = qy; W.dpz[lane] = qz;
+                W.dhx[lane] = nx; W.dhy[lane] = ny; W.dhz[lane] = nz;
+                W.px[lane] = (float)nx; W.py[lane] = (float)ny; W.pz[lane] = (float)nz;
+                W.c2[lane] = (float)(nx * qx + ny * qy + nz * qz);
+                W.pp[lane] = (float)sqrt(qx * qx + qy * qy + qz * qz);
+                W.rpx[lane] = rx; W.rpy[lane] = ry; W.rpz[lane] = rz;
+                // orca3dPolicy.py:387: v_dif = v - 0.5 (vA + vB) if |vB| > 1e-5 else v
+                const double nvB = is_obst ? 0.0 : (double)norm3f_np(ox, oy, oz);
+                const bool mov = nvB > 1e-5;
+                W.ofx[lane] = mov ? (double)__fmul_rn(0.5f, __fadd_rn(a.vx, ox)) : 0.0;
+                W.ofy[lane] = mov ? (double)__fmul_rn(0.5f, __fadd_rn(a.vy, oy)) : 0.0;
+                W.ofz[lane] = mov ? (double)__fmul_rn(0.5f, __fadd_rn(a.vz, oz)) : 0.0;
             }
-            __syncwarp();
+        }
 
-            // ---------------------------------------------------------------- A: posture + compaction
-            int ncand = 0;
-            for (int base = 0; base < C; base += 32) {
-                const int c = base + lane;
-                bool pass = false;
-                if (c < C) {
+        // ---------------------------------------------------------------- A: posture + compaction
+        // cos(angle(vA, rad*u)) = (vA.u)/(|vA||u|) for both shells: one fp32 dot per direction.  The
+        // altitude test pA.z + dt*v.z >= 0 can only fail within dt*max|v| of the ground.
+        int ncand = 0;
+        {
+            const float fnv = (float)a.nvA;
+            const float thr = 0.70710678f * fnv;
+            const float band = 2e-6f * fnv;
+            const double vmax = fmax(fmax(0.5, fabs(a.shell1)), fabs(a.vdz));
+            const bool near_ground = !(a.pz > A.time_step * vmax + 1e-9);
+            for (int base = 0; base < a.N; base += 32) {
+                const int n = base + lane;   // N is a multiple of 32
+                const float4 u = a.dirf[n];
+                const float dt = fmaf(a.vz, u.z, fmaf(a.vy, u.y, a.vx * u.x));
+                bool p0 = dt >= thr, p1 = p0;
+                if (fabsf(dt - thr) <= band || near_ground) {
                     double x, y, z;
-                    cand64(a, c, x, y, z);
-                    pass = posture_ok(a, A.time_step, x, y, z);
+                    cand64(a, n, x, y, z);
+                    p0 = posture_ok(a, A.time_step, x, y, z);
+                    cand64(a, a.N + n, x, y, z);
+                    p1 = posture_ok(a, A.time_step, x, y, z);
                 }
-                const unsigned msk = __ballot_sync(FULL, pass);
-                if (pass) W.list[ncand + __popc(msk & ((1u << lane) - 1))] = (unsigned short)c;
+                unsigned msk = __ballot_sync(FULL, p0);
+                if (p0) W.list[ncand + __popc(msk & ((1u << lane) - 1))] = (unsigned short)n;
+                ncand += __popc(msk);
+                msk = __ballot_sync(FULL, p1);
+                if (p1) W.list[ncand + __popc(msk & ((1u << lane) - 1))] = (unsigned short)(a.N + n);
                 ncand += __popc(msk);
             }
-            __syncwarp();
-
-            // ---------------------------------------------------------------- B: constraint tests
-            for (int j = lane; j < ncand; j += 32) {
-                const int c = W.list[j];
-                float vx, vy, vz;
-                if (c >= 2 * a.N) { vx = (float)a.vdx; vy = (float)a.vdy; vz = (float)a.vdz; }
-                else {
-                    const int n = (c >= a.N) ? c - a.N : c;
-                    const float rad = (c >= a.N) ? (float)a.shell1 : 0.5f;
-                    const float4 u = a.dirf[n];
-                    vx = rad * u.x; vy = rad * u.y; vz = rad * u.z;
-                }
-                const float vv0 = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
-                const float vn = sqrtf(vv0);
-                bool suit = true;
-                for (int k = 0; k < nc && suit; k++) {
-                    bool inside, unsure;
-                    if (!IS_ORCA) {
-                        const float dt = fmaf(W.pz[k], vz, fmaf(W.py[k], vy, W.px[k] * vx)) - W.ph[k];
-                        const float vh = fmaf(W.hz[k], vz, fmaf(W.hy[k], vy, W.hx[k] * vx));
-                        const float vv = fmaf(-2.f, vh, vv0) + W.hh[k];
-                        const float lhs = dt * dt, rhs = vv * W.c2[k];
-                        const float S = W.pp[k] * (vn + W.hn[k]) * (vn + W.hn[k]);
-                        inside = (dt > 0.f) && (lhs > rhs);
-                        unsure = fabsf(lhs - rhs) <= 2e-5f * S;
-                    } else {
-                        const float val = fmaf(W.pz[k], vz, fmaf(W.py[k], vy, W.px[k] * vx)) - W.c2[k];
-                        inside = !(val >= 0.f);
-                        unsure = fabsf(val) <= 1e-5f * (vn + W.pp[k]);
-                    }
-                    if (unsure) {
-                        n_recheck++;
-                        double x, y, z;
-                        cand64(a, c, x, y, z);
-                        if (!IS_ORCA) {
-                            // scaPolicy.py:180: v_dif = new_v + pA - p_0
-                            double dx = __dsub_rn(__dadd_rn(x, a.px), W.dhx[k]), dy = __dsub_rn(__dadd_rn(y, a.py), W.dhy[k]),
-                                   dz = __dsub_rn(__dadd_rn(z, a.pz), W.dhz[k]);
-                            inside = is_intersect64(__dsub_rn(W.dpx[k], a.px), __dsub_rn(W.dpy[k], a.py),
-                                                    __dsub_rn(W.dpz[k], a.pz), W.dR[k], dx, dy, dz);
-                        } else {
-                            // orca3dPolicy.py:328-333 is_inORCA
-                            double val = dot3(__dsub_rn(x, W.dpx[k]), __dsub_rn(y, W.dpy[k]), __dsub_rn(z, W.dpz[k]),
-                                              W.dhx[k], W.dhy[k], W.dhz[k]);
-                            inside = !(val >= 0.0);
-                        }
-                    }
-                    if (inside) suit = false;
-                }
-                W.list[j] = (unsigned short)(c | (suit ? 0x8000 : 0));
-                n_suit += suit ? 1 : 0;
+            const bool pv = posture_ok(a, A.time_step, a.vdx, a.vdy, a.vdz);   // v_pref itself, last (scaPolicy.py:206)
+            if (pv) {
+                if (lane == 0) W.list[ncand] = (unsigned short)(2 * a.N);
+                ncand++;
             }
-            __syncwarp();
+        }
+        __syncwarp();
+
+        // ---------------------------------------------------------------- B: constraint tests
+        for (int j = lane; j < ncand; j += 32) {
+            const int c = W.list[j];
+            float vx, vy, vz;
+            if (c >= 2 * a.N) { vx = (float)a.vdx; vy = (float)a.vdy; vz = (float)a.vdz; }
+            else {
+                const int n = (c >= a.N) ? c - a.N : c;
+                const float rad = (c >= a.N) ? (float)a.shell1 : 0.5f;
+                const float4 u = a.dirf[n];
+                vx = rad * u.x; vy = rad * u.y; vz = rad * u.z;
+            }
+            const float vv0 = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
+            const float vn = sqrtf(vv0);
+            bool suit = true;
+            for (int k = 0; k < nc && suit; k++) {
+                bool inside, unsure;
+                if (!IS_ORCA) {
+                    const float dt = fmaf(W.pz[k], vz, fmaf(W.py[k], vy, W.px[k] * vx)) - W.ph[k];
+                    const float vh = fmaf(W.hz[k], vz, fmaf(W.hy[k], vy, W.hx[k] * vx));
+                    const float vv = fmaf(-2.f, vh, vv0) + W.hh[k];
+                    const float lhs = dt * dt, rhs = vv * W.c2[k];
+                    const float S = W.pp[k] * (vn + W.hn[k]) * (vn + W.hn[k]);
+                    inside = (dt > 0.f) && (lhs > rhs);
+                    unsure = fabsf(lhs - rhs) <= 2e-5f * S;
+                } else {
+                    const float val = fmaf(W.pz[k], vz, fmaf(W.py[k], vy, W.px[k] * vx)) - W.c2[k];
+                    inside = !(val >= 0.f);
+                    unsure = fabsf(val) <= 1e-5f * (vn + W.pp[k]);
+                }
+                if (unsure) {
+                    n_recheck++;
+                    double x, y, z;
+                    cand64(a, c, x, y, z);
+                    if (!IS_ORCA) {
+                        // scaPolicy.py:180: v_dif = new_v + pA - p_0
+                        double dx = __dsub_rn(__dadd_rn(x, a.px), W.dhx[k]), dy = __dsub_rn(__dadd_rn(y, a.py), W.dhy[k]),
+                               dz = __dsub_rn(__dadd_rn(z, a.pz), W.dhz[k]);
+                        inside = is_intersect64(__dsub_rn(W.dpx[k], a.px), __dsub_rn(W.dpy[k], a.py),
+                                                __dsub_rn(W.dpz[k], a.pz), W.dR[k], dx, dy, dz);
+                    } else {
+                        // orca3dPolicy.py:328-333 is_inORCA
+                        double val = dot3(__dsub_rn(x, W.dpx[k]), __dsub_rn(y, W.dpy[k]), __dsub_rn(z, W.dpz[k]),
+                                          W.dhx[k], W.dhy[k], W.dhz[k]);
+                        inside = !(val >= 0.0);
+                    }
+                }
+                if (inside) suit = false;
+            }
+            W.list[j] = (unsigned short)(c | (suit ? 0x8000 : 0));
+            n_suit += suit ? 1 : 0;
+        }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) n_suit += __shfl_xor_sync(FULL, n_suit, o);
+        for (int o = 16; o > 0; o >>= 1) n_suit += __shfl_xor_sync(FULL, n_suit, o);
+        __syncwarp();
 
-            // ---------------------------------------------------------------- C / D: selection
-            // Sorted order of the reference's list.sort == (key, generation index) lexicographic.
-            const bool fallback = (n_suit == 0);
-            tag = fallback ? SCAB_TAG_FALLBACK : SCAB_TAG_SUITABLE;
-            const double thr = (POLICY == SCAB_POLICY_SCA) ? (fallback ? 5e-2 : 3e-2) : 1e-1;
-            const int total = fallback ? C : ncand;
+        // ---------------------------------------------------------------- C / D: selection
+        // Sorted order of the reference's list.sort == (key, generation index) lexicographic.
+        const bool fallback = (n_suit == 0);
+        tag = fallback ? SCAB_TAG_FALLBACK : SCAB_TAG_SUITABLE;
+        const int total = fallback ? C : ncand;
+        const long long thr_units = (POLICY == SCAB_POLICY_SCA) ? (fallback ? 5000 : 3000) : 10000;
+        const double thr = (POLICY == SCAB_POLICY_SCA) ? (fallback ? 5e-2 : 3e-2) : 1e-1;
+        auto slot_cand = [&](int j) -> int { return fallback ? j : (int)(W.list[j] & 0x7fff); };
+        auto slot_live = [&](int j) -> bool { return fallback ? true : (W.list[j] & 0x8000) != 0; };
 
-            // key of candidate slot j (suitable: l3norm(v, v_pref)*1e5 as integer; fallback: fp64 bits)
-            auto slot_cand = [&](int j) -> int { return fallback ? j : (int)(W.list[j] & 0x7fff); };
-            auto slot_live = [&](int j) -> bool { return fallback ? true : (W.list[j] & 0x8000) != 0; };
-            auto key_of = [&](int c) -> unsigned long long {
-                double x, y, z;
-                cand64(a, c, x, y, z);
-                const double dist = __dsqrt_rn(sumsq3(__dsub_rn(x, a.vdx), __dsub_rn(y, a.vdy), __dsub_rn(z, a.vdz)));
-                if (!fallback) return (unsigned long long)py_round5_units(dist);
+        // keys, once per live slot
+        unsigned long long ka = ~0ull;
+        unsigned kb = 0xffffffffu;
+        for (int j = lane; j < total; j += 32) {
+            if (!slot_live(j)) continue;
+            const int c = slot_cand(j);
+            double x, y, z;
+            cand64(a, c, x, y, z);
+            const double dist = __dsqrt_rn(sumsq3(__dsub_rn(x, a.vdx), __dsub_rn(y, a.vdy), __dsub_rn(z, a.vdz)));
+            unsigned long long key;
+            if (!fallback) {
+                key = (unsigned long long)py_round5_units(dist);     // l3norm(v, v_pref) in units of 1e-5
+            } else {
                 // compute_without_suitV (scaPolicy.py:148-165 / orca3dPolicy.py:381-397)
                 double tcmin = 0.0;
                 bool have = false;
@@ -376,103 +413,151 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_policy_sampled(StepArgs 
                     }
                 }
                 const double tcv = __dadd_rn(have ? tcmin : 0.0, 1e-5);
-                const double key = __dadd_rn(__ddiv_rn(0.2, tcv), py_round5(dist));
-                return (unsigned long long)__double_as_longlong(key);   // key > 0: bit pattern is monotone
-            };
-
-            // 1. head of the sorted list
-            unsigned long long ka = ~0ull;
-            unsigned kb = 0xffffffffu;
+                const double kd = __dadd_rn(__ddiv_rn(0.2, tcv), py_round5(dist));
+                key = (unsigned long long)__double_as_longlong(kd);   // kd > 0: the bit pattern is monotone
+            }
+            W.key[j] = key;
+            if (SHUNT) {   // l3norm(v, vA) in units (scaPolicy.py:128)
+                const double dva = __dsqrt_rn(sumsq3(__dsub_rn(x, (double)a.vx), __dsub_rn(y, (double)a.vy), __dsub_rn(z, (double)a.vz)));
+                W.dvu[j] = (unsigned int)py_round5_units(dva);
+            }
+            if (lex_less(key, (unsigned)c, ka, kb)) { ka = key; kb = (unsigned)c; }
+        }
+        // 1. head of the sorted list
+        warp_lexmin(ka, kb);
+        int best = (int)kb;
+        const int live_total = fallback ? C : n_suit;
+        __syncwarp();
+        if (SHUNT && live_total > 1) {
+            // scaPolicy.py:119-145 shunted_strategy
+            double x0, y0, z0;
+            cand64(a, best, x0, y0, z0);
+            const long long d0u = (long long)py_round5_units(
+                __dsqrt_rn(sumsq3(__dsub_rn(x0, (double)a.vx), __dsub_rn(y0, (double)a.vy), __dsub_rn(z0, (double)a.vz))));
+            // 2. first element of the sorted list that breaks the prefix: abs(d0 - di) < thr fails
+            unsigned long long fa = ~0ull;
+            unsigned fb = 0xffffffffu;
+            for (int j = lane; j < total; j += 32) {
+                if (!slot_live(j)) continue;
+                const long long diu = (long long)W.dvu[j];
+                const long long du = d0u > diu ? d0u - diu : diu - d0u;
+                bool within;
+                if (du < thr_units - 1) within = true;
+                else if (du > thr_units + 1) within = false;
+                else within = fabs(__dsub_rn(__ddiv_rn((double)d0u, 1e5), __ddiv_rn((double)diu, 1e5))) < thr;
+                if (!within) {
+                    const int c = slot_cand(j);
+                    if (lex_less(W.key[j], (unsigned)c, fa, fb)) { fa = W.key[j]; fb = (unsigned)c; }
+                }
+            }
+            warp_lexmin(fa, fb);
+            // 3. min-phi / max-phi over the prefix; ties -> first in sorted order
+            long long pmin = LLONG_MAX;
+            unsigned long long pmin_k = ~0ull;
+            unsigned pmin_c = 0xffffffffu;
+            long long pmax = LLONG_MIN;
+            unsigned long long pmax_k = ~0ull;
+            unsigned pmax_c = 0xffffffffu;
             for (int j = lane; j < total; j += 32) {
                 if (!slot_live(j)) continue;
                 const int c = slot_cand(j);
-                const unsigned long long k = key_of(c);
-                if (lex_less(k, (unsigned)c, ka, kb)) { ka = k; kb = (unsigned)c; }
+                const unsigned long long k = W.key[j];
+                if (!lex_less(k, (unsigned)c, fa, fb)) continue;
+                double x, y, z;
+                cand64(a, c, x, y, z);
+                // util.py:145-150 get_phi
+                double phi = (y >= 0) ? atan2(y, x) : __dadd_rn(2 * SCAB_PI, atan2(y, x));
+                const long long pi_units = (long long)trunc(__dmul_rn(phi, 1e5));
+                if (pi_units < pmin || (pi_units == pmin && lex_less(k, (unsigned)c, pmin_k, pmin_c))) {
+                    pmin = pi_units; pmin_k = k; pmin_c = (unsigned)c;
+                }
+                if (pi_units > pmax || (pi_units == pmax && lex_less(k, (unsigned)c, pmax_k, pmax_c))) {
+                    pmax = pi_units; pmax_k = k; pmax_c = (unsigned)c;
+                }
             }
-            warp_lexmin(ka, kb);
-            int best = (int)kb;
-            const int live_total = fallback ? C : n_suit;
-            if (SHUNT && live_total > 1) {
-                // scaPolicy.py:119-145 shunted_strategy
-                double x0, y0, z0;
-                cand64(a, best, x0, y0, z0);
-                const double d0 = l3norm_d(x0, y0, z0, (double)a.vx, (double)a.vy, (double)a.vz);
-                // 2. first element of the sorted list that breaks the prefix
-                unsigned long long fa = ~0ull;
-                unsigned fb = 0xffffffffu;
-                for (int j = lane; j < total; j += 32) {
-                    if (!slot_live(j)) continue;
-                    const int c = slot_cand(j);
-                    double x, y, z;
-                    cand64(a, c, x, y, z);
-                    const double di = l3norm_d(x, y, z, (double)a.vx, (double)a.vy, (double)a.vz);
-                    if (!(fabs(__dsub_rn(d0, di)) < thr)) {
-                        const unsigned long long k = key_of(c);
-                        if (lex_less(k, (unsigned)c, fa, fb)) { fa = k; fb = (unsigned)c; }
-                    }
-                }
-                warp_lexmin(fa, fb);
-                // 3. min-phi / max-phi over the prefix; ties -> first in sorted order
-                long long pmin = LLONG_MAX;
-                unsigned long long pmin_k = ~0ull;
-                unsigned pmin_c = 0xffffffffu;
-                long long pmax = LLONG_MIN;
-                unsigned long long pmax_k = ~0ull;
-                unsigned pmax_c = 0xffffffffu;
-                for (int j = lane; j < total; j += 32) {
-                    if (!slot_live(j)) continue;
-                    const int c = slot_cand(j);
-                    const unsigned long long k = key_of(c);
-                    if (!lex_less(k, (unsigned)c, fa, fb)) continue;
-                    double x, y, z;
-                    cand64(a, c, x, y, z);
-                    // util.py:145-150 get_phi
-                    double phi = (y >= 0) ? atan2(y, x) : __dadd_rn(2 * SCAB_PI, atan2(y, x));
-                    const long long pi_units = (long long)trunc(__dmul_rn(phi, 1e5));
-                    if (pi_units < pmin || (pi_units == pmin && lex_less(k, (unsigned)c, pmin_k, pmin_c))) {
-                        pmin = pi_units; pmin_k = k; pmin_c = (unsigned)c;
-                    }
-                    if (pi_units > pmax || (pi_units == pmax && lex_less(k, (unsigned)c, pmax_k, pmax_c))) {
-                        pmax = pi_units; pmax_k = k; pmax_c = (unsigned)c;
-                    }
-                }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    long long p2 = __shfl_xor_sync(FULL, pmin, o);
-                    unsigned long long k2 = __shfl_xor_sync(FULL, pmin_k, o);
-                    unsigned c2 = __shfl_xor_sync(FULL, pmin_c, o);
-                    if (p2 < pmin || (p2 == pmin && lex_less(k2, c2, pmin_k, pmin_c))) { pmin = p2; pmin_k = k2; pmin_c = c2; }
-                    long long q2 = __shfl_xor_sync(FULL, pmax, o);
-                    unsigned long long l2 = __shfl_xor_sync(FULL, pmax_k, o);
-                    unsigned d2 = __shfl_xor_sync(FULL, pmax_c, o);
-                    if (q2 > pmax || (q2 == pmax && lex_less(l2, d2, pmax_k, pmax_c))) { pmax = q2; pmax_k = l2; pmax_c = d2; }
-                }
-                const double phi_min = __ddiv_rn((double)pmin, 1e5), phi_max = __ddiv_rn((double)pmax, 1e5);
-                best = (fabs(__dsub_rn(phi_max, phi_min)) <= SCAB_PI) ? (int)pmin_c : (int)pmax_c;
+            for (int o = 16; o > 0; o >>= 1) {
+                long long p2 = __shfl_xor_sync(FULL, pmin, o);
+                unsigned long long k2 = __shfl_xor_sync(FULL, pmin_k, o);
+                unsigned c2 = __shfl_xor_sync(FULL, pmin_c, o);
+                if (p2 < pmin || (p2 == pmin && lex_less(k2, c2, pmin_k, pmin_c))) { pmin = p2; pmin_k = k2; pmin_c = c2; }
+                long long q2 = __shfl_xor_sync(FULL, pmax, o);
+                unsigned long long l2 = __shfl_xor_sync(FULL, pmax_k, o);
+                unsigned d2 = __shfl_xor_sync(FULL, pmax_c, o);
+                if (q2 > pmax || (q2 == pmax && lex_less(l2, d2, pmax_k, pmax_c))) { pmax = q2; pmax_k = l2; pmax_c = d2; }
             }
+            const double phi_min = __ddiv_rn((double)pmin, 1e5), phi_max = __ddiv_rn((double)pmax, 1e5);
+            best = (fabs(__dsub_rn(phi_max, phi_min)) <= SCAB_PI) ? (int)pmin_c : (int)pmax_c;
+        }
+        if (lane == 0) {
             double bx, by, bz;
             cand64(a, best, bx, by, bz);
-            vpx = trunc5(bx); vpy = trunc5(by); vpz = trunc5(bz);   // scaPolicy.py:239
-        }
-
-        // ---------------------------------------------------------------- action + kinematic update
-        if (lane == 0) {
-            act = cartesian2spherical(vpx, vpy, vpz, A.st.heading[3 * id], A.st.heading[3 * id + 1], false);
-            kinematic_update(A, id, act, a.px, a.py, a.pz, &npx, &npy, &npz);
-            A.s_newpos[s] = make_double4(npx, npy, npz, 0.0);
-            if (apply_qcoll && qcoll) A.st.status[id] = flags | SCAB_ST_COLLISION;
-            if (!apply_qcoll && A.st.nbr_cnt) A.st.nbr_cnt[id] = -1;
-            if (A.st.vpref_out) { A.st.vpref_out[3 * id] = v_store[0]; A.st.vpref_out[3 * id + 1] = v_store[1]; A.st.vpref_out[3 * id + 2] = v_store[2]; }
-            if (A.st.tag) A.st.tag[id] = tag;
-            if (A.st.n_suit) A.st.n_suit[id] = n_suit;
-            n_ran++;
+            // scaPolicy.py:239 truncation; w packs tag | n_suit << 8
+            A.s_vpost[s] = make_double4(trunc5(bx), trunc5(by), trunc5(bz),
+                                        __longlong_as_double((long long)tag | ((long long)n_suit << 8)));
         }
         __syncwarp();
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_recheck += __shfl_xor_sync(FULL, n_recheck, o);
     if (lane == 0 && n_recheck) atomicAdd(&A.counters[3], n_recheck);
-    if (lane == 0 && n_ran) atomicAdd(&A.counters[0], n_ran);
+}
+
+// ------------------------------------------------------------------ k_integrate (thread per agent)
+template <bool IS_ORCA>
+__global__ void __launch_bounds__(256) k_integrate(StepArgs A)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ran = false;
+    if (s < A.n) {
+        const int id = A.s_id[s];
+        const double4 me = A.s_posr[s];
+        const int flags = __float_as_int(A.s_vel[s].w);
+        Action7 act;
+        double npx, npy, npz;
+        if (flags & FL_INACTIVE) {
+            // mampenv.py:35-36: skipped agents keep the zero action row
+#pragma unroll
+            for (int k = 0; k < 7; k++) act.a[k] = 0.f;
+            kinematic_update(A, id, act, me.x, me.y, me.z, &npx, &npy, &npz);
+            if (A.st.tag) A.st.tag[id] = 0;
+            if (A.st.n_suit) A.st.n_suit[id] = 0;
+        } else {
+            ran = true;
+            const double4 vp = A.s_vpost[s];
+            const long long bits = __double_as_longlong(vp.w);
+            const int tag = (int)(bits & 0xff), n_suit = (int)(bits >> 8);
+            act = cartesian2spherical(vp.x, vp.y, vp.z, A.st.heading[3 * id], A.st.heading[3 * id + 1], false);
+            kinematic_update(A, id, act, me.x, me.y, me.z, &npx, &npy, &npz);
+            // RVO family: computeNeighbors is not called on the zero-velocity shortcut (scaPolicy.py:34-45);
+            // the ORCA policies call it before the gate (orca3dPolicy.py:50-52)
+            const bool nbrs_ran = IS_ORCA || !(tag & SCAB_TAG_FIRST);
+            if (nbrs_ran && A.s_qcoll[s]) A.st.status[id] = flags | SCAB_ST_COLLISION;   // agent.py:83-85
+            if (!nbrs_ran && A.st.nbr_cnt) A.st.nbr_cnt[id] = -1;
+            if (A.st.tag) A.st.tag[id] = tag;
+            if (A.st.n_suit) A.st.n_suit[id] = n_suit;
+        }
+        A.s_newpos[s] = make_double4(npx, npy, npz, 0.0);
+    }
+    const unsigned msk = __ballot_sync(FULL, ran);
+    if ((threadIdx.x & 31) == 0 && msk) {
+        atomicAdd(&A.counters[0], (unsigned long long)__popc(msk));
+        atomicAdd(&A.counters[4], (unsigned long long)__popc(msk));
+    }
+}
+
+template <int POLICY>
+static cudaError_t launch_select(const StepArgs &A, int grid, cudaStream_t s)
+{
+    static bool attr_set = false;
+    const size_t smem = sizeof(WarpSmem) * WARPS_PER_CTA;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_select<POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k_select<POLICY><<<grid, WARPS_PER_CTA * 32, smem, s>>>(A);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_policy_sampled(const StepArgs &A, int policy, cudaStream_t s)
@@ -481,15 +566,35 @@ cudaError_t launch_policy_sampled(const StepArgs &A, int policy, cudaStream_t s)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int need = (A.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    int grid = need < sms * 4 ? need : sms * 4;   // persistent: a multiple of the SM count when saturated
+    const int nb = (A.n + 255) / 256;
+    const int need = (A.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int grid = need < sms * 8 ? need : sms * 8;   // persistent: a multiple of the SM count when saturated
+    cudaError_t e;
     switch (policy) {
-    case SCAB_POLICY_SCA: k_policy_sampled<SCAB_POLICY_SCA><<<grid, WARPS_PER_CTA * 32, 0, s>>>(A); break;
-    case SCAB_POLICY_SRVO3D: k_policy_sampled<SCAB_POLICY_SRVO3D><<<grid, WARPS_PER_CTA * 32, 0, s>>>(A); break;
-    case SCAB_POLICY_RVO3D: k_policy_sampled<SCAB_POLICY_RVO3D><<<grid, WARPS_PER_CTA * 32, 0, s>>>(A); break;
-    case SCAB_POLICY_RVO3D_DUBINS: k_policy_sampled<SCAB_POLICY_RVO3D_DUBINS><<<grid, WARPS_PER_CTA * 32, 0, s>>>(A); break;
-    case SCAB_POLICY_ORCA_SAMPLED: k_policy_sampled<SCAB_POLICY_ORCA_SAMPLED><<<grid, WARPS_PER_CTA * 32, 0, s>>>(A); break;
+    case SCAB_POLICY_SCA:
+        k_vpref<false, true><<<nb, 256, 0, s>>>(A);
+        e = launch_select<SCAB_POLICY_SCA>(A, grid, s);
+        break;
+    case SCAB_POLICY_SRVO3D:
+        k_vpref<false, false><<<nb, 256, 0, s>>>(A);
+        e = launch_select<SCAB_POLICY_SRVO3D>(A, grid, s);
+        break;
+    case SCAB_POLICY_RVO3D:
+        k_vpref<false, false><<<nb, 256, 0, s>>>(A);
+        e = launch_select<SCAB_POLICY_RVO3D>(A, grid, s);
+        break;
+    case SCAB_POLICY_RVO3D_DUBINS:
+        k_vpref<false, true><<<nb, 256, 0, s>>>(A);
+        e = launch_select<SCAB_POLICY_RVO3D_DUBINS>(A, grid, s);
+        break;
+    case SCAB_POLICY_ORCA_SAMPLED:
+        k_vpref<true, false><<<nb, 256, 0, s>>>(A);
+        e = launch_select<SCAB_POLICY_ORCA_SAMPLED>(A, grid, s);
+        break;
     default: return cudaErrorInvalidValue;
     }
+    if (e != cudaSuccess) return e;
+    if (policy == SCAB_POLICY_ORCA_SAMPLED) k_integrate<true><<<nb, 256, 0, s>>>(A);
+    else k_integrate<false><<<nb, 256, 0, s>>>(A);
     return cudaGetLastError();
 }

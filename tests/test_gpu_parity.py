@@ -40,14 +40,14 @@ def _run_fixture(name, max_steps=None):
         r['status_bad'] = int((post['status'] != (s2['status'] & 15)).sum())
         r['stepnum_bad'] = int((post['step_num'] != s2['step_num']).sum())
         # positions follow the action row; only compare where the action matched bit-for-bit
-        same = ~(out['action'].astype(np.float32) != g['action'][t].astype(np.float32)).any(axis=1)
+        same = ~(out['action'].astype(np.float32)[:, :4] != g['action'][t].astype(np.float32)[:, :4]).any(axis=1)
         dp = np.abs(post['pos'] - s2['pos']).max(axis=1)
-        r['pos_bad'] = int((dp[same] > 1e-12).sum())
+        r['pos_bad'] = int((dp[same] > 1e-7).sum())          # a float32-ulp heading flip moves the agent by < 5e-8 m
         r['pos_maxerr'] = float(dp[same].max()) if same.any() else 0.0
         dh = np.abs(post['heading'] - s2['heading']).max(axis=1)
-        r['head_bad'] = int((dh[same] > 1e-12).sum())
+        r['head_bad'] = int((dh[same] > 5e-7).sum())
         dd = np.abs(post['total_dist'] - s2['total_dist'])
-        r['dist_bad'] = int((dd[same] > 1e-12).sum())
+        r['dist_bad'] = int((dd[same] > 1e-9).sum())
         cnt = sw.counters()
         r['active_bad'] = int(cnt['n_active'] != int(ran.sum()))
         r['done_bad'] = int((cnt['n_not_done'] == 0) != bool(g['done'][t]))
@@ -69,5 +69,6 @@ def test_golden_fixture(name):
     # velocities: |dv| <= 2e-5 on every agent-step
     assert tot['vel_bad'] == 0, (name, tot)
     assert tot['pos_bad'] == 0 and tot['head_bad'] == 0 and tot['dist_bad'] == 0, (name, tot)
-    # the float32 action rows are expected to be bit-identical except for ulp-level libm differences
-    assert tot['action_exact'] <= max(2, tot['agents'] // 200), (name, tot)
+    # vx vy vz speed bit-identical as float32; heading deltas within 1e-9 rad
+    assert tot['action_exact'] == 0 and tot['angle_bad'] == 0, (name, tot)
+    assert tot['angle_ulp_flips'] <= max(1, tot['agents'] // 500), (name, tot)
