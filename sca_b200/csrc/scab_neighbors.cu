@@ -70,8 +70,10 @@ __device__ __forceinline__ void write_lists(const StepArgs &A, int s, int id, in
 }
 
 // ------------------------------------------------------------------ KNN over the cell list
+#define KNN_CAP 48
 __global__ void __launch_bounds__(128) k_neighbors_knn(StepArgs A)
 {
+    __shared__ int buf[KNN_CAP][128];
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n) return;
     const int id = A.s_id[s];
@@ -116,10 +118,29 @@ __global__ void __launch_bounds__(128) k_neighbors_knn(StepArgs A)
             }
         }
     }
-    // agents (scaPolicy.py:116)
+    // agents (scaPolicy.py:116).  Two phases keep the warp converged: (1) scan the 27 cells and only
+    // RECORD the candidates whose raw squared distance can be in range (a shared-memory column per
+    // thread); (2) walk the recorded candidates -- all lanes together -- with the exact decimal rounding
+    // and the register-resident top-16 insertion.  A full column is flushed through phase 2 and reused.
     {
+        int nbuf = 0;
+        auto flush = [&]() {
+            for (int i = 0; i < nbuf; i++) {
+                const int j = buf[i][threadIdx.x];
+                const double4 o = A.s_posr[j];
+                const double dsq = l3normsq_d(me.x, me.y, me.z, o.x, o.y, o.z);   // agent.py:81
+                if (!(dsq < rangeSq)) continue;
+                const double rr = __dadd_rn(me.w, o.w);
+                const bool is_c = dsq < __dmul_rn(rr, rr);
+                if (is_c && !coll) { coll = true; L.clear(); }
+                if (coll && !is_c) continue;
+                L.insert(dsq, A.m + A.s_id[j], j);
+            }
+            nbuf = 0;
+        };
         int cx, cy, cz;
         cell_of(A.g, me.x, me.y, me.z, cx, cy, cz);
+        const double lim = rangeSq + 1e-4;   // the 5-decimal rounding cannot bring anything beyond this back in range
         for (int dz = -1; dz <= 1; dz++) {
             int z = cz + dz;
             if (z < 0 || z >= A.g.nz) continue;
@@ -130,20 +151,16 @@ __global__ void __launch_bounds__(128) k_neighbors_knn(StepArgs A)
                 int beg = A.cell_start[row + max(cx - 1, 0)];
                 int end = A.cell_start[row + min(cx + 1, A.g.nx - 1) + 1];
                 for (int j = beg; j < end; j++) {
-                    if (j == s) continue;
                     const double4 o = A.s_posr[j];
-                    const double ss = sumsq3(__dsub_rn(me.x, o.x), __dsub_rn(me.y, o.y), __dsub_rn(me.z, o.z));
-                    if (ss > rangeSq + 1e-4) continue;     // the 5-decimal rounding cannot bring it back in range
-                    double dsq = np_round5(ss);             // agent.py:81 l3normsq
-                    if (!(dsq < rangeSq)) continue;
-                    double rr = __dadd_rn(me.w, o.w);
-                    bool is_c = dsq < __dmul_rn(rr, rr);
-                    if (is_c && !coll) { coll = true; L.clear(); }
-                    if (coll && !is_c) continue;
-                    L.insert(dsq, A.m + A.s_id[j], j);
+                    const double ex = me.x - o.x, ey = me.y - o.y, ez = me.z - o.z;
+                    const double ss = ex * ex + ey * ey + ez * ez;
+                    if (ss > lim || j == s) continue;
+                    if (nbuf == KNN_CAP) flush();
+                    buf[nbuf++][threadIdx.x] = j;
                 }
             }
         }
+        flush();
     }
     write_lists(A, s, id, L.cnt, L.d, L.u, L.s, coll ? 1 : 0);
 }

@@ -28,11 +28,10 @@
 #define FULL 0xffffffffu
 
 struct WarpSmem {
-    // fp32 cones / planes
-    float px[KNBR], py[KNBR], pz[KNBR];   // cone: pB - pA        | plane: normal
-    float hx[KNBR], hy[KNBR], hz[KNBR];   // cone: 0.5 (vA + vB)  | plane: unused
-    float c2[KNBR];                       // cone: max(|p|^2 - R^2, 0) | plane: normal . point
-    float ph[KNBR], hh[KNBR], pp[KNBR], hn[KNBR];
+    // fp32 cones / planes, packed for 128-bit broadcast loads
+    float4 cp[KNBR];   // cone: pB - pA (xyz), p.h (w)            | plane: normal (xyz), normal . point (w)
+    float4 ch[KNBR];   // cone: h = 0.5 (vA + vB) (xyz), h.h (w)  | plane: unused
+    float2 cg[KNBR];   // cone: max(|p|^2 - R^2, 0), guard band   | plane: -, guard band
     // fp64 exact copies for the guard-band recheck and the fallback path
     double dpx[KNBR], dpy[KNBR], dpz[KNBR];   // cone: pB (absolute)  | plane: point
     double dhx[KNBR], dhy[KNBR], dhz[KNBR];   // cone: p0 = pA (+ h)   | plane: normal
@@ -85,6 +84,17 @@ __device__ __noinline__ bool is_intersect64(double ax, double ay, double az, dou
     return !(tb <= tc);
 }
 
+// Guard-band recheck: the same predicate in its algebraic fp64 form, p.v > |v| sqrt(d^2 - R^2) with
+// d = max(|p|, R); only when THAT is within 1e-12 of the boundary is the asin/acos form evaluated.
+__device__ __forceinline__ bool is_intersect64_fast(double ax, double ay, double az, double R, double vx, double vy, double vz)
+{
+    const double pp = dot3(ax, ay, az, ax, ay, az), vv = dot3(vx, vy, vz, vx, vy, vz), dt = dot3(ax, ay, az, vx, vy, vz);
+    const double c2 = fmax(pp - R * R, 0.0);
+    const double df = dt * dt - vv * c2;
+    if (fabs(df) <= 1e-12 * (pp * vv) || !(vv > 0.0)) return is_intersect64(ax, ay, az, R, vx, vy, vz);
+    return dt > 0.0 && df > 0.0;
+}
+
 // lexicographic warp arg-min over (a, b); lanes without a value pass a = ~0ull
 __device__ __forceinline__ void warp_lexmin(unsigned long long &a, unsigned &b)
 {
@@ -98,6 +108,21 @@ __device__ __forceinline__ void warp_lexmin(unsigned long long &a, unsigned &b)
 __device__ __forceinline__ bool lex_less(unsigned long long a, unsigned b, unsigned long long a2, unsigned b2)
 {
     return a < a2 || (a == a2 && b < b2);
+}
+// Same arg-min, but one REDUX when every participating key fits 22 bits (suitable-candidate keys are
+// distances in units of 1e-5, i.e. < 2^22 for speeds below ~20 m/s) and c < 1024.
+__device__ __forceinline__ void warp_min_key_c(unsigned long long &a, unsigned &b)
+{
+    const bool none = (a == ~0ull);
+    const bool small = none || (a < (1ull << 22) && b < 1024u);
+    if (__all_sync(FULL, small)) {
+        const unsigned packed = none ? 0xffffffffu : (((unsigned)a << 10) | b);
+        const unsigned m = __reduce_min_sync(FULL, packed);
+        if (m == 0xffffffffu) { a = ~0ull; b = 0xffffffffu; }
+        else { a = (unsigned long long)(m >> 10); b = m & 1023u; }
+    } else {
+        warp_lexmin(a, b);
+    }
 }
 
 // ------------------------------------------------------------------ k_vpref (thread per agent)
@@ -127,7 +152,7 @@ __global__ void __launch_bounds__(256) k_vpref(StepArgs A)
 
 // ------------------------------------------------------------------ k_select (warp per agent)
 template <int POLICY>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select(StepArgs A)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
 {
     constexpr bool IS_ORCA = (POLICY == SCAB_POLICY_ORCA_SAMPLED);
     constexpr bool SHUNT = (POLICY == SCAB_POLICY_SCA || POLICY == SCAB_POLICY_SRVO3D);
@@ -169,6 +194,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select(StepArgs A)
         const int C = 2 * a.N + 1;
         int tag = 0, n_suit = 0;
         const int nc = A.s_nbr_cnt[s];
+        // largest candidate speed (both shells and v_pref), slightly inflated: scales the fp32 guard bands
+        const float vmaxf = 1.0001f * (float)fmax(fmax(0.5, fabs(a.shell1)),
+                                                  sqrt(a.vdx * a.vdx + a.vdy * a.vdy + a.vdz * a.vdz));
 
         // ---------------------------------------------------------------- constraints (lane k)
         if (lane < nc) {
@@ -205,13 +233,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select(StepArgs A)
                 W.dhz[lane] = at_goal ? a.pz : __dadd_rn(a.pz, (double)hz);
                 const double pp = dot3(rx, ry, rz, rx, ry, rz);
                 const float fpx = (float)rx, fpy = (float)ry, fpz = (float)rz;
-                W.px[lane] = fpx; W.py[lane] = fpy; W.pz[lane] = fpz;
-                W.hx[lane] = hx; W.hy[lane] = hy; W.hz[lane] = hz;
-                W.c2[lane] = (float)fmax(pp - R * R, 0.0);
-                W.ph[lane] = fmaf(fpz, hz, fmaf(fpy, hy, fpx * hx));
-                W.hh[lane] = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
-                W.pp[lane] = (float)pp;
-                W.hn[lane] = sqrtf(W.hh[lane]);
+                const float hh = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
+                W.cp[lane] = make_float4(fpx, fpy, fpz, fmaf(fpz, hz, fmaf(fpy, hy, fpx * hx)));
+                W.ch[lane] = make_float4(hx, hy, hz, hh);
+                // guard band: |lhs - rhs| error <= ~6e-6 * |p|^2 (|v| + |h|)^2 (DESIGN.md "Numerics")
+                const float vh_max = vmaxf + sqrtf(hh);
+                W.cg[lane] = make_float2((float)fmax(pp - R * R, 0.0), 2e-5f * (float)pp * vh_max * vh_max);
             } else {
                 // orca3dPolicy.py:57-107 (== orca3dPolicyOfficial.py:56-106)
                 const double vrx = (double)__fsub_rn(a.vx, ox), vry = (double)__fsub_rn(a.vy, oy),
@@ -259,9 +286,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select(StepArgs A)
                              qz = __dadd_rn((double)a.vz, __dmul_rn(0.5, uz));
                 W.dpx[lane] = qx; W.dpy[lane] = qy; W.dpz[lane] = qz;
                 W.dhx[lane] = nx; W.dhy[lane] = ny; W.dhz[lane] = nz;
-                W.px[lane] = (float)nx; W.py[lane] = (float)ny; W.pz[lane] = (float)nz;
-                W.c2[lane] = (float)(nx * qx + ny * qy + nz * qz);
-                W.pp[lane] = (float)sqrt(qx * qx + qy * qy + qz * qz);
+                W.cp[lane] = make_float4((float)nx, (float)ny, (float)nz, (float)(nx * qx + ny * qy + nz * qz));
+                W.cg[lane] = make_float2(0.f, 1e-5f * (vmaxf + (float)sqrt(qx * qx + qy * qy + qz * qz)));
                 W.rpx[lane] = rx; W.rpy[lane] = ry; W.rpz[lane] = rz;
                 // orca3dPolicy.py:387: v_dif = v - 0.5 (vA + vB) if |vB| > 1e-5 else v
                 const double nvB = is_obst ? 0.0 : (double)norm3f_np(ox, oy, oz);
@@ -321,22 +347,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select(StepArgs A)
                 vx = rad * u.x; vy = rad * u.y; vz = rad * u.z;
             }
             const float vv0 = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
-            const float vn = sqrtf(vv0);
             bool suit = true;
             for (int k = 0; k < nc && suit; k++) {
                 bool inside, unsure;
+                const float4 P = W.cp[k];
+                const float2 G = W.cg[k];
                 if (!IS_ORCA) {
-                    const float dt = fmaf(W.pz[k], vz, fmaf(W.py[k], vy, W.px[k] * vx)) - W.ph[k];
-                    const float vh = fmaf(W.hz[k], vz, fmaf(W.hy[k], vy, W.hx[k] * vx));
-                    const float vv = fmaf(-2.f, vh, vv0) + W.hh[k];
-                    const float lhs = dt * dt, rhs = vv * W.c2[k];
-                    const float S = W.pp[k] * (vn + W.hn[k]) * (vn + W.hn[k]);
-                    inside = (dt > 0.f) && (lhs > rhs);
-                    unsure = fabsf(lhs - rhs) <= 2e-5f * S;
+                    const float4 H = W.ch[k];
+                    const float dt = fmaf(P.z, vz, fmaf(P.y, vy, P.x * vx)) - P.w;
+                    const float vh = fmaf(H.z, vz, fmaf(H.y, vy, H.x * vx));
+                    const float vv = fmaf(-2.f, vh, vv0) + H.w;
+                    const float df = fmaf(dt, dt, -vv * G.x);   // lhs - rhs
+                    inside = (dt > 0.f) && (df > 0.f);
+                    unsure = fabsf(df) <= G.y;
                 } else {
-                    const float val = fmaf(W.pz[k], vz, fmaf(W.py[k], vy, W.px[k] * vx)) - W.c2[k];
+                    const float val = fmaf(P.z, vz, fmaf(P.y, vy, P.x * vx)) - P.w;
                     inside = !(val >= 0.f);
-                    unsure = fabsf(val) <= 1e-5f * (vn + W.pp[k]);
+                    unsure = fabsf(val) <= G.y;
                 }
                 if (unsure) {
                     n_recheck++;
@@ -346,8 +373,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select(StepArgs A)
                         // scaPolicy.py:180: v_dif = new_v + pA - p_0
                         double dx = __dsub_rn(__dadd_rn(x, a.px), W.dhx[k]), dy = __dsub_rn(__dadd_rn(y, a.py), W.dhy[k]),
                                dz = __dsub_rn(__dadd_rn(z, a.pz), W.dhz[k]);
-                        inside = is_intersect64(__dsub_rn(W.dpx[k], a.px), __dsub_rn(W.dpy[k], a.py),
-                                                __dsub_rn(W.dpz[k], a.pz), W.dR[k], dx, dy, dz);
+                        inside = is_intersect64_fast(__dsub_rn(W.dpx[k], a.px), __dsub_rn(W.dpy[k], a.py),
+                                                     __dsub_rn(W.dpz[k], a.pz), W.dR[k], dx, dy, dz);
                     } else {
                         // orca3dPolicy.py:328-333 is_inORCA
                         double val = dot3(__dsub_rn(x, W.dpx[k]), __dsub_rn(y, W.dpy[k]), __dsub_rn(z, W.dpz[k]),
@@ -424,7 +451,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select(StepArgs A)
             if (lex_less(key, (unsigned)c, ka, kb)) { ka = key; kb = (unsigned)c; }
         }
         // 1. head of the sorted list
-        warp_lexmin(ka, kb);
+        warp_min_key_c(ka, kb);
         int best = (int)kb;
         const int live_total = fallback ? C : n_suit;
         __syncwarp();
@@ -450,7 +477,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select(StepArgs A)
                     if (lex_less(W.key[j], (unsigned)c, fa, fb)) { fa = W.key[j]; fb = (unsigned)c; }
                 }
             }
-            warp_lexmin(fa, fb);
+            warp_min_key_c(fa, fb);
             // 3. min-phi / max-phi over the prefix; ties -> first in sorted order
             long long pmin = LLONG_MAX;
             unsigned long long pmin_k = ~0ull;
@@ -475,16 +502,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select(StepArgs A)
                     pmax = pi_units; pmax_k = k; pmax_c = (unsigned)c;
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                long long p2 = __shfl_xor_sync(FULL, pmin, o);
-                unsigned long long k2 = __shfl_xor_sync(FULL, pmin_k, o);
-                unsigned c2 = __shfl_xor_sync(FULL, pmin_c, o);
-                if (p2 < pmin || (p2 == pmin && lex_less(k2, c2, pmin_k, pmin_c))) { pmin = p2; pmin_k = k2; pmin_c = c2; }
-                long long q2 = __shfl_xor_sync(FULL, pmax, o);
-                unsigned long long l2 = __shfl_xor_sync(FULL, pmax_k, o);
-                unsigned d2 = __shfl_xor_sync(FULL, pmax_c, o);
-                if (q2 > pmax || (q2 == pmax && lex_less(l2, d2, pmax_k, pmax_c))) { pmax = q2; pmax_k = l2; pmax_c = d2; }
+            {   // phi in units of 1e-5 is in [-314160, 628319]: bias into unsigned and use REDUX
+                const unsigned umin = (pmin == LLONG_MAX) ? 0xffffffffu : (unsigned)(pmin + 1000000);
+                const unsigned umax = (pmax == LLONG_MIN) ? 0u : (unsigned)(pmax + 1000000);
+                const unsigned gmin = __reduce_min_sync(FULL, umin), gmax = __reduce_max_sync(FULL, umax);
+                if (umin != gmin) { pmin_k = ~0ull; pmin_c = 0xffffffffu; }
+                if (umax != gmax) { pmax_k = ~0ull; pmax_c = 0xffffffffu; }
+                warp_min_key_c(pmin_k, pmin_c);
+                warp_min_key_c(pmax_k, pmax_c);
+                pmin = (long long)gmin - 1000000;
+                pmax = (long long)gmax - 1000000;
             }
             const double phi_min = __ddiv_rn((double)pmin, 1e5), phi_max = __ddiv_rn((double)pmax, 1e5);
             best = (fabs(__dsub_rn(phi_max, phi_min)) <= SCAB_PI) ? (int)pmin_c : (int)pmax_c;
