@@ -63,6 +63,8 @@ typedef enum {
 #define SCAB_ST_TIMEOUT 4
 #define SCAB_ST_RUN_DONE 8
 #define SCAB_ST_ZAXIS 16      /* static: start->goal is vertical (scaPolicy.py:188-190 -> 2x128 candidates) */
+#define SCAB_ST_GHOST 32      /* read-only copy of an agent owned by another GPU (halo): visible as a neighbour /
+                                 collision partner, never stepped, never modified (no reference counterpart) */
 
 /* Branch tags written to state.tag (which path produced the velocity). */
 #define SCAB_TAG_FIRST 1      /* zero-velocity shortcut vA_post = 0.3 v_pref (scaPolicy.py:34-40) */
@@ -110,6 +112,10 @@ typedef struct {
     int32_t *plane_fail;   /* [n] ORCA-LP: linearProgram3's return value                       out */
     int32_t *n_planes;     /* [n] ORCA-LP: len(orcaPlanes)                                     out */
     int32_t *lp4_proj;     /* [n] ORCA-LP: number of inner dir-opt LP3 solves in LP4           out */
+    /* multi-GPU sharding (optional) */
+    const int32_t *gid;    /* [n] global agent id of each row (NULL: row index). Ties and the sequential
+                              collision-check order (mampenv.py:42-46) follow the GLOBAL id              in */
+    int64_t n_global;      /* total agents across all shards (0: n); obstacle ids are reported as n_global + k */
 } scab_state_ptrs;
 
 /* Step counters, read back with scab_read_counters (device->host copy of 8 x int64). */
@@ -163,6 +169,22 @@ int scab_step(scab_handle *h, int policy, int nbr_mode, void *stream);
 int scab_read_counters(scab_handle *h, scab_counters *out_host, void *stream);
 /* Zero the cumulative counters (asynchronously on `stream`). */
 int scab_reset_counters(scab_handle *h, void *stream);
+
+/* ---- Multi-GPU spatial sharding (no reference counterpart: the reference is single-process). ----
+ * Rows [0, n_own) of the bound state are owned; rows [n_own, n) are halo ghosts (SCAB_ST_GHOST).
+ * scab_halo_pack: write the 64-byte record [x y z r | vx vy vz status | gid pad] of every owned agent
+ * whose coordinate along `axis` is within `width` of the slab faces lo_face / hi_face into the device
+ * buffers out_lo / out_hi (`cap` records each; unused slots hold a parked ghost at `park`, a position
+ * inside a reserved empty grid layer).  Fixed-size and asynchronous: nothing is read back. */
+int scab_halo_pack(scab_handle *h, int64_t n_own, int axis, double lo_face, double hi_face, double width,
+                   const double park[3], void *out_lo, void *out_hi, int32_t cap, void *stream);
+/* Scatter `count` received records into state rows [row0, row0 + count). */
+int scab_halo_unpack(scab_handle *h, const void *recs, int32_t count, int64_t row0, void *stream);
+/* After the policy stage: the new positions ([cap,3] f64 per face) of the agents packed by the last scab_halo_pack. */
+int scab_halo_pack_pos(scab_handle *h, double *out_lo, double *out_hi, int32_t cap, const double park[3], void *stream);
+int scab_halo_unpack_pos(scab_handle *h, const double *pos, int32_t count, int64_t row0, void *stream);
+/* Blocking: how many agents the last scab_halo_pack selected per face (> cap means the buffers overflowed). */
+int scab_halo_counts(scab_handle *h, int32_t out_host[2], void *stream);
 
 #ifdef __cplusplus
 }

@@ -13,14 +13,15 @@ POLICIES = {'sca': 0, 'srvo3d': 1, 'rvo3d': 2, 'rvo3d_dubins': 3, 'orca_sampled'
 NBR_KNN, NBR_REF_COMPAT = 0, 1
 K = 16
 
-ST_AT_GOAL, ST_COLLISION, ST_TIMEOUT, ST_RUN_DONE, ST_ZAXIS = 1, 2, 4, 8, 16
+ST_AT_GOAL, ST_COLLISION, ST_TIMEOUT, ST_RUN_DONE, ST_ZAXIS, ST_GHOST = 1, 2, 4, 8, 16, 32
 TAG_FIRST, TAG_SUITABLE, TAG_FALLBACK, TAG_LP3_OK, TAG_LP4 = 1, 2, 4, 8, 16
 
 # every symbol include/scab200.h declares (tests/test_capi_symbols.py checks the header against this)
 SYMBOLS = ['scab_version', 'scab_default_params', 'scab_create', 'scab_destroy', 'scab_last_error', 'scab_set_grid',
            'scab_bind_state', 'scab_set_obstacles', 'scab_kdtree_build', 'scab_kdtree_get_perm', 'scab_build_grid',
            'scab_neighbors', 'scab_policy_step', 'scab_status_step', 'scab_step', 'scab_read_counters',
-           'scab_reset_counters']
+           'scab_reset_counters', 'scab_halo_pack', 'scab_halo_unpack', 'scab_halo_pack_pos', 'scab_halo_unpack_pos',
+           'scab_halo_counts']
 
 
 class ScabError(RuntimeError):
@@ -35,11 +36,11 @@ class Params(C.Structure):
 
 STATE_FIELDS = ['pos', 'vel', 'heading', 'goal', 'radius', 'pref_speed', 'status', 'total_dist', 'step_num',
                 'max_run_dist', 'vpref_ext', 'vpref_out', 'action', 'nbr_cnt', 'nbr_ids', 'nbr_dsq', 'tag', 'n_suit',
-                'plane_fail', 'n_planes', 'lp4_proj']
+                'plane_fail', 'n_planes', 'lp4_proj', 'gid']
 
 
 class StatePtrs(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in STATE_FIELDS]
+    _fields_ = [(k, C.c_void_p) for k in STATE_FIELDS] + [('n_global', C.c_int64)]
 
 
 class Counters(C.Structure):
@@ -79,6 +80,12 @@ def lib():
     L.scab_step.argtypes = [vp, C.c_int, C.c_int, vp]
     L.scab_read_counters.argtypes = [vp, C.POINTER(Counters), vp]
     L.scab_reset_counters.argtypes = [vp, vp]
+    d3 = C.POINTER(C.c_double)
+    L.scab_halo_pack.argtypes = [vp, i64, C.c_int, C.c_double, C.c_double, C.c_double, d3, vp, vp, i32, vp]
+    L.scab_halo_unpack.argtypes = [vp, vp, i32, i64, vp]
+    L.scab_halo_pack_pos.argtypes = [vp, vp, vp, i32, d3, vp]
+    L.scab_halo_unpack_pos.argtypes = [vp, vp, i32, i64, vp]
+    L.scab_halo_counts.argtypes = [vp, C.POINTER(i32), vp]
     _lib = L
     return L
 
@@ -162,3 +169,24 @@ class Handle:
 
     def reset_counters(self, stream=0):
         self._ck(self._L.scab_reset_counters(self._h, stream))
+
+    # ---- multi-GPU halo (device pointers are plain ints: tensor.data_ptr())
+    def halo_pack(self, n_own, axis, lo_face, hi_face, width, park, out_lo, out_hi, cap, stream=0):
+        p = (C.c_double * 3)(*[float(x) for x in park])
+        self._ck(self._L.scab_halo_pack(self._h, int(n_own), int(axis), float(lo_face), float(hi_face), float(width), p,
+                                        out_lo, out_hi, int(cap), stream))
+
+    def halo_unpack(self, recs, count, row0, stream=0):
+        self._ck(self._L.scab_halo_unpack(self._h, recs, int(count), int(row0), stream))
+
+    def halo_pack_pos(self, out_lo, out_hi, cap, park, stream=0):
+        p = (C.c_double * 3)(*[float(x) for x in park])
+        self._ck(self._L.scab_halo_pack_pos(self._h, out_lo, out_hi, int(cap), p, stream))
+
+    def halo_unpack_pos(self, pos, count, row0, stream=0):
+        self._ck(self._L.scab_halo_unpack_pos(self._h, pos, int(count), int(row0), stream))
+
+    def halo_counts(self, stream=0):
+        out = (C.c_int32 * 2)()
+        self._ck(self._L.scab_halo_counts(self._h, out, stream))
+        return int(out[0]), int(out[1])

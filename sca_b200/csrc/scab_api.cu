@@ -35,6 +35,8 @@ struct scab_handle {
     KdNodeDev *d_kd_agent = nullptr;
     int32_t *d_kd_agent_perm = nullptr;
     bool kd_valid = false;
+    // halo bookkeeping (which owned rows were packed for each face, and how many)
+    int32_t *d_sent_lo = nullptr, *d_sent_hi = nullptr, *d_halo_cnt = nullptr;
 };
 
 static int fail(scab_handle *h, int code, const std::string &msg)
@@ -148,21 +150,23 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     const size_t cap = (size_t)capacity;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_posr = carve(cap * sizeof(double4)), o_newpos = carve(cap * sizeof(double4)),
+    const size_t o_posr = carve(cap * sizeof(double4)), o_gid = carve(cap * 4),
                  o_vdes = carve(cap * sizeof(double4)), o_vpost = carve(cap * sizeof(double4)),
                  o_vel = carve(cap * sizeof(float4)), o_id = carve(cap * 4), o_rank = carve(cap * 4),
                  o_cid = carve(cap * 4), o_cloc = carve(cap * 4), o_nbr = carve(cap * 4 * KNBR),
                  o_ncnt = carve(cap * 4), o_qc = carve(cap * 4), o_kdp = carve(cap * 4),
+                 o_slo = carve(cap * 4), o_shi = carve(cap * 4), o_hcnt = carve(64),
                  o_kdn = carve((2 * cap) * sizeof(KdNodeDev));
     e = cudaMalloc(&h->d_block, off);
     if (e != cudaSuccess) { delete h; return SCAB_ERR_NOMEM; }
     char *b = (char *)h->d_block;
-    A.s_posr = (double4 *)(b + o_posr); A.s_newpos = (double4 *)(b + o_newpos); A.s_vel = (float4 *)(b + o_vel);
+    A.s_posr = (double4 *)(b + o_posr); A.s_gid = (int32_t *)(b + o_gid); A.s_vel = (float4 *)(b + o_vel);
     A.s_vdes = (double4 *)(b + o_vdes); A.s_vpost = (double4 *)(b + o_vpost);
     A.s_id = (int32_t *)(b + o_id); A.rank = (int32_t *)(b + o_rank);
     A.cell_id = (int32_t *)(b + o_cid); A.cell_local = (int32_t *)(b + o_cloc);
     A.s_nbr = (int32_t *)(b + o_nbr); A.s_nbr_cnt = (int32_t *)(b + o_ncnt); A.s_qcoll = (int32_t *)(b + o_qc);
     h->d_kd_agent_perm = (int32_t *)(b + o_kdp); h->d_kd_agent = (KdNodeDev *)(b + o_kdn);
+    h->d_sent_lo = (int32_t *)(b + o_slo); h->d_sent_hi = (int32_t *)(b + o_shi); h->d_halo_cnt = (int32_t *)(b + o_hcnt);
     A.kd_agent = h->d_kd_agent; A.kd_agent_perm = h->d_kd_agent_perm;
     // candidate tables
     std::vector<double> d64; std::vector<float4> d32;
@@ -208,6 +212,7 @@ extern "C" int scab_bind_state(scab_handle *h, const scab_state_ptrs *s, int64_t
         return fail(h, SCAB_ERR_INVALID, "scab_bind_state: a required state pointer is NULL");
     h->A.st = *s;
     h->A.n = (int)n;
+    h->A.obst_base = (int)(s->n_global > 0 ? s->n_global : n);
     h->bound = true;
     h->kd_valid = false;
     if ((int64_t)h->kd_perm.size() != n) {   // KDTree.__init__: agentIDs = [0..n) (kdTree.py:43-45)
@@ -410,5 +415,54 @@ extern "C" int scab_reset_counters(scab_handle *h, void *stream)
     if (!h) return SCAB_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU halo
+extern "C" int scab_halo_pack(scab_handle *h, int64_t n_own, int axis, double lo_face, double hi_face, double width,
+                              const double park[3], void *out_lo, void *out_hi, int32_t cap, void *stream)
+{
+    int rc = check_ready(h, "scab_halo_pack");
+    if (rc) return rc;
+    if (n_own < 0 || n_own > h->A.n || axis < 0 || axis > 2 || cap < 0 || cap > h->capacity || !park || (cap > 0 && (!out_lo || !out_hi)))
+        return fail(h, SCAB_ERR_INVALID, "scab_halo_pack: bad argument");
+    CK(launch_halo_pack(h->A, (int)n_own, axis, lo_face, hi_face, width, park, out_lo, out_hi, cap, h->d_sent_lo, h->d_sent_hi,
+                        h->d_halo_cnt, (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int scab_halo_unpack(scab_handle *h, const void *recs, int32_t count, int64_t row0, void *stream)
+{
+    int rc = check_ready(h, "scab_halo_unpack");
+    if (rc) return rc;
+    if (count < 0 || row0 < 0 || row0 + count > h->capacity || (count > 0 && !recs)) return fail(h, SCAB_ERR_INVALID, "scab_halo_unpack: bad argument");
+    CK(launch_halo_unpack(h->A, recs, count, (int)row0, (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int scab_halo_pack_pos(scab_handle *h, double *out_lo, double *out_hi, int32_t cap, const double park[3], void *stream)
+{
+    int rc = check_ready(h, "scab_halo_pack_pos");
+    if (rc) return rc;
+    if (cap < 0 || cap > h->capacity || !park || (cap > 0 && (!out_lo || !out_hi))) return fail(h, SCAB_ERR_INVALID, "scab_halo_pack_pos: bad argument");
+    CK(launch_halo_pack_pos(h->A, h->d_sent_lo, h->d_sent_hi, h->d_halo_cnt, cap, out_lo, out_hi, park, (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int scab_halo_unpack_pos(scab_handle *h, const double *pos, int32_t count, int64_t row0, void *stream)
+{
+    int rc = check_ready(h, "scab_halo_unpack_pos");
+    if (rc) return rc;
+    if (count < 0 || row0 < 0 || row0 + count > h->capacity || (count > 0 && !pos)) return fail(h, SCAB_ERR_INVALID, "scab_halo_unpack_pos: bad argument");
+    CK(launch_halo_unpack_pos(h->A, pos, count, (int)row0, (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int scab_halo_counts(scab_handle *h, int32_t out_host[2], void *stream)
+{
+    if (!h || !out_host) return fail(h, SCAB_ERR_INVALID, "scab_halo_counts: null argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(out_host, h->d_halo_cnt, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
     return SCAB_OK;
 }

@@ -16,7 +16,8 @@
 #define RVO_EPS 1e-5  // mamp/configs/config.py:4
 
 // internal flag bits carried in the snapshot's vel.w (low bits == SCAB_ST_*)
-#define FL_INACTIVE (SCAB_ST_AT_GOAL | SCAB_ST_COLLISION | SCAB_ST_TIMEOUT)
+// agents the policy stage skips: finished ones (mampenv.py:35) and halo ghosts owned by another GPU
+#define FL_INACTIVE (SCAB_ST_AT_GOAL | SCAB_ST_COLLISION | SCAB_ST_TIMEOUT | SCAB_ST_GHOST)
 
 struct GridGeom {
     double ox, oy, oz, inv_cs;
@@ -41,9 +42,10 @@ struct StepArgs {
     // snapshot, sorted by cell
     double4 *s_posr;    // x y z r
     float4 *s_vel;      // vx vy vz, w = status bits
-    int32_t *s_id;      // sorted idx -> agent id
+    int32_t *s_id;      // sorted idx -> row (local agent index)
+    int32_t *s_gid;     // sorted idx -> global agent id (== row unless sharded)
+    int obst_base;      // obstacle k is reported as obst_base + k in nbr_ids (n, or n_global when sharded)
     int32_t *rank;      // agent id -> sorted idx
-    double4 *s_newpos;  // position after the kinematic update (sorted order)
     double4 *s_vdes;    // V_des (x y z) + zero-velocity-gate flag (w)        [k_vpref -> k_select]
     double4 *s_vpost;   // vA_post (x y z) + packed tag | n_suit << 8 (w)     [k_select -> k_integrate]
     int32_t *cell_id, *cell_local, *cell_count, *cell_start;  // [n], [n], [ncell], [ncell+1]
@@ -201,3 +203,10 @@ cudaError_t launch_neighbors(const StepArgs &A, int mode, cudaStream_t s);
 cudaError_t launch_policy_sampled(const StepArgs &A, int policy, cudaStream_t s);
 cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s);
 cudaError_t launch_status(const StepArgs &A, cudaStream_t s);
+cudaError_t launch_halo_pack(const StepArgs &A, int n_own, int axis, double lo_face, double hi_face, double width,
+                             const double park[3], void *out_lo, void *out_hi, int cap, int32_t *sent_lo, int32_t *sent_hi,
+                             int32_t *cnt, cudaStream_t s);
+cudaError_t launch_halo_unpack(const StepArgs &A, const void *recs, int count, int row0, cudaStream_t s);
+cudaError_t launch_halo_pack_pos(const StepArgs &A, const int32_t *sent_lo, const int32_t *sent_hi, const int32_t *cnt, int cap,
+                                 double *out_lo, double *out_hi, const double park[3], cudaStream_t s);
+cudaError_t launch_halo_unpack_pos(const StepArgs &A, const double *p, int count, int row0, cudaStream_t s);

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256) k_reorder(StepArgs A)
     A.s_posr[dst] = p;
     A.s_vel[dst] = v;
     A.s_id[dst] = i;
+    A.s_gid[dst] = A.st.gid ? A.st.gid[i] : i;
     A.rank[i] = dst;
 }
 

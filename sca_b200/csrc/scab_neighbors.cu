@@ -61,7 +61,7 @@ __device__ __forceinline__ void write_lists(const StepArgs &A, int s, int id, in
     if (A.st.nbr_ids) {
 #pragma unroll
         for (int k = 0; k < KNBR; k++)
-            A.st.nbr_ids[(size_t)id * KNBR + k] = (k < cnt) ? (u[k] < A.m ? A.n + u[k] : u[k] - A.m) : -1;
+            A.st.nbr_ids[(size_t)id * KNBR + k] = (k < cnt) ? (u[k] < A.m ? A.obst_base + u[k] : u[k] - A.m) : -1;
     }
     if (A.st.nbr_dsq) {
 #pragma unroll
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(128) k_neighbors_knn(StepArgs A)
                 const bool is_c = dsq < __dmul_rn(rr, rr);
                 if (is_c && !coll) { coll = true; L.clear(); }
                 if (coll && !is_c) continue;
-                L.insert(dsq, A.m + A.s_id[j], j);
+                L.insert(dsq, A.m + A.s_gid[j], j);
             }
             nbuf = 0;
         };

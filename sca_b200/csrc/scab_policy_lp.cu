@@ -202,11 +202,12 @@ __global__ void __launch_bounds__(LP_THREADS) k_policy_lp(StepArgs A)
         const int flags = __float_as_int(mv.w);
         Action7 act;
         double npx, npy, npz;
-        if (flags & FL_INACTIVE) {
+        if (flags & SCAB_ST_GHOST) {
+            // halo copy: owned (and stepped) by another GPU
+        } else if (flags & FL_INACTIVE) {
 #pragma unroll
             for (int k = 0; k < 7; k++) act.a[k] = 0.f;
             kinematic_update(A, id, act, me.x, me.y, me.z, &npx, &npy, &npz);
-            A.s_newpos[s] = make_double4(npx, npy, npz, 0.0);
             if (A.st.tag) A.st.tag[id] = 0;
             if (A.st.plane_fail) A.st.plane_fail[id] = -1;
             if (A.st.n_planes) A.st.n_planes[id] = -1;
@@ -291,7 +292,6 @@ __global__ void __launch_bounds__(LP_THREADS) k_policy_lp(StepArgs A)
             }
             act = cartesian2spherical(res.x, res.y, res.z, A.st.heading[3 * id], A.st.heading[3 * id + 1], true);
             kinematic_update(A, id, act, me.x, me.y, me.z, &npx, &npy, &npz);
-            A.s_newpos[s] = make_double4(npx, npy, npz, 0.0);
             if (A.s_qcoll[s]) A.st.status[id] = flags | SCAB_ST_COLLISION;   // agent.py:83-85
             if (A.st.vpref_out) { A.st.vpref_out[3 * id] = v_store[0]; A.st.vpref_out[3 * id + 1] = v_store[1]; A.st.vpref_out[3 * id + 2] = v_store[2]; }
             if (A.st.tag) A.st.tag[id] = tag;

@@ -32,6 +32,7 @@ struct WarpSmem {
     float4 cp[KNBR];   // cone: pB - pA (xyz), p.h (w)            | plane: normal (xyz), normal . point (w)
     float4 ch[KNBR];   // cone: h = 0.5 (vA + vB) (xyz), h.h (w)  | plane: unused
     float2 cg[KNBR];   // cone: max(|p|^2 - R^2, 0), guard band   | plane: -, guard band
+    int cidx[KNBR];    // compacted slot -> neighbour index k (the fp64 copies below stay indexed by k)
     // fp64 exact copies for the guard-band recheck and the fallback path
     double dpx[KNBR], dpy[KNBR], dpz[KNBR];   // cone: pB (absolute)  | plane: point
     double dhx[KNBR], dhy[KNBR], dhz[KNBR];   // cone: p0 = pA (+ h)   | plane: normal
@@ -95,6 +96,11 @@ __device__ __forceinline__ bool is_intersect64_fast(double ax, double ay, double
     return dt > 0.0 && df > 0.0;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // lexicographic warp arg-min over (a, b); lanes without a value pass a = ~0ull
 __device__ __forceinline__ void warp_lexmin(unsigned long long &a, unsigned &b)
 {
@@ -144,7 +150,9 @@ __global__ void __launch_bounds__(256) k_vpref(StepArgs A)
     // first-step gate: l3norm(vA,0) <= 1e-5 (scaPolicy.py:34) / distance(vA,0) <= 1e-5 (orca3dPolicy.py:52)
     const double nv32 = __dsqrt_rn(sumsq_f32(mv.x, mv.y, mv.z));
     const bool first = USE_DISTANCE ? (py_round5(__dadd_rn(nv32, 1e-5)) <= 1e-5) : (py_round5(nv32) <= 1e-5);
-    A.s_vdes[s] = make_double4(v_des[0], v_des[1], v_des[2], first ? 1.0 : 0.0);
+    // w carries pref_speed (> 0); its sign is the zero-velocity-gate flag
+    const double pref_w = A.st.pref_speed[id];
+    A.s_vdes[s] = make_double4(v_des[0], v_des[1], v_des[2], first ? -pref_w : pref_w);
     if (A.st.vpref_out) {
         A.st.vpref_out[3 * id] = v_store[0]; A.st.vpref_out[3 * id + 1] = v_store[1]; A.st.vpref_out[3 * id + 2] = v_store[2];
     }
@@ -168,18 +176,33 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
         const int flags = __float_as_int(mv.w);
         if (flags & FL_INACTIVE) continue;
         const double4 vd = A.s_vdes[s];
-        if (vd.w != 0.0) {   // zero-velocity shortcut: vA_post = 0.3 v_pref (scaPolicy.py:38)
+        {   // hide the two dependent global round trips of the NEXT agents behind this agent's arithmetic:
+            // header lines two agents ahead -> L2; neighbour records one agent ahead -> L2 (their index list
+            // was prefetched one iteration ago)
+            const int s2 = s + 2 * warps_total, s1 = s + warps_total;
+            if (s2 < A.n) {
+                if (lane == 0) prefetch_l2(&A.s_vel[s2]);
+                if (lane == 1) prefetch_l2(&A.s_vdes[s2]);
+                if (lane == 2) prefetch_l2(&A.s_posr[s2]);
+                if (lane == 3) prefetch_l2(&A.s_nbr_cnt[s2]);
+                if (lane == 4) prefetch_l2(&A.s_nbr[(size_t)s2 * KNBR]);
+            }
+            if (s1 < A.n && lane < KNBR) {
+                const int e1 = A.s_nbr[(size_t)s1 * KNBR + lane];
+                if (e1 >= 0 && e1 < A.n) { prefetch_l2(&A.s_posr[e1]); prefetch_l2(&A.s_vel[e1]); }
+            }
+        }
+        if (vd.w < 0.0) {   // zero-velocity shortcut: vA_post = 0.3 v_pref (scaPolicy.py:38)
             if (lane == 0)
                 A.s_vpost[s] = make_double4(__dmul_rn(0.3, vd.x), __dmul_rn(0.3, vd.y), __dmul_rn(0.3, vd.z),
                                             __longlong_as_double((long long)SCAB_TAG_FIRST));
             continue;
         }
-        const int id = A.s_id[s];
         const double4 me = A.s_posr[s];
         Agent a;
         a.px = me.x; a.py = me.y; a.pz = me.z; a.r = me.w;
         a.vx = mv.x; a.vy = mv.y; a.vz = mv.z;
-        a.pref = A.st.pref_speed[id];
+        a.pref = vd.w;
         a.nvA = (double)norm3f_np(a.vx, a.vy, a.vz);
         const bool zaxis = (POLICY == SCAB_POLICY_SCA) && (flags & SCAB_ST_ZAXIS);
         a.N = zaxis ? 128 : 256;
@@ -199,6 +222,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
                                                   sqrt(a.vdx * a.vdx + a.vdy * a.vdy + a.vdz * a.vdz));
 
         // ---------------------------------------------------------------- constraints (lane k)
+        // Culling: every candidate that passes the posture test lies in the solid cone {|v| <= vmax,
+        // angle(v, vA) <= pi/4}, which fits in the ball B(m, rho), m = vmax/sqrt2 * vA/|vA|, rho = vmax/sqrt2.
+        // A constraint whose forbidden region stays >= 1e-2 clear of that ball cannot reject (or come near
+        // the guard band of) any tested candidate, so phase B skips it.  (Phase D uses all of them.)
+        float4 cP = make_float4(0.f, 0.f, 0.f, 0.f), cH = cP;
+        float2 cG = make_float2(0.f, 0.f);
+        bool keep = false;
+        const float fnvA = (float)a.nvA;
+        const float ball_r = 0.70711f * vmaxf;
+        const float bmx = ball_r * a.vx / fnvA, bmy = ball_r * a.vy / fnvA, bmz = ball_r * a.vz / fnvA;
         if (lane < nc) {
             const int e = A.s_nbr[(size_t)s * KNBR + lane];
             double4 o;
@@ -234,11 +267,21 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
                 const double pp = dot3(rx, ry, rz, rx, ry, rz);
                 const float fpx = (float)rx, fpy = (float)ry, fpz = (float)rz;
                 const float hh = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
-                W.cp[lane] = make_float4(fpx, fpy, fpz, fmaf(fpz, hz, fmaf(fpy, hy, fpx * hx)));
-                W.ch[lane] = make_float4(hx, hy, hz, hh);
+                cP = make_float4(fpx, fpy, fpz, fmaf(fpz, hz, fmaf(fpy, hy, fpx * hx)));
+                cH = make_float4(hx, hy, hz, hh);
                 // guard band: |lhs - rhs| error <= ~6e-6 * |p|^2 (|v| + |h|)^2 (DESIGN.md "Numerics")
                 const float vh_max = vmaxf + sqrtf(hh);
-                W.cg[lane] = make_float2((float)fmax(pp - R * R, 0.0), 2e-5f * (float)pp * vh_max * vh_max);
+                const float c2f = (float)fmax(pp - R * R, 0.0);
+                cG = make_float2(c2f, 2e-5f * (float)pp * vh_max * vh_max);
+                {   // distance from the ball centre (relative to the apex h) to the cone {w: p.w > |w| c}
+                    const float d = sqrtf((float)pp), Rf = (float)R;
+                    const float qx = bmx - hx, qy = bmy - hy, qz = bmz - hz;
+                    const float qa = (qx * fpx + qy * fpy + qz * fpz) / d;
+                    const float qr = sqrtf(fmaxf(qx * qx + qy * qy + qz * qz - qa * qa, 0.f));
+                    const float sn = fminf(Rf / d, 1.f), cs = sqrtf(c2f) / d;
+                    const float dist = qr * cs - qa * sn;
+                    keep = !(dist > ball_r + 1e-2f) || !((float)pp > 1.02f * Rf * Rf);
+                }
             } else {
                 // orca3dPolicy.py:57-107 (== orca3dPolicyOfficial.py:56-106)
                 const double vrx = (double)__fsub_rn(a.vx, ox), vry = (double)__fsub_rn(a.vy, oy),
@@ -286,8 +329,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
                              qz = __dadd_rn((double)a.vz, __dmul_rn(0.5, uz));
                 W.dpx[lane] = qx; W.dpy[lane] = qy; W.dpz[lane] = qz;
                 W.dhx[lane] = nx; W.dhy[lane] = ny; W.dhz[lane] = nz;
-                W.cp[lane] = make_float4((float)nx, (float)ny, (float)nz, (float)(nx * qx + ny * qy + nz * qz));
-                W.cg[lane] = make_float2(0.f, 1e-5f * (vmaxf + (float)sqrt(qx * qx + qy * qy + qz * qz)));
+                cP = make_float4((float)nx, (float)ny, (float)nz, (float)(nx * qx + ny * qy + nz * qz));
+                cG = make_float2(0.f, 1e-5f * (vmaxf + (float)sqrt(qx * qx + qy * qy + qz * qz)));
+                // half-space n.v >= n.point: the smallest n.v over the ball is n.m - rho
+                keep = !((cP.x * bmx + cP.y * bmy + cP.z * bmz) - ball_r - cP.w > 1e-2f);
                 W.rpx[lane] = rx; W.rpy[lane] = ry; W.rpz[lane] = rz;
                 // orca3dPolicy.py:387: v_dif = v - 0.5 (vA + vB) if |vB| > 1e-5 else v
                 const double nvB = is_obst ? 0.0 : (double)norm3f_np(ox, oy, oz);
@@ -296,6 +341,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
                 W.ofy[lane] = mov ? (double)__fmul_rn(0.5f, __fadd_rn(a.vy, oy)) : 0.0;
                 W.ofz[lane] = mov ? (double)__fmul_rn(0.5f, __fadd_rn(a.vz, oz)) : 0.0;
             }
+        }
+
+        const unsigned keep_mask = __ballot_sync(FULL, keep);
+        const int nce = __popc(keep_mask);
+        if (keep) {
+            const int slot = __popc(keep_mask & ((1u << lane) - 1));
+            W.cp[slot] = cP; W.ch[slot] = cH; W.cg[slot] = cG; W.cidx[slot] = lane;
         }
 
         // ---------------------------------------------------------------- A: posture + compaction
@@ -348,12 +400,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
             }
             const float vv0 = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
             bool suit = true;
-            for (int k = 0; k < nc && suit; k++) {
+            for (int kk = 0; kk < nce && suit; kk++) {
                 bool inside, unsure;
-                const float4 P = W.cp[k];
-                const float2 G = W.cg[k];
+                const float4 P = W.cp[kk];
+                const float2 G = W.cg[kk];
                 if (!IS_ORCA) {
-                    const float4 H = W.ch[k];
+                    const float4 H = W.ch[kk];
                     const float dt = fmaf(P.z, vz, fmaf(P.y, vy, P.x * vx)) - P.w;
                     const float vh = fmaf(H.z, vz, fmaf(H.y, vy, H.x * vx));
                     const float vv = fmaf(-2.f, vh, vv0) + H.w;
@@ -366,6 +418,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
                     unsure = fabsf(val) <= G.y;
                 }
                 if (unsure) {
+                    const int k = W.cidx[kk];
                     n_recheck++;
                     double x, y, z;
                     cand64(a, c, x, y, z);
@@ -542,7 +595,9 @@ __global__ void __launch_bounds__(256) k_integrate(StepArgs A)
         const int flags = __float_as_int(A.s_vel[s].w);
         Action7 act;
         double npx, npy, npz;
-        if (flags & FL_INACTIVE) {
+        if (flags & SCAB_ST_GHOST) {
+            // halo copy: owned (and stepped) by another GPU
+        } else if (flags & FL_INACTIVE) {
             // mampenv.py:35-36: skipped agents keep the zero action row
 #pragma unroll
             for (int k = 0; k < 7; k++) act.a[k] = 0.f;
@@ -564,7 +619,6 @@ __global__ void __launch_bounds__(256) k_integrate(StepArgs A)
             if (A.st.tag) A.st.tag[id] = tag;
             if (A.st.n_suit) A.st.n_suit[id] = n_suit;
         }
-        A.s_newpos[s] = make_double4(npx, npy, npz, 0.0);
     }
     const unsigned msk = __ballot_sync(FULL, ran);
     if ((threadIdx.x & 31) == 0 && msk) {
@@ -576,13 +630,18 @@ __global__ void __launch_bounds__(256) k_integrate(StepArgs A)
 template <int POLICY>
 static cudaError_t launch_select(const StepArgs &A, int grid, cudaStream_t s)
 {
-    static bool attr_set = false;
+    static int per_sm = 0;
     const size_t smem = sizeof(WarpSmem) * WARPS_PER_CTA;
-    if (!attr_set) {
+    if (per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(k_select<POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_select<POLICY>, WARPS_PER_CTA * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
     }
+    // persistent kernel, exactly one resident wave: grid = SMs x resident CTAs per SM
+    const int need = (A.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    grid = need < grid * per_sm ? need : grid * per_sm;
     k_select<POLICY><<<grid, WARPS_PER_CTA * 32, smem, s>>>(A);
     return cudaGetLastError();
 }
@@ -594,8 +653,7 @@ cudaError_t launch_policy_sampled(const StepArgs &A, int policy, cudaStream_t s)
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int nb = (A.n + 255) / 256;
-    const int need = (A.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const int grid = need < sms * 8 ? need : sms * 8;   // persistent: a multiple of the SM count when saturated
+    const int grid = sms;   // launch_select multiplies by the resident CTAs per SM
     cudaError_t e;
     switch (policy) {
     case SCAB_POLICY_SCA:

@@ -15,11 +15,14 @@ __global__ void __launch_bounds__(128) k_status(StepArgs A)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     bool not_done = false, collided = false;
-    if (s < A.n) {
+    const int snap_flags = (s < A.n) ? __float_as_int(A.s_vel[s].w) : SCAB_ST_GHOST;
+    if (!(snap_flags & SCAB_ST_GHOST)) {   // halo ghosts are partners only: their owner GPU flags them
         const int id = A.s_id[s];
+        const int gid = A.s_gid[s];
         const double4 oldp = A.s_posr[s];
-        const double4 newp = A.s_newpos[s];
-        const int snap_flags = __float_as_int(A.s_vel[s].w);
+        // positions after the kinematic update: the policy stage wrote them in place (ghost rows are
+        // refreshed by the halo exchange between the two stages)
+        const double4 newp = make_double4(A.st.pos[3 * id], A.st.pos[3 * id + 1], A.st.pos[3 * id + 2], 0.0);
         const bool was_goal = (snap_flags & SCAB_ST_AT_GOAL) != 0;
         int st = A.st.status[id];   // includes the collision bit a neighbour query may have raised this step
         if (!was_goal) A.st.step_num[id] += 1;   // mampenv.py:44-45
@@ -66,10 +69,11 @@ __global__ void __launch_bounds__(128) k_status(StepArgs A)
                         const double R = __dadd_rn(oldp.w, oo.w);
                         const double lim = R + 2.5;
                         if (ex * ex + ey * ey + ez * ez > lim * lim) continue;
-                        const double4 on = A.s_newpos[j];
-                        const int jid = A.s_id[j];
+                        const int jrow = A.s_id[j];
+                        const double4 on = make_double4(A.st.pos[3 * jrow], A.st.pos[3 * jrow + 1], A.st.pos[3 * jrow + 2], 0.0);
+                        const int jid = A.s_gid[j];
                         bool hit;
-                        if (id < jid)
+                        if (gid < jid)
                             hit = l3norm_d(newp.x, newp.y, newp.z, oo.x, oo.y, oo.z) <= R ||
                                   l3norm_d(newp.x, newp.y, newp.z, on.x, on.y, on.z) <= R;
                         else

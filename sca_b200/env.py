@@ -1,0 +1,59 @@
+"""BatchedEnv: MACAEnv (mamp/envs/mampenv.py:8-105) with the whole step resident on the device.
+
+    env = BatchedEnv('srvo3d'); env.set_agents(pos6, goal6, obstacles)
+    while not env.step(): pass
+    env.metrics()
+
+`set_agents` takes the same [x, y, z, yaw, pitch, roll] rows Agent(start_pos=..., goal_pos=...) takes
+(mamp/agents/agent.py:9-20); `step()` returns what MACAEnv.step returns (all agents done).
+"""
+import numpy as np
+
+from . import capi
+from .swarm import Swarm
+
+
+class BatchedEnv(object):
+    def __init__(self, policy, nbr_mode=capi.NBR_KNN, device='cuda:0', debug=False):
+        self.policy = policy
+        self.nbr_mode = nbr_mode
+        self.device = device
+        self.debug = debug
+        self.sw = None
+        self.steps = 0
+
+    def set_agents(self, pos6, goal6, obstacles=None, radius=0.5, pref_speed=1.0, vel=None, margin=20.0):
+        pos6, goal6 = np.asarray(pos6, 'float64'), np.asarray(goal6, 'float64')
+        n = len(pos6)
+        self.sw = Swarm(n, device=self.device, debug=self.debug)
+        self.sw.set_state(pos6[:, :3], goal6[:, :3], heading=pos6[:, 3:6], vel=vel, radius=radius, pref_speed=pref_speed,
+                          initial_pos=pos6, goal_pos=goal6)
+        self.sw.set_obstacles(obstacles)
+        lo = np.minimum(pos6[:, :3].min(0), goal6[:, :3].min(0)) - margin
+        hi = np.maximum(pos6[:, :3].max(0), goal6[:, :3].max(0)) + margin
+        self.sw.fit_grid(lo, hi)
+        # agent.py:51-52 (metrics): straight_path_length = l3norm(start, goal) - 0.5, desire_steps
+        d = np.round(np.sqrt(((pos6[:, :3] - goal6[:, :3]) ** 2).sum(1)), 5)
+        self.straight_len = d - 0.5
+        self.desire_steps = (self.straight_len / (np.broadcast_to(pref_speed, (n,)) * 0.1)).astype(np.int64)
+        self.steps = 0
+        return self
+
+    def step(self, sync=True):
+        """One MACAEnv.step.  With sync=False nothing is read back (returns None): call is_done() when needed."""
+        self.sw.step(self.policy, self.nbr_mode)
+        self.steps += 1
+        return self.sw.is_done() if sync else None
+
+    def is_done(self):
+        return self.sw.is_done()
+
+    def run(self, max_steps=100000, check_every=16):
+        while self.steps < max_steps:
+            self.step(sync=False)
+            if self.steps % check_every == 0 and self.is_done():
+                break
+        return self.steps
+
+    def metrics(self):
+        return self.sw.metrics(self.straight_len, self.desire_steps)

@@ -1,0 +1,248 @@
+"""Multi-GPU spatial sharding: one process per GPU, slabs along x, NCCL halo exchange.
+
+The reference is single-process; this is the only parallelism the new build adds.
+Per step and per rank (all asynchronous on the step's stream, fixed-size buffers, no host round trips):
+
+    halo_pack  ->  NCCL send/recv with the <= 2 slab neighbours  ->  halo_unpack   (ghost rows)
+    cell list  ->  16-NN  ->  policy kernels (owned agents only)
+    halo_pack_pos -> NCCL send/recv -> halo_unpack_pos                               (ghosts' new positions)
+    status kernel (owned agents only)
+
+Every `migrate_every` steps agents that left their slab move to the neighbour rank (full state rows).
+Ties and the sequential collision-check order follow GLOBAL agent ids, so an S-shard run reproduces the
+1-GPU run of the same kernels bit for bit (tests/test_sharding_gpu.py).
+
+`SlabPlan` and the row packing are plain host logic (device agnostic) and are covered on CPU with a
+world_size-2 gloo test (tests/test_sharding_host.py).
+"""
+import numpy as np
+import torch
+
+from . import capi
+
+REC_DOUBLES = 8          # 64-byte halo record
+ROW_COLS = 22            # full state row used for migration (19 used + 3 spare)
+
+
+class SlabPlan:
+    """Equal-count slabs along one axis + the halo geometry."""
+
+    def __init__(self, coord, world, neighbor_dist=10.0, max_speed=1.0, dt=0.1, migrate_every=16, axis=0):
+        coord = np.asarray(coord, 'float64')
+        self.world = int(world)
+        self.axis = axis
+        qs = np.quantile(coord, np.linspace(0, 1, world + 1)[1:-1]) if world > 1 else np.zeros(0)
+        self.edges = np.concatenate([[-np.inf], qs, [np.inf]])
+        self.migrate_every = int(migrate_every)
+        # an agent may sit up to `drift` outside its owner's slab before it migrates, and so may the ghosts
+        self.drift = migrate_every * max_speed * dt
+        self.width = neighbor_dist + 2.0 * self.drift + 1e-6
+
+    def owner(self, coord):
+        return np.clip(np.searchsorted(self.edges, np.asarray(coord, 'float64'), side='right') - 1, 0, self.world - 1)
+
+    def faces(self, rank):
+        return float(self.edges[rank]), float(self.edges[rank + 1])
+
+    def min_slab_width(self):
+        w = np.diff(self.edges[1:-1]) if self.world > 2 else np.array([np.inf])
+        return float(w.min()) if len(w) else np.inf
+
+
+def pack_rows(t, idx):
+    """Full state rows (float64 [k, ROW_COLS]) of agents `idx` -- exact for f32 / int32 columns."""
+    f = lambda k: t[k][idx].to(torch.float64)
+    return torch.cat([f('pos'), f('vel'), f('heading'), f('goal'), f('radius')[:, None], f('pref_speed')[:, None],
+                      f('status')[:, None], f('total_dist')[:, None], f('step_num')[:, None], f('max_run_dist')[:, None],
+                      f('gid')[:, None], torch.zeros((len(idx), 3), dtype=torch.float64, device=t['pos'].device)], dim=1)
+
+
+def unpack_rows(t, rows, row0):
+    k = rows.shape[0]
+    sl = slice(row0, row0 + k)
+    t['pos'][sl] = rows[:, 0:3]
+    t['vel'][sl] = rows[:, 3:6].to(torch.float32)
+    t['heading'][sl] = rows[:, 6:9]
+    t['goal'][sl] = rows[:, 9:12]
+    t['radius'][sl] = rows[:, 12]
+    t['pref_speed'][sl] = rows[:, 13]
+    t['status'][sl] = rows[:, 14].to(torch.int32)
+    t['total_dist'][sl] = rows[:, 15]
+    t['step_num'][sl] = rows[:, 16].to(torch.int32)
+    t['max_run_dist'][sl] = rows[:, 17]
+    t['gid'][sl] = rows[:, 18].to(torch.int32)
+
+
+def exchange_with_neighbours(send_lo, send_hi, recv_lo, recv_hi, rank, world, dist=None):
+    """One grouped send/recv with the slab neighbours (rank-1 receives send_lo, rank+1 receives send_hi)."""
+    if world == 1:
+        return
+    dist = dist or torch.distributed
+    ops = []
+    if rank > 0:
+        ops += [dist.P2POp(dist.isend, send_lo, rank - 1), dist.P2POp(dist.irecv, recv_lo, rank - 1)]
+    if rank < world - 1:
+        ops += [dist.P2POp(dist.isend, send_hi, rank + 1), dist.P2POp(dist.irecv, recv_hi, rank + 1)]
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+
+
+def exchange_variable(rows_lo, rows_hi, rank, world, dist=None):
+    """Variable-length row exchange (migration): counts first, then payloads.  Returns (from_lo, from_hi)."""
+    dist = dist or torch.distributed
+    dev = rows_lo.device
+    c_send = torch.tensor([rows_lo.shape[0], rows_hi.shape[0]], dtype=torch.int64, device=dev)
+    c_lo, c_hi = torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(1, dtype=torch.int64, device=dev)
+    exchange_with_neighbours(c_send[0:1].clone(), c_send[1:2].clone(), c_lo, c_hi, rank, world, dist)
+    n_lo, n_hi = int(c_lo.item()), int(c_hi.item())
+    cols = rows_lo.shape[1]
+    from_lo = torch.zeros((n_lo, cols), dtype=rows_lo.dtype, device=dev)
+    from_hi = torch.zeros((n_hi, cols), dtype=rows_lo.dtype, device=dev)
+    ops = []
+    if rank > 0:
+        if rows_lo.shape[0]:
+            ops.append(dist.P2POp(dist.isend, rows_lo.contiguous(), rank - 1))
+        if n_lo:
+            ops.append(dist.P2POp(dist.irecv, from_lo, rank - 1))
+    if rank < world - 1:
+        if rows_hi.shape[0]:
+            ops.append(dist.P2POp(dist.isend, rows_hi.contiguous(), rank + 1))
+        if n_hi:
+            ops.append(dist.P2POp(dist.irecv, from_hi, rank + 1))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    return from_lo, from_hi
+
+
+class ShardedSwarm:
+    """The rank-local part of a swarm sharded over `world` GPUs.  Same step()/counters() surface as Swarm."""
+
+    def __init__(self, pos6, goal6, rank, world, device, lo, hi, radius=0.5, pref_speed=1.0, migrate_every=16,
+                 halo_cap=None, debug=False):
+        from .swarm import Swarm
+        pos6, goal6 = np.asarray(pos6, 'float64'), np.asarray(goal6, 'float64')
+        n_global = len(pos6)
+        self.rank, self.world, self.n_global = rank, world, n_global
+        self.plan = SlabPlan(pos6[:, 0], world, migrate_every=migrate_every)
+        mine = np.nonzero(self.plan.owner(pos6[:, 0]) == rank)[0]
+        self.n_own = len(mine)
+        # halo capacity per face: agents within `width` of a face, with head room
+        if halo_cap is None:
+            lo_f, hi_f = self.plan.faces(rank)
+            x = pos6[mine, 0]
+            near = max(int((x < lo_f + self.plan.width).sum()) if rank > 0 else 0,
+                       int((x >= hi_f - self.plan.width).sum()) if rank < world - 1 else 0)
+            halo_cap = int(near * 1.5) + 1024
+        self.cap = int(halo_cap) if world > 1 else 0
+        capacity = int(self.n_own * 1.25) + 2 * self.cap + 4096
+        self.own_cap = capacity - 2 * self.cap
+        sw = Swarm(self.n_own, device=device, debug=debug, capacity=capacity)
+        sw.set_state(pos6[mine, :3], goal6[mine, :3], heading=pos6[mine, 3:6], radius=radius, pref_speed=pref_speed,
+                     initial_pos=pos6[mine], goal_pos=goal6[mine])
+        sw.set_global_ids(mine.astype(np.int32), n_global)
+        # two extra z layers: an empty buffer layer and the layer where unused ghost slots are parked
+        lo, hi = np.asarray(lo, 'float64'), np.asarray(hi, 'float64')
+        cell = float(max(sw.params.cell_size, sw.params.neighbor_dist))
+        dim = np.maximum(1, np.ceil((hi - lo) / cell).astype(np.int64))
+        self.park = (float(lo[0] + 0.5 * cell), float(lo[1] + 0.5 * cell), float(lo[2] + (dim[2] + 1.5) * cell))
+        dim[2] += 2
+        sw.h.set_grid(lo, cell, dim)
+        self.sw = sw
+        dev = sw.device
+        f8 = dict(dtype=torch.float64, device=dev)
+        self.send_lo, self.send_hi = torch.zeros((self.cap, REC_DOUBLES), **f8), torch.zeros((self.cap, REC_DOUBLES), **f8)
+        self.recv = torch.zeros((2 * self.cap, REC_DOUBLES), **f8)
+        self.psend_lo, self.psend_hi = torch.zeros((self.cap, 3), **f8), torch.zeros((self.cap, 3), **f8)
+        self.precv = torch.zeros((2 * self.cap, 3), **f8)
+        self.steps = 0
+        self._fill_parked()
+        sw._bind(self.n_own + 2 * self.cap)
+
+    # ------------------------------------------------------------------
+    def _fill_parked(self):
+        """Edge ranks never receive from one side: those ghost slots stay parked."""
+        if self.cap == 0:
+            return
+        self.recv.zero_()
+        self.recv[:, 0], self.recv[:, 1], self.recv[:, 2] = self.park
+        dummy_status_gid = np.array([capi.ST_GHOST | capi.ST_AT_GOAL | capi.ST_RUN_DONE], np.int32)
+        # columns 4-5 hold (vx, vy) and (vz, status) as raw bytes; 6 holds (gid, pad)
+        raw = self.recv.view(torch.int32).view(2 * self.cap, 2 * REC_DOUBLES)
+        raw[:, 11] = int(dummy_status_gid[0])
+        raw[:, 12] = 0x7fffffff
+        self.precv[:, 0], self.precv[:, 1], self.precv[:, 2] = self.park
+
+    @property
+    def t(self):
+        return self.sw.t
+
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _ghost_exchange_pre(self):
+        sw, cap = self.sw, self.cap
+        lo_f, hi_f = self.plan.faces(self.rank)
+        lo_face = lo_f if self.rank > 0 else -1e300            # no neighbour on that side: select nothing
+        hi_face = hi_f if self.rank < self.world - 1 else 1e300
+        sw.h.halo_pack(self.n_own, self.plan.axis, lo_face, hi_face, self.plan.width, self.park,
+                       self.send_lo.data_ptr(), self.send_hi.data_ptr(), cap, self._stream())
+        exchange_with_neighbours(self.send_lo, self.send_hi, self.recv[:cap], self.recv[cap:], self.rank, self.world)
+        sw.h.halo_unpack(self.recv.data_ptr(), 2 * cap, self.n_own, self._stream())
+
+    def _ghost_exchange_post(self):
+        sw, cap = self.sw, self.cap
+        sw.h.halo_pack_pos(self.psend_lo.data_ptr(), self.psend_hi.data_ptr(), cap, self.park, self._stream())
+        exchange_with_neighbours(self.psend_lo, self.psend_hi, self.precv[:cap], self.precv[cap:], self.rank, self.world)
+        sw.h.halo_unpack_pos(self.precv.data_ptr(), 2 * cap, self.n_own, self._stream())
+
+    def step(self, policy, nbr_mode=capi.NBR_KNN):
+        sw = self.sw
+        pol = capi.POLICIES[policy] if isinstance(policy, str) else int(policy)
+        if self.world > 1:
+            if self.steps and self.steps % self.plan.migrate_every == 0:
+                self.migrate()
+            self._ghost_exchange_pre()
+        s = self._stream()
+        sw.h.build_grid(s)
+        sw.h.neighbors(nbr_mode, s)
+        sw.h.policy_step(pol, s)
+        if self.world > 1:
+            self._ghost_exchange_post()
+        sw.h.status_step(s)
+        self.steps += 1
+
+    # ------------------------------------------------------------------ migration
+    def migrate(self):
+        """Hand agents that left the slab to the neighbour rank (rare: every `migrate_every` steps)."""
+        sw, t = self.sw, self.sw.t
+        n = self.n_own
+        lo_f, hi_f = self.plan.faces(self.rank)
+        x = t['pos'][:n, self.plan.axis]
+        go_lo = (x < lo_f) if self.rank > 0 else torch.zeros_like(x, dtype=torch.bool)
+        go_hi = (x >= hi_f) if self.rank < self.world - 1 else torch.zeros_like(x, dtype=torch.bool)
+        c_lo, c_hi = sw.h.halo_counts(self._stream())
+        if max(c_lo, c_hi) > self.cap:
+            raise capi.ScabError('halo buffers overflowed (%d, %d > cap %d): raise halo_cap' % (c_lo, c_hi, self.cap))
+        idx_lo, idx_hi = torch.nonzero(go_lo)[:, 0], torch.nonzero(go_hi)[:, 0]
+        rows_lo, rows_hi = pack_rows(t, idx_lo), pack_rows(t, idx_hi)
+        from_lo, from_hi = exchange_variable(rows_lo, rows_hi, self.rank, self.world)
+        keep = torch.nonzero(~(go_lo | go_hi))[:, 0]
+        kept = pack_rows(t, keep)
+        rows = torch.cat([kept, from_lo, from_hi])
+        if rows.shape[0] > self.own_cap:
+            raise capi.ScabError('shard grew beyond its capacity (%d > %d)' % (rows.shape[0], self.own_cap))
+        unpack_rows(t, rows, 0)
+        self.n_own = rows.shape[0]
+        sw._zaxis[:self.n_own] = t['status'][:self.n_own] & capi.ST_ZAXIS
+        sw._bind(self.n_own + 2 * self.cap)
+
+    # ------------------------------------------------------------------ results
+    def counters(self):
+        return self.sw.counters()
+
+    def gather_state(self, keys=('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')):
+        """Owned rows keyed by global id (host)."""
+        torch.cuda.synchronize()
+        gid = self.sw.t['gid'][:self.n_own].cpu().numpy()
+        return gid, {k: self.sw.t[k][:self.n_own].cpu().numpy() for k in keys}

@@ -35,6 +35,7 @@ class Swarm:
         if not torch.cuda.is_available():
             raise capi.ScabError('sca_b200.Swarm needs a CUDA device; there is no CPU fallback')
         self.n = int(n)
+        self.capacity = int(capacity or max(self.n, 1))
         self.device = torch.device(device)
         self.debug = bool(debug)
         self.params = params if params is not None else capi.default_params()
@@ -42,19 +43,32 @@ class Swarm:
         for k, (dt, shp, opt) in _FIELDS.items():
             if k == 'vpref_ext' or (k in _DEBUG and not self.debug):
                 continue
-            self.t[k] = torch.zeros((self.n,) + shp, dtype=dt, device=self.device)
-        self.h = capi.Handle(self.params, self.device.index or 0, int(capacity or max(self.n, 1)))
+            self.t[k] = torch.zeros((self.capacity,) + shp, dtype=dt, device=self.device)
+        self.h = capi.Handle(self.params, self.device.index or 0, self.capacity)
         self.m = 0
         self._pinned = {}
         self._bind()
 
     # ------------------------------------------------------------------ binding
-    def _bind(self):
+    def _bind(self, n=None):
+        """(Re)bind the SoA pointers; `n` <= capacity is the number of live rows (owned + halo ghosts)."""
+        if n is not None:
+            self.n = int(n)
         p = capi.StatePtrs()
         for k in capi.STATE_FIELDS:
             tns = self.t.get(k)
             setattr(p, k, tns.data_ptr() if tns is not None else None)
+        p.n_global = int(getattr(self, 'n_global', 0))
         self.h.bind_state(p, self.n)
+
+    def set_global_ids(self, gid, n_global):
+        """Sharded runs: global id of every row (ties and the collision-check order follow it)."""
+        if 'gid' not in self.t:
+            self.t['gid'] = torch.zeros(self.capacity, dtype=_I4, device=self.device)
+        g = torch.as_tensor(gid, dtype=_I4)
+        self.t['gid'][:g.numel()].copy_(g)
+        self.n_global = int(n_global)
+        self._bind()
 
     def __getattr__(self, k):
         t = self.__dict__.get('t')
@@ -72,9 +86,9 @@ class Swarm:
             return
         v = torch.as_tensor(np.ascontiguousarray(v, dtype='float64')) if not torch.is_tensor(v) else v
         if 'vpref_ext' not in self.t:
-            self.t['vpref_ext'] = torch.zeros((self.n, 3), dtype=_F8, device=self.device)
+            self.t['vpref_ext'] = torch.zeros((self.capacity, 3), dtype=_F8, device=self.device)
             self._bind()
-        self.t['vpref_ext'].copy_(v.to(self.device, _F8))
+        self.t['vpref_ext'][:v.shape[0]].copy_(v.to(self.device, _F8))
 
     # ------------------------------------------------------------------ state in / out
     def set_state(self, pos, goal, heading=None, vel=None, radius=0.5, pref_speed=1.0, status=None,
@@ -97,9 +111,10 @@ class Swarm:
             'step_num': np.zeros(n, np.int32) if step_num is None else np.ascontiguousarray(step_num, np.int32),
             'max_run_dist': f8(max_run_dist, (n,)),
         }
-        self._zaxis = torch.as_tensor(zaxis).to(self.device)
+        self._zaxis = torch.zeros(self.capacity, dtype=_I4, device=self.device)
+        self._zaxis[:n].copy_(torch.as_tensor(zaxis))
         for k, a in host.items():
-            self.t[k].copy_(torch.from_numpy(np.array(a, copy=True)))
+            self.t[k][:n].copy_(torch.from_numpy(np.array(a, copy=True)))
         return self
 
     def set_obstacles(self, xyzr):
@@ -111,7 +126,7 @@ class Swarm:
         """Size the uniform grid from a bounding box (default: current positions and goals)."""
         cell = float(cell or max(self.params.cell_size, self.params.neighbor_dist))
         if lo is None or hi is None:
-            both = torch.cat([self.t['pos'], self.t['goal']])
+            both = torch.cat([self.t['pos'][:self.n], self.t['goal'][:self.n]])
             lo = (both.min(0).values - margin).cpu().numpy()
             hi = (both.max(0).values + margin).cpu().numpy()
         lo, hi = np.asarray(lo, 'float64'), np.asarray(hi, 'float64')
@@ -132,14 +147,14 @@ class Swarm:
             src = host[k]
             if k == 'status':
                 src = src  # caller supplies SCAB_ST_* bits; the static ZAXIS bit is OR-ed below
-            self.t[k].copy_(src, non_blocking=True)
+            self.t[k][:src.shape[0]].copy_(src, non_blocking=True)
             nbytes += src.numel() * src.element_size()
         if 'status' in host:
             self.t['status'].bitwise_or_(self._zaxis)
         return nbytes
 
     def download(self, keys=('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num', 'action')):
-        return {k: self.t[k].cpu().numpy() for k in keys if k in self.t}
+        return {k: self.t[k][:self.n].cpu().numpy() for k in keys if k in self.t}
 
     # ------------------------------------------------------------------ the step
     @staticmethod
