@@ -128,11 +128,15 @@ class ShardedSwarm:
         mine = np.nonzero(self.plan.owner(pos6[:, 0]) == rank)[0]
         self.n_own = len(mine)
         # halo capacity per face: agents within `width` of a face, with head room
+        # (the SAME value on every rank: the face buffers are exchanged as fixed-size messages)
         if halo_cap is None:
-            lo_f, hi_f = self.plan.faces(rank)
-            x = pos6[mine, 0]
-            near = max(int((x < lo_f + self.plan.width).sum()) if rank > 0 else 0,
-                       int((x >= hi_f - self.plan.width).sum()) if rank < world - 1 else 0)
+            near = 0
+            own_all = self.plan.owner(pos6[:, 0])
+            for r in range(world):
+                lo_f, hi_f = self.plan.faces(r)
+                x = pos6[own_all == r, 0]
+                near = max(near, int((x < lo_f + self.plan.width).sum()) if r > 0 else 0,
+                           int((x >= hi_f - self.plan.width).sum()) if r < world - 1 else 0)
             halo_cap = int(near * 1.5) + 1024
         self.cap = int(halo_cap) if world > 1 else 0
         capacity = int(self.n_own * 1.25) + 2 * self.cap + 4096
@@ -157,7 +161,12 @@ class ShardedSwarm:
         self.precv = torch.zeros((2 * self.cap, 3), **f8)
         self.steps = 0
         self._fill_parked()
+        # a dedicated (non-default) stream: the legacy default stream would implicitly serialise the step
+        # against NCCL's own stream
+        self.stream = torch.cuda.Stream(device=dev)
+        self.debug_phase = None
         sw._bind(self.n_own + 2 * self.cap)
+        torch.cuda.synchronize(dev)
 
     # ------------------------------------------------------------------
     def _fill_parked(self):
@@ -178,7 +187,11 @@ class ShardedSwarm:
         return self.sw.t
 
     def _stream(self):
-        return torch.cuda.current_stream().cuda_stream
+        return self.stream.cuda_stream
+
+    def _mark(self, what):
+        if self.debug_phase is not None:
+            self.debug_phase(what)
 
     def _ghost_exchange_pre(self):
         sw, cap = self.sw, self.cap
@@ -199,18 +212,62 @@ class ShardedSwarm:
     def step(self, policy, nbr_mode=capi.NBR_KNN):
         sw = self.sw
         pol = capi.POLICIES[policy] if isinstance(policy, str) else int(policy)
-        if self.world > 1:
-            if self.steps and self.steps % self.plan.migrate_every == 0:
-                self.migrate()
-            self._ghost_exchange_pre()
-        s = self._stream()
-        sw.h.build_grid(s)
-        sw.h.neighbors(nbr_mode, s)
-        sw.h.policy_step(pol, s)
-        if self.world > 1:
-            self._ghost_exchange_post()
-        sw.h.status_step(s)
+        with torch.cuda.stream(self.stream):
+            if self.world > 1:
+                if self.steps and self.steps % self.plan.migrate_every == 0:
+                    self._mark('migrate')
+                    self.migrate()
+                self._mark('pre-exchange')
+                self._ghost_exchange_pre()
+            s = self._stream()
+            self._mark('grid')
+            sw.h.build_grid(s)
+            self._mark('neighbors')
+            sw.h.neighbors(nbr_mode, s)
+            self._mark('policy')
+            sw.h.policy_step(pol, s)
+            if self.world > 1:
+                self._mark('post-exchange')
+                self._ghost_exchange_post()
+            self._mark('status')
+            sw.h.status_step(s)
         self.steps += 1
+
+    def warm_up(self, policy, nbr_mode=capi.NBR_KNN):
+        """Load every kernel of the step before any NCCL traffic (lazy module loading while a peer is
+        spinning inside a collective is a classic deadlock), on a throw-away copy of nothing: the stages
+        run over zero owned agents... no -- they run over the real state but all writes are reverted."""
+        sw = self.sw
+        pol = capi.POLICIES[policy] if isinstance(policy, str) else int(policy)
+        keep = {k: v.clone() for k, v in sw.t.items()}
+        with torch.cuda.stream(self.stream):
+            s = self._stream()
+            if self.world > 1:
+                sw.h.halo_pack(self.n_own, self.plan.axis, -1e300, 1e300, self.plan.width, self.park,
+                               self.send_lo.data_ptr(), self.send_hi.data_ptr(), self.cap, s)
+                sw.h.halo_unpack(self.recv.data_ptr(), 2 * self.cap, self.n_own, s)
+                sw.h.halo_pack_pos(self.psend_lo.data_ptr(), self.psend_hi.data_ptr(), self.cap, self.park, s)
+                sw.h.halo_unpack_pos(self.precv.data_ptr(), 2 * self.cap, self.n_own, s)
+            sw.h.build_grid(s)
+            sw.h.neighbors(nbr_mode, s)
+            sw.h.policy_step(pol, s)
+            sw.h.status_step(s)
+            self.stream.synchronize()
+            for k, v in keep.items():
+                sw.t[k].copy_(v)
+            sw.h.reset_counters(s)
+            # ... and every torch op migrate() uses (their kernels are loaded lazily too)
+            t = sw.t
+            x = t['pos'][:self.n_own, self.plan.axis]
+            m = (x < 0.0) | (x >= 1e300) | torch.zeros_like(x, dtype=torch.bool)
+            idx = torch.nonzero(~m)[:8, 0]
+            rows = torch.cat([pack_rows(t, idx), pack_rows(t, idx[:0])])
+            scratch = {k: v[:16].clone() for k, v in t.items()}
+            unpack_rows(scratch, rows, 0)
+            _ = (t['status'][:8] & capi.ST_ZAXIS).sum().item()
+            c = torch.tensor([1, 2], dtype=torch.int64, device=x.device)
+            _ = int(c[0:1].clone().item())
+            self.stream.synchronize()
 
     # ------------------------------------------------------------------ migration
     def migrate(self):
@@ -221,12 +278,16 @@ class ShardedSwarm:
         x = t['pos'][:n, self.plan.axis]
         go_lo = (x < lo_f) if self.rank > 0 else torch.zeros_like(x, dtype=torch.bool)
         go_hi = (x >= hi_f) if self.rank < self.world - 1 else torch.zeros_like(x, dtype=torch.bool)
+        self._mark('migrate: counts')
         c_lo, c_hi = sw.h.halo_counts(self._stream())
+        self._mark('migrate: counts=%d,%d' % (c_lo, c_hi))
         if max(c_lo, c_hi) > self.cap:
             raise capi.ScabError('halo buffers overflowed (%d, %d > cap %d): raise halo_cap' % (c_lo, c_hi, self.cap))
         idx_lo, idx_hi = torch.nonzero(go_lo)[:, 0], torch.nonzero(go_hi)[:, 0]
         rows_lo, rows_hi = pack_rows(t, idx_lo), pack_rows(t, idx_hi)
+        self._mark('migrate: exchange %d %d' % (rows_lo.shape[0], rows_hi.shape[0]))
         from_lo, from_hi = exchange_variable(rows_lo, rows_hi, self.rank, self.world)
+        self._mark('migrate: received %d %d' % (from_lo.shape[0], from_hi.shape[0]))
         keep = torch.nonzero(~(go_lo | go_hi))[:, 0]
         kept = pack_rows(t, keep)
         rows = torch.cat([kept, from_lo, from_hi])
@@ -239,10 +300,11 @@ class ShardedSwarm:
 
     # ------------------------------------------------------------------ results
     def counters(self):
-        return self.sw.counters()
+        return self.sw.h.read_counters(self._stream())
 
     def gather_state(self, keys=('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')):
         """Owned rows keyed by global id (host)."""
+        self.stream.synchronize()
         torch.cuda.synchronize()
         gid = self.sw.t['gid'][:self.n_own].cpu().numpy()
         return gid, {k: self.sw.t[k][:self.n_own].cpu().numpy() for k in keys}

@@ -6,6 +6,7 @@ kernels BIT FOR BIT (positions, velocities, headings, flags, counters), includin
 import os
 import sys
 
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -18,11 +19,14 @@ from sca_b200.swarm import Swarm  # noqa: E402
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get('SHARD_WATCHDOG', '75')), exit=True)
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     local = int(os.environ.get('LOCAL_RANK', rank))
     torch.cuda.set_device(local)
     dev = 'cuda:%d' % local
-    dist.init_process_group('nccl', device_id=torch.device(dev))
+    import datetime
+    dist.init_process_group('nccl', device_id=torch.device(dev), timeout=datetime.timedelta(seconds=90))
     n = int(os.environ.get('SHARD_N', '30000'))
     steps = int(os.environ.get('SHARD_STEPS', '40'))
     policy = os.environ.get('SHARD_POLICY', 'sca')
@@ -31,6 +35,13 @@ def main():
     L = (n / density) ** (1 / 3)
     lo, hi = np.array([-20.0, -20.0, 0.0]), np.array([L + 20.0, L + 20.0, L + 40.0])
     sh = ShardedSwarm(pos, goal, rank, world, dev, lo, hi, migrate_every=8)
+    sh.warm_up(policy, capi.NBR_KNN)
+    if os.environ.get('SHARD_DEBUG'):
+        def _dbg(w):
+            sh.stream.synchronize()
+            print('[rank %d step %d] reached %s (everything before it completed)' % (rank, sh.steps, w), flush=True)
+        sh.debug_phase = _dbg
+    dist.barrier()
     moved = 0
     for _ in range(steps):
         n0 = sh.n_own
