@@ -233,7 +233,8 @@ def run_ours(args):
                           'policy': policy, 'agents': n_total, 'l2': 'per-step working set (~%d MB) exceeds the 126 MB L2'
                                                                      % (n_total * 420 // 1000000),
                           'parallelism': 'spatial slabs x%d + halo exchange' % world if world > 1 else 'single GPU'},
-               'gpu_launches': KERNELS_PER_STEP * args.steps, 'clocks': clocks}
+               # + 5 halo kernels per step when sharded: k_halo_fill, k_halo_pack, k_halo_unpack, k_halo_pack_pos, k_halo_unpack_pos
+               'gpu_launches': (KERNELS_PER_STEP + (5 if world > 1 else 0)) * args.steps, 'clocks': clocks}
         if roof:
             out['roofline'] = roof
         if e2e:

@@ -1,0 +1,83 @@
+"""-m gpu: KNN neighbour mode at larger N against the C oracle on seeded synthetic swarms
+(the configurations of BASELINE configs 3-5 at sizes the oracle finishes in seconds)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(pos6, goal6, obstacles, policy, steps, lo=None, hi=None):
+    import torch
+    from oracle import oracle as orc
+    from sca_b200 import capi
+    from sca_b200.swarm import Swarm
+    import gpu_util as G
+    n = len(pos6)
+    orc.set_threads(8)
+    w = orc.World(pos6[:, :3], goal6[:, :3], heading=pos6[:, 3:6], obstacles=obstacles, initial_pos=pos6, goal_pos=goal6)
+    sw = Swarm(n, debug=True)
+    sw.set_state(pos6[:, :3], goal6[:, :3], heading=pos6[:, 3:6], initial_pos=pos6, goal_pos=goal6,
+                 max_run_dist=w.max_run_dist)
+    sw.set_obstacles(obstacles)
+    lo = np.minimum(pos6[:, :3].min(0), goal6[:, :3].min(0)) - 15 if lo is None else lo
+    hi = np.maximum(pos6[:, :3].max(0), goal6[:, :3].max(0)) + 15 if hi is None else hi
+    sw.fit_grid(lo, hi)
+    tot = dict(agents=0, nbr=0, tag=0, nsuit=0, vel=0, status=0, planes=0, flips=0)
+    for t in range(steps):
+        pre = dict(pos=w.pos.copy(), vel=w.vel.copy(), heading=w.heading.copy(), status=w.status.copy(),
+                   total_dist=w.total_dist.copy(), step_num=w.step_num.copy())
+        G.force_state(sw, pre)                       # teacher-forced from the oracle's state
+        w.policy_step(policy, orc.NBR_KNN)
+        sw.stage_grid(); sw.stage_neighbors(capi.NBR_KNN); sw.stage_policy(policy)
+        out = G.policy_outputs(sw, pre['status'])
+        ran = w.ran.astype(bool)
+        assert np.array_equal(out['ran'].astype(bool), ran)
+        has = ran & (w.nbr_cnt >= 0)
+        tot['agents'] += int(ran.sum())
+        tot['nbr'] += int(((out['nbr_ids'][has] != w.nbr_ids[has]).any(1) | (out['nbr_cnt'][has] != w.nbr_cnt[has])).sum())
+        tot['tag'] += int((out['tag'][ran] != w.tag[ran]).sum())
+        if policy != 'orca_lp':
+            tot['nsuit'] += int((out['n_suit'][ran] != w.n_suit[ran]).sum())
+        else:
+            tot['planes'] += int(((out['plane_fail'][ran] != w.plane_fail[ran]) | (out['lp4_proj'][ran] != w.lp4_proj[ran])).sum())
+        dv = np.abs(out['action'][:, :4].astype('float64') - w.action[:, :4].astype('float64')).max(1)
+        tot['vel'] += int((dv[ran] > 2e-5).sum())
+        tot['flips'] += int((dv[ran] > 0).sum())
+        w.env_update(fast=True)
+        sw.stage_status()
+        post = G.post_state(sw)
+        tot['status'] += int((post['status'] != w.status).sum())
+    return tot
+
+
+@pytest.mark.parametrize('policy', ['sca', 'srvo3d', 'rvo3d', 'orca_sampled', 'orca_lp'])
+def test_uniform_swarm_config5_density(policy):
+    from sca_b200 import scenarios
+    pos, goal, obs = scenarios.uniform_box_numpy(6000, 3.0 * 1.0e6 / 560.0 ** 3, seed=11)
+    rng = np.random.default_rng(5)
+    L = pos[:, :3].max()
+    obs = np.c_[rng.uniform(0, L, (40, 3)) + [0, 0, 20], rng.uniform(0.5, 2.0, 40)]
+    tot = _compare(pos, goal, obs, policy, steps=5)
+    print(policy, tot)
+    assert tot['agents'] > 20000
+    for k in ('nbr', 'tag', 'nsuit', 'vel', 'status', 'planes'):
+        assert tot[k] == 0, (policy, tot)
+
+
+def test_takeoff_landing_tiled_config3():
+    from sca_b200 import scenarios
+    pos, goal, obs = scenarios.takeoff_landing_tiled(pads=64)       # 1024 UAVs, 512 obstacles
+    tot = _compare(pos, goal, obs, 'sca', steps=8)
+    print(tot)
+    for k in ('nbr', 'tag', 'nsuit', 'vel', 'status'):
+        assert tot[k] == 0, tot
+
+
+@pytest.mark.parametrize('policy', ['rvo3d', 'srvo3d'])
+def test_dense_sphere_config4(policy):
+    from sca_b200 import scenarios
+    pos, goal, obs = scenarios.dense_sphere(4000)
+    tot = _compare(pos, goal, obs, policy, steps=5)
+    print(policy, tot)
+    for k in ('nbr', 'tag', 'nsuit', 'vel', 'status'):
+        assert tot[k] == 0, (policy, tot)
