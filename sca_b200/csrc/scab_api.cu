@@ -156,6 +156,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
                  o_cid = carve(cap * 4), o_cloc = carve(cap * 4), o_nbr = carve(cap * 4 * KNBR),
                  o_ncnt = carve(cap * 4), o_qc = carve(cap * 4), o_kdp = carve(cap * 4),
                  o_slo = carve(cap * 4), o_shi = carve(cap * 4), o_hcnt = carve(64),
+                 o_slow = carve(cap * 4), o_slowc = carve(64),
                  o_kdn = carve((2 * cap) * sizeof(KdNodeDev));
     e = cudaMalloc(&h->d_block, off);
     if (e != cudaSuccess) { delete h; return SCAB_ERR_NOMEM; }
@@ -166,6 +167,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     A.cell_id = (int32_t *)(b + o_cid); A.cell_local = (int32_t *)(b + o_cloc);
     A.s_nbr = (int32_t *)(b + o_nbr); A.s_nbr_cnt = (int32_t *)(b + o_ncnt); A.s_qcoll = (int32_t *)(b + o_qc);
     h->d_kd_agent_perm = (int32_t *)(b + o_kdp); h->d_kd_agent = (KdNodeDev *)(b + o_kdn);
+    A.slow_list = (int32_t *)(b + o_slow); A.slow_count = (int32_t *)(b + o_slowc);
     h->d_sent_lo = (int32_t *)(b + o_slo); h->d_sent_hi = (int32_t *)(b + o_shi); h->d_halo_cnt = (int32_t *)(b + o_hcnt);
     A.kd_agent = h->d_kd_agent; A.kd_agent_perm = h->d_kd_agent_perm;
     // candidate tables

@@ -52,6 +52,8 @@ struct StepArgs {
     int32_t *s_nbr;     // [n,16] sorted idx, or n + sorted obstacle idx
     int32_t *s_nbr_cnt; // [n]
     int32_t *s_qcoll;   // [n] collision flag raised by the neighbour query (agent.py:83-85)
+    int32_t *slow_list; // [n] agents the 8-lane fast selection kernel hands to the general kernel
+    int32_t *slow_count;
     // obstacles (sorted by obstacle cell) + reference kd-trees
     const double4 *o_posr;
     const int32_t *o_id, *o_cell_start;

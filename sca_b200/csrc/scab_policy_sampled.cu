@@ -159,7 +159,10 @@ __global__ void __launch_bounds__(256) k_vpref(StepArgs A)
 }
 
 // ------------------------------------------------------------------ k_select (warp per agent)
-template <int POLICY>
+#include "scab_select_fast.cuh"
+
+// USE_LIST: process only the agents the fast kernel appended to A.slow_list
+template <int POLICY, bool USE_LIST>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
 {
     constexpr bool IS_ORCA = (POLICY == SCAB_POLICY_ORCA_SAMPLED);
@@ -171,12 +174,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
     const int warps_total = gridDim.x * WARPS_PER_CTA;
     unsigned long long n_recheck = 0;
 
-    for (int s = blockIdx.x * WARPS_PER_CTA + wid; s < A.n; s += warps_total) {
+    const int n_work = USE_LIST ? min(*A.slow_count, A.n) : A.n;
+    for (int wi = blockIdx.x * WARPS_PER_CTA + wid; wi < n_work; wi += warps_total) {
+        const int s = USE_LIST ? A.slow_list[wi] : wi;
         const float4 mv = A.s_vel[s];
         const int flags = __float_as_int(mv.w);
         if (flags & FL_INACTIVE) continue;
         const double4 vd = A.s_vdes[s];
-        {   // hide the two dependent global round trips of the NEXT agents behind this agent's arithmetic:
+        if (!USE_LIST) {   // hide the two dependent global round trips of the NEXT agents behind this agent's arithmetic:
             // header lines two agents ahead -> L2; neighbour records one agent ahead -> L2 (their index list
             // was prefetched one iteration ago)
             const int s2 = s + 2 * warps_total, s1 = s + warps_total;
@@ -628,21 +633,35 @@ __global__ void __launch_bounds__(256) k_integrate(StepArgs A)
 }
 
 template <int POLICY>
-static cudaError_t launch_select(const StepArgs &A, int grid, cudaStream_t s)
+static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
 {
-    static int per_sm = 0;
-    const size_t smem = sizeof(WarpSmem) * WARPS_PER_CTA;
+    static int per_sm = 0, per_sm_fast = 0, no_fast = -1;
+    const size_t smem = sizeof(WarpSmem) * WARPS_PER_CTA, smem_fast = sizeof(GroupSmem) * FG_WARPS * FG_PER_WARP;
     if (per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(k_select<POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_select<POLICY>, WARPS_PER_CTA * 32, smem);
+        cudaError_t e = cudaFuncSetAttribute(k_select<POLICY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select<POLICY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select_fast<POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_select<POLICY, true>, WARPS_PER_CTA * 32, smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fast, k_select_fast<POLICY>, FG_WARPS * 32, smem_fast);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
+        if (per_sm_fast < 1) per_sm_fast = 1;
+        const char *ev = getenv("SCAB_NO_FAST");   // A/B switch: route every agent through the general kernel
+        no_fast = (ev && ev[0] == '1') ? 1 : 0;
     }
-    // persistent kernel, exactly one resident wave: grid = SMs x resident CTAs per SM
+    // persistent kernels, exactly one resident wave each: grid = SMs x resident CTAs per SM
     const int need = (A.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    grid = need < grid * per_sm ? need : grid * per_sm;
-    k_select<POLICY><<<grid, WARPS_PER_CTA * 32, smem, s>>>(A);
+    const int grid = need < sms * per_sm ? need : sms * per_sm;
+    if (no_fast) {
+        k_select<POLICY, false><<<grid, WARPS_PER_CTA * 32, smem, s>>>(A);
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaMemsetAsync(A.slow_count, 0, sizeof(int32_t), s);
+    if (e != cudaSuccess) return e;
+    const int need_f = (A.n + FG_WARPS * FG_PER_WARP - 1) / (FG_WARPS * FG_PER_WARP);
+    const int grid_f = need_f < sms * per_sm_fast ? need_f : sms * per_sm_fast;
+    k_select_fast<POLICY><<<grid_f, FG_WARPS * 32, smem_fast, s>>>(A);
+    k_select<POLICY, true><<<grid, WARPS_PER_CTA * 32, smem, s>>>(A);    // the agents the fast kernel deferred
     return cudaGetLastError();
 }
 

@@ -1,0 +1,400 @@
+// scab_select_fast.cuh -- the common-case candidate search: EIGHT lanes per agent, four agents per warp.
+// (Included by scab_policy_sampled.cu after the shared helpers.)
+//
+// k_select (one warp per agent, scab_policy_sampled.cu) leaves most lanes idle outside the cone loop: per
+// agent only ~75 of the 513 candidates survive the posture test and ~45 stay suitable, while the scalar
+// prologue/epilogue and the reductions are paid once per WARP.  Here a group of 8 lanes owns an agent, so a
+// warp instruction advances four agents.  Groups run independently (every warp primitive uses the group's
+// 8-lane mask).  Anything outside the common case -- no suitable candidate (scaPolicy.py:224-238), more
+// surviving directions than DIR_CAP, keys beyond 22 bits -- is appended to a work list and handled by the
+// general kernel k_select afterwards, so both kernels together cover every agent exactly once.
+//
+// Per group:  constraints (2 per lane) -> A: posture test per DIRECTION (both shells share cos(angle))
+//             -> B: cone tests per direction, the two shells share the dot products p.u and h.u
+//             -> C: keys (fp64, decimal-rounded, packed key<<10|c) + REDUX selection / shunting.
+#pragma once
+
+#define FG_LANES 8
+#define FG_PER_WARP 4
+#define FG_WARPS 4        // warps per CTA
+#define DIR_CAP 64        // surviving directions per agent (a pi/4 cap holds ~38 of 256)
+#define LIVE_CAP 136      // 2 * DIR_CAP + v_pref, rounded up
+#define VPREF_ENTRY 0x3ff
+
+struct GroupSmem {
+    float4 cp[KNBR];
+    float4 ch[KNBR];
+    float2 cg[KNBR];
+    double dpx[KNBR], dpy[KNBR], dpz[KNBR];
+    double dhx[KNBR], dhy[KNBR], dhz[KNBR];
+    double dR[KNBR];
+    int cidx[KNBR];
+    unsigned short dirs[DIR_CAP];    // n | shell mask << 12 ; VPREF_ENTRY = v_pref itself
+    unsigned int kc[LIVE_CAP];       // live candidates: c, later key << 10 | c
+    unsigned int dvu[LIVE_CAP];      // l3norm(v, vA) in units of 1e-5
+    int pad[4];                      // sizeof % 128 == 16: the four groups of a warp hit different banks
+};
+
+__device__ __forceinline__ void push_slow(const StepArgs &A, int s)
+{
+    const int w = atomicAdd(A.slow_count, 1);
+    A.slow_list[w] = s;
+}
+
+template <int POLICY>
+__global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
+{
+    constexpr bool IS_ORCA = (POLICY == SCAB_POLICY_ORCA_SAMPLED);
+    constexpr bool SHUNT = (POLICY == SCAB_POLICY_SCA || POLICY == SCAB_POLICY_SRVO3D);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GroupSmem *gs = reinterpret_cast<GroupSmem *>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 3, l8 = lane & 7;
+    const unsigned gmask = 0xffu << (8 * g);
+    const unsigned lt8 = (1u << l8) - 1;
+    GroupSmem &W = gs[wid * FG_PER_WARP + g];
+    const int groups_total = gridDim.x * FG_WARPS * FG_PER_WARP;
+    unsigned long long n_recheck = 0;
+
+    for (int s = (blockIdx.x * FG_WARPS + wid) * FG_PER_WARP + g; s < A.n; s += groups_total) {
+        const float4 mv = A.s_vel[s];
+        const int flags = __float_as_int(mv.w);
+        {   // L2 prefetch of this group's next agent (header lines) and of its neighbour records
+            const int s1 = s + groups_total;
+            if (s1 < A.n) {
+                if (l8 == 0) prefetch_l2(&A.s_vel[s1]);
+                if (l8 == 1) prefetch_l2(&A.s_vdes[s1]);
+                if (l8 == 2) prefetch_l2(&A.s_posr[s1]);
+                if (l8 == 3) prefetch_l2(&A.s_nbr[(size_t)s1 * KNBR]);
+            }
+        }
+        if (flags & FL_INACTIVE) continue;
+        const double4 vd = A.s_vdes[s];
+        if (vd.w < 0.0) {   // zero-velocity shortcut: vA_post = 0.3 v_pref (scaPolicy.py:38)
+            if (l8 == 0)
+                A.s_vpost[s] = make_double4(__dmul_rn(0.3, vd.x), __dmul_rn(0.3, vd.y), __dmul_rn(0.3, vd.z),
+                                            __longlong_as_double((long long)SCAB_TAG_FIRST));
+            continue;
+        }
+        const double4 me = A.s_posr[s];
+        Agent a;
+        a.px = me.x; a.py = me.y; a.pz = me.z; a.r = me.w;
+        a.vx = mv.x; a.vy = mv.y; a.vz = mv.z;
+        a.pref = vd.w;
+        a.nvA = (double)norm3f_np(a.vx, a.vy, a.vz);
+        const bool zaxis = (POLICY == SCAB_POLICY_SCA) && (flags & SCAB_ST_ZAXIS);
+        a.N = zaxis ? 128 : 256;
+        a.dir = zaxis ? A.dir128 : A.dir256;
+        a.dirf = zaxis ? A.dir128f : A.dir256f;
+        {
+            double stepv = __dsub_rn(a.pref, 0.5);
+            double second = __dadd_rn(0.5, stepv);
+            a.shell1 = __dadd_rn(0.5, __dsub_rn(second, 0.5));
+        }
+        a.vdx = vd.x; a.vdy = vd.y; a.vdz = vd.z;
+        const int nc = A.s_nbr_cnt[s];
+        const float r1f = (float)a.shell1;
+        const float vmaxf = 1.0001f * (float)fmax(fmax(0.5, fabs(a.shell1)), sqrt(a.vdx * a.vdx + a.vdy * a.vdy + a.vdz * a.vdz));
+        const float fnvA = (float)a.nvA;
+        const float ball_r = 0.70711f * vmaxf;
+        const float bmx = ball_r * a.vx / fnvA, bmy = ball_r * a.vy / fnvA, bmz = ball_r * a.vz / fnvA;
+
+        // ------------------------------------------------------------ constraints: lane l8 builds k = l8, l8 + 8
+        int nce = 0;
+        for (int kb = 0; kb < nc; kb += FG_LANES) {
+            const int k = kb + l8;
+            float4 cP = make_float4(0.f, 0.f, 0.f, 0.f), cH = cP;
+            float2 cG = make_float2(0.f, 0.f);
+            bool keep = false;
+            if (k < nc) {
+                const int e = A.s_nbr[(size_t)s * KNBR + k];
+                double4 o;
+                float ox = 0.f, oy = 0.f, oz = 0.f;
+                bool at_goal = true;
+                if (e < A.n) {
+                    o = A.s_posr[e];
+                    const float4 ov = A.s_vel[e];
+                    ox = ov.x; oy = ov.y; oz = ov.z;
+                    at_goal = (__float_as_int(ov.w) & SCAB_ST_AT_GOAL) != 0;
+                } else if (e < A.n + A.m) {
+                    o = A.o_posr[e - A.n];
+                } else {
+                    o = A.o_posr_by_id[e - A.n - A.m];
+                }
+                const double R = IS_ORCA ? __dadd_rn(__dadd_rn(a.r, 0.05), __dadd_rn(o.w, 0.05))
+                                         : __dadd_rn(__dadd_rn(o.w, 0.05), __dadd_rn(a.r, 0.05));
+                const double rx = __dsub_rn(o.x, a.px), ry = __dsub_rn(o.y, a.py), rz = __dsub_rn(o.z, a.pz);
+                W.dR[k] = R;
+                if (!IS_ORCA) {   // scaPolicy.py:47-60
+                    float hx = 0.f, hy = 0.f, hz = 0.f;
+                    if (!at_goal) {
+                        hx = __fmul_rn(0.5f, __fadd_rn(ox, a.vx));
+                        hy = __fmul_rn(0.5f, __fadd_rn(oy, a.vy));
+                        hz = __fmul_rn(0.5f, __fadd_rn(oz, a.vz));
+                    }
+                    W.dpx[k] = o.x; W.dpy[k] = o.y; W.dpz[k] = o.z;
+                    W.dhx[k] = at_goal ? a.px : __dadd_rn(a.px, (double)hx);
+                    W.dhy[k] = at_goal ? a.py : __dadd_rn(a.py, (double)hy);
+                    W.dhz[k] = at_goal ? a.pz : __dadd_rn(a.pz, (double)hz);
+                    const double pp = dot3(rx, ry, rz, rx, ry, rz);
+                    const float fpx = (float)rx, fpy = (float)ry, fpz = (float)rz;
+                    const float hh = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
+                    cP = make_float4(fpx, fpy, fpz, fmaf(fpz, hz, fmaf(fpy, hy, fpx * hx)));
+                    cH = make_float4(hx, hy, hz, hh);
+                    const float vh_max = vmaxf + sqrtf(hh);
+                    const float c2f = (float)fmax(pp - R * R, 0.0);
+                    cG = make_float2(c2f, 2e-5f * (float)pp * vh_max * vh_max);
+                    const float d = sqrtf((float)pp), Rf = (float)R;
+                    const float qx = bmx - hx, qy = bmy - hy, qz = bmz - hz;
+                    const float qa = (qx * fpx + qy * fpy + qz * fpz) / d;
+                    const float qr = sqrtf(fmaxf(qx * qx + qy * qy + qz * qz - qa * qa, 0.f));
+                    const float sn = fminf(Rf / d, 1.f), cs = sqrtf(c2f) / d;
+                    keep = !(qr * cs - qa * sn > ball_r + 1e-2f) || !((float)pp > 1.02f * Rf * Rf);
+                } else {          // orca3dPolicy.py:57-107
+                    const double vrx = (double)__fsub_rn(a.vx, ox), vry = (double)__fsub_rn(a.vy, oy), vrz = (double)__fsub_rn(a.vz, oz);
+                    const double distSq = dot3(rx, ry, rz, rx, ry, rz);
+                    const double RSq = __dmul_rn(R, R);
+                    double nx, ny, nz, ux, uy, uz;
+                    if (distSq > RSq) {
+                        const double invT = A.inv_time_horizon;
+                        double wx = __dsub_rn(vrx, __dmul_rn(invT, rx)), wy = __dsub_rn(vry, __dmul_rn(invT, ry)), wz = __dsub_rn(vrz, __dmul_rn(invT, rz));
+                        double wl2 = dot3(wx, wy, wz, wx, wy, wz);
+                        double dp = dot3(wx, wy, wz, rx, ry, rz);
+                        if (dp < 0.0 && __dmul_rn(dp, dp) > __dmul_rn(RSq, wl2)) {
+                            double wl = __dsqrt_rn(wl2);
+                            nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
+                            double sc = __dsub_rn(__dmul_rn(R, invT), wl);
+                            ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
+                        } else {
+                            double difSq = __dsub_rn(distSq, RSq);
+                            double dpr = dot3(rx, ry, rz, vrx, vry, vrz);
+                            double cx = __dsub_rn(__dmul_rn(ry, vrz), __dmul_rn(rz, vry));
+                            double cy = __dsub_rn(__dmul_rn(rz, vrx), __dmul_rn(rx, vrz));
+                            double cz = __dsub_rn(__dmul_rn(rx, vry), __dmul_rn(ry, vrx));
+                            double wwSq = __ddiv_rn(dot3(cx, cy, cz, cx, cy, cz), difSq);
+                            double pl = __dsqrt_rn(distSq);
+                            double t = __ddiv_rn(__dadd_rn(__ddiv_rn(dpr, pl), __dmul_rn(__dsqrt_rn(wwSq), __ddiv_rn(R, pl))), pl);
+                            double wx = __dsub_rn(vrx, __dmul_rn(t, rx)), wy = __dsub_rn(vry, __dmul_rn(t, ry)), wz = __dsub_rn(vrz, __dmul_rn(t, rz));
+                            double wl = __dsqrt_rn(dot3(wx, wy, wz, wx, wy, wz));
+                            nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
+                            double sc = __dsub_rn(__dmul_rn(R, t), wl);
+                            ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
+                        }
+                    } else {
+                        const double invDt = A.inv_time_step;
+                        double wx = __dsub_rn(vrx, __dmul_rn(invDt, rx)), wy = __dsub_rn(vry, __dmul_rn(invDt, ry)), wz = __dsub_rn(vrz, __dmul_rn(invDt, rz));
+                        double wl = __dsqrt_rn(dot3(wx, wy, wz, wx, wy, wz));
+                        nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
+                        double sc = __dsub_rn(__dmul_rn(R, invDt), wl);
+                        ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
+                    }
+                    const double qx = __dadd_rn((double)a.vx, __dmul_rn(0.5, ux)), qy = __dadd_rn((double)a.vy, __dmul_rn(0.5, uy)),
+                                 qz = __dadd_rn((double)a.vz, __dmul_rn(0.5, uz));
+                    W.dpx[k] = qx; W.dpy[k] = qy; W.dpz[k] = qz;
+                    W.dhx[k] = nx; W.dhy[k] = ny; W.dhz[k] = nz;
+                    cP = make_float4((float)nx, (float)ny, (float)nz, (float)(nx * qx + ny * qy + nz * qz));
+                    cG = make_float2(0.f, 1e-5f * (vmaxf + (float)sqrt(qx * qx + qy * qy + qz * qz)));
+                    keep = !((cP.x * bmx + cP.y * bmy + cP.z * bmz) - ball_r - cP.w > 1e-2f);
+                }
+            }
+            const unsigned km = (__ballot_sync(gmask, keep) >> (8 * g)) & 0xffu;
+            if (keep) {
+                const int slot = nce + __popc(km & lt8);
+                W.cp[slot] = cP; W.ch[slot] = cH; W.cg[slot] = cG; W.cidx[slot] = k;
+            }
+            nce += __popc(km);
+        }
+
+        // ------------------------------------------------------------ A: posture per direction
+        int ndir = 0;
+        {
+            const float thr = 0.70710678f * fnvA;
+            const float band = 2e-6f * fnvA;
+            const double vmax = fmax(fmax(0.5, fabs(a.shell1)), fabs(a.vdz));
+            const bool near_ground = !(a.pz > A.time_step * vmax + 1e-9);
+            for (int base = 0; base < a.N; base += FG_LANES) {
+                const int n = base + l8;
+                const float4 u = a.dirf[n];
+                const float dt = fmaf(a.vz, u.z, fmaf(a.vy, u.y, a.vx * u.x));
+                bool p0 = dt >= thr, p1 = p0;
+                if (fabsf(dt - thr) <= band || near_ground) {
+                    double x, y, z;
+                    cand64(a, n, x, y, z);
+                    p0 = posture_ok(a, A.time_step, x, y, z);
+                    cand64(a, a.N + n, x, y, z);
+                    p1 = posture_ok(a, A.time_step, x, y, z);
+                }
+                const unsigned msk = (__ballot_sync(gmask, p0 || p1) >> (8 * g)) & 0xffu;
+                if (p0 || p1) {
+                    const int slot = ndir + __popc(msk & lt8);
+                    if (slot < DIR_CAP) W.dirs[slot] = (unsigned short)(n | ((p0 ? 1 : 0) | (p1 ? 2 : 0)) << 12);
+                }
+                ndir += __popc(msk);
+            }
+            if (ndir < DIR_CAP && posture_ok(a, A.time_step, a.vdx, a.vdy, a.vdz)) {   // v_pref itself, last
+                if (l8 == 0) W.dirs[ndir] = (unsigned short)(VPREF_ENTRY | (1 << 12));
+                ndir++;
+            }
+        }
+        if (ndir >= DIR_CAP) {           // not the common case: leave it to the general kernel
+            if (l8 == 0) push_slow(A, s);
+            continue;
+        }
+        __syncwarp(gmask);
+
+        // ------------------------------------------------------------ B: cone tests per direction
+        int nlive = 0;
+        for (int jb = 0; jb < ndir; jb += FG_LANES) {
+            const int j = jb + l8;
+            bool s0 = false, s1 = false;
+            int n = 0;
+            if (j < ndir) {
+                const unsigned ent = W.dirs[j];
+                n = ent & 0x3ff;
+                s0 = (ent >> 12) & 1; s1 = (ent >> 13) & 1;
+                const bool isv = (n == VPREF_ENTRY);
+                float4 u;
+                if (isv) u = make_float4((float)a.vdx, (float)a.vdy, (float)a.vdz, 0.f);
+                else u = a.dirf[n];
+                const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x));
+                const float ra = isv ? 1.f : 0.5f, rb = r1f;
+                for (int kk = 0; kk < nce && (s0 || s1); kk++) {
+                    const float4 P = W.cp[kk];
+                    const float2 G = W.cg[kk];
+                    const float pa = fmaf(P.z, u.z, fmaf(P.y, u.y, P.x * u.x));
+                    float df0, df1, dt0, dt1;
+                    if (!IS_ORCA) {
+                        const float4 H = W.ch[kk];
+                        const float hb = fmaf(H.z, u.z, fmaf(H.y, u.y, H.x * u.x));
+                        dt0 = fmaf(ra, pa, -P.w); dt1 = fmaf(rb, pa, -P.w);
+                        const float vv0 = fmaf(-2.f * ra, hb, ra * ra * uu) + H.w, vv1 = fmaf(-2.f * rb, hb, rb * rb * uu) + H.w;
+                        df0 = fmaf(dt0, dt0, -vv0 * G.x); df1 = fmaf(dt1, dt1, -vv1 * G.x);
+                    } else {
+                        dt0 = 1.f; dt1 = 1.f;
+                        df0 = -(fmaf(ra, pa, -P.w)); df1 = -(fmaf(rb, pa, -P.w));   // inside (violated) iff n.v - n.q < 0
+                    }
+                    bool in0, in1;
+                    if (!IS_ORCA) { in0 = (dt0 > 0.f) && (df0 > 0.f); in1 = (dt1 > 0.f) && (df1 > 0.f); }
+                    else { in0 = !(-df0 >= 0.f); in1 = !(-df1 >= 0.f); }
+                    const bool un0 = s0 && fabsf(df0) <= G.y, un1 = s1 && fabsf(df1) <= G.y;
+                    if (un0 || un1) {
+                        const int k = W.cidx[kk];
+                        for (int sh = 0; sh < 2; sh++) {
+                            if (!(sh ? un1 : un0)) continue;
+                            n_recheck++;
+                            const int c = isv ? 2 * a.N : (sh ? a.N + n : n);
+                            double x, y, z;
+                            cand64(a, c, x, y, z);
+                            bool ins;
+                            if (!IS_ORCA) {
+                                double dx = __dsub_rn(__dadd_rn(x, a.px), W.dhx[k]), dy = __dsub_rn(__dadd_rn(y, a.py), W.dhy[k]),
+                                       dz = __dsub_rn(__dadd_rn(z, a.pz), W.dhz[k]);
+                                ins = is_intersect64_fast(__dsub_rn(W.dpx[k], a.px), __dsub_rn(W.dpy[k], a.py), __dsub_rn(W.dpz[k], a.pz),
+                                                          W.dR[k], dx, dy, dz);
+                            } else {
+                                double val = dot3(__dsub_rn(x, W.dpx[k]), __dsub_rn(y, W.dpy[k]), __dsub_rn(z, W.dpz[k]),
+                                                  W.dhx[k], W.dhy[k], W.dhz[k]);
+                                ins = !(val >= 0.0);
+                            }
+                            if (sh) in1 = ins; else in0 = ins;
+                        }
+                    }
+                    if (in0) s0 = false;
+                    if (in1) s1 = false;
+                }
+            }
+            // compact the surviving candidates of this round (generation index c) into the live list
+            const bool isv = (n == VPREF_ENTRY);
+            unsigned m0 = (__ballot_sync(gmask, s0) >> (8 * g)) & 0xffu;
+            if (s0) W.kc[nlive + __popc(m0 & lt8)] = isv ? 2 * a.N : n;
+            nlive += __popc(m0);
+            unsigned m1 = (__ballot_sync(gmask, s1) >> (8 * g)) & 0xffu;
+            if (s1) W.kc[nlive + __popc(m1 & lt8)] = a.N + n;
+            nlive += __popc(m1);
+        }
+        if (nlive == 0) {                // "no suitable velocity" (scaPolicy.py:224-238): general kernel
+            if (l8 == 0) push_slow(A, s);
+            continue;
+        }
+        __syncwarp(gmask);
+
+        // ------------------------------------------------------------ C: keys + selection
+        unsigned local_min = 0xffffffffu;
+        bool overflow = false;
+        for (int jb = 0; jb < nlive; jb += FG_LANES) {
+            const int j = jb + l8;
+            if (j < nlive) {
+                const int c = (int)W.kc[j];
+                double x, y, z;
+                cand64(a, c, x, y, z);
+                const double dist = __dsqrt_rn(sumsq3(__dsub_rn(x, a.vdx), __dsub_rn(y, a.vdy), __dsub_rn(z, a.vdz)));
+                const double ku = py_round5_units(dist);          // l3norm(v, v_pref) in units of 1e-5
+                if (!(ku < 4194304.0)) overflow = true;
+                const unsigned packed = ((unsigned)ku << 10) | (unsigned)c;
+                W.kc[j] = packed;
+                if (SHUNT) {
+                    const double dva = __dsqrt_rn(sumsq3(__dsub_rn(x, (double)a.vx), __dsub_rn(y, (double)a.vy), __dsub_rn(z, (double)a.vz)));
+                    W.dvu[j] = (unsigned int)py_round5_units(dva);
+                }
+                local_min = min(local_min, packed);
+            }
+        }
+        if (__any_sync(gmask, overflow)) {
+            if (l8 == 0) push_slow(A, s);
+            continue;
+        }
+        const unsigned head = __reduce_min_sync(gmask, local_min);
+        int best = (int)(head & 1023u);
+        if (SHUNT && nlive > 1) {
+            // scaPolicy.py:119-145 shunted_strategy
+            const long long thr_units = (POLICY == SCAB_POLICY_SCA) ? 3000 : 10000;
+            const double thr = (POLICY == SCAB_POLICY_SCA) ? 3e-2 : 1e-1;
+            double x0, y0, z0;
+            cand64(a, best, x0, y0, z0);
+            const long long d0u = (long long)py_round5_units(
+                __dsqrt_rn(sumsq3(__dsub_rn(x0, (double)a.vx), __dsub_rn(y0, (double)a.vy), __dsub_rn(z0, (double)a.vz))));
+            unsigned fmin = 0xffffffffu;
+            for (int jb = 0; jb < nlive; jb += FG_LANES) {
+                const int j = jb + l8;
+                if (j < nlive) {
+                    const long long diu = (long long)W.dvu[j];
+                    const long long du = d0u > diu ? d0u - diu : diu - d0u;
+                    bool within;
+                    if (du < thr_units - 1) within = true;
+                    else if (du > thr_units + 1) within = false;
+                    else within = fabs(__dsub_rn(__ddiv_rn((double)d0u, 1e5), __ddiv_rn((double)diu, 1e5))) < thr;
+                    if (!within) fmin = min(fmin, W.kc[j]);
+                }
+            }
+            const unsigned kfail = __reduce_min_sync(gmask, fmin);   // first element that breaks the prefix
+            unsigned umin = 0xffffffffu, umax = 0u, kmin = 0xffffffffu, kmax = 0xffffffffu;
+            for (int jb = 0; jb < nlive; jb += FG_LANES) {
+                const int j = jb + l8;
+                if (j < nlive) {
+                    const unsigned kcj = W.kc[j];
+                    if (kcj < kfail) {
+                        double x, y, z;
+                        cand64(a, (int)(kcj & 1023u), x, y, z);
+                        double phi = (y >= 0) ? atan2(y, x) : __dadd_rn(2 * SCAB_PI, atan2(y, x));   // util.py:145-150
+                        const unsigned pu = (unsigned)((long long)trunc(__dmul_rn(phi, 1e5)) + 1000000);
+                        if (pu < umin || (pu == umin && kcj < kmin)) { umin = pu; kmin = kcj; }
+                        if (pu > umax || (pu == umax && kcj < kmax) || kmax == 0xffffffffu) { umax = pu; kmax = kcj; }
+                    }
+                }
+            }
+            const unsigned gmin = __reduce_min_sync(gmask, umin), gmax = __reduce_max_sync(gmask, umax);
+            const unsigned cmin = __reduce_min_sync(gmask, umin == gmin ? kmin : 0xffffffffu);
+            const unsigned cmax = __reduce_min_sync(gmask, (umax == gmax && kmax != 0xffffffffu) ? kmax : 0xffffffffu);
+            const double phi_min = __ddiv_rn((double)((long long)gmin - 1000000), 1e5), phi_max = __ddiv_rn((double)((long long)gmax - 1000000), 1e5);
+            best = (fabs(__dsub_rn(phi_max, phi_min)) <= SCAB_PI) ? (int)(cmin & 1023u) : (int)(cmax & 1023u);
+        }
+        if (l8 == 0) {
+            double bx, by, bz;
+            cand64(a, best, bx, by, bz);
+            A.s_vpost[s] = make_double4(trunc5(bx), trunc5(by), trunc5(bz),
+                                        __longlong_as_double((long long)SCAB_TAG_SUITABLE | ((long long)nlive << 8)));
+        }
+        __syncwarp(gmask);
+    }
+    for (int o = 4; o > 0; o >>= 1) n_recheck += __shfl_xor_sync(gmask, n_recheck, o);
+    if (l8 == 0 && n_recheck) atomicAdd(&A.counters[3], n_recheck);
+}
