@@ -636,7 +636,7 @@ template <int POLICY>
 static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
 {
     static int per_sm = 0, per_sm_fast = 0, no_fast = -1;
-    const size_t smem = sizeof(WarpSmem) * WARPS_PER_CTA, smem_fast = sizeof(GroupSmem) * FG_WARPS * FG_PER_WARP;
+    const size_t smem = sizeof(WarpSmem) * WARPS_PER_CTA, smem_fast = sizeof(GroupSmem) * FG_WARPS * FG_PER_WARP + 384 * sizeof(float4);
     if (per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(k_select<POLICY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select<POLICY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -54,6 +54,12 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
     GroupSmem &W = gs[wid * FG_PER_WARP + g];
     const int groups_total = gridDim.x * FG_WARPS * FG_PER_WARP;
     unsigned long long n_recheck = 0;
+    // fp32 direction tables, once per CTA (6 KB): conflict-free float4 reads in phases A and B
+    float4 *s_dir256 = reinterpret_cast<float4 *>(smem_raw + sizeof(GroupSmem) * FG_WARPS * FG_PER_WARP);
+    float4 *s_dir128 = s_dir256 + 256;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_dir256[i] = A.dir256f[i];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_dir128[i] = A.dir128f[i];
+    __syncthreads();
 
     for (int s = (blockIdx.x * FG_WARPS + wid) * FG_PER_WARP + g; s < A.n; s += groups_total) {
         const float4 mv = A.s_vel[s];
@@ -205,34 +211,53 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
         }
 
         // ------------------------------------------------------------ A: posture per direction
+        // Lane l8 owns directions n = 8 i + l8 and collects pass bits (bit i) for both shells; slots in the
+        // compacted list come from one 8-lane exclusive prefix of the pop-counts (no per-iteration ballots).
         int ndir = 0;
         {
             const float thr = 0.70710678f * fnvA;
             const float band = 2e-6f * fnvA;
             const double vmax = fmax(fmax(0.5, fabs(a.shell1)), fabs(a.vdz));
             const bool near_ground = !(a.pz > A.time_step * vmax + 1e-9);
-            for (int base = 0; base < a.N; base += FG_LANES) {
-                const int n = base + l8;
-                const float4 u = a.dirf[n];
+            const float4 *tab = zaxis ? s_dir128 : s_dir256;
+            unsigned m0 = 0, m1 = 0;
+            const int iters = a.N / FG_LANES;
+#pragma unroll 4
+            for (int i = 0; i < iters; i++) {
+                const float4 u = tab[FG_LANES * i + l8];
                 const float dt = fmaf(a.vz, u.z, fmaf(a.vy, u.y, a.vx * u.x));
                 bool p0 = dt >= thr, p1 = p0;
                 if (fabsf(dt - thr) <= band || near_ground) {
                     double x, y, z;
-                    cand64(a, n, x, y, z);
+                    cand64(a, FG_LANES * i + l8, x, y, z);
                     p0 = posture_ok(a, A.time_step, x, y, z);
-                    cand64(a, a.N + n, x, y, z);
+                    cand64(a, a.N + FG_LANES * i + l8, x, y, z);
                     p1 = posture_ok(a, A.time_step, x, y, z);
                 }
-                const unsigned msk = (__ballot_sync(gmask, p0 || p1) >> (8 * g)) & 0xffu;
-                if (p0 || p1) {
-                    const int slot = ndir + __popc(msk & lt8);
-                    if (slot < DIR_CAP) W.dirs[slot] = (unsigned short)(n | ((p0 ? 1 : 0) | (p1 ? 2 : 0)) << 12);
-                }
-                ndir += __popc(msk);
+                m0 |= (p0 ? 1u : 0u) << i;
+                m1 |= (p1 ? 1u : 0u) << i;
             }
-            if (ndir < DIR_CAP && posture_ok(a, A.time_step, a.vdx, a.vdy, a.vdz)) {   // v_pref itself, last
-                if (l8 == 0) W.dirs[ndir] = (unsigned short)(VPREF_ENTRY | (1 << 12));
-                ndir++;
+            unsigned bits = m0 | m1;
+            const int cnt = __popc(bits);
+            int pre = cnt;
+#pragma unroll
+            for (int o = 1; o < FG_LANES; o <<= 1) {
+                const int t = __shfl_up_sync(gmask, pre, o, FG_LANES);
+                if (l8 >= o) pre += t;
+            }
+            ndir = __shfl_sync(gmask, pre, FG_LANES - 1, FG_LANES);
+            int slot = pre - cnt;
+            if (ndir < DIR_CAP) {
+                while (bits) {
+                    const int i = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int n = FG_LANES * i + l8;
+                    W.dirs[slot++] = (unsigned short)(n | (((m0 >> i) & 1u) | (((m1 >> i) & 1u) << 1)) << 12);
+                }
+                if (posture_ok(a, A.time_step, a.vdx, a.vdy, a.vdz)) {   // v_pref itself, last (scaPolicy.py:206)
+                    if (l8 == 0) W.dirs[ndir] = (unsigned short)(VPREF_ENTRY | (1 << 12));
+                    ndir++;
+                }
             }
         }
         if (ndir >= DIR_CAP) {           // not the common case: leave it to the general kernel
@@ -254,7 +279,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
                 const bool isv = (n == VPREF_ENTRY);
                 float4 u;
                 if (isv) u = make_float4((float)a.vdx, (float)a.vdy, (float)a.vdz, 0.f);
-                else u = a.dirf[n];
+                else u = (zaxis ? s_dir128 : s_dir256)[n];
                 const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x));
                 const float ra = isv ? 1.f : 0.5f, rb = r1f;
                 for (int kk = 0; kk < nce && (s0 || s1); kk++) {

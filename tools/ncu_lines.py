@@ -9,7 +9,7 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 inst = defaultdict(float); samp = defaultdict(float); src = {}
 cur = None; hdr = None; fname = ''
 for r in rows:
-    if len(r) >= 2 and r[0] == 'File Name':
+    if len(r) >= 2 and r[0] in ('File Name', 'File Path'):
         fname = r[1].split('/')[-1]; continue
     if len(r) > 4 and r[0] == 'Line No':
         hdr = r; continue
