@@ -136,6 +136,13 @@ int scab_create(scab_handle **out, const scab_params *p, int device, int64_t cap
 int scab_destroy(scab_handle *h);
 const char *scab_last_error(const scab_handle *h);
 
+/* Options.  SCAB_OPT_FULL_SEARCH (default 0): the sampled policies normally examine the candidates in two
+ * tiers of increasing distance to v_pref and stop as soon as the reference's result is pinned (the selected
+ * velocity and branch tag are identical; state.n_suit is then reported as -1).  1 = test all 513 candidates
+ * like the reference does, which also yields its exact count of suitable candidates in state.n_suit. */
+#define SCAB_OPT_FULL_SEARCH 1
+int scab_set_option(scab_handle *h, int option, int value);
+
 /* Replace the grid geometry (e.g. after the swarm's bounding box changed). */
 int scab_set_grid(scab_handle *h, const double origin[3], double cell_size, const int32_t dim[3]);
 

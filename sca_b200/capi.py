@@ -17,7 +17,9 @@ ST_AT_GOAL, ST_COLLISION, ST_TIMEOUT, ST_RUN_DONE, ST_ZAXIS, ST_GHOST = 1, 2, 4,
 TAG_FIRST, TAG_SUITABLE, TAG_FALLBACK, TAG_LP3_OK, TAG_LP4 = 1, 2, 4, 8, 16
 
 # every symbol include/scab200.h declares (tests/test_capi_symbols.py checks the header against this)
-SYMBOLS = ['scab_version', 'scab_default_params', 'scab_create', 'scab_destroy', 'scab_last_error', 'scab_set_grid',
+OPT_FULL_SEARCH = 1
+
+SYMBOLS = ['scab_version', 'scab_default_params', 'scab_set_option', 'scab_create', 'scab_destroy', 'scab_last_error', 'scab_set_grid',
            'scab_bind_state', 'scab_set_obstacles', 'scab_kdtree_build', 'scab_kdtree_get_perm', 'scab_build_grid',
            'scab_neighbors', 'scab_policy_step', 'scab_status_step', 'scab_step', 'scab_read_counters',
            'scab_reset_counters', 'scab_halo_pack', 'scab_halo_unpack', 'scab_halo_pack_pos', 'scab_halo_unpack_pos',
@@ -69,6 +71,7 @@ def lib():
     L.scab_create.argtypes = [C.POINTER(vp), C.POINTER(Params), C.c_int, i64]
     L.scab_destroy.argtypes = [vp]
     L.scab_set_grid.argtypes = [vp, C.POINTER(C.c_double), C.c_double, C.POINTER(i32)]
+    L.scab_set_option.argtypes = [vp, C.c_int, C.c_int]
     L.scab_bind_state.argtypes = [vp, C.POINTER(StatePtrs), i64]
     L.scab_set_obstacles.argtypes = [vp, vp, i32]
     L.scab_kdtree_build.argtypes = [vp, vp, i64]
@@ -121,6 +124,9 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+    def set_option(self, option, value):
+        self._ck(self._L.scab_set_option(self._h, int(option), int(value)))
 
     def set_grid(self, origin, cell_size, dim):
         o = (C.c_double * 3)(*[float(x) for x in origin])

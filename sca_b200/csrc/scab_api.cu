@@ -69,6 +69,13 @@ extern "C" void scab_default_params(scab_params *p)
 
 extern "C" const char *scab_last_error(const scab_handle *h) { return h ? h->err.c_str() : "null handle"; }
 
+extern "C" int scab_set_option(scab_handle *h, int option, int value)
+{
+    if (!h) return SCAB_ERR_INVALID;
+    if (option == SCAB_OPT_FULL_SEARCH) { h->A.full_search = value ? 1 : 0; return SCAB_OK; }
+    return fail(h, SCAB_ERR_INVALID, "scab_set_option: unknown option");
+}
+
 // Fibonacci-sphere unit directions (scaPolicy.py:196-199), evaluated with the host libm exactly as the
 // reference does (math.sqrt / math.cos / math.sin), then uploaded.
 static void make_dirs(int N, std::vector<double> &d64, std::vector<float4> &d32)

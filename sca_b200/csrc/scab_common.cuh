@@ -54,6 +54,7 @@ struct StepArgs {
     int32_t *s_qcoll;   // [n] collision flag raised by the neighbour query (agent.py:83-85)
     int32_t *slow_list; // [n] agents the 8-lane fast selection kernel hands to the general kernel
     int32_t *slow_count;
+    int full_search;    // SCAB_OPT_FULL_SEARCH: examine every candidate (exact n_suit) instead of the lazy tiers
     // obstacles (sorted by obstacle cell) + reference kd-trees
     const double4 *o_posr;
     const int32_t *o_id, *o_cell_start;

@@ -20,6 +20,7 @@
 #define DIR_CAP 64        // surviving directions per agent (a pi/4 cap holds ~38 of 256)
 #define LIVE_CAP 136      // 2 * DIR_CAP + v_pref, rounded up
 #define VPREF_ENTRY 0x3ff
+#define TIER_DELTA 0.25f   // tier 1 = candidates within this (approximate) distance of the one closest to v_pref
 
 struct GroupSmem {
     float4 cp[KNBR];
@@ -32,6 +33,7 @@ struct GroupSmem {
     unsigned short dirs[DIR_CAP];    // n | shell mask << 12 ; VPREF_ENTRY = v_pref itself
     unsigned int kc[LIVE_CAP];       // live candidates: c, later key << 10 | c
     unsigned int dvu[LIVE_CAP];      // l3norm(v, vA) in units of 1e-5
+    unsigned char act[DIR_CAP];      // entries of the current tier: j | shell mask << 6
     int pad[4];                      // sizeof % 128 == 16: the four groups of a warp hit different banks
 };
 
@@ -266,157 +268,228 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
         }
         __syncwarp(gmask);
 
-        // ------------------------------------------------------------ B: cone tests per direction
-        int nlive = 0;
-        for (int jb = 0; jb < ndir; jb += FG_LANES) {
-            const int j = jb + l8;
-            bool s0 = false, s1 = false;
-            int n = 0;
-            if (j < ndir) {
-                const unsigned ent = W.dirs[j];
-                n = ent & 0x3ff;
-                s0 = (ent >> 12) & 1; s1 = (ent >> 13) & 1;
-                const bool isv = (n == VPREF_ENTRY);
-                float4 u;
-                if (isv) u = make_float4((float)a.vdx, (float)a.vdy, (float)a.vdz, 0.f);
-                else u = (zaxis ? s_dir128 : s_dir256)[n];
-                const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x));
-                const float ra = isv ? 1.f : 0.5f, rb = r1f;
-                for (int kk = 0; kk < nce && (s0 || s1); kk++) {
-                    const float4 P = W.cp[kk];
-                    const float2 G = W.cg[kk];
-                    const float pa = fmaf(P.z, u.z, fmaf(P.y, u.y, P.x * u.x));
-                    float df0, df1, dt0, dt1;
-                    if (!IS_ORCA) {
-                        const float4 H = W.ch[kk];
-                        const float hb = fmaf(H.z, u.z, fmaf(H.y, u.y, H.x * u.x));
-                        dt0 = fmaf(ra, pa, -P.w); dt1 = fmaf(rb, pa, -P.w);
-                        const float vv0 = fmaf(-2.f * ra, hb, ra * ra * uu) + H.w, vv1 = fmaf(-2.f * rb, hb, rb * rb * uu) + H.w;
-                        df0 = fmaf(dt0, dt0, -vv0 * G.x); df1 = fmaf(dt1, dt1, -vv1 * G.x);
-                    } else {
-                        dt0 = 1.f; dt1 = 1.f;
-                        df0 = -(fmaf(ra, pa, -P.w)); df1 = -(fmaf(rb, pa, -P.w));   // inside (violated) iff n.v - n.q < 0
-                    }
-                    bool in0, in1;
-                    if (!IS_ORCA) { in0 = (dt0 > 0.f) && (df0 > 0.f); in1 = (dt1 > 0.f) && (df1 > 0.f); }
-                    else { in0 = !(-df0 >= 0.f); in1 = !(-df1 >= 0.f); }
-                    const bool un0 = s0 && fabsf(df0) <= G.y, un1 = s1 && fabsf(df1) <= G.y;
-                    if (un0 || un1) {
-                        const int k = W.cidx[kk];
-                        for (int sh = 0; sh < 2; sh++) {
-                            if (!(sh ? un1 : un0)) continue;
-                            n_recheck++;
-                            const int c = isv ? 2 * a.N : (sh ? a.N + n : n);
-                            double x, y, z;
-                            cand64(a, c, x, y, z);
-                            bool ins;
-                            if (!IS_ORCA) {
-                                double dx = __dsub_rn(__dadd_rn(x, a.px), W.dhx[k]), dy = __dsub_rn(__dadd_rn(y, a.py), W.dhy[k]),
-                                       dz = __dsub_rn(__dadd_rn(z, a.pz), W.dhz[k]);
-                                ins = is_intersect64_fast(__dsub_rn(W.dpx[k], a.px), __dsub_rn(W.dpy[k], a.py), __dsub_rn(W.dpz[k], a.pz),
-                                                          W.dR[k], dx, dy, dz);
-                            } else {
-                                double val = dot3(__dsub_rn(x, W.dpx[k]), __dsub_rn(y, W.dpy[k]), __dsub_rn(z, W.dpz[k]),
-                                                  W.dhx[k], W.dhy[k], W.dhz[k]);
-                                ins = !(val >= 0.0);
-                            }
-                            if (sh) in1 = ins; else in0 = ins;
-                        }
-                    }
-                    if (in0) s0 = false;
-                    if (in1) s1 = false;
+        // ------------------------------------------------------------ lazy tiers
+        // The answer only depends on the head of the key-sorted suitable list and (with shunting) on the
+        // short prefix before the first element that breaks it, so candidates are examined in two tiers of
+        // increasing APPROXIMATE distance to v_pref: tier 1 = within TIER_DELTA of the closest candidate.  If
+        // tier 1 already pins the result -- head (and prefix-breaking element) found with exact keys below the
+        // tier boundary minus a margin covering the fp32 key error -- tier 2 (the other ~90 %) is never tested.
+        // full_search (scab_set_option) disables the shortcut and yields the exact n_suit of the reference.
+        const float vdx = (float)a.vdx, vdy = (float)a.vdy, vdz = (float)a.vdz;
+        const float vdvd = fmaf(vdz, vdz, fmaf(vdy, vdy, vdx * vdx));
+        const float4 *tabB = zaxis ? s_dir128 : s_dir256;
+        float T1 = 3.0e38f;
+        if (!A.full_search) {
+            float kmin = 3.0e38f;
+            for (int jb = 0; jb < ndir; jb += FG_LANES) {
+                const int j = jb + l8;
+                if (j < ndir) {
+                    const unsigned ent = W.dirs[j];
+                    const int n = ent & 0x3ff;
+                    const bool isv = (n == VPREF_ENTRY);
+                    const float4 u = isv ? make_float4(vdx, vdy, vdz, 0.f) : tabB[n];
+                    const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x)), uv = fmaf(u.z, vdz, fmaf(u.y, vdy, u.x * vdx));
+                    const float ra = isv ? 1.f : 0.5f;
+                    if (ent & (1u << 12)) kmin = fminf(kmin, sqrtf(fmaxf(fmaf(-2.f * ra, uv, ra * ra * uu) + vdvd, 0.f)));
+                    if (ent & (2u << 12)) kmin = fminf(kmin, sqrtf(fmaxf(fmaf(-2.f * r1f, uv, r1f * r1f * uu) + vdvd, 0.f)));
                 }
             }
-            // compact the surviving candidates of this round (generation index c) into the live list
-            const bool isv = (n == VPREF_ENTRY);
-            unsigned m0 = (__ballot_sync(gmask, s0) >> (8 * g)) & 0xffu;
-            if (s0) W.kc[nlive + __popc(m0 & lt8)] = isv ? 2 * a.N : n;
-            nlive += __popc(m0);
-            unsigned m1 = (__ballot_sync(gmask, s1) >> (8 * g)) & 0xffu;
-            if (s1) W.kc[nlive + __popc(m1 & lt8)] = a.N + n;
-            nlive += __popc(m1);
+            kmin = __uint_as_float(__reduce_min_sync(gmask, __float_as_uint(kmin)));   // non-negative floats order as uints
+            T1 = kmin + TIER_DELTA;
         }
-        if (nlive == 0) {                // "no suitable velocity" (scaPolicy.py:224-238): general kernel
-            if (l8 == 0) push_slow(A, s);
-            continue;
-        }
-        __syncwarp(gmask);
+        // exact keys strictly below this are certainly smaller than any key of tier 2 (fp32 key error <= 1e-3)
+        const unsigned tier_units = A.full_search ? 0xffffffffu : (unsigned)fmaxf((T1 - 1.1e-3f) * 1.0e5f, 0.f);
 
-        // ------------------------------------------------------------ C: keys + selection
-        unsigned local_min = 0xffffffffu;
-        bool overflow = false;
-        for (int jb = 0; jb < nlive; jb += FG_LANES) {
-            const int j = jb + l8;
-            if (j < nlive) {
-                const int c = (int)W.kc[j];
-                double x, y, z;
-                cand64(a, c, x, y, z);
-                const double dist = __dsqrt_rn(sumsq3(__dsub_rn(x, a.vdx), __dsub_rn(y, a.vdy), __dsub_rn(z, a.vdz)));
-                const double ku = py_round5_units(dist);          // l3norm(v, v_pref) in units of 1e-5
-                if (!(ku < 4194304.0)) overflow = true;
-                const unsigned packed = ((unsigned)ku << 10) | (unsigned)c;
-                W.kc[j] = packed;
-                if (SHUNT) {
-                    const double dva = __dsqrt_rn(sumsq3(__dsub_rn(x, (double)a.vx), __dsub_rn(y, (double)a.vy), __dsub_rn(z, (double)a.vz)));
-                    W.dvu[j] = (unsigned int)py_round5_units(dva);
+        int nlive = 0, best = -1;
+        unsigned kfail = 0xffffffffu;
+        bool overflow = false, decided = false;
+        for (int pass = 0; pass < 2 && !decided; pass++) {
+            // ---- entries (and shells) of this tier, compacted: act[] = j | shell mask << 6
+            int nact = 0;
+            {
+                unsigned abits = 0, am = 0;          // per lane: entry l8 + 8 i -> bit i ; 2-bit masks packed in `am`
+                for (int i = 0; FG_LANES * i + l8 < ndir; i++) {
+                    const int j = FG_LANES * i + l8;
+                    const unsigned ent = W.dirs[j];
+                    const int n = ent & 0x3ff;
+                    const bool isv = (n == VPREF_ENTRY);
+                    const float4 u = isv ? make_float4(vdx, vdy, vdz, 0.f) : tabB[n];
+                    const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x)), uv = fmaf(u.z, vdz, fmaf(u.y, vdy, u.x * vdx));
+                    const float ra = isv ? 1.f : 0.5f;
+                    const float k0 = sqrtf(fmaxf(fmaf(-2.f * ra, uv, ra * ra * uu) + vdvd, 0.f));
+                    const float k1 = sqrtf(fmaxf(fmaf(-2.f * r1f, uv, r1f * r1f * uu) + vdvd, 0.f));
+                    const unsigned t1 = (k0 <= T1 ? 1u : 0u) | (k1 <= T1 ? 2u : 0u);
+                    const unsigned m = ((ent >> 12) & 3u) & (pass == 0 ? t1 : ~t1);
+                    if (m) { abits |= 1u << i; am |= m << (2 * i); }
                 }
-                local_min = min(local_min, packed);
+                const int cnt = __popc(abits);
+                int pre = cnt;
+#pragma unroll
+                for (int o = 1; o < FG_LANES; o <<= 1) {
+                    const int t = __shfl_up_sync(gmask, pre, o, FG_LANES);
+                    if (l8 >= o) pre += t;
+                }
+                nact = __shfl_sync(gmask, pre, FG_LANES - 1, FG_LANES);
+                int slot = pre - cnt;
+                while (abits) {
+                    const int i = __ffs(abits) - 1;
+                    abits &= abits - 1;
+                    W.act[slot++] = (unsigned char)((FG_LANES * i + l8) | (((am >> (2 * i)) & 3u) << 6));
+                }
             }
-        }
-        if (__any_sync(gmask, overflow)) {
-            if (l8 == 0) push_slow(A, s);
-            continue;
-        }
-        const unsigned head = __reduce_min_sync(gmask, local_min);
-        int best = (int)(head & 1023u);
-        if (SHUNT && nlive > 1) {
-            // scaPolicy.py:119-145 shunted_strategy
-            const long long thr_units = (POLICY == SCAB_POLICY_SCA) ? 3000 : 10000;
-            const double thr = (POLICY == SCAB_POLICY_SCA) ? 3e-2 : 1e-1;
-            double x0, y0, z0;
-            cand64(a, best, x0, y0, z0);
-            const long long d0u = (long long)py_round5_units(
-                __dsqrt_rn(sumsq3(__dsub_rn(x0, (double)a.vx), __dsub_rn(y0, (double)a.vy), __dsub_rn(z0, (double)a.vz))));
-            unsigned fmin = 0xffffffffu;
-            for (int jb = 0; jb < nlive; jb += FG_LANES) {
+            __syncwarp(gmask);
+            const int nlive_before = nlive;
+
+            // ---- B: cone tests per direction (the two shells share p.u and h.u)
+            for (int jb = 0; jb < nact; jb += FG_LANES) {
+                const int ja = jb + l8;
+                bool s0 = false, s1 = false;
+                int n = 0;
+                if (ja < nact) {
+                    const unsigned ae = W.act[ja];
+                    const unsigned ent = W.dirs[ae & 63u];
+                    n = ent & 0x3ff;
+                    s0 = (ae >> 6) & 1; s1 = (ae >> 7) & 1;
+                    const bool isv = (n == VPREF_ENTRY);
+                    const float4 u = isv ? make_float4(vdx, vdy, vdz, 0.f) : tabB[n];
+                    const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x));
+                    const float ra = isv ? 1.f : 0.5f, rb = r1f;
+                    for (int kk = 0; kk < nce && (s0 || s1); kk++) {
+                        const float4 P = W.cp[kk];
+                        const float2 G = W.cg[kk];
+                        const float pa = fmaf(P.z, u.z, fmaf(P.y, u.y, P.x * u.x));
+                        float df0, df1, dt0, dt1;
+                        if (!IS_ORCA) {
+                            const float4 H = W.ch[kk];
+                            const float hb = fmaf(H.z, u.z, fmaf(H.y, u.y, H.x * u.x));
+                            dt0 = fmaf(ra, pa, -P.w); dt1 = fmaf(rb, pa, -P.w);
+                            const float vv0 = fmaf(-2.f * ra, hb, ra * ra * uu) + H.w, vv1 = fmaf(-2.f * rb, hb, rb * rb * uu) + H.w;
+                            df0 = fmaf(dt0, dt0, -vv0 * G.x); df1 = fmaf(dt1, dt1, -vv1 * G.x);
+                        } else {
+                            dt0 = 1.f; dt1 = 1.f;
+                            df0 = -(fmaf(ra, pa, -P.w)); df1 = -(fmaf(rb, pa, -P.w));   // violated iff n.v - n.q < 0
+                        }
+                        bool in0, in1;
+                        if (!IS_ORCA) { in0 = (dt0 > 0.f) && (df0 > 0.f); in1 = (dt1 > 0.f) && (df1 > 0.f); }
+                        else { in0 = !(-df0 >= 0.f); in1 = !(-df1 >= 0.f); }
+                        const bool un0 = s0 && fabsf(df0) <= G.y, un1 = s1 && fabsf(df1) <= G.y;
+                        if (un0 || un1) {
+                            const int k = W.cidx[kk];
+                            for (int sh = 0; sh < 2; sh++) {
+                                if (!(sh ? un1 : un0)) continue;
+                                n_recheck++;
+                                const int c = isv ? 2 * a.N : (sh ? a.N + n : n);
+                                double x, y, z;
+                                cand64(a, c, x, y, z);
+                                bool ins;
+                                if (!IS_ORCA) {
+                                    double dx = __dsub_rn(__dadd_rn(x, a.px), W.dhx[k]), dy = __dsub_rn(__dadd_rn(y, a.py), W.dhy[k]),
+                                           dz = __dsub_rn(__dadd_rn(z, a.pz), W.dhz[k]);
+                                    ins = is_intersect64_fast(__dsub_rn(W.dpx[k], a.px), __dsub_rn(W.dpy[k], a.py), __dsub_rn(W.dpz[k], a.pz),
+                                                              W.dR[k], dx, dy, dz);
+                                } else {
+                                    double val = dot3(__dsub_rn(x, W.dpx[k]), __dsub_rn(y, W.dpy[k]), __dsub_rn(z, W.dpz[k]),
+                                                      W.dhx[k], W.dhy[k], W.dhz[k]);
+                                    ins = !(val >= 0.0);
+                                }
+                                if (sh) in1 = ins; else in0 = ins;
+                            }
+                        }
+                        if (in0) s0 = false;
+                        if (in1) s1 = false;
+                    }
+                }
+                // compact the surviving candidates of this round (generation index c) into the live list
+                const bool isv = (n == VPREF_ENTRY);
+                unsigned m0 = (__ballot_sync(gmask, s0) >> (8 * g)) & 0xffu;
+                if (s0) W.kc[nlive + __popc(m0 & lt8)] = isv ? 2 * a.N : n;
+                nlive += __popc(m0);
+                unsigned m1 = (__ballot_sync(gmask, s1) >> (8 * g)) & 0xffu;
+                if (s1) W.kc[nlive + __popc(m1 & lt8)] = a.N + n;
+                nlive += __popc(m1);
+            }
+            __syncwarp(gmask);
+
+            // ---- C: exact keys of the new live candidates
+            for (int jb = nlive_before; jb < nlive; jb += FG_LANES) {
                 const int j = jb + l8;
                 if (j < nlive) {
+                    const int c = (int)W.kc[j];
+                    double x, y, z;
+                    cand64(a, c, x, y, z);
+                    const double dist = __dsqrt_rn(sumsq3(__dsub_rn(x, a.vdx), __dsub_rn(y, a.vdy), __dsub_rn(z, a.vdz)));
+                    const double ku = py_round5_units(dist);          // l3norm(v, v_pref) in units of 1e-5
+                    if (!(ku < 4194304.0)) overflow = true;
+                    W.kc[j] = ((unsigned)ku << 10) | (unsigned)c;
+                    if (SHUNT) {
+                        const double dva = __dsqrt_rn(sumsq3(__dsub_rn(x, (double)a.vx), __dsub_rn(y, (double)a.vy), __dsub_rn(z, (double)a.vz)));
+                        W.dvu[j] = (unsigned int)py_round5_units(dva);
+                    }
+                }
+            }
+            if (__any_sync(gmask, overflow)) break;
+            __syncwarp(gmask);
+            if (nlive == 0) continue;          // nothing suitable in this tier: look at the next one
+
+            // ---- head of the sorted list, and (shunting) the first element that breaks the prefix
+            unsigned local_min = 0xffffffffu;
+            for (int j = l8; j < nlive; j += FG_LANES) local_min = min(local_min, W.kc[j]);
+            const unsigned head = __reduce_min_sync(gmask, local_min);
+            best = (int)(head & 1023u);
+            if (SHUNT) {
+                const long long thr_units = (POLICY == SCAB_POLICY_SCA) ? 3000 : 10000;
+                const double thr = (POLICY == SCAB_POLICY_SCA) ? 3e-2 : 1e-1;
+                double x0, y0, z0;
+                cand64(a, best, x0, y0, z0);
+                const long long d0u = (long long)py_round5_units(
+                    __dsqrt_rn(sumsq3(__dsub_rn(x0, (double)a.vx), __dsub_rn(y0, (double)a.vy), __dsub_rn(z0, (double)a.vz))));
+                unsigned fmin_ = 0xffffffffu;
+                for (int j = l8; j < nlive; j += FG_LANES) {
                     const long long diu = (long long)W.dvu[j];
                     const long long du = d0u > diu ? d0u - diu : diu - d0u;
                     bool within;
                     if (du < thr_units - 1) within = true;
                     else if (du > thr_units + 1) within = false;
                     else within = fabs(__dsub_rn(__ddiv_rn((double)d0u, 1e5), __ddiv_rn((double)diu, 1e5))) < thr;
-                    if (!within) fmin = min(fmin, W.kc[j]);
+                    if (!within) fmin_ = min(fmin_, W.kc[j]);
                 }
+                kfail = __reduce_min_sync(gmask, fmin_);
+                decided = (pass == 1) || (kfail != 0xffffffffu && (kfail >> 10) < tier_units);
+            } else {
+                decided = (pass == 1) || ((head >> 10) < tier_units);
             }
-            const unsigned kfail = __reduce_min_sync(gmask, fmin);   // first element that breaks the prefix
-            unsigned umin = 0xffffffffu, umax = 0u, kmin = 0xffffffffu, kmax = 0xffffffffu;
-            for (int jb = 0; jb < nlive; jb += FG_LANES) {
-                const int j = jb + l8;
-                if (j < nlive) {
-                    const unsigned kcj = W.kc[j];
-                    if (kcj < kfail) {
-                        double x, y, z;
-                        cand64(a, (int)(kcj & 1023u), x, y, z);
-                        double phi = (y >= 0) ? atan2(y, x) : __dadd_rn(2 * SCAB_PI, atan2(y, x));   // util.py:145-150
-                        const unsigned pu = (unsigned)((long long)trunc(__dmul_rn(phi, 1e5)) + 1000000);
-                        if (pu < umin || (pu == umin && kcj < kmin)) { umin = pu; kmin = kcj; }
-                        if (pu > umax || (pu == umax && kcj < kmax) || kmax == 0xffffffffu) { umax = pu; kmax = kcj; }
-                    }
+        }
+        if (overflow || nlive == 0) {     // keys beyond 22 bits, or "no suitable velocity" (scaPolicy.py:224-238): general kernel
+            if (l8 == 0) push_slow(A, s);
+            continue;
+        }
+        if (SHUNT && nlive > 1) {
+            // scaPolicy.py:136-145: min-phi / max-phi over the prefix {(key, c) < kfail}; ties -> first in sorted order
+            unsigned umin = 0xffffffffu, umax = 0u, kmin_ = 0xffffffffu, kmax_ = 0xffffffffu;
+            for (int j = l8; j < nlive; j += FG_LANES) {
+                const unsigned kcj = W.kc[j];
+                if (kcj < kfail) {
+                    double x, y, z;
+                    cand64(a, (int)(kcj & 1023u), x, y, z);
+                    double phi = (y >= 0) ? atan2(y, x) : __dadd_rn(2 * SCAB_PI, atan2(y, x));   // util.py:145-150
+                    const unsigned pu = (unsigned)((long long)trunc(__dmul_rn(phi, 1e5)) + 1000000);
+                    if (pu < umin || (pu == umin && kcj < kmin_)) { umin = pu; kmin_ = kcj; }
+                    if (pu > umax || (pu == umax && kcj < kmax_) || kmax_ == 0xffffffffu) { umax = pu; kmax_ = kcj; }
                 }
             }
             const unsigned gmin = __reduce_min_sync(gmask, umin), gmax = __reduce_max_sync(gmask, umax);
-            const unsigned cmin = __reduce_min_sync(gmask, umin == gmin ? kmin : 0xffffffffu);
-            const unsigned cmax = __reduce_min_sync(gmask, (umax == gmax && kmax != 0xffffffffu) ? kmax : 0xffffffffu);
+            const unsigned cmin = __reduce_min_sync(gmask, umin == gmin ? kmin_ : 0xffffffffu);
+            const unsigned cmax = __reduce_min_sync(gmask, (umax == gmax && kmax_ != 0xffffffffu) ? kmax_ : 0xffffffffu);
             const double phi_min = __ddiv_rn((double)((long long)gmin - 1000000), 1e5), phi_max = __ddiv_rn((double)((long long)gmax - 1000000), 1e5);
             best = (fabs(__dsub_rn(phi_max, phi_min)) <= SCAB_PI) ? (int)(cmin & 1023u) : (int)(cmax & 1023u);
         }
         if (l8 == 0) {
             double bx, by, bz;
             cand64(a, best, bx, by, bz);
+            // n_suit is only known when every candidate was examined (full_search); otherwise report -1
+            const long long ns = A.full_search ? (long long)nlive : -1ll;
             A.s_vpost[s] = make_double4(trunc5(bx), trunc5(by), trunc5(bz),
-                                        __longlong_as_double((long long)SCAB_TAG_SUITABLE | ((long long)nlive << 8)));
+                                        __longlong_as_double((long long)SCAB_TAG_SUITABLE | (ns << 8)));
         }
         __syncwarp(gmask);
     }

@@ -53,7 +53,10 @@ def compare_step(g, t, out, check_nbrs=True, vel_tol=2e-5, who='', dsq_rtol=0.0)
         dd = np.abs(out['nbr_dsq'][nv] - g['nbr_dsq'][t][nv])
         res['nbr_dsq'] = int((dd > dsq_rtol * np.abs(g['nbr_dsq'][t][nv])).any(axis=1).sum())
     if 'n_suit' in out and (g['tag'][t] & (TAG_SUITABLE | TAG_FALLBACK)).any():
-        res['n_suit'] = int((out['n_suit'][ran] != g['n_suit'][t][ran]).sum())
+        # -1 = not computed (lazy tiers decided before every candidate was examined, SCAB_OPT_FULL_SEARCH off)
+        ns = out['n_suit'][ran]
+        res['n_suit'] = int(((ns != g['n_suit'][t][ran]) & (ns >= 0)).sum())
+        res['n_suit_known'] = int((ns >= 0).sum())
     if str(g['policy']) == 'orca_lp':
         res['plane_fail'] = int((out['plane_fail'][ran] != g['plane_fail'][t][ran]).sum())
         res['n_planes'] = int((out['n_planes'][ran] != g['n_planes'][t][ran]).sum())

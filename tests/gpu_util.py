@@ -4,10 +4,12 @@ import numpy as np
 import golden_util as gu
 
 
-def swarm_from_golden(g, debug=True):
+def swarm_from_golden(g, debug=True, full_search=True):
+    from sca_b200 import capi
     from sca_b200.swarm import Swarm
     n = g['pos'].shape[1]
     sw = Swarm(n, debug=debug)
+    sw.h.set_option(capi.OPT_FULL_SEARCH, 1 if full_search else 0)
     s0 = gu.state_at(g, 0)
     sw.set_state(s0['pos'], g['goal'], heading=s0['heading'], vel=s0['vel'].astype(np.float32), radius=g['radius'],
                  pref_speed=g['pref_speed'], max_run_dist=g['max_run_dist'], initial_pos=g['initial_pos'],

@@ -6,7 +6,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _compare(pos6, goal6, obstacles, policy, steps, lo=None, hi=None):
+def _compare(pos6, goal6, obstacles, policy, steps, lo=None, hi=None, full_search=True):
     import torch
     from oracle import oracle as orc
     from sca_b200 import capi
@@ -16,6 +16,7 @@ def _compare(pos6, goal6, obstacles, policy, steps, lo=None, hi=None):
     orc.set_threads(8)
     w = orc.World(pos6[:, :3], goal6[:, :3], heading=pos6[:, 3:6], obstacles=obstacles, initial_pos=pos6, goal_pos=goal6)
     sw = Swarm(n, debug=True)
+    sw.h.set_option(capi.OPT_FULL_SEARCH, 1 if full_search else 0)
     sw.set_state(pos6[:, :3], goal6[:, :3], heading=pos6[:, 3:6], initial_pos=pos6, goal_pos=goal6,
                  max_run_dist=w.max_run_dist)
     sw.set_obstacles(obstacles)
@@ -37,7 +38,7 @@ def _compare(pos6, goal6, obstacles, policy, steps, lo=None, hi=None):
         tot['nbr'] += int(((out['nbr_ids'][has] != w.nbr_ids[has]).any(1) | (out['nbr_cnt'][has] != w.nbr_cnt[has])).sum())
         tot['tag'] += int((out['tag'][ran] != w.tag[ran]).sum())
         if policy != 'orca_lp':
-            tot['nsuit'] += int((out['n_suit'][ran] != w.n_suit[ran]).sum())
+            tot['nsuit'] += int(((out['n_suit'][ran] != w.n_suit[ran]) & (out['n_suit'][ran] >= 0)).sum())
         else:
             tot['planes'] += int(((out['plane_fail'][ran] != w.plane_fail[ran]) | (out['lp4_proj'][ran] != w.lp4_proj[ran])).sum())
         dv = np.abs(out['action'][:, :4].astype('float64') - w.action[:, :4].astype('float64')).max(1)
@@ -50,14 +51,15 @@ def _compare(pos6, goal6, obstacles, policy, steps, lo=None, hi=None):
     return tot
 
 
+@pytest.mark.parametrize('full_search', [True, False], ids=['full', 'lazy'])
 @pytest.mark.parametrize('policy', ['sca', 'srvo3d', 'rvo3d', 'orca_sampled', 'orca_lp'])
-def test_uniform_swarm_config5_density(policy):
+def test_uniform_swarm_config5_density(policy, full_search):
     from sca_b200 import scenarios
     pos, goal, obs = scenarios.uniform_box_numpy(6000, 3.0 * 1.0e6 / 560.0 ** 3, seed=11)
     rng = np.random.default_rng(5)
     L = pos[:, :3].max()
     obs = np.c_[rng.uniform(0, L, (40, 3)) + [0, 0, 20], rng.uniform(0.5, 2.0, 40)]
-    tot = _compare(pos, goal, obs, policy, steps=5)
+    tot = _compare(pos, goal, obs, policy, steps=5, full_search=full_search)
     print(policy, tot)
     assert tot['agents'] > 20000
     for k in ('nbr', 'tag', 'nsuit', 'vel', 'status', 'planes'):

@@ -15,12 +15,12 @@ pytestmark = pytest.mark.gpu
 NBR_KNN, NBR_REF_COMPAT = 0, 1
 
 
-def _run_fixture(name, max_steps=None):
+def _run_fixture(name, max_steps=None, full_search=True):
     import gpu_util as G
     g = gu.load(name)
     pol = str(g['policy'])
     T = g['pos'].shape[0] if max_steps is None else min(max_steps, g['pos'].shape[0])
-    sw = G.swarm_from_golden(g)
+    sw = G.swarm_from_golden(g, full_search=full_search)
     tot = {}
     for t in range(T):
         s = gu.state_at(g, t)
@@ -60,10 +60,13 @@ EXACT = ('tag', 'coll_query', 'nbr_cnt', 'nbr_ids', 'nbr_dsq', 'plane_fail', 'n_
          'status_bad', 'stepnum_bad', 'active_bad', 'done_bad', 'n_suit')
 
 
+@pytest.mark.parametrize('full_search', [True, False], ids=['full', 'lazy'])
 @pytest.mark.parametrize('name', gu.golden_names())
-def test_golden_fixture(name):
-    tot = _run_fixture(name)
+def test_golden_fixture(name, full_search):
+    tot = _run_fixture(name, full_search=full_search)
     print(name, tot)
+    if full_search and 'n_suit_known' in tot:
+        assert tot['n_suit_known'] == tot['agents'] - tot.get('first', 0) or tot['n_suit_known'] > 0
     for k in EXACT:
         assert tot.get(k, 0) == 0, (name, k, tot)
     # velocities: |dv| <= 2e-5 on every agent-step
