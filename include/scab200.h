@@ -143,6 +143,10 @@ const char *scab_last_error(const scab_handle *h);
 #define SCAB_OPT_FULL_SEARCH 1
 int scab_set_option(scab_handle *h, int option, int value);
 
+/* Largest agent radius in the swarm (0 = unknown).  When known, the status stage reuses the step's neighbour
+ * lists instead of re-scanning the cell list wherever those lists provably hold every possible collision partner. */
+int scab_set_max_radius(scab_handle *h, double r_max);
+
 /* Replace the grid geometry (e.g. after the swarm's bounding box changed). */
 int scab_set_grid(scab_handle *h, const double origin[3], double cell_size, const int32_t dim[3]);
 

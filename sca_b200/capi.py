@@ -19,7 +19,7 @@ TAG_FIRST, TAG_SUITABLE, TAG_FALLBACK, TAG_LP3_OK, TAG_LP4 = 1, 2, 4, 8, 16
 # every symbol include/scab200.h declares (tests/test_capi_symbols.py checks the header against this)
 OPT_FULL_SEARCH = 1
 
-SYMBOLS = ['scab_version', 'scab_default_params', 'scab_set_option', 'scab_create', 'scab_destroy', 'scab_last_error', 'scab_set_grid',
+SYMBOLS = ['scab_version', 'scab_default_params', 'scab_set_option', 'scab_set_max_radius', 'scab_create', 'scab_destroy', 'scab_last_error', 'scab_set_grid',
            'scab_bind_state', 'scab_set_obstacles', 'scab_kdtree_build', 'scab_kdtree_get_perm', 'scab_build_grid',
            'scab_neighbors', 'scab_policy_step', 'scab_status_step', 'scab_step', 'scab_read_counters',
            'scab_reset_counters', 'scab_halo_pack', 'scab_halo_unpack', 'scab_halo_pack_pos', 'scab_halo_unpack_pos',
@@ -72,6 +72,7 @@ def lib():
     L.scab_destroy.argtypes = [vp]
     L.scab_set_grid.argtypes = [vp, C.POINTER(C.c_double), C.c_double, C.POINTER(i32)]
     L.scab_set_option.argtypes = [vp, C.c_int, C.c_int]
+    L.scab_set_max_radius.argtypes = [vp, C.c_double]
     L.scab_bind_state.argtypes = [vp, C.POINTER(StatePtrs), i64]
     L.scab_set_obstacles.argtypes = [vp, vp, i32]
     L.scab_kdtree_build.argtypes = [vp, vp, i64]
@@ -124,6 +125,9 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+    def set_max_radius(self, r_max):
+        self._ck(self._L.scab_set_max_radius(self._h, float(r_max)))
 
     def set_option(self, option, value):
         self._ck(self._L.scab_set_option(self._h, int(option), int(value)))

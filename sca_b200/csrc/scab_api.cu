@@ -69,6 +69,13 @@ extern "C" void scab_default_params(scab_params *p)
 
 extern "C" const char *scab_last_error(const scab_handle *h) { return h ? h->err.c_str() : "null handle"; }
 
+extern "C" int scab_set_max_radius(scab_handle *h, double r_max)
+{
+    if (!h || !(r_max >= 0.0)) return fail(h, SCAB_ERR_INVALID, "scab_set_max_radius: bad argument");
+    h->A.max_radius = r_max;
+    return SCAB_OK;
+}
+
 extern "C" int scab_set_option(scab_handle *h, int option, int value)
 {
     if (!h) return SCAB_ERR_INVALID;
@@ -374,6 +381,7 @@ extern "C" int scab_neighbors(scab_handle *h, int mode, void *stream)
     if (mode == SCAB_NBR_REF_COMPAT && !h->kd_valid && h->A.n > 0)
         return fail(h, SCAB_ERR_INVALID, "scab_neighbors: REF_COMPAT needs scab_kdtree_build first");
     CK(launch_neighbors(h->A, mode, (cudaStream_t)stream));
+    h->A.last_nbr_mode = mode;
     return SCAB_OK;
 }
 

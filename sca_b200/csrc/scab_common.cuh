@@ -54,6 +54,8 @@ struct StepArgs {
     int32_t *s_qcoll;   // [n] collision flag raised by the neighbour query (agent.py:83-85)
     int32_t *slow_list; // [n] agents the 8-lane fast selection kernel hands to the general kernel
     int32_t *slow_count;
+    double max_radius;  // largest agent radius (0: unknown -> the status stage always scans the cell list)
+    int last_nbr_mode;  // mode of the neighbour lists currently in s_nbr
     int full_search;    // SCAB_OPT_FULL_SEARCH: examine every candidate (exact n_suit) instead of the lazy tiers
     // obstacles (sorted by obstacle cell) + reference kd-trees
     const double4 *o_posr;

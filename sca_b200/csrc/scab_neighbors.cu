@@ -69,6 +69,64 @@ __device__ __forceinline__ void write_lists(const StepArgs &A, int s, int id, in
     }
 }
 
+// Same list without the tie-break id in registers: ties on the decimal-rounded distance are rare, so the
+// id (obstacle id, or m + global agent id) is looked up only when two distances compare equal.
+struct TopK2 {
+    double d[KNBR];
+    int s[KNBR];  // payload: sorted index (agents) or n + sorted obstacle index
+    int cnt;
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int k = 0; k < KNBR; k++) { d[k] = DBL_MAX; s[k] = -1; }
+        cnt = 0;
+    }
+    static __device__ __forceinline__ int uid(const StepArgs &A, int sx)
+    {
+        return sx < 0 ? INT_MAX : (sx >= A.n ? A.o_id[sx - A.n] : A.m + A.s_gid[sx]);
+    }
+    static __device__ __forceinline__ bool less(const StepArgs &A, double d1, int s1, double d2, int s2)
+    {
+        if (d1 != d2) return d1 < d2;
+        return uid(A, s1) < uid(A, s2);
+    }
+    __device__ __forceinline__ void insert(const StepArgs &A, double nd, int ns)
+    {
+        if (!less(A, nd, ns, d[KNBR - 1], s[KNBR - 1])) return;
+#pragma unroll
+        for (int k = KNBR - 1; k >= 1; k--) {
+            const bool lt_prev = less(A, nd, ns, d[k - 1], s[k - 1]);
+            const bool lt_here = less(A, nd, ns, d[k], s[k]);
+            if (lt_prev) { d[k] = d[k - 1]; s[k] = s[k - 1]; }
+            else if (lt_here) { d[k] = nd; s[k] = ns; }
+        }
+        if (less(A, nd, ns, d[0], s[0])) { d[0] = nd; s[0] = ns; }
+        cnt = min(cnt + 1, KNBR);
+    }
+};
+
+__device__ __forceinline__ void write_lists2(const StepArgs &A, int s, int id, const TopK2 &L, int qcoll)
+{
+    A.s_nbr_cnt[s] = L.cnt;
+    A.s_qcoll[s] = qcoll;
+    int4 *dst = reinterpret_cast<int4 *>(A.s_nbr + (size_t)s * KNBR);
+#pragma unroll
+    for (int q = 0; q < KNBR / 4; q++) dst[q] = make_int4(L.s[4 * q], L.s[4 * q + 1], L.s[4 * q + 2], L.s[4 * q + 3]);
+    if (A.st.nbr_cnt) A.st.nbr_cnt[id] = L.cnt;
+    if (A.st.nbr_ids) {
+#pragma unroll
+        for (int k = 0; k < KNBR; k++) {
+            int v = -1;
+            if (k < L.cnt) v = (L.s[k] >= A.n) ? A.obst_base + A.o_id[L.s[k] - A.n] : A.s_gid[L.s[k]];
+            A.st.nbr_ids[(size_t)id * KNBR + k] = v;
+        }
+    }
+    if (A.st.nbr_dsq) {
+#pragma unroll
+        for (int k = 0; k < KNBR; k++) A.st.nbr_dsq[(size_t)id * KNBR + k] = (k < L.cnt) ? L.d[k] : 0.0;
+    }
+}
+
 // ------------------------------------------------------------------ KNN over the cell list
 #define KNN_CAP 48
 __global__ void __launch_bounds__(128) k_neighbors_knn(StepArgs A)
@@ -85,7 +143,7 @@ __global__ void __launch_bounds__(128) k_neighbors_knn(StepArgs A)
         return;
     }
     const double4 me = A.s_posr[s];
-    TopK L;
+    TopK2 L;
     L.clear();
     bool coll = false;
     const double rangeSq = A.nbr_dist_sq;
@@ -113,7 +171,7 @@ __global__ void __launch_bounds__(128) k_neighbors_knn(StepArgs A)
                     double rr = __dadd_rn(me.w, o.w);
                     bool is_c = dsq1 < __dmul_rn(rr, rr) && dsq < rangeSq;
                     if (is_c && !coll) { coll = true; L.clear(); }
-                    if (coll ? is_c : (dsq < rangeSq)) L.insert(dsq, A.o_id[j], A.n + j);
+                    if (coll ? is_c : (dsq < rangeSq)) L.insert(A, dsq, A.n + j);
                 }
             }
         }
@@ -134,7 +192,7 @@ __global__ void __launch_bounds__(128) k_neighbors_knn(StepArgs A)
                 const bool is_c = dsq < __dmul_rn(rr, rr);
                 if (is_c && !coll) { coll = true; L.clear(); }
                 if (coll && !is_c) continue;
-                L.insert(dsq, A.m + A.s_gid[j], j);
+                L.insert(A, dsq, j);
             }
             nbuf = 0;
         };
@@ -150,19 +208,25 @@ __global__ void __launch_bounds__(128) k_neighbors_knn(StepArgs A)
                 int row = (z * A.g.ny + y) * A.g.nx;
                 int beg = A.cell_start[row + max(cx - 1, 0)];
                 int end = A.cell_start[row + min(cx + 1, A.g.nx - 1) + 1];
-                for (int j = beg; j < end; j++) {
-                    const double4 o = A.s_posr[j];
-                    const double ex = me.x - o.x, ey = me.y - o.y, ez = me.z - o.z;
-                    const double ss = ex * ex + ey * ey + ez * ez;
-                    if (ss > lim || j == s) continue;
-                    if (nbuf == KNN_CAP) flush();
-                    buf[nbuf++][threadIdx.x] = j;
+                for (int j0 = beg; j0 < end; j0 += 4) {
+                    double4 o[4];          // four independent loads in flight per thread
+#pragma unroll
+                    for (int q = 0; q < 4; q++) o[q] = A.s_posr[min(j0 + q, end - 1)];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int j = j0 + q;
+                        const double ex = me.x - o[q].x, ey = me.y - o[q].y, ez = me.z - o[q].z;
+                        const double ss = ex * ex + ey * ey + ez * ez;
+                        if (j >= end || ss > lim || j == s) continue;
+                        if (nbuf == KNN_CAP) flush();
+                        buf[nbuf++][threadIdx.x] = j;
+                    }
                 }
             }
         }
         flush();
     }
-    write_lists(A, s, id, L.cnt, L.d, L.u, L.s, coll ? 1 : 0);
+    write_lists2(A, s, id, L, coll ? 1 : 0);
 }
 
 // ------------------------------------------------------------------ REF_COMPAT: literal replay

@@ -49,7 +49,50 @@ __global__ void __launch_bounds__(128) k_status(StepArgs A)
             }
         }
         // agents (mampenv.py:68-75) through the pair rule
-        {
+        auto test_pair = [&](int j) {
+            const double4 oo = A.s_posr[j];
+            // cheap reject on the old positions: both agents move < 1 m per step
+            const double ex = oo.x - oldp.x, ey = oo.y - oldp.y, ez = oo.z - oldp.z;
+            const double R = __dadd_rn(oldp.w, oo.w);
+            const double lim = R + 2.5;
+            if (ex * ex + ey * ey + ez * ez > lim * lim) return;
+            const int jrow = A.s_id[j];
+            const double4 on = make_double4(A.st.pos[3 * jrow], A.st.pos[3 * jrow + 1], A.st.pos[3 * jrow + 2], 0.0);
+            const int jid = A.s_gid[j];
+            bool hit;
+            if (gid < jid)
+                hit = l3norm_d(newp.x, newp.y, newp.z, oo.x, oo.y, oo.z) <= R ||
+                      l3norm_d(newp.x, newp.y, newp.z, on.x, on.y, on.z) <= R;
+            else
+                hit = l3norm_d(on.x, on.y, on.z, oldp.x, oldp.y, oldp.z) <= R ||
+                      l3norm_d(on.x, on.y, on.z, newp.x, newp.y, newp.z) <= R;
+            coll_agent |= hit;
+        };
+        // Shortcut: this step's neighbour list already holds EVERY agent within reach when it is not
+        // saturated, or (true-KNN lists) when its farthest entry is an agent beyond r_i + r_max + 2.6 m.
+        bool from_list = false;
+        int ncnt = -1;
+        if (A.max_radius > 0.0) {
+            ncnt = A.s_nbr_cnt[s];
+            if (ncnt >= 0 && !A.s_qcoll[s]) {
+                if (ncnt < KNBR) from_list = true;
+                else if (A.last_nbr_mode == SCAB_NBR_KNN) {
+                    const int e = A.s_nbr[(size_t)s * KNBR + KNBR - 1];
+                    if (e < A.n) {
+                        const double4 oo = A.s_posr[e];
+                        const double ex = oo.x - oldp.x, ey = oo.y - oldp.y, ez = oo.z - oldp.z;
+                        const double lim = oldp.w + A.max_radius + 2.6;
+                        from_list = ex * ex + ey * ey + ez * ez > lim * lim;
+                    }
+                }
+            }
+        }
+        if (from_list) {
+            for (int k = 0; k < ncnt; k++) {
+                const int e = A.s_nbr[(size_t)s * KNBR + k];
+                if (e < A.n) test_pair(e);
+            }
+        } else {
             int cx, cy, cz;
             cell_of(A.g, oldp.x, oldp.y, oldp.z, cx, cy, cz);
             for (int dz = -1; dz <= 1; dz++) {
@@ -63,23 +106,7 @@ __global__ void __launch_bounds__(128) k_status(StepArgs A)
                     int end = A.cell_start[row + min(cx + 1, A.g.nx - 1) + 1];
                     for (int j = beg; j < end; j++) {
                         if (j == s) continue;
-                        const double4 oo = A.s_posr[j];
-                        // cheap reject on the old positions: both agents move < 1 m per step
-                        const double ex = oo.x - oldp.x, ey = oo.y - oldp.y, ez = oo.z - oldp.z;
-                        const double R = __dadd_rn(oldp.w, oo.w);
-                        const double lim = R + 2.5;
-                        if (ex * ex + ey * ey + ez * ez > lim * lim) continue;
-                        const int jrow = A.s_id[j];
-                        const double4 on = make_double4(A.st.pos[3 * jrow], A.st.pos[3 * jrow + 1], A.st.pos[3 * jrow + 2], 0.0);
-                        const int jid = A.s_gid[j];
-                        bool hit;
-                        if (gid < jid)
-                            hit = l3norm_d(newp.x, newp.y, newp.z, oo.x, oo.y, oo.z) <= R ||
-                                  l3norm_d(newp.x, newp.y, newp.z, on.x, on.y, on.z) <= R;
-                        else
-                            hit = l3norm_d(on.x, on.y, on.z, oldp.x, oldp.y, oldp.z) <= R ||
-                                  l3norm_d(on.x, on.y, on.z, newp.x, newp.y, newp.z) <= R;
-                        coll_agent |= hit;
+                        test_pair(j);
                     }
                 }
             }

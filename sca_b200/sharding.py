@@ -142,8 +142,11 @@ class ShardedSwarm:
         capacity = int(self.n_own * 1.25) + 2 * self.cap + 4096
         self.own_cap = capacity - 2 * self.cap
         sw = Swarm(self.n_own, device=device, debug=debug, capacity=capacity)
-        sw.set_state(pos6[mine, :3], goal6[mine, :3], heading=pos6[mine, 3:6], radius=radius, pref_speed=pref_speed,
+        rad_g = np.broadcast_to(np.asarray(radius, 'float64'), (n_global,))
+        pref_g = np.broadcast_to(np.asarray(pref_speed, 'float64'), (n_global,))
+        sw.set_state(pos6[mine, :3], goal6[mine, :3], heading=pos6[mine, 3:6], radius=rad_g[mine], pref_speed=pref_g[mine],
                      initial_pos=pos6[mine], goal_pos=goal6[mine])
+        sw.h.set_max_radius(float(rad_g.max()))      # ghosts included: the bound must hold across shards
         sw.set_global_ids(mine.astype(np.int32), n_global)
         # two extra z layers: an empty buffer layer and the layer where unused ghost slots are parked
         lo, hi = np.asarray(lo, 'float64'), np.asarray(hi, 'float64')

@@ -111,6 +111,7 @@ class Swarm:
             'step_num': np.zeros(n, np.int32) if step_num is None else np.ascontiguousarray(step_num, np.int32),
             'max_run_dist': f8(max_run_dist, (n,)),
         }
+        self.h.set_max_radius(float(np.max(host['radius'])) if n else 0.0)
         self._zaxis = torch.zeros(self.capacity, dtype=_I4, device=self.device)
         self._zaxis[:n].copy_(torch.as_tensor(zaxis))
         for k, a in host.items():
