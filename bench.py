@@ -243,7 +243,12 @@ def run_ours(args):
             out['cpu_baseline'] = cpu
         print(json.dumps(out))
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # captured graphs hold NCCL work: release them, then leave without the (blocking) group teardown
+        sw.close()
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def cpu_baseline(n_agents, threads, policy, budget_s=15.0, steps=None):

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(256) k_halo_pack(StepArgs A, int n_own, int ax
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_own) return;
+    if (A.st.status[i] & SCAB_ST_GHOST) return;   // unused owned slots are kept as parked ghosts (static row count)
     const double c = A.st.pos[3 * i + axis];
     const bool to_lo = c < lo_face + width, to_hi = c >= hi_face - width;
     if (!to_lo && !to_hi) return;

@@ -668,9 +668,12 @@ static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
 cudaError_t launch_policy_sampled(const StepArgs &A, int policy, cudaStream_t s)
 {
     if (A.n <= 0) return cudaSuccess;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
     const int nb = (A.n + 255) / 256;
     const int grid = sms;   // launch_select multiplies by the resident CTAs per SM
     cudaError_t e;

@@ -116,22 +116,29 @@ def exchange_variable(rows_lo, rows_hi, rank, world, dist=None):
 
 
 class ShardedSwarm:
-    """The rank-local part of a swarm sharded over `world` GPUs.  Same step()/counters() surface as Swarm."""
+    """The rank-local part of a swarm sharded over `world` GPUs.  Same step()/counters() surface as Swarm.
+
+    Row layout (STATIC row count, so one captured CUDA graph replays every step):
+        [0, own_cap)                 owned slots: n_own live agents, then parked ghosts
+        [own_cap, own_cap + 2 cap)   halo ghosts received from the lower / upper slab neighbour
+    Parked ghosts sit in a reserved, otherwise empty layer of the uniform grid: no kernel ever sees them as
+    neighbours and every per-agent stage skips SCAB_ST_GHOST rows.
+    """
 
     def __init__(self, pos6, goal6, rank, world, device, lo, hi, radius=0.5, pref_speed=1.0, migrate_every=16,
-                 halo_cap=None, debug=False):
+                 halo_cap=None, debug=False, use_graph=True):
         from .swarm import Swarm
         pos6, goal6 = np.asarray(pos6, 'float64'), np.asarray(goal6, 'float64')
         n_global = len(pos6)
         self.rank, self.world, self.n_global = rank, world, n_global
         self.plan = SlabPlan(pos6[:, 0], world, migrate_every=migrate_every)
-        mine = np.nonzero(self.plan.owner(pos6[:, 0]) == rank)[0]
+        own_all = self.plan.owner(pos6[:, 0])
+        mine = np.nonzero(own_all == rank)[0]
         self.n_own = len(mine)
         # halo capacity per face: agents within `width` of a face, with head room
         # (the SAME value on every rank: the face buffers are exchanged as fixed-size messages)
         if halo_cap is None:
             near = 0
-            own_all = self.plan.owner(pos6[:, 0])
             for r in range(world):
                 lo_f, hi_f = self.plan.faces(r)
                 x = pos6[own_all == r, 0]
@@ -139,19 +146,20 @@ class ShardedSwarm:
                            int((x >= hi_f - self.plan.width).sum()) if r < world - 1 else 0)
             halo_cap = int(near * 1.5) + 1024
         self.cap = int(halo_cap) if world > 1 else 0
-        capacity = int(self.n_own * 1.25) + 2 * self.cap + 4096
-        self.own_cap = capacity - 2 * self.cap
-        sw = Swarm(self.n_own, device=device, debug=debug, capacity=capacity)
+        self.own_cap = int(self.n_own * 1.25) + 4096
+        self.n_rows = self.own_cap + 2 * self.cap
+        sw = Swarm(self.n_own, device=device, debug=debug, capacity=self.n_rows)
         rad_g = np.broadcast_to(np.asarray(radius, 'float64'), (n_global,))
         pref_g = np.broadcast_to(np.asarray(pref_speed, 'float64'), (n_global,))
         sw.set_state(pos6[mine, :3], goal6[mine, :3], heading=pos6[mine, 3:6], radius=rad_g[mine], pref_speed=pref_g[mine],
                      initial_pos=pos6[mine], goal_pos=goal6[mine])
         sw.h.set_max_radius(float(rad_g.max()))      # ghosts included: the bound must hold across shards
         sw.set_global_ids(mine.astype(np.int32), n_global)
-        # two extra z layers: an empty buffer layer and the layer where unused ghost slots are parked
+        # two extra z layers: an empty buffer layer and the layer where unused slots are parked
         lo, hi = np.asarray(lo, 'float64'), np.asarray(hi, 'float64')
         cell = float(max(sw.params.cell_size, sw.params.neighbor_dist))
         dim = np.maximum(1, np.ceil((hi - lo) / cell).astype(np.int64))
+        self._park_geom = (lo.copy(), cell, dim.copy())
         self.park = (float(lo[0] + 0.5 * cell), float(lo[1] + 0.5 * cell), float(lo[2] + (dim[2] + 1.5) * cell))
         dim[2] += 2
         sw.h.set_grid(lo, cell, dim)
@@ -164,24 +172,42 @@ class ShardedSwarm:
         self.precv = torch.zeros((2 * self.cap, 3), **f8)
         self.steps = 0
         self._fill_parked()
+        self._park_rows(self.n_own, self.n_rows)
         # a dedicated (non-default) stream: the legacy default stream would implicitly serialise the step
         # against NCCL's own stream
         self.stream = torch.cuda.Stream(device=dev)
         self.debug_phase = None
-        sw._bind(self.n_own + 2 * self.cap)
+        self.use_graph = bool(use_graph)
+        self._graphs = {}
+        sw._bind(self.n_rows)
         torch.cuda.synchronize(dev)
 
     # ------------------------------------------------------------------
+    def _park_rows(self, r0, r1):
+        """Turn state rows [r0, r1) into parked ghosts, spread over the cells of the parking layer."""
+        if r1 <= r0:
+            return
+        t = self.sw.t
+        lo, cell, dim = self._park_geom
+        dev = t['pos'].device
+        i = torch.arange(r0, r1, device=dev)
+        t['pos'][r0:r1, 0] = float(lo[0]) + ((i * 7919) % int(dim[0])).to(torch.float64) * cell + 0.5 * cell
+        t['pos'][r0:r1, 1] = float(lo[1]) + ((i * 104729) % int(dim[1])).to(torch.float64) * cell + 0.5 * cell
+        t['pos'][r0:r1, 2] = self.park[2]
+        t['vel'][r0:r1] = 0
+        t['radius'][r0:r1] = 0
+        t['status'][r0:r1] = capi.ST_GHOST | capi.ST_AT_GOAL | capi.ST_RUN_DONE
+        t['gid'][r0:r1] = 0x7fffffff
+
     def _fill_parked(self):
-        """Edge ranks never receive from one side: those ghost slots stay parked."""
+        """Edge ranks never receive from one side: those receive slots stay parked."""
         if self.cap == 0:
             return
         self.recv.zero_()
         self.recv[:, 0], self.recv[:, 1], self.recv[:, 2] = self.park
-        dummy_status_gid = np.array([capi.ST_GHOST | capi.ST_AT_GOAL | capi.ST_RUN_DONE], np.int32)
-        # columns 4-5 hold (vx, vy) and (vz, status) as raw bytes; 6 holds (gid, pad)
+        # ints 8-10 = vx vy vz, 11 = status, 12 = gid (64-byte halo record)
         raw = self.recv.view(torch.int32).view(2 * self.cap, 2 * REC_DOUBLES)
-        raw[:, 11] = int(dummy_status_gid[0])
+        raw[:, 11] = capi.ST_GHOST | capi.ST_AT_GOAL | capi.ST_RUN_DONE
         raw[:, 12] = 0x7fffffff
         self.precv[:, 0], self.precv[:, 1], self.precv[:, 2] = self.park
 
@@ -190,7 +216,7 @@ class ShardedSwarm:
         return self.sw.t
 
     def _stream(self):
-        return self.stream.cuda_stream
+        return torch.cuda.current_stream().cuda_stream
 
     def _mark(self, what):
         if self.debug_phase is not None:
@@ -201,56 +227,86 @@ class ShardedSwarm:
         lo_f, hi_f = self.plan.faces(self.rank)
         lo_face = lo_f if self.rank > 0 else -1e300            # no neighbour on that side: select nothing
         hi_face = hi_f if self.rank < self.world - 1 else 1e300
-        sw.h.halo_pack(self.n_own, self.plan.axis, lo_face, hi_face, self.plan.width, self.park,
+        sw.h.halo_pack(self.own_cap, self.plan.axis, lo_face, hi_face, self.plan.width, self.park,
                        self.send_lo.data_ptr(), self.send_hi.data_ptr(), cap, self._stream())
         exchange_with_neighbours(self.send_lo, self.send_hi, self.recv[:cap], self.recv[cap:], self.rank, self.world)
-        sw.h.halo_unpack(self.recv.data_ptr(), 2 * cap, self.n_own, self._stream())
+        sw.h.halo_unpack(self.recv.data_ptr(), 2 * cap, self.own_cap, self._stream())
 
     def _ghost_exchange_post(self):
         sw, cap = self.sw, self.cap
         sw.h.halo_pack_pos(self.psend_lo.data_ptr(), self.psend_hi.data_ptr(), cap, self.park, self._stream())
         exchange_with_neighbours(self.psend_lo, self.psend_hi, self.precv[:cap], self.precv[cap:], self.rank, self.world)
-        sw.h.halo_unpack_pos(self.precv.data_ptr(), 2 * cap, self.n_own, self._stream())
+        sw.h.halo_unpack_pos(self.precv.data_ptr(), 2 * cap, self.own_cap, self._stream())
+
+    def _step_body(self, pol, nbr_mode):
+        """Everything between two migrations: static shapes, static pointers -> capturable in a CUDA graph."""
+        sw = self.sw
+        if self.world > 1:
+            self._mark('pre-exchange')
+            self._ghost_exchange_pre()
+        s = self._stream()
+        self._mark('grid')
+        sw.h.build_grid(s)
+        self._mark('neighbors')
+        sw.h.neighbors(nbr_mode, s)
+        self._mark('policy')
+        sw.h.policy_step(pol, s)
+        if self.world > 1:
+            self._mark('post-exchange')
+            self._ghost_exchange_post()
+        self._mark('status')
+        sw.h.status_step(s)
 
     def step(self, policy, nbr_mode=capi.NBR_KNN):
-        sw = self.sw
         pol = capi.POLICIES[policy] if isinstance(policy, str) else int(policy)
         with torch.cuda.stream(self.stream):
-            if self.world > 1:
-                if self.steps and self.steps % self.plan.migrate_every == 0:
-                    self._mark('migrate')
-                    self.migrate()
-                self._mark('pre-exchange')
-                self._ghost_exchange_pre()
-            s = self._stream()
-            self._mark('grid')
-            sw.h.build_grid(s)
-            self._mark('neighbors')
-            sw.h.neighbors(nbr_mode, s)
-            self._mark('policy')
-            sw.h.policy_step(pol, s)
-            if self.world > 1:
-                self._mark('post-exchange')
-                self._ghost_exchange_post()
-            self._mark('status')
-            sw.h.status_step(s)
+            if self.world > 1 and self.steps and self.steps % self.plan.migrate_every == 0:
+                self._mark('migrate')
+                self.migrate()
+            key = (pol, nbr_mode)
+            # the first steps run eagerly (NCCL creates its channels lazily on first use), then one graph replays
+            if self.use_graph and self.debug_phase is None and self.steps >= 2:
+                g = self._graphs.get(key)
+                if g is None:
+                    g = self._capture(pol, nbr_mode)
+                if g is not False:
+                    g.replay()
+                else:
+                    self._step_body(pol, nbr_mode)
+            else:
+                self._step_body(pol, nbr_mode)
         self.steps += 1
 
+    def _capture(self, pol, nbr_mode):
+        """Capture one step (kernels + both NCCL exchanges) into a CUDA graph; fall back to eager launches
+        if the capture is refused."""
+        try:
+            g = torch.cuda.CUDAGraph()
+            self.stream.synchronize()
+            with torch.cuda.graph(g, stream=self.stream):
+                self._step_body(pol, nbr_mode)
+            self._graphs[(pol, nbr_mode)] = g
+            return g
+        except Exception as e:   # pragma: no cover - depends on the NCCL / driver combination
+            import warnings
+            warnings.warn('CUDA graph capture of the sharded step failed (%s); using eager launches' % (e,))
+            self._graphs[(pol, nbr_mode)] = False
+            return False
+
     def warm_up(self, policy, nbr_mode=capi.NBR_KNN):
-        """Load every kernel of the step before any NCCL traffic (lazy module loading while a peer is
-        spinning inside a collective is a classic deadlock), on a throw-away copy of nothing: the stages
-        run over zero owned agents... no -- they run over the real state but all writes are reverted."""
+        """Load every kernel of the step (and every torch op migrate() uses) before any NCCL traffic: lazy
+        module loading while a peer spins inside a collective is a classic deadlock.  State is restored."""
         sw = self.sw
         pol = capi.POLICIES[policy] if isinstance(policy, str) else int(policy)
         keep = {k: v.clone() for k, v in sw.t.items()}
         with torch.cuda.stream(self.stream):
             s = self._stream()
             if self.world > 1:
-                sw.h.halo_pack(self.n_own, self.plan.axis, -1e300, 1e300, self.plan.width, self.park,
+                sw.h.halo_pack(self.own_cap, self.plan.axis, -1e300, 1e300, self.plan.width, self.park,
                                self.send_lo.data_ptr(), self.send_hi.data_ptr(), self.cap, s)
-                sw.h.halo_unpack(self.recv.data_ptr(), 2 * self.cap, self.n_own, s)
+                sw.h.halo_unpack(self.recv.data_ptr(), 2 * self.cap, self.own_cap, s)
                 sw.h.halo_pack_pos(self.psend_lo.data_ptr(), self.psend_hi.data_ptr(), self.cap, self.park, s)
-                sw.h.halo_unpack_pos(self.precv.data_ptr(), 2 * self.cap, self.n_own, s)
+                sw.h.halo_unpack_pos(self.precv.data_ptr(), 2 * self.cap, self.own_cap, s)
             sw.h.build_grid(s)
             sw.h.neighbors(nbr_mode, s)
             sw.h.policy_step(pol, s)
@@ -259,7 +315,6 @@ class ShardedSwarm:
             for k, v in keep.items():
                 sw.t[k].copy_(v)
             sw.h.reset_counters(s)
-            # ... and every torch op migrate() uses (their kernels are loaded lazily too)
             t = sw.t
             x = t['pos'][:self.n_own, self.plan.axis]
             m = (x < 0.0) | (x >= 1e300) | torch.zeros_like(x, dtype=torch.bool)
@@ -270,6 +325,7 @@ class ShardedSwarm:
             _ = (t['status'][:8] & capi.ST_ZAXIS).sum().item()
             c = torch.tensor([1, 2], dtype=torch.int64, device=x.device)
             _ = int(c[0:1].clone().item())
+            self._fill_parked()
             self.stream.synchronize()
 
     # ------------------------------------------------------------------ migration
@@ -281,29 +337,33 @@ class ShardedSwarm:
         x = t['pos'][:n, self.plan.axis]
         go_lo = (x < lo_f) if self.rank > 0 else torch.zeros_like(x, dtype=torch.bool)
         go_hi = (x >= hi_f) if self.rank < self.world - 1 else torch.zeros_like(x, dtype=torch.bool)
-        self._mark('migrate: counts')
         c_lo, c_hi = sw.h.halo_counts(self._stream())
-        self._mark('migrate: counts=%d,%d' % (c_lo, c_hi))
         if max(c_lo, c_hi) > self.cap:
             raise capi.ScabError('halo buffers overflowed (%d, %d > cap %d): raise halo_cap' % (c_lo, c_hi, self.cap))
         idx_lo, idx_hi = torch.nonzero(go_lo)[:, 0], torch.nonzero(go_hi)[:, 0]
         rows_lo, rows_hi = pack_rows(t, idx_lo), pack_rows(t, idx_hi)
-        self._mark('migrate: exchange %d %d' % (rows_lo.shape[0], rows_hi.shape[0]))
         from_lo, from_hi = exchange_variable(rows_lo, rows_hi, self.rank, self.world)
-        self._mark('migrate: received %d %d' % (from_lo.shape[0], from_hi.shape[0]))
         keep = torch.nonzero(~(go_lo | go_hi))[:, 0]
         kept = pack_rows(t, keep)
         rows = torch.cat([kept, from_lo, from_hi])
         if rows.shape[0] > self.own_cap:
             raise capi.ScabError('shard grew beyond its capacity (%d > %d)' % (rows.shape[0], self.own_cap))
         unpack_rows(t, rows, 0)
-        self.n_own = rows.shape[0]
+        n_new = rows.shape[0]
+        self._park_rows(n_new, max(n, n_new))      # slots vacated at the tail become parked ghosts
+        self.n_own = n_new
         sw._zaxis[:self.n_own] = t['status'][:self.n_own] & capi.ST_ZAXIS
-        sw._bind(self.n_own + 2 * self.cap)
+
+    def close(self):
+        """Drop the captured graphs (they hold NCCL work; destroy_process_group would wait on them forever)."""
+        self.stream.synchronize()
+        self._graphs.clear()
+        torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ results
     def counters(self):
-        return self.sw.h.read_counters(self._stream())
+        with torch.cuda.stream(self.stream):
+            return self.sw.h.read_counters(self._stream())
 
     def gather_state(self, keys=('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')):
         """Owned rows keyed by global id (host)."""

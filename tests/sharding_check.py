@@ -80,8 +80,12 @@ def main():
                                              int((full['status'] & 2).astype(bool).sum()), 'OK' if ok else 'FAIL'), flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
-    dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) else 1)
+    rc = 0 if int(flag.item()) else 1
+    sh.close()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(rc)      # skip the blocking process-group teardown
 
 
 if __name__ == '__main__':
