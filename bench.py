@@ -128,6 +128,15 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         sw.step(policy, capi.NBR_KNN)
     barrier()
+    if os.environ.get('SCAB_BENCH_TRACE'):        # debug: per-step wall times (synchronised), not part of the measurement
+        tr = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            sw.step(policy, capi.NBR_KNN)
+            tstream.synchronize()
+            tr.append(round((time.perf_counter() - t0) * 1e3, 2))
+        if rank == 0:
+            sys.stderr.write('TRACE ms/step: %s\n' % tr)
     c0 = sw.counters()['n_active_total']
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -194,6 +194,18 @@ int scab_halo_unpack(scab_handle *h, const void *recs, int32_t count, int64_t ro
 /* After the policy stage: the new positions ([cap,3] f64 per face) of the agents packed by the last scab_halo_pack. */
 int scab_halo_pack_pos(scab_handle *h, double *out_lo, double *out_hi, int32_t cap, const double park[3], void *stream);
 int scab_halo_unpack_pos(scab_handle *h, const double *pos, int32_t count, int64_t row0, void *stream);
+/* Device-side migration between slabs (asynchronous, fixed size, no host round trip).
+ * scab_migrate_pack: every owned agent (rows [0, own_cap), ghosts skipped) whose coordinate left
+ * [lo_face, hi_face) is written as a 128-byte full-state row into out_lo / out_hi (1 header row carrying the
+ * count + `cap` rows each), its state row becomes a parked ghost and is pushed on the caller-owned device free
+ * list (`free_list` int32[own_cap], `free_count` int32).  park_geom = {x0, y0, cell, z} and nx, ny spread the
+ * parked rows over the reserved grid layer.  scab_migrate_unpack pops one free row per received agent.
+ * `cnt` (device int32[4]): [0],[1] packed per face, [2] agents that did not fit (stay put), [3] arrivals lost. */
+int scab_migrate_pack(scab_handle *h, int64_t own_cap, int axis, double lo_face, double hi_face, const double park_geom[4],
+                      int32_t nx, int32_t ny, void *out_lo, void *out_hi, int32_t cap, int32_t *free_list, int32_t *free_count,
+                      int32_t *cnt, void *stream);
+int scab_migrate_unpack(scab_handle *h, const void *in_lo, const void *in_hi, int32_t cap, int use_lo, int use_hi,
+                        int32_t *free_list, int32_t *free_count, int32_t *cnt, void *stream);
 /* Blocking: how many agents the last scab_halo_pack selected per face (> cap means the buffers overflowed). */
 int scab_halo_counts(scab_handle *h, int32_t out_host[2], void *stream);
 

@@ -23,7 +23,7 @@ SYMBOLS = ['scab_version', 'scab_default_params', 'scab_set_option', 'scab_set_m
            'scab_bind_state', 'scab_set_obstacles', 'scab_kdtree_build', 'scab_kdtree_get_perm', 'scab_build_grid',
            'scab_neighbors', 'scab_policy_step', 'scab_status_step', 'scab_step', 'scab_read_counters',
            'scab_reset_counters', 'scab_halo_pack', 'scab_halo_unpack', 'scab_halo_pack_pos', 'scab_halo_unpack_pos',
-           'scab_halo_counts']
+           'scab_halo_counts', 'scab_migrate_pack', 'scab_migrate_unpack']
 
 
 class ScabError(RuntimeError):
@@ -90,6 +90,8 @@ def lib():
     L.scab_halo_pack_pos.argtypes = [vp, vp, vp, i32, d3, vp]
     L.scab_halo_unpack_pos.argtypes = [vp, vp, i32, i64, vp]
     L.scab_halo_counts.argtypes = [vp, C.POINTER(i32), vp]
+    L.scab_migrate_pack.argtypes = [vp, i64, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), i32, i32, vp, vp, i32, vp, vp, vp, vp]
+    L.scab_migrate_unpack.argtypes = [vp, vp, vp, i32, C.c_int, C.c_int, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -195,6 +197,14 @@ class Handle:
 
     def halo_unpack_pos(self, pos, count, row0, stream=0):
         self._ck(self._L.scab_halo_unpack_pos(self._h, pos, int(count), int(row0), stream))
+
+    def migrate_pack(self, own_cap, axis, lo_face, hi_face, park_geom, nx, ny, out_lo, out_hi, cap, free_list, free_count, cnt, stream=0):
+        g = (C.c_double * 4)(*[float(x) for x in park_geom])
+        self._ck(self._L.scab_migrate_pack(self._h, int(own_cap), int(axis), float(lo_face), float(hi_face), g, int(nx), int(ny),
+                                           out_lo, out_hi, int(cap), free_list, free_count, cnt, stream))
+
+    def migrate_unpack(self, in_lo, in_hi, cap, use_lo, use_hi, free_list, free_count, cnt, stream=0):
+        self._ck(self._L.scab_migrate_unpack(self._h, in_lo, in_hi, int(cap), int(use_lo), int(use_hi), free_list, free_count, cnt, stream))
 
     def halo_counts(self, stream=0):
         out = (C.c_int32 * 2)()

@@ -483,3 +483,27 @@ extern "C" int scab_halo_counts(scab_handle *h, int32_t out_host[2], void *strea
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return SCAB_OK;
 }
+
+extern "C" int scab_migrate_pack(scab_handle *h, int64_t own_cap, int axis, double lo_face, double hi_face, const double park_geom[4],
+                                 int32_t nx, int32_t ny, void *out_lo, void *out_hi, int32_t cap, int32_t *free_list, int32_t *free_count,
+                                 int32_t *cnt, void *stream)
+{
+    int rc = check_ready(h, "scab_migrate_pack");
+    if (rc) return rc;
+    if (own_cap < 0 || own_cap > h->A.n || axis < 0 || axis > 2 || cap <= 0 || !park_geom || nx <= 0 || ny <= 0 || !out_lo || !out_hi ||
+        !free_list || !free_count || !cnt)
+        return fail(h, SCAB_ERR_INVALID, "scab_migrate_pack: bad argument");
+    CK(launch_migrate_pack(h->A, (int)own_cap, axis, lo_face, hi_face, park_geom, nx, ny, out_lo, out_hi, cap, free_list, free_count, cnt,
+                           (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int scab_migrate_unpack(scab_handle *h, const void *in_lo, const void *in_hi, int32_t cap, int use_lo, int use_hi,
+                                   int32_t *free_list, int32_t *free_count, int32_t *cnt, void *stream)
+{
+    int rc = check_ready(h, "scab_migrate_unpack");
+    if (rc) return rc;
+    if (cap <= 0 || !in_lo || !in_hi || !free_list || !free_count || !cnt) return fail(h, SCAB_ERR_INVALID, "scab_migrate_unpack: bad argument");
+    CK(launch_migrate_unpack(h->A, in_lo, in_hi, cap, use_lo, use_hi, free_list, free_count, cnt, (cudaStream_t)stream));
+    return SCAB_OK;
+}

@@ -215,3 +215,7 @@ cudaError_t launch_halo_unpack(const StepArgs &A, const void *recs, int count, i
 cudaError_t launch_halo_pack_pos(const StepArgs &A, const int32_t *sent_lo, const int32_t *sent_hi, const int32_t *cnt, int cap,
                                  double *out_lo, double *out_hi, const double park[3], cudaStream_t s);
 cudaError_t launch_halo_unpack_pos(const StepArgs &A, const double *p, int count, int row0, cudaStream_t s);
+cudaError_t launch_migrate_pack(const StepArgs &A, int own_cap, int axis, double lo_face, double hi_face, const double geom[4], int nx, int ny,
+                                void *out_lo, void *out_hi, int cap, int32_t *free_list, int32_t *free_count, int32_t *cnt, cudaStream_t s);
+cudaError_t launch_migrate_unpack(const StepArgs &A, const void *in_lo, const void *in_hi, int cap, int use_lo, int use_hi,
+                                  int32_t *free_list, int32_t *free_count, int32_t *cnt, cudaStream_t s);

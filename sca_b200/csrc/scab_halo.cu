@@ -128,3 +128,107 @@ cudaError_t launch_halo_unpack_pos(const StepArgs &A, const double *p, int count
     if (count > 0) k_halo_unpack_pos<<<(count + 255) / 256, 256, 0, s>>>(A, p, count, row0);
     return cudaGetLastError();
 }
+
+// ------------------------------------------------------------------ device-side migration
+// Agents that left the slab move to the neighbour GPU as 128-byte full-state rows through fixed-size
+// buffers (row 0 of each buffer is a header carrying the count), entirely on the device: the vacated
+// state row becomes a parked ghost and its index is pushed on a free list; arrivals pop free rows.
+struct MigRow {        // 128 B
+    double pos[3];
+    double heading[3];
+    double goal[3];
+    double radius, pref_speed, total_dist, max_run_dist;
+    float vel[3];
+    int32_t status, step_num, gid;
+};
+static_assert(sizeof(MigRow) == 128, "MigRow must be 128 bytes");
+
+struct ParkGeom { double lox, loy, cell, z; int nx, ny; };
+
+__device__ __forceinline__ void park_row(const StepArgs &A, int i, const ParkGeom &P)
+{
+    A.st.pos[3 * i] = P.lox + (((long long)i * 7919) % P.nx + 0.5) * P.cell;
+    A.st.pos[3 * i + 1] = P.loy + (((long long)i * 104729) % P.ny + 0.5) * P.cell;
+    A.st.pos[3 * i + 2] = P.z;
+    A.st.vel[3 * i] = A.st.vel[3 * i + 1] = A.st.vel[3 * i + 2] = 0.f;
+    ((double *)A.st.radius)[i] = 0.0;
+    A.st.status[i] = SCAB_ST_GHOST | SCAB_ST_AT_GOAL | SCAB_ST_RUN_DONE;
+    if (A.st.gid) ((int32_t *)A.st.gid)[i] = 0x7fffffff;
+}
+
+__global__ void __launch_bounds__(256) k_migrate_pack(StepArgs A, int own_cap, int axis, double lo_face, double hi_face, ParkGeom P,
+                                                      MigRow *out_lo, MigRow *out_hi, int cap, int32_t *free_list, int32_t *free_count,
+                                                      int32_t *cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= own_cap) return;
+    const int st = A.st.status[i];
+    if (st & SCAB_ST_GHOST) return;
+    const double c = A.st.pos[3 * i + axis];
+    const int side = (c < lo_face) ? 0 : (c >= hi_face ? 1 : -1);
+    if (side < 0) return;
+    const int slot = atomicAdd(&cnt[side], 1);
+    if (slot >= cap) { atomicAdd(&cnt[2], 1); return; }      // overflow: the agent stays (and is counted)
+    MigRow r;
+    for (int d = 0; d < 3; d++) {
+        r.pos[d] = A.st.pos[3 * i + d]; r.heading[d] = A.st.heading[3 * i + d]; r.goal[d] = A.st.goal[3 * i + d];
+        r.vel[d] = A.st.vel[3 * i + d];
+    }
+    r.radius = A.st.radius[i]; r.pref_speed = A.st.pref_speed[i]; r.total_dist = A.st.total_dist[i];
+    r.max_run_dist = A.st.max_run_dist[i];
+    r.status = st; r.step_num = A.st.step_num[i]; r.gid = A.st.gid ? A.st.gid[i] : i;
+    (side ? out_hi : out_lo)[1 + slot] = r;
+    park_row(A, i, P);
+    free_list[atomicAdd(free_count, 1)] = i;
+}
+
+__global__ void k_migrate_header(MigRow *out_lo, MigRow *out_hi, int cap, const int32_t *cnt)
+{
+    if (threadIdx.x == 0) { out_lo[0].gid = min(cnt[0], cap); out_hi[0].gid = min(cnt[1], cap); }
+}
+
+__global__ void __launch_bounds__(256) k_migrate_unpack(StepArgs A, const MigRow *in_lo, const MigRow *in_hi, int cap, int use_lo, int use_hi,
+                                                        int32_t *free_list, int32_t *free_count, int32_t *cnt)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * cap) return;
+    const int side = k / cap, slot = k - side * cap;
+    if (side == 0 ? !use_lo : !use_hi) return;
+    const MigRow *in = side ? in_hi : in_lo;
+    const int count = min(max(in[0].gid, 0), cap);
+    if (slot >= count) return;
+    const int fi = atomicSub(free_count, 1) - 1;
+    if (fi < 0) { atomicAdd(free_count, 1); atomicAdd(&cnt[3], 1); return; }   // no free row: counted as lost (never expected)
+    const int i = free_list[fi];
+    const MigRow r = in[1 + slot];
+    for (int d = 0; d < 3; d++) {
+        A.st.pos[3 * i + d] = r.pos[d]; A.st.heading[3 * i + d] = r.heading[d]; ((double *)A.st.goal)[3 * i + d] = r.goal[d];
+        A.st.vel[3 * i + d] = r.vel[d];
+    }
+    ((double *)A.st.radius)[i] = r.radius; ((double *)A.st.pref_speed)[i] = r.pref_speed; A.st.total_dist[i] = r.total_dist;
+    ((double *)A.st.max_run_dist)[i] = r.max_run_dist;
+    A.st.status[i] = r.status; A.st.step_num[i] = r.step_num;
+    if (A.st.gid) ((int32_t *)A.st.gid)[i] = r.gid;
+}
+
+cudaError_t launch_migrate_pack(const StepArgs &A, int own_cap, int axis, double lo_face, double hi_face, const double geom[4], int nx, int ny,
+                                void *out_lo, void *out_hi, int cap, int32_t *free_list, int32_t *free_count, int32_t *cnt, cudaStream_t s)
+{
+    cudaError_t e = cudaMemsetAsync(cnt, 0, 2 * sizeof(int32_t), s);    // cnt[2], cnt[3] (overflow / lost) accumulate
+    if (e != cudaSuccess) return e;
+    ParkGeom P{geom[0], geom[1], geom[2], geom[3], nx, ny};
+    if (own_cap > 0)
+        k_migrate_pack<<<(own_cap + 255) / 256, 256, 0, s>>>(A, own_cap, axis, lo_face, hi_face, P, (MigRow *)out_lo, (MigRow *)out_hi, cap,
+                                                            free_list, free_count, cnt);
+    k_migrate_header<<<1, 32, 0, s>>>((MigRow *)out_lo, (MigRow *)out_hi, cap, cnt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_migrate_unpack(const StepArgs &A, const void *in_lo, const void *in_hi, int cap, int use_lo, int use_hi,
+                                  int32_t *free_list, int32_t *free_count, int32_t *cnt, cudaStream_t s)
+{
+    if (cap > 0)
+        k_migrate_unpack<<<(2 * cap + 255) / 256, 256, 0, s>>>(A, (const MigRow *)in_lo, (const MigRow *)in_hi, cap, use_lo, use_hi, free_list,
+                                                              free_count, cnt);
+    return cudaGetLastError();
+}

@@ -125,8 +125,8 @@ class ShardedSwarm:
     neighbours and every per-agent stage skips SCAB_ST_GHOST rows.
     """
 
-    def __init__(self, pos6, goal6, rank, world, device, lo, hi, radius=0.5, pref_speed=1.0, migrate_every=16,
-                 halo_cap=None, debug=False, use_graph=True):
+    def __init__(self, pos6, goal6, rank, world, device, lo, hi, radius=0.5, pref_speed=1.0, migrate_every=8,
+                 halo_cap=None, debug=False, use_graph=True, mig_cap=4096):
         from .swarm import Swarm
         pos6, goal6 = np.asarray(pos6, 'float64'), np.asarray(goal6, 'float64')
         n_global = len(pos6)
@@ -170,6 +170,16 @@ class ShardedSwarm:
         self.recv = torch.zeros((2 * self.cap, REC_DOUBLES), **f8)
         self.psend_lo, self.psend_hi = torch.zeros((self.cap, 3), **f8), torch.zeros((self.cap, 3), **f8)
         self.precv = torch.zeros((2 * self.cap, 3), **f8)
+        # device-side migration: 128-byte full-state rows, 1 header row + mig_cap rows per face, and the free list
+        self.mig_cap = int(mig_cap)
+        mk = lambda: torch.zeros((self.mig_cap + 1, 16), **f8)
+        self.msend_lo, self.msend_hi, self.mrecv_lo, self.mrecv_hi = mk(), mk(), mk(), mk()
+        i4 = dict(dtype=torch.int32, device=dev)
+        self.free_list = torch.zeros(self.own_cap, **i4)
+        nfree = self.own_cap - self.n_own
+        self.free_list[:nfree] = torch.arange(self.own_cap - 1, self.n_own - 1, -1, **i4)
+        self.free_count = torch.tensor([nfree], **i4)
+        self.mig_cnt = torch.zeros(4, **i4)
         self.steps = 0
         self._fill_parked()
         self._park_rows(self.n_own, self.n_rows)
@@ -177,7 +187,8 @@ class ShardedSwarm:
         # against NCCL's own stream
         self.stream = torch.cuda.Stream(device=dev)
         self.debug_phase = None
-        self.use_graph = bool(use_graph)
+        import os as _os
+        self.use_graph = bool(use_graph) and _os.environ.get('SCAB_NO_GRAPH', '0') != '1'
         self._graphs = {}
         sw._bind(self.n_rows)
         torch.cuda.synchronize(dev)
@@ -238,10 +249,28 @@ class ShardedSwarm:
         exchange_with_neighbours(self.psend_lo, self.psend_hi, self.precv[:cap], self.precv[cap:], self.rank, self.world)
         sw.h.halo_unpack_pos(self.precv.data_ptr(), 2 * cap, self.own_cap, self._stream())
 
-    def _step_body(self, pol, nbr_mode):
-        """Everything between two migrations: static shapes, static pointers -> capturable in a CUDA graph."""
+    def _migrate_device(self):
+        """Agents that left the slab move to the neighbour rank -- on the device, fixed-size, no host sync."""
+        sw = self.sw
+        lo_f, hi_f = self.plan.faces(self.rank)
+        lo_face = lo_f if self.rank > 0 else -1e300
+        hi_face = hi_f if self.rank < self.world - 1 else 1e300
+        lo, cell, dim = self._park_geom
+        s = self._stream()
+        sw.h.migrate_pack(self.own_cap, self.plan.axis, lo_face, hi_face, (lo[0], lo[1], cell, self.park[2]), int(dim[0]), int(dim[1]),
+                          self.msend_lo.data_ptr(), self.msend_hi.data_ptr(), self.mig_cap, self.free_list.data_ptr(),
+                          self.free_count.data_ptr(), self.mig_cnt.data_ptr(), s)
+        exchange_with_neighbours(self.msend_lo, self.msend_hi, self.mrecv_lo, self.mrecv_hi, self.rank, self.world)
+        sw.h.migrate_unpack(self.mrecv_lo.data_ptr(), self.mrecv_hi.data_ptr(), self.mig_cap, self.rank > 0, self.rank < self.world - 1,
+                            self.free_list.data_ptr(), self.free_count.data_ptr(), self.mig_cnt.data_ptr(), s)
+
+    def _step_body(self, pol, nbr_mode, with_migration=False):
+        """One step: static shapes, static pointers -> capturable in a CUDA graph (two variants)."""
         sw = self.sw
         if self.world > 1:
+            if with_migration:
+                self._mark('migrate')
+                self._migrate_device()
             self._mark('pre-exchange')
             self._ghost_exchange_pre()
         s = self._stream()
@@ -260,37 +289,36 @@ class ShardedSwarm:
     def step(self, policy, nbr_mode=capi.NBR_KNN):
         pol = capi.POLICIES[policy] if isinstance(policy, str) else int(policy)
         with torch.cuda.stream(self.stream):
-            if self.world > 1 and self.steps and self.steps % self.plan.migrate_every == 0:
-                self._mark('migrate')
-                self.migrate()
-            key = (pol, nbr_mode)
-            # the first steps run eagerly (NCCL creates its channels lazily on first use), then one graph replays
-            if self.use_graph and self.debug_phase is None and self.steps >= 2:
+            # step 1 also migrates, so that both graph variants are exercised eagerly during any warm-up
+            mig = self.world > 1 and self.steps > 0 and (self.steps % self.plan.migrate_every == 0 or self.steps == 1)
+            key = (pol, nbr_mode, mig)
+            # the first steps run eagerly (NCCL creates its channels lazily on first use), then graphs replay
+            if self.use_graph and self.debug_phase is None and self.steps >= 3:
                 g = self._graphs.get(key)
                 if g is None:
-                    g = self._capture(pol, nbr_mode)
+                    g = self._capture(pol, nbr_mode, mig)
                 if g is not False:
                     g.replay()
                 else:
-                    self._step_body(pol, nbr_mode)
+                    self._step_body(pol, nbr_mode, mig)
             else:
-                self._step_body(pol, nbr_mode)
+                self._step_body(pol, nbr_mode, mig)
         self.steps += 1
 
-    def _capture(self, pol, nbr_mode):
+    def _capture(self, pol, nbr_mode, mig=False):
         """Capture one step (kernels + both NCCL exchanges) into a CUDA graph; fall back to eager launches
         if the capture is refused."""
         try:
             g = torch.cuda.CUDAGraph()
             self.stream.synchronize()
             with torch.cuda.graph(g, stream=self.stream):
-                self._step_body(pol, nbr_mode)
-            self._graphs[(pol, nbr_mode)] = g
+                self._step_body(pol, nbr_mode, mig)
+            self._graphs[(pol, nbr_mode, mig)] = g
             return g
         except Exception as e:   # pragma: no cover - depends on the NCCL / driver combination
             import warnings
             warnings.warn('CUDA graph capture of the sharded step failed (%s); using eager launches' % (e,))
-            self._graphs[(pol, nbr_mode)] = False
+            self._graphs[(pol, nbr_mode, mig)] = False
             return False
 
     def warm_up(self, policy, nbr_mode=capi.NBR_KNN):
@@ -307,6 +335,14 @@ class ShardedSwarm:
                 sw.h.halo_unpack(self.recv.data_ptr(), 2 * self.cap, self.own_cap, s)
                 sw.h.halo_pack_pos(self.psend_lo.data_ptr(), self.psend_hi.data_ptr(), self.cap, self.park, s)
                 sw.h.halo_unpack_pos(self.precv.data_ptr(), 2 * self.cap, self.own_cap, s)
+                lo, cell, dim = self._park_geom
+                fc = self.free_count.clone()
+                sw.h.migrate_pack(self.own_cap, self.plan.axis, -1e300, 1e300, (lo[0], lo[1], cell, self.park[2]), int(dim[0]), int(dim[1]),
+                                  self.msend_lo.data_ptr(), self.msend_hi.data_ptr(), self.mig_cap, self.free_list.data_ptr(),
+                                  self.free_count.data_ptr(), self.mig_cnt.data_ptr(), s)
+                sw.h.migrate_unpack(self.mrecv_lo.data_ptr(), self.mrecv_hi.data_ptr(), self.mig_cap, 0, 0,
+                                    self.free_list.data_ptr(), self.free_count.data_ptr(), self.mig_cnt.data_ptr(), s)
+                self.free_count.copy_(fc)
             sw.h.build_grid(s)
             sw.h.neighbors(nbr_mode, s)
             sw.h.policy_step(pol, s)
@@ -316,43 +352,19 @@ class ShardedSwarm:
                 sw.t[k].copy_(v)
             sw.h.reset_counters(s)
             t = sw.t
-            x = t['pos'][:self.n_own, self.plan.axis]
-            m = (x < 0.0) | (x >= 1e300) | torch.zeros_like(x, dtype=torch.bool)
-            idx = torch.nonzero(~m)[:8, 0]
-            rows = torch.cat([pack_rows(t, idx), pack_rows(t, idx[:0])])
-            scratch = {k: v[:16].clone() for k, v in t.items()}
-            unpack_rows(scratch, rows, 0)
-            _ = (t['status'][:8] & capi.ST_ZAXIS).sum().item()
-            c = torch.tensor([1, 2], dtype=torch.int64, device=x.device)
-            _ = int(c[0:1].clone().item())
             self._fill_parked()
             self.stream.synchronize()
 
-    # ------------------------------------------------------------------ migration
-    def migrate(self):
-        """Hand agents that left the slab to the neighbour rank (rare: every `migrate_every` steps)."""
-        sw, t = self.sw, self.sw.t
-        n = self.n_own
-        lo_f, hi_f = self.plan.faces(self.rank)
-        x = t['pos'][:n, self.plan.axis]
-        go_lo = (x < lo_f) if self.rank > 0 else torch.zeros_like(x, dtype=torch.bool)
-        go_hi = (x >= hi_f) if self.rank < self.world - 1 else torch.zeros_like(x, dtype=torch.bool)
-        c_lo, c_hi = sw.h.halo_counts(self._stream())
-        if max(c_lo, c_hi) > self.cap:
-            raise capi.ScabError('halo buffers overflowed (%d, %d > cap %d): raise halo_cap' % (c_lo, c_hi, self.cap))
-        idx_lo, idx_hi = torch.nonzero(go_lo)[:, 0], torch.nonzero(go_hi)[:, 0]
-        rows_lo, rows_hi = pack_rows(t, idx_lo), pack_rows(t, idx_hi)
-        from_lo, from_hi = exchange_variable(rows_lo, rows_hi, self.rank, self.world)
-        keep = torch.nonzero(~(go_lo | go_hi))[:, 0]
-        kept = pack_rows(t, keep)
-        rows = torch.cat([kept, from_lo, from_hi])
-        if rows.shape[0] > self.own_cap:
-            raise capi.ScabError('shard grew beyond its capacity (%d > %d)' % (rows.shape[0], self.own_cap))
-        unpack_rows(t, rows, 0)
-        n_new = rows.shape[0]
-        self._park_rows(n_new, max(n, n_new))      # slots vacated at the tail become parked ghosts
-        self.n_own = n_new
-        sw._zaxis[:self.n_own] = t['status'][:self.n_own] & capi.ST_ZAXIS
+    # ------------------------------------------------------------------ diagnostics
+    def check_overflow(self):
+        """Blocking: raise if a halo / migration buffer ever overflowed or an arrival found no free row."""
+        with torch.cuda.stream(self.stream):
+            c_lo, c_hi = self.sw.h.halo_counts(self._stream())
+        m = self.mig_cnt.cpu().numpy()
+        if max(c_lo, c_hi) > self.cap or m[2] or m[3]:
+            raise capi.ScabError('sharding buffers overflowed: halo %d,%d (cap %d); migration deferred %d, lost %d'
+                                 % (c_lo, c_hi, self.cap, m[2], m[3]))
+        return {'halo': (c_lo, c_hi), 'migrated_last': (int(m[0]), int(m[1]))}
 
     def close(self):
         """Drop the captured graphs (they hold NCCL work; destroy_process_group would wait on them forever)."""
@@ -369,5 +381,7 @@ class ShardedSwarm:
         """Owned rows keyed by global id (host)."""
         self.stream.synchronize()
         torch.cuda.synchronize()
-        gid = self.sw.t['gid'][:self.n_own].cpu().numpy()
-        return gid, {k: self.sw.t[k][:self.n_own].cpu().numpy() for k in keys}
+        t = self.sw.t
+        own = torch.nonzero((t['status'][:self.own_cap] & capi.ST_GHOST) == 0)[:, 0]
+        self.n_own = int(own.numel())
+        return t['gid'][own].cpu().numpy(), {k: t[k][own].cpu().numpy() for k in keys}

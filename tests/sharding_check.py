@@ -34,7 +34,7 @@ def main():
     pos, goal, _ = scenarios.uniform_box_numpy(n, density, seed=3)
     L = (n / density) ** (1 / 3)
     lo, hi = np.array([-20.0, -20.0, 0.0]), np.array([L + 20.0, L + 20.0, L + 40.0])
-    sh = ShardedSwarm(pos, goal, rank, world, dev, lo, hi, migrate_every=8)
+    sh = ShardedSwarm(pos, goal, rank, world, dev, lo, hi, migrate_every=4)
     sh.warm_up(policy, capi.NBR_KNN)
     if os.environ.get('SHARD_DEBUG'):
         def _dbg(w):
@@ -42,12 +42,12 @@ def main():
             print('[rank %d step %d] reached %s (everything before it completed)' % (rank, sh.steps, w), flush=True)
         sh.debug_phase = _dbg
     dist.barrier()
-    moved = 0
+    own0 = set(np.nonzero(sh.plan.owner(pos[:, 0]) == rank)[0].tolist())
     for _ in range(steps):
-        n0 = sh.n_own
         sh.step(policy, capi.NBR_KNN)
-        moved += abs(sh.n_own - n0)
+    sh.check_overflow()
     gid, st = sh.gather_state()
+    moved = len(set(gid.tolist()) - own0)          # agents this rank owns now but did not own at the start
     act = sh.counters()
     gathered = [None] * world
     dist.gather_object((gid, st, act, moved), gathered if rank == 0 else None, dst=0)
