@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#define TIER_DELTA_DEFAULT 0.3f   // measured on B200: 0.12 -> 5.0 ms, 0.18 -> 4.1, 0.25 -> 3.0, 0.4 -> 3.0, 0.55 -> 3.6, 0.75 -> 4.9 (policy stage, 1M SCA)
+
 struct scab_handle {
     int device = 0;
     int64_t capacity = 0;
@@ -160,6 +162,8 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     A.inv_time_step = 1.0 / p->time_step;
     A.max_speed = p->max_speed;
     A.near_goal = p->near_goal;
+    A.tier_delta = TIER_DELTA_DEFAULT;
+    if (const char *td = getenv("SCAB_TIER_DELTA")) { float v = (float)atof(td); if (v > 0.f) A.tier_delta = v; }   // tuning knob
     // one block for all per-agent scratch
     const size_t cap = (size_t)capacity;
     size_t off = 0;

@@ -56,6 +56,7 @@ struct StepArgs {
     int32_t *slow_count;
     double max_radius;  // largest agent radius (0: unknown -> the status stage always scans the cell list)
     int last_nbr_mode;  // mode of the neighbour lists currently in s_nbr
+    float tier_delta;   // lazy tiers: tier 1 = candidates within this distance of the one closest to v_pref
     int full_search;    // SCAB_OPT_FULL_SEARCH: examine every candidate (exact n_suit) instead of the lazy tiers
     // obstacles (sorted by obstacle cell) + reference kd-trees
     const double4 *o_posr;

@@ -20,7 +20,7 @@
 #define DIR_CAP 64        // surviving directions per agent (a pi/4 cap holds ~38 of 256)
 #define LIVE_CAP 136      // 2 * DIR_CAP + v_pref, rounded up
 #define VPREF_ENTRY 0x3ff
-#define TIER_DELTA 0.25f   // tier 1 = candidates within this (approximate) distance of the one closest to v_pref
+// tier 1 = candidates within StepArgs::tier_delta (default 0.3, SCAB_TIER_DELTA) of the one closest to v_pref
 
 struct GroupSmem {
     float4 cp[KNBR];
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
                 }
             }
             kmin = __uint_as_float(__reduce_min_sync(gmask, __float_as_uint(kmin)));   // non-negative floats order as uints
-            T1 = kmin + TIER_DELTA;
+            T1 = kmin + A.tier_delta;
         }
         // exact keys strictly below this are certainly smaller than any key of tier 2 (fp32 key error <= 1e-3)
         const unsigned tier_units = A.full_search ? 0xffffffffu : (unsigned)fmaxf((T1 - 1.1e-3f) * 1.0e5f, 0.f);
