@@ -172,7 +172,8 @@ def run_ours(args):
             evs[k][3].record(); sw.stage_status()
             evs[k][4].record()
         torch.cuda.synchronize()
-        act = (sw.counters()['n_active_total'] - act0) / args.steps
+        cdiag = sw.counters()
+        act = (cdiag['n_active_total'] - act0) / args.steps
         stage_ms = {nm: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)]))
                     for i, nm in enumerate(names)}
         dom = max(stage_ms, key=stage_ms.get)
@@ -190,6 +191,7 @@ def run_ours(args):
                 'achieved': round(achieved, 2), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 5),
                 'traffic': traffic, 'peak_source': how, 'algorithmic_bytes_per_agent_step': ALGO_BYTES[dom],
                 'units_per_launch': int(units), 'stage_ms': {k: round(v, 4) for k, v in stage_ms.items()},
+                'last_step_diag': {k: cdiag[k] for k in ('n_active', 'n_recheck', 'n_tier2', 'n_slow', 'n_collision')},
                 'note': 'SCA candidate search is fp32/fp64-ALU-bound (SURVEY.md 8d): HBM fraction is reported as asked, '
                         'stage_ms shows where the step goes'}
 

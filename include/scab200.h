@@ -125,7 +125,9 @@ typedef struct {
     int64_t n_collision;   /* agents with the collision flag after the step */
     int64_t n_recheck;     /* fp32 guard-band hits re-evaluated in fp64 (diagnostic) */
     int64_t n_active_total;/* cumulative n_active since scab_create / scab_reset_counters (agent-steps) */
-    int64_t reserved[3];
+    int64_t n_tier2;       /* diagnostics: agents whose lazy tier 1 did not pin the result (tier 2 examined) */
+    int64_t n_slow;        /* diagnostics: agents handed to the general selection kernel */
+    int64_t reserved;
 } scab_counters;
 
 const char *scab_version(void);

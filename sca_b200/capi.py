@@ -47,7 +47,8 @@ class StatePtrs(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [('n_active', C.c_int64), ('n_not_done', C.c_int64), ('n_collision', C.c_int64),
-                ('n_recheck', C.c_int64), ('n_active_total', C.c_int64), ('reserved', C.c_int64 * 3)]
+                ('n_recheck', C.c_int64), ('n_active_total', C.c_int64), ('n_tier2', C.c_int64), ('n_slow', C.c_int64),
+                ('reserved', C.c_int64)]
 
 
 _lib = None
@@ -177,7 +178,7 @@ class Handle:
         c = Counters()
         self._ck(self._L.scab_read_counters(self._h, C.byref(c), stream))
         return {'n_active': c.n_active, 'n_not_done': c.n_not_done, 'n_collision': c.n_collision,
-                'n_recheck': c.n_recheck, 'n_active_total': c.n_active_total}
+                'n_recheck': c.n_recheck, 'n_active_total': c.n_active_total, 'n_tier2': c.n_tier2, 'n_slow': c.n_slow}
 
     def reset_counters(self, stream=0):
         self._ck(self._L.scab_reset_counters(self._h, stream))

@@ -428,6 +428,7 @@ extern "C" int scab_read_counters(scab_handle *h, scab_counters *out, void *stre
     memset(out, 0, sizeof(*out));
     out->n_active = (int64_t)v[0]; out->n_not_done = (int64_t)v[1]; out->n_collision = (int64_t)v[2]; out->n_recheck = (int64_t)v[3];
     out->n_active_total = (int64_t)v[4];
+    out->n_tier2 = (int64_t)v[5]; out->n_slow = (int64_t)v[6];
     return SCAB_OK;
 }
 

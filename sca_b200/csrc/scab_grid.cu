@@ -88,7 +88,9 @@ cudaError_t launch_grid_build(const StepArgs &A, cudaStream_t s)
 {
     cudaError_t e = cudaMemsetAsync(A.cell_count, 0, sizeof(int32_t) * A.g.ncell, s);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(A.counters, 0, sizeof(unsigned long long) * 4, s);
+    e = cudaMemsetAsync(A.counters, 0, sizeof(unsigned long long) * 4, s);     // per-step counters [0..3]
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(A.counters + 5, 0, sizeof(unsigned long long) * 2, s); // per-step diagnostics [5..6]
     if (e != cudaSuccess) return e;
     if (A.n > 0) {
         int nb = (A.n + 255) / 256;

@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
     unsigned long long n_recheck = 0;
 
     const int n_work = USE_LIST ? min(*A.slow_count, A.n) : A.n;
+    if (USE_LIST && blockIdx.x == 0 && threadIdx.x == 0) A.counters[6] = (unsigned long long)n_work;
     for (int wi = blockIdx.x * WARPS_PER_CTA + wid; wi < n_work; wi += warps_total) {
         const int s = USE_LIST ? A.slow_list[wi] : wi;
         const float4 mv = A.s_vel[s];

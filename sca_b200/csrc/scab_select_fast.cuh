@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
     const unsigned lt8 = (1u << l8) - 1;
     GroupSmem &W = gs[wid * FG_PER_WARP + g];
     const int groups_total = gridDim.x * FG_WARPS * FG_PER_WARP;
-    unsigned long long n_recheck = 0;
+    unsigned long long n_recheck = 0, n_tier2 = 0;
     // fp32 direction tables, once per CTA (6 KB): conflict-free float4 reads in phases A and B
     float4 *s_dir256 = reinterpret_cast<float4 *>(smem_raw + sizeof(GroupSmem) * FG_WARPS * FG_PER_WARP);
     float4 *s_dir128 = s_dir256 + 256;
@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
             }
             __syncwarp(gmask);
             const int nlive_before = nlive;
+            if (pass == 1 && l8 == 0) n_tier2++;
 
             // ---- B: cone tests per direction (the two shells share p.u and h.u)
             for (int jb = 0; jb < nact; jb += FG_LANES) {
@@ -495,4 +496,5 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
     }
     for (int o = 4; o > 0; o >>= 1) n_recheck += __shfl_xor_sync(gmask, n_recheck, o);
     if (l8 == 0 && n_recheck) atomicAdd(&A.counters[3], n_recheck);
+    if (l8 == 0 && n_tier2) atomicAdd(&A.counters[5], n_tier2);
 }

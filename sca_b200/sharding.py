@@ -156,8 +156,16 @@ class ShardedSwarm:
         sw.h.set_max_radius(float(rad_g.max()))      # ghosts included: the bound must hold across shards
         sw.set_global_ids(mine.astype(np.int32), n_global)
         # two extra z layers: an empty buffer layer and the layer where unused slots are parked
-        lo, hi = np.asarray(lo, 'float64'), np.asarray(hi, 'float64')
+        lo, hi = np.asarray(lo, 'float64').copy(), np.asarray(hi, 'float64').copy()
         cell = float(max(sw.params.cell_size, sw.params.neighbor_dist))
+        # the cell list only has to cover this slab plus its halo (agents beyond are clamped into the border
+        # cells, which is still correct): the per-step scan over cells shrinks with the number of GPUs
+        lo_f, hi_f = self.plan.faces(rank)
+        ax = self.plan.axis
+        if rank > 0:
+            lo[ax] = max(lo[ax], lo_f - self.plan.width - 2 * cell)
+        if rank < world - 1:
+            hi[ax] = min(hi[ax], hi_f + self.plan.width + 2 * cell)
         dim = np.maximum(1, np.ceil((hi - lo) / cell).astype(np.int64))
         self._park_geom = (lo.copy(), cell, dim.copy())
         self.park = (float(lo[0] + 0.5 * cell), float(lo[1] + 0.5 * cell), float(lo[2] + (dim[2] + 1.5) * cell))
