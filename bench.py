@@ -198,26 +198,22 @@ def run_ours(args):
     # ---- end to end through host buffers (pinned H2D of the inputs, D2H of the results, every step)
     e2e = None
     if world == 1:
-        keys_in = ('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')
-        keys_out = ('action', 'status', 'pos', 'heading', 'total_dist', 'step_num')
-        host_in = {k: sw.t[k].cpu().pin_memory() for k in keys_in}
-        host_in['status'] &= 15
-        host_out = {k: torch.empty_like(sw.t[k], device='cpu').pin_memory() for k in keys_out}
-        h2d = sum(v.numel() * v.element_size() for v in host_in.values())
-        d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+        # host-resident state (pinned): every step uploads it, steps on the device, and downloads the new state
+        # straight back into the same pinned buffers plus the float32 action matrix the reference env consumes
+        keys_state = ('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')
+        host = {k: sw.t[k].cpu().pin_memory() for k in keys_state}
+        host_action = torch.empty_like(sw.t['action'], device='cpu').pin_memory()
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = h2d + host_action.numel() * host_action.element_size()
         steps_e = max(3, min(args.steps, 20))
 
         def one():
-            sw.upload(host_in)
+            sw.upload(host)
             sw.step(policy, capi.NBR_KNN)
-            for k in keys_out:
-                host_out[k].copy_(sw.t[k], non_blocking=True)
+            for k in keys_state:
+                host[k].copy_(sw.t[k], non_blocking=True)
+            host_action.copy_(sw.t['action'], non_blocking=True)
             torch.cuda.synchronize()          # the caller needs the results on the host before the next step
-            for k in keys_in:                 # next step's inputs = this step's results (host-resident state)
-                if k in host_out:
-                    host_in[k].copy_(host_out[k])
-            host_in['vel'].copy_(host_out['action'][:, :3])
-            host_in['status'] &= 15
         one()
         a0 = sw.counters()['n_active_total']
         torch.cuda.synchronize()
