@@ -116,6 +116,8 @@ typedef struct {
     const int32_t *gid;    /* [n] global agent id of each row (NULL: row index). Ties and the sequential
                               collision-check order (mampenv.py:42-46) follow the GLOBAL id              in */
     int64_t n_global;      /* total agents across all shards (0: n); obstacle ids are reported as n_global + k */
+    /* Dubins v_pref provider (optional; see scab_dubins_enable) */
+    const double *goal_heading; /* [n,3] goal_heading_frame = goal_pos[3:6] (agent.py:21); NULL: zeros           in */
 } scab_state_ptrs;
 
 /* Step counters, read back with scab_read_counters (device->host copy of 8 x int64). */
@@ -177,6 +179,16 @@ int scab_policy_step(scab_handle *h, int policy, void *stream);
 int scab_status_step(scab_handle *h, void *stream);
 /* Stages 1-4 back to back: one MACAEnv.step (mampenv.py:22-25). */
 int scab_step(scab_handle *h, int policy, int nbr_mode, void *stream);
+
+/* SCA's Dubins v_pref provider on the device (replaces compute_v_pref / compute_dubins / update_dubins,
+ * mamp/policies/sca/scaPolicy.py:92-104,243-338, with dubinsmaneuver3d.py:34-162 and dubinsmaneuver2d.py:33-297).
+ * on = 1 allocates (once) and resets one tracker state per agent row (agent.is_use_dubins = False); from then on
+ * SCAB_POLICY_SCA and SCAB_POLICY_RVO3D_DUBINS take V_des from the tracker whenever state.vpref_ext is NULL.
+ * on = 0 returns to the straight-line v_pref.  Single-GPU only (tracker states do not migrate between slabs). */
+int scab_dubins_enable(scab_handle *h, int on, void *stream);
+/* Test hook: bytes per tracker state, and a blocking copy of the first n states to host memory. */
+int64_t scab_dubins_state_size(void);
+int scab_dubins_read(scab_handle *h, void *out_host, int64_t n, void *stream);
 
 /* Blocking read of the counters written by the last scab_status_step on `stream`. */
 int scab_read_counters(scab_handle *h, scab_counters *out_host, void *stream);

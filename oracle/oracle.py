@@ -18,8 +18,8 @@ K = 16
 
 
 def build(force=False):
-    src = os.path.join(HERE, 'sca_oracle.c')
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, f) for f in ('sca_oracle.c', 'sca_dubins.c', 'Makefile')]
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(['make', '-C', HERE, '-B' if force else '-s'], stdout=subprocess.DEVNULL)
     return LIB
 
@@ -141,6 +141,69 @@ class World:
     def step(self, policy, nbr_mode=NBR_REF_COMPAT, fast=False):
         self.policy_step(policy, nbr_mode)
         return self.env_update(fast)
+
+    def step_dubins(self, policy, prov, goal_heading, nbr_mode=NBR_REF_COMPAT):
+        """One step of 'sca' / 'rvo3d_dubins' with V_des from the stateful Dubins tracker (scaPolicy.py:264-338)."""
+        v = np.zeros((self.n, 3))
+        act = np.nonzero((self.status & 7) == 0)[0]
+        for i in act:
+            v[i] = prov.vpref(i, self.pos[i], self.vel[i], self.heading[i], self.goal[i], goal_heading[i],
+                              float(self.pref_speed[i]), bool(self.is_zaxis[i]))
+        self.set_vpref_ext(v)
+        self.policy_step(policy, nbr_mode)
+        for i in act:
+            if self.nbr_cnt[i] >= 0:      # computeNeighbors ran (not the zero-velocity shortcut)
+                c = int(self.nbr_cnt[i])
+                prov.set_last_neighbor(i, c > 0, float(self.nbr_dsq[i][0]) if c > 0 else 0.0)
+        return self.env_update()
+
+
+class Man2D(C.Structure):
+    _fields_ = [('qi', C.c_double * 3), ('r', C.c_double), ('t', C.c_double), ('p', C.c_double), ('q', C.c_double),
+                ('mode', C.c_int32 * 3), ('ok', C.c_int32), ('length', C.c_double)]
+
+
+class DubinsState(C.Structure):
+    _fields_ = [('in_use', C.c_int32), ('n_points', C.c_int32), ('cursor', C.c_int32), ('ss', C.c_double),
+                ('length', C.c_double), ('qi0', C.c_double * 3), ('h', Man2D), ('v', Man2D), ('now_goal', C.c_double * 3),
+                ('v_pref', C.c_double * 3), ('nbr0_dsq', C.c_double), ('has_nbr', C.c_int32), ('replans', C.c_int32)]
+
+
+def dubins3d(qi, qf, rmin, pitchlims):
+    """mamp/policies/sca/dubinsmaneuver3d.py:34 dubinsmaneuver3d -> DubinsState (length, n_points, manoeuvres)."""
+    L = lib()
+    assert L.orc_sizeof_dubins_state() == C.sizeof(DubinsState)
+    S = DubinsState()
+    a = lambda v: (C.c_double * len(v))(*[float(x) for x in v])
+    L.orc_dubins3d(a(qi), a(qf), C.c_double(rmin), a(pitchlims), C.byref(S))
+    return S
+
+
+def dubins_point(S, i):
+    out = (C.c_double * 3)()
+    lib().orc_dubins_point(C.byref(S), int(i), out)
+    return np.array(out[:])
+
+
+class DubinsProvider:
+    """Per-agent stateful Dubins v_pref tracker (scaPolicy.py:264-338), one DubinsState per agent."""
+
+    def __init__(self, n):
+        assert lib().orc_sizeof_dubins_state() == C.sizeof(DubinsState)
+        self.S = (DubinsState * n)()
+        self.n = n
+
+    def set_last_neighbor(self, i, has, dsq):
+        self.S[i].has_nbr = int(bool(has))
+        self.S[i].nbr0_dsq = float(dsq)
+
+    def vpref(self, i, pos, vel, heading, goal, goal_heading, pref_speed, is_zaxis):
+        out = (C.c_double * 3)()
+        d = lambda v: (C.c_double * 3)(*[float(x) for x in v])
+        f = (C.c_float * 3)(*[float(np.float32(x)) for x in vel])
+        lib().orc_dubins_vpref(C.byref(self.S[i]), d(pos), f, d(heading), d(goal), d(goal_heading), C.c_double(pref_speed),
+                               int(is_zaxis), out)
+        return np.array(out[:])
 
 
 def set_threads(t):

@@ -23,7 +23,8 @@ SYMBOLS = ['scab_version', 'scab_default_params', 'scab_set_option', 'scab_set_m
            'scab_bind_state', 'scab_set_obstacles', 'scab_kdtree_build', 'scab_kdtree_get_perm', 'scab_build_grid',
            'scab_neighbors', 'scab_policy_step', 'scab_status_step', 'scab_step', 'scab_read_counters',
            'scab_reset_counters', 'scab_halo_pack', 'scab_halo_unpack', 'scab_halo_pack_pos', 'scab_halo_unpack_pos',
-           'scab_halo_counts', 'scab_migrate_pack', 'scab_migrate_unpack']
+           'scab_halo_counts', 'scab_migrate_pack', 'scab_migrate_unpack', 'scab_dubins_enable', 'scab_dubins_state_size',
+           'scab_dubins_read']
 
 
 class ScabError(RuntimeError):
@@ -42,7 +43,14 @@ STATE_FIELDS = ['pos', 'vel', 'heading', 'goal', 'radius', 'pref_speed', 'status
 
 
 class StatePtrs(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in STATE_FIELDS] + [('n_global', C.c_int64)]
+    _fields_ = [(k, C.c_void_p) for k in STATE_FIELDS] + [('n_global', C.c_int64), ('goal_heading', C.c_void_p)]
+
+
+# mirror of DubState / Man2D in csrc/scab_dubins.cu (test hook only)
+_MAN2D = [('qi', '<f8', 3), ('r', '<f8'), ('t', '<f8'), ('p', '<f8'), ('q', '<f8'), ('length', '<f8'), ('mode', '<i4', 3), ('ok', '<i4')]
+DUBINS_STATE_DTYPE = [('in_use', '<i4'), ('n_points', '<i4'), ('cursor', '<i4'), ('has_nbr', '<i4'), ('ss', '<f8'), ('length', '<f8'),
+                      ('qi0', '<f8', 3), ('h', _MAN2D), ('v', _MAN2D), ('now_goal', '<f8', 3), ('v_pref', '<f8', 3), ('nbr0_dsq', '<f8'),
+                      ('replans', '<i4'), ('pad', '<i4')]
 
 
 class Counters(C.Structure):
@@ -85,6 +93,10 @@ def lib():
     L.scab_step.argtypes = [vp, C.c_int, C.c_int, vp]
     L.scab_read_counters.argtypes = [vp, C.POINTER(Counters), vp]
     L.scab_reset_counters.argtypes = [vp, vp]
+    L.scab_dubins_enable.argtypes = [vp, C.c_int, vp]
+    L.scab_dubins_state_size.restype = i64
+    L.scab_dubins_state_size.argtypes = []
+    L.scab_dubins_read.argtypes = [vp, vp, i64, vp]
     d3 = C.POINTER(C.c_double)
     L.scab_halo_pack.argtypes = [vp, i64, C.c_int, C.c_double, C.c_double, C.c_double, d3, vp, vp, i32, vp]
     L.scab_halo_unpack.argtypes = [vp, vp, i32, i64, vp]
@@ -182,6 +194,19 @@ class Handle:
 
     def reset_counters(self, stream=0):
         self._ck(self._L.scab_reset_counters(self._h, stream))
+
+    # ---- Dubins v_pref provider (scaPolicy.py:264-338 on the device)
+    def dubins_enable(self, on=True, stream=0):
+        self._ck(self._L.scab_dubins_enable(self._h, 1 if on else 0, stream))
+
+    def dubins_read(self, n, stream=0):
+        """Tracker states of rows [0, n) as a structured numpy array (test hook)."""
+        import numpy as np
+        out = np.zeros(int(n), dtype=DUBINS_STATE_DTYPE)
+        assert out.dtype.itemsize == self._L.scab_dubins_state_size(), (out.dtype.itemsize, self._L.scab_dubins_state_size())
+        if n:
+            self._ck(self._L.scab_dubins_read(self._h, out.ctypes.data, int(n), stream))
+        return out
 
     # ---- multi-GPU halo (device pointers are plain ints: tensor.data_ptr())
     def halo_pack(self, n_own, axis, lo_face, hi_face, width, park, out_lo, out_hi, cap, stream=0):

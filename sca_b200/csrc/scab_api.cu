@@ -39,6 +39,9 @@ struct scab_handle {
     bool kd_valid = false;
     // halo bookkeeping (which owned rows were packed for each face, and how many)
     int32_t *d_sent_lo = nullptr, *d_sent_hi = nullptr, *d_halo_cnt = nullptr;
+    // Dubins v_pref provider (allocated by the first scab_dubins_enable)
+    void *d_dub_states = nullptr;
+    double *d_dub_d0 = nullptr;
 };
 
 static int fail(scab_handle *h, int code, const std::string &msg)
@@ -217,7 +220,8 @@ extern "C" int scab_destroy(scab_handle *h)
     if (!h) return SCAB_ERR_INVALID;
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_block, h->d_cell_count, h->d_cell_start, h->d_dir256, h->d_dir128, h->d_dir256f, h->d_dir128f,
-                    h->d_counters, h->d_o_posr, h->d_o_posr_by_id, h->d_o_id, h->d_o_cell_start, h->d_kd_obst_perm, h->d_kd_obst};
+                    h->d_counters, h->d_o_posr, h->d_o_posr_by_id, h->d_o_id, h->d_o_cell_start, h->d_kd_obst_perm, h->d_kd_obst,
+                    h->d_dub_states, h->d_dub_d0};
     for (void *q : ptrs) if (q) cudaFree(q);
     delete h;
     return SCAB_OK;
@@ -416,6 +420,41 @@ extern "C" int scab_step(scab_handle *h, int policy, int nbr_mode, void *stream)
     rc = scab_policy_step(h, policy, stream);
     if (rc) return rc;
     return scab_status_step(h, stream);
+}
+
+// ------------------------------------------------------------------ Dubins v_pref provider
+extern "C" int64_t scab_dubins_state_size(void) { return (int64_t)scab_dubins_state_bytes(); }
+
+extern "C" int scab_dubins_enable(scab_handle *h, int on, void *stream)
+{
+    if (!h) return SCAB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!on) { h->A.dub_states = nullptr; h->A.dub_d0 = nullptr; return SCAB_OK; }
+    const size_t bytes = scab_dubins_state_bytes() * (size_t)h->capacity;
+    if (!h->d_dub_states) {
+        if (cudaMalloc(&h->d_dub_states, bytes) != cudaSuccess || cudaMalloc(&h->d_dub_d0, sizeof(double) * (size_t)h->capacity) != cudaSuccess) {
+            if (h->d_dub_states) cudaFree(h->d_dub_states);
+            h->d_dub_states = nullptr; h->d_dub_d0 = nullptr;
+            (void)cudaGetLastError();
+            return fail(h, SCAB_ERR_NOMEM, "scab_dubins_enable: out of device memory");
+        }
+    }
+    // all-zero state == agent.is_use_dubins False, empty path, no neighbours seen yet
+    CK(cudaMemsetAsync(h->d_dub_states, 0, bytes, (cudaStream_t)stream));
+    CK(cudaMemsetAsync(h->d_dub_d0, 0, sizeof(double) * (size_t)h->capacity, (cudaStream_t)stream));
+    h->A.dub_states = h->d_dub_states;
+    h->A.dub_d0 = h->d_dub_d0;
+    return SCAB_OK;
+}
+
+extern "C" int scab_dubins_read(scab_handle *h, void *out_host, int64_t n, void *stream)
+{
+    if (!h || !out_host || n < 0 || n > h->capacity) return fail(h, SCAB_ERR_INVALID, "scab_dubins_read: bad argument");
+    if (!h->d_dub_states) return fail(h, SCAB_ERR_INVALID, "scab_dubins_read: the provider was never enabled");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(out_host, h->d_dub_states, scab_dubins_state_bytes() * (size_t)n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return SCAB_OK;
 }
 
 extern "C" int scab_read_counters(scab_handle *h, scab_counters *out, void *stream)

@@ -68,6 +68,9 @@ struct StepArgs {
     const double *dir256, *dir128;   // [N,3] f64
     const float4 *dir256f, *dir128f; // [N] f32 (x y z 0)
     unsigned long long *counters;    // scab_counters
+    // Dubins v_pref provider (scab_dubins.cu); both NULL while it is disabled
+    void *dub_states;                // [capacity] DubState, indexed by row
+    double *dub_d0;                  // [capacity] this step's agent.neighbors[0][1] (-1: empty list), indexed by row
 };
 
 // ------------------------------------------------------------------ rounding conventions
@@ -209,6 +212,8 @@ cudaError_t launch_neighbors(const StepArgs &A, int mode, cudaStream_t s);
 cudaError_t launch_policy_sampled(const StepArgs &A, int policy, cudaStream_t s);
 cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s);
 cudaError_t launch_status(const StepArgs &A, cudaStream_t s);
+cudaError_t launch_vpref_dubins(const StepArgs &A, cudaStream_t s);
+size_t scab_dubins_state_bytes();
 cudaError_t launch_halo_pack(const StepArgs &A, int n_own, int axis, double lo_face, double hi_face, double width,
                              const double park[3], void *out_lo, void *out_hi, int cap, int32_t *sent_lo, int32_t *sent_hi,
                              int32_t *cnt, cudaStream_t s);

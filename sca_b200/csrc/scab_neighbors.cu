@@ -54,6 +54,7 @@ __device__ __forceinline__ void write_lists(const StepArgs &A, int s, int id, in
 {
     A.s_nbr_cnt[s] = cnt;
     A.s_qcoll[s] = qcoll;
+    if (A.dub_d0) A.dub_d0[id] = cnt > 0 ? d[0] : -1.0;
     int4 *dst = reinterpret_cast<int4 *>(A.s_nbr + (size_t)s * KNBR);
 #pragma unroll
     for (int q = 0; q < KNBR / 4; q++) dst[q] = make_int4(sx[4 * q], sx[4 * q + 1], sx[4 * q + 2], sx[4 * q + 3]);
@@ -109,6 +110,7 @@ __device__ __forceinline__ void write_lists2(const StepArgs &A, int s, int id, c
 {
     A.s_nbr_cnt[s] = L.cnt;
     A.s_qcoll[s] = qcoll;
+    if (A.dub_d0) A.dub_d0[id] = L.cnt > 0 ? L.d[0] : -1.0;
     int4 *dst = reinterpret_cast<int4 *>(A.s_nbr + (size_t)s * KNBR);
 #pragma unroll
     for (int q = 0; q < KNBR / 4; q++) dst[q] = make_int4(L.s[4 * q], L.s[4 * q + 1], L.s[4 * q + 2], L.s[4 * q + 3]);

@@ -680,7 +680,8 @@ cudaError_t launch_policy_sampled(const StepArgs &A, int policy, cudaStream_t s)
     cudaError_t e;
     switch (policy) {
     case SCAB_POLICY_SCA:
-        k_vpref<false, true><<<nb, 256, 0, s>>>(A);
+        if (A.dub_states && !A.st.vpref_ext) { e = launch_vpref_dubins(A, s); if (e != cudaSuccess) return e; }
+        else k_vpref<false, true><<<nb, 256, 0, s>>>(A);
         e = launch_select<SCAB_POLICY_SCA>(A, grid, s);
         break;
     case SCAB_POLICY_SRVO3D:
@@ -692,7 +693,8 @@ cudaError_t launch_policy_sampled(const StepArgs &A, int policy, cudaStream_t s)
         e = launch_select<SCAB_POLICY_RVO3D>(A, grid, s);
         break;
     case SCAB_POLICY_RVO3D_DUBINS:
-        k_vpref<false, true><<<nb, 256, 0, s>>>(A);
+        if (A.dub_states && !A.st.vpref_ext) { e = launch_vpref_dubins(A, s); if (e != cudaSuccess) return e; }
+        else k_vpref<false, true><<<nb, 256, 0, s>>>(A);
         e = launch_select<SCAB_POLICY_RVO3D_DUBINS>(A, grid, s);
         break;
     case SCAB_POLICY_ORCA_SAMPLED:

@@ -59,6 +59,8 @@ class Swarm:
             tns = self.t.get(k)
             setattr(p, k, tns.data_ptr() if tns is not None else None)
         p.n_global = int(getattr(self, 'n_global', 0))
+        gh = self.t.get('goal_heading')
+        p.goal_heading = gh.data_ptr() if gh is not None else None
         self.h.bind_state(p, self.n)
 
     def set_global_ids(self, gid, n_global):
@@ -89,6 +91,24 @@ class Swarm:
             self.t['vpref_ext'] = torch.zeros((self.capacity, 3), dtype=_F8, device=self.device)
             self._bind()
         self.t['vpref_ext'][:v.shape[0]].copy_(v.to(self.device, _F8))
+
+    def enable_dubins(self, goal_heading=None, on=True):
+        """SCA / RVO3D+Dubins: take V_des from the on-device Dubins tracker (scaPolicy.py:264-338) instead of an
+        external provider.  `goal_heading` [n,3] = goal_pos[3:6] (agent.py:21); resets every tracker."""
+        if on:
+            if 'goal_heading' not in self.t:
+                self.t['goal_heading'] = torch.zeros((self.capacity, 3), dtype=_F8, device=self.device)
+            self.t['goal_heading'].zero_()
+            if goal_heading is not None:
+                g = torch.as_tensor(np.ascontiguousarray(goal_heading, dtype='float64'))
+                self.t['goal_heading'][:g.shape[0]].copy_(g)
+            self.set_external_vpref(None)
+            self._bind()
+        self.h.dubins_enable(on, self._stream())
+        return self
+
+    def dubins_states(self):
+        return self.h.dubins_read(self.n, self._stream())
 
     # ------------------------------------------------------------------ state in / out
     def set_state(self, pos, goal, heading=None, vel=None, radius=0.5, pref_speed=1.0, status=None,

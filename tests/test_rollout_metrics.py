@@ -1,0 +1,81 @@
+"""Rollout-level statistics (run_example/run_sca.py:228-250: SuccessRate, ExtraTime, ExtraDistance,
+AverageSpeed) on the reference's own scenarios, free-running to completion.
+CPU: the oracle vs the reference's recorded metrics.  GPU (-m gpu): BatchedEnv vs the same."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+FULL = ['circle16_rvo3d', 'circle16_srvo3d', 'circle16_orca_lp']
+
+
+def _metrics(status, total_dist, step_num, straight, desire, n):
+    ok = (status & 6) == 0
+    ns = int(ok.sum())
+    return np.array([ns / n, ((step_num[ok].sum() - desire[ok].sum()) * 0.1) / ns, (total_dist[ok].sum() - straight[ok].sum()) / ns,
+                     total_dist[ok].sum() / step_num[ok].sum() / 0.1])
+
+
+@pytest.mark.parametrize('name', FULL)
+def test_oracle_rollout_matches_reference(name):
+    from oracle import oracle as orc
+    g = gu.load(name)
+    pol = str(g['policy'])
+    w = orc.World(g['pos'][0], g['goal'], heading=g['heading'][0], radius=g['radius'], pref_speed=g['pref_speed'],
+                  obstacles=g['obstacles'], initial_pos=g['initial_pos'], goal_pos=g['goal_pos'])
+    steps, done = 0, False
+    while not done and steps < 3000:
+        done = w.step(pol, orc.NBR_REF_COMPAT)
+        steps += 1
+    m = _metrics(w.status, w.total_dist, w.step_num, g['straight_len'], g['desire_steps'], w.n)
+    print(name, steps, int(g['rollout_steps']), m, g['metrics'])
+    assert done and steps == int(g['rollout_steps'])          # the reference loop breaks on the step that finishes
+    assert m[0] == g['metrics'][0]
+    assert np.allclose(m[1:], g['metrics'][1:], rtol=0, atol=1e-6)
+
+
+DUBINS = ['circle16_sca', 'circle16_rvo3d_dubins', 'takeoff16_sca', 'dense40_sca', 'circle100_sca']
+
+
+@pytest.mark.parametrize('name', DUBINS)
+def test_oracle_dubins_rollout_matches_reference(name):
+    """Free-running (no teacher forcing): oracle policy + oracle Dubins tracker for as many steps as the reference
+    was recorded; the final state and the metrics are the reference's."""
+    from oracle import oracle as orc
+    g = gu.load(name)
+    pol = str(g['policy'])
+    w = orc.World(g['pos'][0], g['goal'], heading=g['heading'][0], radius=g['radius'], pref_speed=g['pref_speed'],
+                  obstacles=g['obstacles'], initial_pos=g['initial_pos'], goal_pos=g['goal_pos'])
+    prov = orc.DubinsProvider(w.n)
+    T = int(g['rollout_steps'])
+    for _ in range(T):
+        w.step_dubins(pol, prov, g['goal_pos'][:, 3:6])
+    s = gu.state_at(g, T)
+    print(name, T, np.abs(w.pos - s['pos']).max())
+    assert np.array_equal(w.status & 15, s['status'] & 15) and np.array_equal(w.step_num, s['step_num'])
+    assert np.abs(w.pos - s['pos']).max() <= 1e-9
+    m = _metrics(w.status, w.total_dist, w.step_num, g['straight_len'], g['desire_steps'], w.n)
+    assert m[0] == g['metrics'][0] and np.allclose(m[1:], g['metrics'][1:], rtol=0, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', FULL)
+def test_gpu_rollout_matches_reference(name):
+    from sca_b200 import capi
+    from sca_b200.env import BatchedEnv
+    g = gu.load(name)
+    env = BatchedEnv(str(g['policy']), nbr_mode=capi.NBR_REF_COMPAT)
+    env.set_agents(g['initial_pos'], g['goal_pos'], g['obstacles'], radius=g['radius'], pref_speed=g['pref_speed'])
+    done = False
+    while not done and env.steps < 3000:
+        done = env.step()
+    m = env.metrics()
+    ref = g['metrics']
+    print(name, env.steps, int(g['rollout_steps']), m, ref)
+    assert done
+    # last-ulp libm differences (device vs NumPy sin/cos/atan2) can shift an arrival by a step: statistics, not bits
+    assert abs(env.steps - int(g['rollout_steps'])) <= max(2, int(0.01 * g['rollout_steps']))
+    assert m['SuccessRate'] == ref[0]
+    assert abs(m['ExtraTime'] - ref[1]) <= 0.05 + 0.01 * abs(ref[1])
+    assert abs(m['ExtraDistance'] - ref[2]) <= 0.01 + 0.01 * abs(ref[2])
+    assert abs(m['AverageSpeed'] - ref[3]) <= 0.005
