@@ -7,8 +7,8 @@
 //   is_parallel         mamp/util.py:125-137
 // The reference materialises the sampled path as a Python list and pops points off it; here the path is its
 // two 2-D manoeuvres plus a cursor, and sample i is evaluated on demand with the same arithmetic.
-// One thread per agent (fp64).  A re-plan costs ~100 radius trials x 12 Dubins words; agents that keep
-// tracking their path only evaluate one or two samples.
+// Two kernels, one thread per agent, fp64: k_dubins_track follows the current path (one or two samples) and lists
+// the agents that need a new plan; k_dubins_replan plans those (~100 radius trials x 12 Dubins words each).
 #include "scab_common.cuh"
 
 struct Man2D {
@@ -34,12 +34,11 @@ size_t scab_dubins_state_bytes() { return sizeof(DubState); }
 __device__ __forceinline__ double mod2pi_d(double th) { return th - 2.0 * SCAB_PI * floor(th / 2.0 / SCAB_PI); }
 
 // dubinsmaneuver2d.py:33-145
-__device__ bool plan_word(int w, double alpha, double beta, double d, double &t, double &p, double &q, int *mode)
+struct WordTrig { double sa, ca, sb, cb, c_ab; };   // the five trig values every word shares, evaluated once per 2-D plan
+
+__device__ __forceinline__ bool plan_word(int w, double alpha, double beta, double d, const WordTrig &T, double &t, double &p, double &q, int *mode)
 {
-    double sa, ca, sb, cb;
-    sincos(alpha, &sa, &ca);
-    sincos(beta, &sb, &cb);
-    const double c_ab = cos(alpha - beta);
+    const double sa = T.sa, ca = T.ca, sb = T.sb, cb = T.cb, c_ab = T.c_ab;
     switch (w) {
     case 0: {   // LSL
         mode[0] = ML; mode[1] = MS; mode[2] = ML;
@@ -112,10 +111,15 @@ __device__ __noinline__ void plan2d(const double *start, const double *end, doub
     const double theta = mod2pi_d(atan2(ey, ex));
     const double alpha = mod2pi_d(start[2] - theta), beta = mod2pi_d(end[2] - theta);
     double bcost = INFINITY;
+    WordTrig T;
+    sincos(alpha, &T.sa, &T.ca);
+    sincos(beta, &T.sb, &T.cb);
+    T.c_ab = cos(alpha - beta);
+#pragma unroll
     for (int w = 0; w < 6; w++) {
         double t, p, q;
         int mode[3];
-        if (!plan_word(w, alpha, beta, d, t, p, q, mode)) continue;
+        if (!plan_word(w, alpha, beta, d, T, t, p, q, mode)) continue;
         const double cost = c * (fabs(t) + fabs(p) + fabs(q));
         if (bcost > cost) {
             m.t = t; m.p = p; m.q = q;
@@ -249,71 +253,119 @@ __device__ void update_dubins(DubState &S, const double *pos, const double *goal
     }
 }
 
-// k_vpref with the Dubins tracker as the v_pref source (thread per agent, cell-sorted order)
-__global__ void __launch_bounds__(64) k_vpref_dubins(const StepArgs A, DubState *states)
+// Inputs of one agent's compute_v_pref, gathered once
+struct AgentIn {
+    int id, flags;
+    float4 mv;
+    double pos[3], goal[3], heading[3], gh[3], pref, dis_goal;
+};
+
+__device__ __forceinline__ void load_agent(const StepArgs &A, int s, AgentIn &I)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= A.n) return;
-    const float4 mv = A.s_vel[s];
-    const int flags = __float_as_int(mv.w);
-    if (flags & FL_INACTIVE) return;
-    const int id = A.s_id[s];
+    I.mv = A.s_vel[s];
+    I.flags = __float_as_int(I.mv.w);
+    I.id = A.s_id[s];
+    const int id = I.id;
     const double4 me = A.s_posr[s];
-    DubState &S = states[id];
-    const double pos[3] = {me.x, me.y, me.z};
-    const double goal[3] = {A.st.goal[3 * id], A.st.goal[3 * id + 1], A.st.goal[3 * id + 2]};
-    const double heading[3] = {A.st.heading[3 * id], A.st.heading[3 * id + 1], A.st.heading[3 * id + 2]};
-    double gh[3] = {0.0, 0.0, 0.0};
-    if (A.st.goal_heading) { gh[0] = A.st.goal_heading[3 * id]; gh[1] = A.st.goal_heading[3 * id + 1]; gh[2] = A.st.goal_heading[3 * id + 2]; }
-    const double pref = A.st.pref_speed[id];
-    const bool zaxis = (flags & SCAB_ST_ZAXIS) != 0;
-    // scaPolicy.py:264-338
-    const double dis_goal = l3norm_d(pos[0], pos[1], pos[2], goal[0], goal[1], goal[2]);
-    const double k = 3.0 * 1.5;
-    double dif[3];
-    if (!S.in_use) {
-        S.in_use = 1;
-        replan(S, pos, heading, goal, gh);
-        for (int d = 0; d < 3; d++) dif[d] = S.now_goal[d] - pos[d];
-    } else {
-        update_dubins(S, pos, goal);
-        const double dis = l3norm_d(pos[0], pos[1], pos[2], S.now_goal[0], S.now_goal[1], S.now_goal[2]);
-        const double max_size = py_round5(6 * S.ss);
-        const double gx = goal[0] - pos[0], gy = goal[1] - pos[1], gz = goal[2] - pos[2];
-        const double ct = dot3((double)mv.x, (double)mv.y, (double)mv.z, gx, gy, gz) /
-                          ((double)norm3f_np(mv.x, mv.y, mv.z) * sqrt(dot3(gx, gy, gz, gx, gy, gz)));
-        const double cm = (1.0 < ct) ? 1.0 : ct;             // python min(ct, 1.0) keeps a NaN
-        const double theta = py_round5(acos(cm));
-        const double deg100 = py_round5(100.0 * (SCAB_PI / 180.0));
-        const double min_dist_ob = S.has_nbr ? py_round5(sqrt(S.nbr0_dsq)) : 10.0;
-        const bool condition_dist = zaxis ? (min_dist_ob >= 2.0 * 1.5) : false;
-        if (((is_parallel_d(mv.x, mv.y, mv.z, S.v_pref) || dis_goal <= k) && dis < max_size) || (theta >= deg100) || condition_dist) {
-            update_dubins(S, pos, goal);
-            if (S.cursor < S.n_points) for (int d = 0; d < 3; d++) dif[d] = S.now_goal[d] - pos[d];
-            else for (int d = 0; d < 3; d++) dif[d] = goal[d] - pos[d];
-        } else {
-            replan(S, pos, heading, goal, gh);
-            for (int d = 0; d < 3; d++) dif[d] = S.now_goal[d] - pos[d];
-        }
+    I.pos[0] = me.x; I.pos[1] = me.y; I.pos[2] = me.z;
+    for (int d = 0; d < 3; d++) {
+        I.goal[d] = A.st.goal[3 * id + d];
+        I.heading[d] = A.st.heading[3 * id + d];
+        I.gh[d] = A.st.goal_heading ? A.st.goal_heading[3 * id + d] : 0.0;
     }
+    I.pref = A.st.pref_speed[id];
+    I.dis_goal = l3norm_d(I.pos[0], I.pos[1], I.pos[2], I.goal[0], I.goal[1], I.goal[2]);
+}
+
+// scaPolicy.py:329-338: normalise, the at-goal zero, the 1e-5 truncation; then remember this step's
+// agent.neighbors[0][1] (read by the NEXT compute_v_pref, scaPolicy.py:299)
+__device__ __forceinline__ void finish_vpref(const StepArgs &A, int s, const AgentIn &I, DubState &S, const double *dif)
+{
+    const int id = I.id;
     const double nrm = py_round5(__dsqrt_rn(sumsq3(dif[0], dif[1], dif[2])));
-    for (int d = 0; d < 3; d++) S.v_pref[d] = __ddiv_rn(__dmul_rn(dif[d], pref), nrm);
-    if (dis_goal < 0.2) S.v_pref[0] = S.v_pref[1] = S.v_pref[2] = 0.0;     // reached(goal, pos, 0.2)
-    const double nv32 = __dsqrt_rn(sumsq_f32(mv.x, mv.y, mv.z));
-    const bool first = py_round5(nv32) <= 1e-5;                            // scaPolicy.py:34
-    A.s_vdes[s] = make_double4(trunc5(S.v_pref[0]), trunc5(S.v_pref[1]), trunc5(S.v_pref[2]), first ? -pref : pref);
+    for (int d = 0; d < 3; d++) S.v_pref[d] = __ddiv_rn(__dmul_rn(dif[d], I.pref), nrm);
+    if (I.dis_goal < 0.2) S.v_pref[0] = S.v_pref[1] = S.v_pref[2] = 0.0;     // reached(goal, pos, 0.2)
+    const double nv32 = __dsqrt_rn(sumsq_f32(I.mv.x, I.mv.y, I.mv.z));
+    const bool first = py_round5(nv32) <= 1e-5;                              // scaPolicy.py:34
+    A.s_vdes[s] = make_double4(trunc5(S.v_pref[0]), trunc5(S.v_pref[1]), trunc5(S.v_pref[2]), first ? -I.pref : I.pref);
     if (A.st.vpref_out) { A.st.vpref_out[3 * id] = S.v_pref[0]; A.st.vpref_out[3 * id + 1] = S.v_pref[1]; A.st.vpref_out[3 * id + 2] = S.v_pref[2]; }
-    // agent.neighbors[0][1] as this step's computeNeighbors leaves it (read by the NEXT compute_v_pref,
-    // scaPolicy.py:299); the zero-velocity shortcut does not query neighbours (scaPolicy.py:34-45)
-    if (!first) {
+    if (!first) {   // the zero-velocity shortcut does not query neighbours (scaPolicy.py:34-45)
         const double d0 = A.dub_d0[id];
         S.has_nbr = d0 >= 0.0;
         S.nbr0_dsq = d0 >= 0.0 ? d0 : 0.0;
     }
 }
 
+// Pass 1 (thread per agent, cell-sorted order): follow the current path (scaPolicy.py:264-327).  Agents that need
+// a new plan are appended to A.slow_list -- a re-plan is ~100x the work of tracking, so it runs in its own
+// kernel with full warps instead of a few divergent lanes.
+__global__ void __launch_bounds__(128) k_dubins_track(const StepArgs A, DubState *states)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    bool need_plan = false;
+    if (s < A.n && !(__float_as_int(A.s_vel[s].w) & FL_INACTIVE)) {
+        AgentIn I;
+        load_agent(A, s, I);
+        DubState &S = states[I.id];
+        if (!S.in_use) {
+            need_plan = true;
+        } else {
+            update_dubins(S, I.pos, I.goal);
+            const double dis = l3norm_d(I.pos[0], I.pos[1], I.pos[2], S.now_goal[0], S.now_goal[1], S.now_goal[2]);
+            const double max_size = py_round5(6 * S.ss);
+            const double gx = I.goal[0] - I.pos[0], gy = I.goal[1] - I.pos[1], gz = I.goal[2] - I.pos[2];
+            const double ct = dot3((double)I.mv.x, (double)I.mv.y, (double)I.mv.z, gx, gy, gz) /
+                              ((double)norm3f_np(I.mv.x, I.mv.y, I.mv.z) * sqrt(dot3(gx, gy, gz, gx, gy, gz)));
+            const double cm = (1.0 < ct) ? 1.0 : ct;             // python min(ct, 1.0) keeps a NaN
+            const double theta = py_round5(acos(cm));
+            const double deg100 = py_round5(100.0 * (SCAB_PI / 180.0));
+            const double min_dist_ob = S.has_nbr ? py_round5(sqrt(S.nbr0_dsq)) : 10.0;
+            const bool condition_dist = (I.flags & SCAB_ST_ZAXIS) ? (min_dist_ob >= 2.0 * 1.5) : false;
+            if (((is_parallel_d(I.mv.x, I.mv.y, I.mv.z, S.v_pref) || I.dis_goal <= 3.0 * 1.5) && dis < max_size) || (theta >= deg100) ||
+                condition_dist) {
+                update_dubins(S, I.pos, I.goal);
+                double dif[3];
+                if (S.cursor < S.n_points) for (int d = 0; d < 3; d++) dif[d] = S.now_goal[d] - I.pos[d];
+                else for (int d = 0; d < 3; d++) dif[d] = I.goal[d] - I.pos[d];
+                finish_vpref(A, s, I, S, dif);
+            } else {
+                need_plan = true;
+            }
+        }
+    }
+    // warp-aggregated append
+    const unsigned msk = __ballot_sync(0xffffffffu, need_plan);
+    if (msk) {
+        const int lane = threadIdx.x & 31, leader = __ffs(msk) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(A.slow_count, __popc(msk));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (need_plan) A.slow_list[base + __popc(msk & ((1u << lane) - 1))] = s;
+    }
+}
+
+// Pass 2 (thread per listed agent): compute_dubins + the first pops (scaPolicy.py:92-104,275-279,322-327)
+__global__ void __launch_bounds__(64) k_dubins_replan(const StepArgs A, DubState *states)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= *A.slow_count) return;
+    const int s = A.slow_list[k];
+    AgentIn I;
+    load_agent(A, s, I);
+    DubState &S = states[I.id];
+    S.in_use = 1;
+    replan(S, I.pos, I.heading, I.goal, I.gh);
+    double dif[3];
+    for (int d = 0; d < 3; d++) dif[d] = S.now_goal[d] - I.pos[d];
+    finish_vpref(A, s, I, S, dif);
+}
+
 cudaError_t launch_vpref_dubins(const StepArgs &A, cudaStream_t s)
 {
-    if (A.n > 0) k_vpref_dubins<<<(A.n + 63) / 64, 64, 0, s>>>(A, (DubState *)A.dub_states);
+    if (A.n <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(A.slow_count, 0, sizeof(int32_t), s);
+    if (e != cudaSuccess) return e;
+    k_dubins_track<<<(A.n + 127) / 128, 128, 0, s>>>(A, (DubState *)A.dub_states);
+    k_dubins_replan<<<(A.n + 63) / 64, 64, 0, s>>>(A, (DubState *)A.dub_states);   // surplus blocks exit on the device-side count
     return cudaGetLastError();
 }

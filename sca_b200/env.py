@@ -14,8 +14,11 @@ from .swarm import Swarm
 
 
 class BatchedEnv(object):
-    def __init__(self, policy, nbr_mode=capi.NBR_KNN, device='cuda:0', debug=False):
+    def __init__(self, policy, nbr_mode=capi.NBR_KNN, device='cuda:0', debug=False, dubins=None):
+        """`dubins` (default: True for 'sca' and 'rvo3d_dubins', the two policies whose reference v_pref is the
+        Dubins tracker of scaPolicy.py:264-338): run that tracker on the device; False = straight-line v_pref."""
         self.policy = policy
+        self.dubins = (policy in ('sca', 'rvo3d_dubins')) if dubins is None else bool(dubins)
         self.nbr_mode = nbr_mode
         self.device = device
         self.debug = debug
@@ -32,6 +35,8 @@ class BatchedEnv(object):
         lo = np.minimum(pos6[:, :3].min(0), goal6[:, :3].min(0)) - margin
         hi = np.maximum(pos6[:, :3].max(0), goal6[:, :3].max(0)) + margin
         self.sw.fit_grid(lo, hi)
+        if self.dubins:
+            self.sw.enable_dubins(goal6[:, 3:6])
         # agent.py:51-52 (metrics): straight_path_length = l3norm(start, goal) - 0.5, desire_steps
         d = np.round(np.sqrt(((pos6[:, :3] - goal6[:, :3]) ** 2).sum(1)), 5)
         self.straight_len = d - 0.5

@@ -56,6 +56,10 @@ class GPUKDTree(object):
         lo = np.minimum(pos.min(0), goal.min(0)) - 20.0
         hi = np.maximum(pos.max(0), goal.max(0)) + 20.0
         self.sw.fit_grid(lo, hi)
+        if self.vpref_provider == 'device':
+            # the Dubins tracker itself on the GPU (scab_dubins_enable) instead of the host-side reference tracker
+            self.sw.enable_dubins(np.array([a.goal_pos for a in agents], 'float64')[:, 3:6])
+            self.vpref_provider = None
         self._host = {k: torch.zeros_like(self.sw.t[k], device='cpu').pin_memory()
                       for k in ('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')}
         self._vp = torch.zeros((n, 3), dtype=torch.float64).pin_memory()
