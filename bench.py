@@ -94,7 +94,14 @@ def make_swarm(n_total, rank, world, device, seed=0):
     lo, hi = np.array([-15.0, -15.0, 5.0]), np.array([L + 15.0, L + 15.0, L + 35.0])
     if world == 1:
         sw = Swarm(n_total, device=device, debug=False)
-        sw.set_state(pos[:, :3], goal[:, :3], heading=pos[:, 3:])
+        if os.environ.get('SCAB_BENCH_NO_SORT', '0') != '1':
+            # rows laid out cell by cell at t = 0 (ids travel in gid; results are independent of the row order)
+            order = scenarios.spatial_order(pos[:, :3])
+            pos, goal = pos[order], goal[order]
+            sw.set_state(pos[:, :3], goal[:, :3], heading=pos[:, 3:])
+            sw.set_global_ids(order.astype(np.int32), n_total)
+        else:
+            sw.set_state(pos[:, :3], goal[:, :3], heading=pos[:, 3:])
         sw.fit_grid(lo, hi)
         return sw
     from sca_b200.sharding import ShardedSwarm

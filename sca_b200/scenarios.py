@@ -158,3 +158,15 @@ def uniform_box_torch(n, density=1.0e6 / 560.0 ** 3, seed=0, min_sep=1.1, device
     goal[:, :3] = torch.rand((n, 3), generator=g, device=device, dtype=torch.float64) * L
     goal[:, 2] += 20.0
     return pos.cpu().numpy(), goal.cpu().numpy(), np.zeros((0, 4))
+
+
+def spatial_order(pos, cell=10.0):
+    """Permutation that lists the agents cell by cell (z-major, the order of the library's cell list).  Laying the
+    state rows out in this order at t = 0 (the agents' own ids travel in `gid`, Swarm.set_global_ids) makes every
+    gather / scatter between the caller's rows and the cell-sorted snapshot nearly coalesced; results do not depend
+    on the row order because ties and the collision-check order follow the ids.  Agents move <= 0.1 m per step, so
+    the layout stays coherent for thousands of steps."""
+    p = np.asarray(pos, 'float64')[:, :3]
+    c = np.floor((p - p.min(0)) / cell).astype(np.int64)
+    dim = c.max(0) + 1
+    return np.argsort((c[:, 2] * dim[1] + c[:, 1]) * dim[0] + c[:, 0], kind='stable')

@@ -134,6 +134,8 @@ class ShardedSwarm:
         self.plan = SlabPlan(pos6[:, 0], world, migrate_every=migrate_every)
         own_all = self.plan.owner(pos6[:, 0])
         mine = np.nonzero(own_all == rank)[0]
+        from .scenarios import spatial_order
+        mine = mine[spatial_order(pos6[mine, :3])]     # rows laid out cell by cell: coalesced gathers / scatters
         self.n_own = len(mine)
         # halo capacity per face: agents within `width` of a face, with head room
         # (the SAME value on every rank: the face buffers are exchanged as fixed-size messages)
