@@ -12,6 +12,7 @@
 // `< 100.0` / `< (rA+rB)^2` cuts are reproduced exactly.
 #include "scab_common.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 struct Key {
     double d;
@@ -131,20 +132,10 @@ __device__ __forceinline__ void write_lists2(const StepArgs &A, int s, int id, c
 
 // ------------------------------------------------------------------ KNN over the cell list
 #define KNN_CAP 48
-__global__ void __launch_bounds__(128) k_neighbors_knn(StepArgs A)
+// The exact general path (obstacles, ties on the decimal-rounded distance, more than KNN_CAP raw candidates):
+// fp64 keys + the (distSq, obstacles-before-agents, id) comparator, register-resident top-16 insertion.
+__device__ __noinline__ void knn_exact(const StepArgs &A, int s, int id, const double4 me, int (*buf)[128])
 {
-    __shared__ int buf[KNN_CAP][128];
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= A.n) return;
-    const int id = A.s_id[s];
-    const int flags = __float_as_int(A.s_vel[s].w);
-    if (flags & FL_INACTIVE) {
-        A.s_nbr_cnt[s] = -1;
-        A.s_qcoll[s] = 0;
-        if (A.st.nbr_cnt) A.st.nbr_cnt[id] = -1;
-        return;
-    }
-    const double4 me = A.s_posr[s];
     TopK2 L;
     L.clear();
     bool coll = false;
@@ -229,6 +220,118 @@ __global__ void __launch_bounds__(128) k_neighbors_knn(StepArgs A)
         flush();
     }
     write_lists2(A, s, id, L, coll ? 1 : 0);
+}
+
+
+// Fast path of the common case (no obstacles, distinct distance keys): the decimal-rounded squared distance is an
+// exact integer number of 1e-5 units (< 2^24 for neighbor_dist < 12.9 m), so (units << 8 | candidate slot) is a
+// 32-bit sort key and inserting into the sorted top-16 is a branch-free min/max network on 16 registers:
+//     new[k] = min(old[k], max(old[k-1], x)).
+// A tie on the distance (the reference breaks it by agent id) is detected afterwards -- two equal neighbours in
+// the list, or the best rejected key equal to the last kept one -- and sends the agent to knn_exact.
+__global__ void __launch_bounds__(128, 6) k_neighbors_knn(const __grid_constant__ StepArgs A, int fast_ok)
+{
+    __shared__ int buf[KNN_CAP][128];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= A.n) return;
+    const int id = A.s_id[s];
+    const int flags = __float_as_int(A.s_vel[s].w);
+    if (flags & FL_INACTIVE) {
+        A.s_nbr_cnt[s] = -1;
+        A.s_qcoll[s] = 0;
+        if (A.st.nbr_cnt) A.st.nbr_cnt[id] = -1;
+        return;
+    }
+    const double4 me = A.s_posr[s];
+    if (!fast_ok) { knn_exact(A, s, id, me, buf); return; }
+    const double rangeSq = A.nbr_dist_sq;
+    // phase 1: record the candidates whose raw squared distance can be in range (a shared-memory column per thread)
+    int nbuf = 0;
+    bool overflow = false;
+    {
+        int cx, cy, cz;
+        cell_of(A.g, me.x, me.y, me.z, cx, cy, cz);
+        const double lim = rangeSq + 1e-4;   // the 5-decimal rounding cannot bring anything beyond this back in range
+        for (int dz = -1; dz <= 1; dz++) {
+            const int z = cz + dz;
+            if (z < 0 || z >= A.g.nz) continue;
+            for (int dy = -1; dy <= 1; dy++) {
+                const int y = cy + dy;
+                if (y < 0 || y >= A.g.ny) continue;
+                const int row = (z * A.g.ny + y) * A.g.nx;
+                const int beg = A.cell_start[row + max(cx - 1, 0)];
+                const int end = A.cell_start[row + min(cx + 1, A.g.nx - 1) + 1];
+                for (int j0 = beg; j0 < end; j0 += 4) {
+                    double4 o[4];          // four independent loads in flight per thread
+#pragma unroll
+                    for (int q = 0; q < 4; q++) o[q] = A.s_posr[min(j0 + q, end - 1)];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int j = j0 + q;
+                        const double ex = me.x - o[q].x, ey = me.y - o[q].y, ez = me.z - o[q].z;
+                        const double ss = ex * ex + ey * ey + ez * ez;
+                        if (j >= end || ss > lim || j == s) continue;
+                        if (nbuf < KNN_CAP) buf[nbuf++][threadIdx.x] = j;
+                        else overflow = true;
+                    }
+                }
+            }
+        }
+    }
+    // phase 2: exact keys, all lanes together
+    unsigned L[KNBR];
+#pragma unroll
+    for (int k = 0; k < KNBR; k++) L[k] = 0xffffffffu;
+    unsigned rej_min = 0xffffffffu;
+    int cnt = 0;
+    bool coll = false;
+    for (int i = 0; i < nbuf; i++) {
+        const int j = buf[i][threadIdx.x];
+        const double4 o = A.s_posr[j];
+        // l3normsq (util.py:99-100): round(sum, 5) = rint(sum * 1e5) / 1e5
+        const double units = rint(__dmul_rn(sumsq3(__dsub_rn(me.x, o.x), __dsub_rn(me.y, o.y), __dsub_rn(me.z, o.z)), 1e5));
+        const double dsq = __ddiv_rn(units, 1e5);
+        if (!(dsq < rangeSq)) continue;
+        const double rr = __dadd_rn(me.w, o.w);
+        const bool is_c = dsq < __dmul_rn(rr, rr);      // agent.py:83-85: from the first collider on, colliders only
+        if (is_c && !coll) {
+            coll = true;
+#pragma unroll
+            for (int k = 0; k < KNBR; k++) L[k] = 0xffffffffu;
+            rej_min = 0xffffffffu;
+            cnt = 0;
+        }
+        if (coll && !is_c) continue;
+        const unsigned x = ((unsigned)(int)units << 8) | (unsigned)i;
+        rej_min = min(rej_min, max(L[KNBR - 1], x));
+#pragma unroll
+        for (int k = KNBR - 1; k >= 1; k--) L[k] = min(L[k], max(L[k - 1], x));
+        L[0] = min(L[0], x);
+        cnt++;
+    }
+    const int n_in = min(cnt, KNBR);
+    bool tie = overflow || (cnt > KNBR && (rej_min >> 8) == (L[KNBR - 1] >> 8));
+#pragma unroll
+    for (int k = 1; k < KNBR; k++) tie |= (k < n_in) && ((L[k] >> 8) == (L[k - 1] >> 8));
+    if (tie) { knn_exact(A, s, id, me, buf); return; }
+    int sx[KNBR];
+#pragma unroll
+    for (int k = 0; k < KNBR; k++) sx[k] = (k < n_in) ? buf[L[k] & 0xffu][threadIdx.x] : -1;
+    A.s_nbr_cnt[s] = n_in;
+    A.s_qcoll[s] = coll ? 1 : 0;
+    if (A.dub_d0) A.dub_d0[id] = n_in > 0 ? __ddiv_rn((double)(L[0] >> 8), 1e5) : -1.0;
+    int4 *dst = reinterpret_cast<int4 *>(A.s_nbr + (size_t)s * KNBR);
+#pragma unroll
+    for (int q = 0; q < KNBR / 4; q++) dst[q] = make_int4(sx[4 * q], sx[4 * q + 1], sx[4 * q + 2], sx[4 * q + 3]);
+    if (A.st.nbr_cnt) A.st.nbr_cnt[id] = n_in;
+    if (A.st.nbr_ids) {
+#pragma unroll
+        for (int k = 0; k < KNBR; k++) A.st.nbr_ids[(size_t)id * KNBR + k] = (k < n_in) ? A.s_gid[sx[k]] : -1;
+    }
+    if (A.st.nbr_dsq) {
+#pragma unroll
+        for (int k = 0; k < KNBR; k++) A.st.nbr_dsq[(size_t)id * KNBR + k] = (k < n_in) ? __ddiv_rn((double)(L[k] >> 8), 1e5) : 0.0;
+    }
 }
 
 // ------------------------------------------------------------------ REF_COMPAT: literal replay
@@ -357,6 +460,11 @@ cudaError_t launch_neighbors(const StepArgs &A, int mode, cudaStream_t s)
     if (A.n <= 0) return cudaSuccess;
     int nb = (A.n + 127) / 128;
     if (mode == SCAB_NBR_REF_COMPAT) k_neighbors_compat<<<nb, 128, 0, s>>>(A);
-    else k_neighbors_knn<<<nb, 128, 0, s>>>(A);
+    else {
+        // the integer-key fast path needs: no obstacles in the merged list, and distance keys below 2^24 units of 1e-5
+        static const bool no_fast = []() { const char *e = getenv("SCAB_KNN_EXACT"); return e && e[0] == '1'; }();   // A/B switch
+        const int fast_ok = (A.m == 0 && A.nbr_dist_sq * 1e5 < 16777215.0 && !no_fast) ? 1 : 0;
+        k_neighbors_knn<<<nb, 128, 0, s>>>(A, fast_ok);
+    }
     return cudaGetLastError();
 }
