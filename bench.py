@@ -31,7 +31,7 @@ import numpy as np  # noqa: E402
 
 DENSITY = 1.0e6 / 560.0 ** 3          # agents per m^3 of BASELINE config 5
 ALGO_BYTES = {'grid': 168, 'neighbors': 116, 'policy': 660, 'status': 144}   # SURVEY.md 8(d), per agent-step
-KERNELS_PER_STEP = 9                  # k_cell_count, k_cell_scan, k_reorder, k_neighbors_knn, k_vpref, k_select_fast, k_select, k_integrate, k_status
+KERNELS_PER_STEP = 11                 # k_cell_count, k_scan_tile_sums, k_scan_tiles, k_scan_apply, k_reorder, k_neighbors_knn, k_vpref, k_select_fast, k_select, k_integrate, k_status
 METRIC = 'agent-steps/sec (SCA, 1M UAVs)'
 
 

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libscab200.so')
+LIB_PATH = os.environ.get('SCAB_LIB_PATH') or os.path.join(HERE, 'libscab200.so')   # override: A/B builds
 
 POLICIES = {'sca': 0, 'srvo3d': 1, 'rvo3d': 2, 'rvo3d_dubins': 3, 'orca_sampled': 4, 'orca_lp': 5}
 NBR_KNN, NBR_REF_COMPAT = 0, 1

@@ -22,6 +22,7 @@
 //   D  the "no suitable velocity" path (scaPolicy.py:148-165, 224-238) entirely in fp64.
 #include "scab_common.cuh"
 #include <limits.h>
+#include <type_traits>
 
 #define WARPS_PER_CTA 4
 #define MAX_CAND 513
@@ -463,9 +464,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
         // keys, once per live slot
         unsigned long long ka = ~0ull;
         unsigned kb = 0xffffffffu;
-        for (int j = lane; j < total; j += 32) {
-            if (!slot_live(j)) continue;
-            const int c = slot_cand(j);
+        // `heavy`: run the time-to-collision loop of compute_without_suitV (posture-passing candidates only)
+        auto eval_key = [&](int j, int c, bool heavy) {
             double x, y, z;
             cand64(a, c, x, y, z);
             const double dist = __dsqrt_rn(sumsq3(__dsub_rn(x, a.vdx), __dsub_rn(y, a.vdy), __dsub_rn(z, a.vdz)));
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
                 // compute_without_suitV (scaPolicy.py:148-165 / orca3dPolicy.py:381-397)
                 double tcmin = 0.0;
                 bool have = false;
-                if (posture_ok(a, A.time_step, x, y, z)) {
+                if (heavy) {
                     for (int k = 0; k < nc; k++) {
                         double ax, ay, az, dx, dy, dz;
                         if (!IS_ORCA) {
@@ -487,7 +487,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
                             ax = W.rpx[k]; ay = W.rpy[k]; az = W.rpz[k];
                             dx = __dsub_rn(x, W.ofx[k]); dy = __dsub_rn(y, W.ofy[k]); dz = __dsub_rn(z, W.ofz[k]);
                         }
-                        if (is_intersect64(ax, ay, az, W.dR[k], dx, dy, dz)) {
+                        // same decision as is_intersect64: the algebraic form defers to asin/acos near the boundary
+                        if (is_intersect64_fast(ax, ay, az, W.dR[k], dx, dy, dz)) {
                             const double dv = dot3(dx, dy, dz, ax, ay, az);
                             const double v2 = dot3(dx, dy, dz, dx, dy, dz);
                             const double discr = __dsub_rn(__dmul_rn(dv, dv),
@@ -508,6 +509,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
                 W.dvu[j] = (unsigned int)py_round5_units(dva);
             }
             if (lex_less(key, (unsigned)c, ka, kb)) { ka = key; kb = (unsigned)c; }
+        };
+        if (!fallback) {
+            for (int j = lane; j < total; j += 32)
+                if (slot_live(j)) eval_key(j, slot_cand(j), false);
+        } else {
+            // Every one of the C candidates gets a key, but only those that pass the posture test (the compacted
+            // list of phase A, ~15 %) walk the neighbours; doing them first, lanes together, keeps this path
+            // -- one warp, a single agent's latency -- short.
+            for (int j = lane; j < C; j += 32) W.key[j] = ~0ull;
+            __syncwarp();
+            for (int j = lane; j < ncand; j += 32) {
+                const int c = (int)(W.list[j] & 0x7fff);
+                eval_key(c, c, true);
+            }
+            __syncwarp();
+            for (int j = lane; j < C; j += 32)
+                if (W.key[j] == ~0ull) eval_key(j, j, false);
         }
         // 1. head of the sorted list
         warp_min_key_c(ka, kb);
@@ -637,7 +655,7 @@ template <int POLICY>
 static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
 {
     static int per_sm = 0, per_sm_fast = 0, no_fast = -1;
-    const size_t smem = sizeof(WarpSmem) * WARPS_PER_CTA, smem_fast = sizeof(GroupSmem) * FG_WARPS * FG_PER_WARP + 384 * sizeof(float4);
+    const size_t smem = sizeof(WarpSmem) * WARPS_PER_CTA, smem_fast = sizeof(GroupSmemT<POLICY == SCAB_POLICY_ORCA_SAMPLED>) * FG_WARPS * FG_PER_WARP + 384 * sizeof(float4);
     if (per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(k_select<POLICY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select<POLICY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -20,22 +20,60 @@
 #define DIR_CAP 64        // surviving directions per agent (a pi/4 cap holds ~38 of 256)
 #define LIVE_CAP 136      // 2 * DIR_CAP + v_pref, rounded up
 #define VPREF_ENTRY 0x3ff
+#ifndef FG_MIN_CTAS
+#define FG_MIN_CTAS 5   // resident CTAs per SM the cone policies are compiled for (registers <= 96)
+#endif
 // tier 1 = candidates within StepArgs::tier_delta (default 0.3, SCAB_TIER_DELTA) of the one closest to v_pref
 
-struct GroupSmem {
+// fp64 copies of the constraints for the guard-band recheck.  Only the ORCA planes keep them in shared memory;
+// a cone is cheap to rebuild from the neighbour record (recheck_cone64), and without these 896 bytes a fifth CTA
+// fits on the SM.
+struct Exact64 {
+    double dpx[KNBR], dpy[KNBR], dpz[KNBR];
+    double dhx[KNBR], dhy[KNBR], dhz[KNBR];
+};
+struct NoExact64 {};
+
+template <bool WITH64>
+struct GroupSmemT : public std::conditional<WITH64, Exact64, NoExact64>::type {
     float4 cp[KNBR];
     float4 ch[KNBR];
     float2 cg[KNBR];
-    double dpx[KNBR], dpy[KNBR], dpz[KNBR];
-    double dhx[KNBR], dhy[KNBR], dhz[KNBR];
-    double dR[KNBR];
     int cidx[KNBR];
     unsigned short dirs[DIR_CAP];    // n | shell mask << 12 ; VPREF_ENTRY = v_pref itself
     unsigned int kc[LIVE_CAP];       // live candidates: c, later key << 10 | c
     unsigned int dvu[LIVE_CAP];      // l3norm(v, vA) in units of 1e-5
     unsigned char act[DIR_CAP];      // entries of the current tier: j | shell mask << 6
-    int pad[4];                      // sizeof % 128 == 16: the four groups of a warp hit different banks
+    int pad[4];                      // sizeof % 128 == 80: the four groups of a warp start in different banks
 };
+
+// the guard-band recheck of one cone (scaPolicy.py:47-60,180 + util.py:30-41) rebuilt from the neighbour record
+__device__ __noinline__ bool recheck_cone64(const StepArgs &A, int s, int k, const Agent &a, double x, double y, double z)
+{
+    const int e = A.s_nbr[(size_t)s * KNBR + k];
+    double4 o;
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    bool at_goal = true;
+    if (e < A.n) {
+        o = A.s_posr[e];
+        const float4 ov = A.s_vel[e];
+        ox = ov.x; oy = ov.y; oz = ov.z;
+        at_goal = (__float_as_int(ov.w) & SCAB_ST_AT_GOAL) != 0;
+    } else if (e < A.n + A.m) {
+        o = A.o_posr[e - A.n];
+    } else {
+        o = A.o_posr_by_id[e - A.n - A.m];
+    }
+    const double R = __dadd_rn(__dadd_rn(o.w, 0.05), __dadd_rn(a.r, 0.05));
+    double p0x = a.px, p0y = a.py, p0z = a.pz;
+    if (!at_goal) {
+        p0x = __dadd_rn(a.px, (double)__fmul_rn(0.5f, __fadd_rn(ox, a.vx)));
+        p0y = __dadd_rn(a.py, (double)__fmul_rn(0.5f, __fadd_rn(oy, a.vy)));
+        p0z = __dadd_rn(a.pz, (double)__fmul_rn(0.5f, __fadd_rn(oz, a.vz)));
+    }
+    const double dx = __dsub_rn(__dadd_rn(x, a.px), p0x), dy = __dsub_rn(__dadd_rn(y, a.py), p0y), dz = __dsub_rn(__dadd_rn(z, a.pz), p0z);
+    return is_intersect64_fast(__dsub_rn(o.x, a.px), __dsub_rn(o.y, a.py), __dsub_rn(o.z, a.pz), R, dx, dy, dz);
+}
 
 __device__ __forceinline__ void push_slow(const StepArgs &A, int s)
 {
@@ -44,10 +82,11 @@ __device__ __forceinline__ void push_slow(const StepArgs &A, int s)
 }
 
 template <int POLICY>
-__global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
+__global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAMPLED) ? 4 : FG_MIN_CTAS) k_select_fast(const __grid_constant__ StepArgs A)
 {
     constexpr bool IS_ORCA = (POLICY == SCAB_POLICY_ORCA_SAMPLED);
     constexpr bool SHUNT = (POLICY == SCAB_POLICY_SCA || POLICY == SCAB_POLICY_SRVO3D);
+    typedef GroupSmemT<IS_ORCA> GroupSmem;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GroupSmem *gs = reinterpret_cast<GroupSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 3, l8 = lane & 7;
@@ -131,7 +170,6 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
                 const double R = IS_ORCA ? __dadd_rn(__dadd_rn(a.r, 0.05), __dadd_rn(o.w, 0.05))
                                          : __dadd_rn(__dadd_rn(o.w, 0.05), __dadd_rn(a.r, 0.05));
                 const double rx = __dsub_rn(o.x, a.px), ry = __dsub_rn(o.y, a.py), rz = __dsub_rn(o.z, a.pz);
-                W.dR[k] = R;
                 if (!IS_ORCA) {   // scaPolicy.py:47-60
                     float hx = 0.f, hy = 0.f, hz = 0.f;
                     if (!at_goal) {
@@ -139,10 +177,6 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
                         hy = __fmul_rn(0.5f, __fadd_rn(oy, a.vy));
                         hz = __fmul_rn(0.5f, __fadd_rn(oz, a.vz));
                     }
-                    W.dpx[k] = o.x; W.dpy[k] = o.y; W.dpz[k] = o.z;
-                    W.dhx[k] = at_goal ? a.px : __dadd_rn(a.px, (double)hx);
-                    W.dhy[k] = at_goal ? a.py : __dadd_rn(a.py, (double)hy);
-                    W.dhz[k] = at_goal ? a.pz : __dadd_rn(a.pz, (double)hz);
                     const double pp = dot3(rx, ry, rz, rx, ry, rz);
                     const float fpx = (float)rx, fpy = (float)ry, fpz = (float)rz;
                     const float hh = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
@@ -197,8 +231,10 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
                     }
                     const double qx = __dadd_rn((double)a.vx, __dmul_rn(0.5, ux)), qy = __dadd_rn((double)a.vy, __dmul_rn(0.5, uy)),
                                  qz = __dadd_rn((double)a.vz, __dmul_rn(0.5, uz));
-                    W.dpx[k] = qx; W.dpy[k] = qy; W.dpz[k] = qz;
-                    W.dhx[k] = nx; W.dhy[k] = ny; W.dhz[k] = nz;
+                    if constexpr (IS_ORCA) {
+                        W.dpx[k] = qx; W.dpy[k] = qy; W.dpz[k] = qz;
+                        W.dhx[k] = nx; W.dhy[k] = ny; W.dhz[k] = nz;
+                    }
                     cP = make_float4((float)nx, (float)ny, (float)nz, (float)(nx * qx + ny * qy + nz * qz));
                     cG = make_float2(0.f, 1e-5f * (vmaxf + (float)sqrt(qx * qx + qy * qy + qz * qz)));
                     keep = !((cP.x * bmx + cP.y * bmy + cP.z * bmz) - ball_r - cP.w > 1e-2f);
@@ -224,8 +260,19 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
             const float4 *tab = zaxis ? s_dir128 : s_dir256;
             unsigned m0 = 0, m1 = 0;
             const int iters = a.N / FG_LANES;
+            // The directions are a Fibonacci sphere, u_n.z = (2n - 1)/N - 1 increasing in n (scaPolicy.py:196-199), and
+            // a direction within pi/4 of vA has a polar angle within pi/4 of vA's: only that z band can pass.
+            int i_lo = 0, i_hi = iters;
+            {
+                const float th = acosf(fminf(fmaxf(a.vz / fnvA, -1.f), 1.f));
+                const float zlo = cosf(fminf(th + 0.7853982f, 3.1415927f)) - 0.02f, zhi = cosf(fmaxf(th - 0.7853982f, 0.f)) + 0.02f;
+                const float half = 0.5f * (float)a.N;
+                i_lo = max((int)floorf((zlo + 1.f) * half) / FG_LANES - 1, 0);
+                i_hi = min((int)ceilf((zhi + 1.f) * half) / FG_LANES + 2, iters);
+                if (!(fnvA > 0.f)) { i_lo = 0; i_hi = iters; }
+            }
 #pragma unroll 4
-            for (int i = 0; i < iters; i++) {
+            for (int i = i_lo; i < i_hi; i++) {
                 const float4 u = tab[FG_LANES * i + l8];
                 const float dt = fmaf(a.vz, u.z, fmaf(a.vy, u.y, a.vx * u.x));
                 bool p0 = dt >= thr, p1 = p0;
@@ -290,13 +337,14 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
                     const float4 u = isv ? make_float4(vdx, vdy, vdz, 0.f) : tabB[n];
                     const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x)), uv = fmaf(u.z, vdz, fmaf(u.y, vdy, u.x * vdx));
                     const float ra = isv ? 1.f : 0.5f;
-                    if (ent & (1u << 12)) kmin = fminf(kmin, sqrtf(fmaxf(fmaf(-2.f * ra, uv, ra * ra * uu) + vdvd, 0.f)));
-                    if (ent & (2u << 12)) kmin = fminf(kmin, sqrtf(fmaxf(fmaf(-2.f * r1f, uv, r1f * r1f * uu) + vdvd, 0.f)));
+                    if (ent & (1u << 12)) kmin = fminf(kmin, fmaxf(fmaf(-2.f * ra, uv, ra * ra * uu) + vdvd, 0.f));     // squared distances:
+                    if (ent & (2u << 12)) kmin = fminf(kmin, fmaxf(fmaf(-2.f * r1f, uv, r1f * r1f * uu) + vdvd, 0.f));  // one sqrt after the min
                 }
             }
-            kmin = __uint_as_float(__reduce_min_sync(gmask, __float_as_uint(kmin)));   // non-negative floats order as uints
+            kmin = sqrtf(__uint_as_float(__reduce_min_sync(gmask, __float_as_uint(kmin))));   // non-negative floats order as uints
             T1 = kmin + A.tier_delta;
         }
+        const float T1sq = T1 * T1;      // (+inf under full_search)
         // exact keys strictly below this are certainly smaller than any key of tier 2 (fp32 key error <= 1e-3)
         const unsigned tier_units = A.full_search ? 0xffffffffu : (unsigned)fmaxf((T1 - 1.1e-3f) * 1.0e5f, 0.f);
 
@@ -316,9 +364,9 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
                     const float4 u = isv ? make_float4(vdx, vdy, vdz, 0.f) : tabB[n];
                     const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x)), uv = fmaf(u.z, vdz, fmaf(u.y, vdy, u.x * vdx));
                     const float ra = isv ? 1.f : 0.5f;
-                    const float k0 = sqrtf(fmaxf(fmaf(-2.f * ra, uv, ra * ra * uu) + vdvd, 0.f));
-                    const float k1 = sqrtf(fmaxf(fmaf(-2.f * r1f, uv, r1f * r1f * uu) + vdvd, 0.f));
-                    const unsigned t1 = (k0 <= T1 ? 1u : 0u) | (k1 <= T1 ? 2u : 0u);
+                    const float k0 = fmaxf(fmaf(-2.f * ra, uv, ra * ra * uu) + vdvd, 0.f);      // |v - v_pref|^2, fp32
+                    const float k1 = fmaxf(fmaf(-2.f * r1f, uv, r1f * r1f * uu) + vdvd, 0.f);
+                    const unsigned t1 = (k0 <= T1sq ? 1u : 0u) | (k1 <= T1sq ? 2u : 0u);
                     const unsigned m = ((ent >> 12) & 3u) & (pass == 0 ? t1 : ~t1);
                     if (m) { abits |= 1u << i; am |= m << (2 * i); }
                 }
@@ -383,11 +431,8 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
                                 double x, y, z;
                                 cand64(a, c, x, y, z);
                                 bool ins;
-                                if (!IS_ORCA) {
-                                    double dx = __dsub_rn(__dadd_rn(x, a.px), W.dhx[k]), dy = __dsub_rn(__dadd_rn(y, a.py), W.dhy[k]),
-                                           dz = __dsub_rn(__dadd_rn(z, a.pz), W.dhz[k]);
-                                    ins = is_intersect64_fast(__dsub_rn(W.dpx[k], a.px), __dsub_rn(W.dpy[k], a.py), __dsub_rn(W.dpz[k], a.pz),
-                                                              W.dR[k], dx, dy, dz);
+                                if constexpr (!IS_ORCA) {
+                                    ins = recheck_cone64(A, s, k, a, x, y, z);
                                 } else {
                                     double val = dot3(__dsub_rn(x, W.dpx[k]), __dsub_rn(y, W.dpy[k]), __dsub_rn(z, W.dpz[k]),
                                                       W.dhx[k], W.dhy[k], W.dhz[k]);
@@ -464,7 +509,12 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 4) k_select_fast(StepArgs A)
             if (l8 == 0) push_slow(A, s);
             continue;
         }
+        int nprefix = 0;
         if (SHUNT && nlive > 1) {
+            for (int j = l8; j < nlive; j += FG_LANES) nprefix += (W.kc[j] < kfail) ? 1 : 0;
+            nprefix = __reduce_add_sync(gmask, nprefix);
+        }
+        if (SHUNT && nprefix > 1) {      // a one-element prefix is its own min-phi / max-phi: best stays the head
             // scaPolicy.py:136-145: min-phi / max-phi over the prefix {(key, c) < kfail}; ties -> first in sorted order
             unsigned umin = 0xffffffffu, umax = 0u, kmin_ = 0xffffffffu, kmax_ = 0xffffffffu;
             for (int j = l8; j < nlive; j += FG_LANES) {
