@@ -21,7 +21,7 @@
 #define LIVE_CAP 136      // 2 * DIR_CAP + v_pref, rounded up
 #define VPREF_ENTRY 0x3ff
 #ifndef FG_MIN_CTAS
-#define FG_MIN_CTAS 5   // resident CTAs per SM the cone policies are compiled for (registers <= 96)
+#define FG_MIN_CTAS 4   // resident CTAs per SM the kernel is compiled for; 5 (<= 96 registers) spills and measured 2.6 % slower
 #endif
 // tier 1 = candidates within StepArgs::tier_delta (default 0.3, SCAB_TIER_DELTA) of the one closest to v_pref
 
