@@ -252,28 +252,43 @@ __global__ void __launch_bounds__(128, 6) k_neighbors_knn(const __grid_constant_
         int cx, cy, cz;
         cell_of(A.g, me.x, me.y, me.z, cx, cy, cz);
         const double lim = rangeSq + 1e-4;   // the 5-decimal rounding cannot bring anything beyond this back in range
-        for (int dz = -1; dz <= 1; dz++) {
-            const int z = cz + dz;
-            if (z < 0 || z >= A.g.nz) continue;
-            for (int dy = -1; dy <= 1; dy++) {
-                const int y = cy + dy;
-                if (y < 0 || y >= A.g.ny) continue;
-                const int row = (z * A.g.ny + y) * A.g.nx;
-                const int beg = A.cell_start[row + max(cx - 1, 0)];
-                const int end = A.cell_start[row + min(cx + 1, A.g.nx - 1) + 1];
-                for (int j0 = beg; j0 < end; j0 += 4) {
-                    double4 o[4];          // four independent loads in flight per thread
+        // Trim the 27-cell block to the cells the query ball actually reaches: (fx, fy, fz) is the offset inside
+        // the own cell, so the gap to a neighbouring slab is f or cs - f.  (Agents clamped into a border cell from
+        // outside the grid scan the full block; cell contents are never closer than their cell.)
+        const double cs = 1.0 / A.g.inv_cs;
+        const double fx = (me.x - A.g.ox) - cx * cs, fy = (me.y - A.g.oy) - cy * cs, fz = (me.z - A.g.oz) - cz * cs;
+        const bool trim = fx >= 0.0 && fx <= cs && fy >= 0.0 && fy <= cs && fz >= 0.0 && fz <= cs;
+        const double limt = lim + 1e-6;
+        // the (up to) nine x-rows of the block: all their cell_start bounds are fetched before any row is scanned
+        int rbeg[9], rend[9];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) o[q] = A.s_posr[min(j0 + q, end - 1)];
+        for (int r = 0; r < 9; r++) {
+            const int dz = r / 3 - 1, dy = r % 3 - 1;
+            const int z = cz + dz, y = cy + dy;
+            const double gz = dz == 0 ? 0.0 : (dz < 0 ? fz : cs - fz);
+            const double gy = dy == 0 ? 0.0 : (dy < 0 ? fy : cs - fy);
+            const double rem = limt - gz * gz - gy * gy;
+            const bool skip = z < 0 || z >= A.g.nz || y < 0 || y >= A.g.ny || (trim && rem < 0.0);
+            const int x0 = (trim && fx * fx > rem) ? cx : cx - 1, x1 = (trim && (cs - fx) * (cs - fx) > rem) ? cx : cx + 1;
+            const int row = (z * A.g.ny + y) * A.g.nx;
+            rbeg[r] = skip ? 0 : A.cell_start[row + max(x0, 0)];
+            rend[r] = skip ? 0 : A.cell_start[row + min(x1, A.g.nx - 1) + 1];
+        }
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int j = j0 + q;
-                        const double ex = me.x - o[q].x, ey = me.y - o[q].y, ez = me.z - o[q].z;
-                        const double ss = ex * ex + ey * ey + ez * ez;
-                        if (j >= end || ss > lim || j == s) continue;
-                        if (nbuf < KNN_CAP) buf[nbuf++][threadIdx.x] = j;
-                        else overflow = true;
-                    }
+        for (int r = 0; r < 9; r++) {
+            const int beg = rbeg[r], end = rend[r];
+            for (int j0 = beg; j0 < end; j0 += 4) {
+                double4 o[4];          // four independent loads in flight per thread
+#pragma unroll
+                for (int q = 0; q < 4; q++) o[q] = A.s_posr[min(j0 + q, end - 1)];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int j = j0 + q;
+                    const double ex = me.x - o[q].x, ey = me.y - o[q].y, ez = me.z - o[q].z;
+                    const double ss = ex * ex + ey * ey + ez * ez;
+                    if (j >= end || ss > lim || j == s) continue;
+                    if (nbuf < KNN_CAP) buf[nbuf++][threadIdx.x] = j;
+                    else overflow = true;
                 }
             }
         }
@@ -285,29 +300,36 @@ __global__ void __launch_bounds__(128, 6) k_neighbors_knn(const __grid_constant_
     unsigned rej_min = 0xffffffffu;
     int cnt = 0;
     bool coll = false;
-    for (int i = 0; i < nbuf; i++) {
-        const int j = buf[i][threadIdx.x];
-        const double4 o = A.s_posr[j];
-        // l3normsq (util.py:99-100): round(sum, 5) = rint(sum * 1e5) / 1e5
-        const double units = rint(__dmul_rn(sumsq3(__dsub_rn(me.x, o.x), __dsub_rn(me.y, o.y), __dsub_rn(me.z, o.z)), 1e5));
-        const double dsq = __ddiv_rn(units, 1e5);
-        if (!(dsq < rangeSq)) continue;
-        const double rr = __dadd_rn(me.w, o.w);
-        const bool is_c = dsq < __dmul_rn(rr, rr);      // agent.py:83-85: from the first collider on, colliders only
-        if (is_c && !coll) {
-            coll = true;
+    for (int i0 = 0; i0 < nbuf; i0 += 4) {
+        double4 o4[4];             // four gathers in flight per thread (the records were just read: L1 / L2 hits)
 #pragma unroll
-            for (int k = 0; k < KNBR; k++) L[k] = 0xffffffffu;
-            rej_min = 0xffffffffu;
-            cnt = 0;
+        for (int q = 0; q < 4; q++) o4[q] = A.s_posr[buf[min(i0 + q, nbuf - 1)][threadIdx.x]];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = i0 + q;
+            if (i >= nbuf) continue;
+            const double4 o = o4[q];
+            // l3normsq (util.py:99-100): round(sum, 5) = rint(sum * 1e5) / 1e5
+            const double units = rint(__dmul_rn(sumsq3(__dsub_rn(me.x, o.x), __dsub_rn(me.y, o.y), __dsub_rn(me.z, o.z)), 1e5));
+            const double dsq = __ddiv_rn(units, 1e5);
+            if (!(dsq < rangeSq)) continue;
+            const double rr = __dadd_rn(me.w, o.w);
+            const bool is_c = dsq < __dmul_rn(rr, rr);      // agent.py:83-85: from the first collider on, colliders only
+            if (is_c && !coll) {
+                coll = true;
+#pragma unroll
+                for (int k = 0; k < KNBR; k++) L[k] = 0xffffffffu;
+                rej_min = 0xffffffffu;
+                cnt = 0;
+            }
+            if (coll && !is_c) continue;
+            const unsigned x = ((unsigned)(int)units << 8) | (unsigned)i;
+            rej_min = min(rej_min, max(L[KNBR - 1], x));
+#pragma unroll
+            for (int k = KNBR - 1; k >= 1; k--) L[k] = min(L[k], max(L[k - 1], x));
+            L[0] = min(L[0], x);
+            cnt++;
         }
-        if (coll && !is_c) continue;
-        const unsigned x = ((unsigned)(int)units << 8) | (unsigned)i;
-        rej_min = min(rej_min, max(L[KNBR - 1], x));
-#pragma unroll
-        for (int k = KNBR - 1; k >= 1; k--) L[k] = min(L[k], max(L[k - 1], x));
-        L[0] = min(L[0], x);
-        cnt++;
     }
     const int n_in = min(cnt, KNBR);
     bool tie = overflow || (cnt > KNBR && (rej_min >> 8) == (L[KNBR - 1] >> 8));

@@ -20,6 +20,9 @@
 #define DIR_CAP 64        // surviving directions per agent (a pi/4 cap holds ~38 of 256)
 #define LIVE_CAP 136      // 2 * DIR_CAP + v_pref, rounded up
 #define VPREF_ENTRY 0x3ff
+#ifndef FG_A_UNROLL
+#define FG_A_UNROLL 2   // posture loop; 4 is 230 instructions larger and measured 0.7 % slower (instruction-fetch bound)
+#endif
 #ifndef FG_MIN_CTAS
 #define FG_MIN_CTAS 4   // resident CTAs per SM the kernel is compiled for; 5 (<= 96 registers) spills and measured 2.6 % slower
 #endif
@@ -259,19 +262,22 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
             const bool near_ground = !(a.pz > A.time_step * vmax + 1e-9);
             const float4 *tab = zaxis ? s_dir128 : s_dir256;
             unsigned m0 = 0, m1 = 0;
+            constexpr int kAUnroll = FG_A_UNROLL;
             const int iters = a.N / FG_LANES;
             // The directions are a Fibonacci sphere, u_n.z = (2n - 1)/N - 1 increasing in n (scaPolicy.py:196-199), and
             // a direction within pi/4 of vA has a polar angle within pi/4 of vA's: only that z band can pass.
             int i_lo = 0, i_hi = iters;
             {
-                const float th = acosf(fminf(fmaxf(a.vz / fnvA, -1.f), 1.f));
-                const float zlo = cosf(fminf(th + 0.7853982f, 3.1415927f)) - 0.02f, zhi = cosf(fmaxf(th - 0.7853982f, 0.f)) + 0.02f;
+                // cos(theta -+ pi/4) = (hz +- sqrt(1 - hz^2)) / sqrt2, clamped at the poles
+                const float hz = fminf(fmaxf(a.vz / fnvA, -1.f), 1.f), sh = sqrtf(fmaxf(1.f - hz * hz, 0.f));
+                const float zhi = (hz >= 0.70710678f ? 1.f : 0.70710678f * (hz + sh)) + 0.02f;
+                const float zlo = (hz <= -0.70710678f ? -1.f : 0.70710678f * (hz - sh)) - 0.02f;
                 const float half = 0.5f * (float)a.N;
                 i_lo = max((int)floorf((zlo + 1.f) * half) / FG_LANES - 1, 0);
                 i_hi = min((int)ceilf((zhi + 1.f) * half) / FG_LANES + 2, iters);
                 if (!(fnvA > 0.f)) { i_lo = 0; i_hi = iters; }
             }
-#pragma unroll 4
+#pragma unroll kAUnroll
             for (int i = i_lo; i < i_hi; i++) {
                 const float4 u = tab[FG_LANES * i + l8];
                 const float dt = fmaf(a.vz, u.z, fmaf(a.vy, u.y, a.vx * u.x));
@@ -328,6 +334,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
         float T1 = 3.0e38f;
         if (!A.full_search) {
             float kmin = 3.0e38f;
+#pragma unroll 1      // code size: the kernel is instruction-fetch bound (its hot path is larger than the 32 KB L1.5 I-cache)
             for (int jb = 0; jb < ndir; jb += FG_LANES) {
                 const int j = jb + l8;
                 if (j < ndir) {
@@ -356,6 +363,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
             int nact = 0;
             {
                 unsigned abits = 0, am = 0;          // per lane: entry l8 + 8 i -> bit i ; 2-bit masks packed in `am`
+#pragma unroll 1
                 for (int i = 0; FG_LANES * i + l8 < ndir; i++) {
                     const int j = FG_LANES * i + l8;
                     const unsigned ent = W.dirs[j];
@@ -479,6 +487,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
 
             // ---- head of the sorted list, and (shunting) the first element that breaks the prefix
             unsigned local_min = 0xffffffffu;
+#pragma unroll 1
             for (int j = l8; j < nlive; j += FG_LANES) local_min = min(local_min, W.kc[j]);
             const unsigned head = __reduce_min_sync(gmask, local_min);
             best = (int)(head & 1023u);
@@ -511,6 +520,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
         }
         int nprefix = 0;
         if (SHUNT && nlive > 1) {
+#pragma unroll 1
             for (int j = l8; j < nlive; j += FG_LANES) nprefix += (W.kc[j] < kfail) ? 1 : 0;
             nprefix = __reduce_add_sync(gmask, nprefix);
         }

@@ -88,9 +88,19 @@ __global__ void __launch_bounds__(128) k_status(StepArgs A)
             }
         }
         if (from_list) {
+            // the list is sorted by distance (both modes insert in order): without obstacle entries mixed in, the
+            // first agent beyond reach ends the walk -- typically after one or two entries
+            const double brk = oldp.w + A.max_radius + 2.51;
+            const bool sorted_agents = (A.m == 0);
             for (int k = 0; k < ncnt; k++) {
                 const int e = A.s_nbr[(size_t)s * KNBR + k];
-                if (e < A.n) test_pair(e);
+                if (e >= A.n) continue;
+                if (sorted_agents) {
+                    const double4 oo = A.s_posr[e];
+                    const double ex = oo.x - oldp.x, ey = oo.y - oldp.y, ez = oo.z - oldp.z;
+                    if (ex * ex + ey * ey + ez * ez > brk * brk) break;
+                }
+                test_pair(e);
             }
         } else {
             int cx, cy, cz;
