@@ -144,6 +144,26 @@ def run_ours(args):
             tr.append(round((time.perf_counter() - t0) * 1e3, 2))
         if rank == 0:
             sys.stderr.write('TRACE ms/step: %s\n' % tr)
+    if os.environ.get('SCAB_BENCH_PHASES') and world > 1:   # debug: eager per-phase device times of the sharded step
+        marks = []
+        def mark(what):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream())
+            marks.append((what, e))
+        sw.debug_phase = mark
+        acc = {}
+        for _ in range(args.steps):
+            del marks[:]
+            sw.step(policy, capi.NBR_KNN)
+            with torch.cuda.stream(sw.stream):
+                mark('end')
+            sw.stream.synchronize()
+            for (w, e), (_, e2) in zip(marks[:-1], marks[1:]):
+                acc[w] = acc.get(w, 0.0) + e.elapsed_time(e2)
+        sw.debug_phase = None
+        sys.stderr.write('PHASES rank %d ms/step (eager): %s rows=%d own=%d cap=%d\n' % (
+            rank, {k: round(v / args.steps, 4) for k, v in acc.items()}, sw.n_rows, sw.n_own, sw.cap))
+        barrier()
     c0 = sw.counters()['n_active_total']
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
