@@ -213,7 +213,7 @@ def run_ours(args):
                 traffic = json.load(f).get(dom)
         except Exception:
             pass
-        roof = {'bound': 'hbm', 'kernel': {'grid': 'k_reorder+k_cell_count+k_cell_scan', 'neighbors': 'k_neighbors_knn',
+        roof = {'bound': 'hbm', 'kernel': {'grid': 'k_cell_count+k_scan_*+k_reorder', 'neighbors': 'k_neighbors_knn',
                                            'policy': 'k_vpref+k_select_fast<SCA>+k_select<SCA>+k_integrate', 'status': 'k_status'}[dom],
                 'achieved': round(achieved, 2), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 5),
                 'traffic': traffic, 'peak_source': how, 'algorithmic_bytes_per_agent_step': ALGO_BYTES[dom],
