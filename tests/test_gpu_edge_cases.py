@@ -1,0 +1,144 @@
+"""-m gpu: edge cases of the C ABI path -- empty and tiny swarms, everything finished, obstacles only,
+the two 16-NN code paths against each other and against the oracle, and the error behaviour of the boundary."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+POLICIES = ['sca', 'srvo3d', 'rvo3d', 'rvo3d_dubins', 'orca_sampled', 'orca_lp']
+
+
+def _swarm(pos, goal, obstacles=None, debug=True, **kw):
+    from sca_b200.swarm import Swarm
+    sw = Swarm(len(pos), debug=debug)
+    sw.set_state(pos, goal, **kw)
+    sw.set_obstacles(obstacles)
+    both = np.r_[pos, goal]
+    sw.fit_grid(both.min(0) - 15, both.max(0) + 15)
+    return sw
+
+
+def test_empty_swarm_steps_to_done():
+    import ctypes as C
+    from sca_b200 import capi
+    from sca_b200.swarm import Swarm
+    sw = Swarm(0, capacity=16)
+    assert sw.n == 0
+    for pol in POLICIES:
+        sw.step(pol, capi.NBR_KNN)
+    c = sw.counters()
+    assert c['n_active'] == 0 and c['n_not_done'] == 0 and c['n_collision'] == 0
+    assert sw.is_done()
+
+
+@pytest.mark.parametrize('policy', POLICIES)
+def test_single_agent_flies_straight_like_the_oracle(policy):
+    import torch
+    from oracle import oracle as orc
+    from sca_b200 import capi
+    pos, goal = np.array([[0.0, 0.0, 20.0]]), np.array([[6.0, 3.0, 24.0]])
+    w = orc.World(pos, goal)
+    sw = _swarm(pos, goal)
+    done = False
+    for t in range(200):
+        d_o = w.step(policy, orc.NBR_KNN)
+        sw.step(policy, capi.NBR_KNN)
+        torch.cuda.synchronize()
+        a = sw.action.cpu().numpy()[0].astype('float64')
+        assert np.abs(a[:4] - w.action[0, :4]).max() <= 2e-5, (policy, t, a, w.action[0])
+        assert int(sw.status.cpu().numpy()[0] & 15) == int(w.status[0]), (policy, t)
+        assert sw.is_done() == d_o
+        if d_o:
+            done = True
+            break
+    assert done and (w.status[0] & 1), 'the lone agent reaches its goal'
+    assert np.abs(sw.pos.cpu().numpy()[0] - w.pos[0]).max() <= 1e-4
+
+
+def test_all_finished_is_a_no_op():
+    import torch
+    from sca_b200 import capi
+    rng = np.random.default_rng(2)
+    pos = rng.uniform(0, 30, (64, 3)) + [0, 0, 20]
+    sw = _swarm(pos, pos + 0.1)          # everybody starts within near_goal of its goal
+    sw.step('sca', capi.NBR_KNN)          # first step: flags AT_GOAL
+    torch.cuda.synchronize()
+    before = sw.download()
+    assert ((before['status'] & 1) == 1).all() and sw.is_done()
+    sw.step('sca', capi.NBR_KNN)
+    torch.cuda.synchronize()
+    after = sw.download()
+    assert sw.counters()['n_active'] == 0
+    for k in ('pos', 'heading', 'total_dist', 'step_num'):
+        assert np.array_equal(before[k], after[k]), k
+    assert (after['action'] == 0).all()
+
+
+@pytest.mark.parametrize('policy', ['sca', 'orca_lp'])
+def test_one_agent_among_obstacles_matches_oracle(policy):
+    import torch
+    from oracle import oracle as orc
+    from sca_b200 import capi
+    rng = np.random.default_rng(4)
+    pos, goal = np.array([[0.0, 0.0, 25.0]]), np.array([[30.0, 0.0, 25.0]])
+    obs = np.c_[rng.uniform(4, 26, 30), rng.uniform(-6, 6, 30), rng.uniform(19, 31, 30), rng.uniform(0.4, 1.2, 30)]
+    w = orc.World(pos, goal, obstacles=obs)
+    sw = _swarm(pos, goal, obstacles=obs)
+    for t in range(120):
+        d_o = w.step(policy, orc.NBR_KNN)
+        sw.step(policy, capi.NBR_KNN)
+        torch.cuda.synchronize()
+        if w.nbr_cnt[0] >= 0:
+            c = int(w.nbr_cnt[0])
+            assert int(sw.nbr_cnt.cpu().numpy()[0]) == c
+            assert np.array_equal(sw.nbr_ids.cpu().numpy()[0, :c], w.nbr_ids[0, :c]), (policy, t)
+        a = sw.action.cpu().numpy()[0].astype('float64')
+        assert np.abs(a[:4] - w.action[0, :4]).max() <= 2e-5, (policy, t)
+        assert int(sw.status.cpu().numpy()[0] & 15) == int(w.status[0]), (policy, t)
+        if d_o:
+            break
+
+
+def test_knn_integer_key_path_equals_exact_path_and_oracle():
+    """No obstacles -> the 32-bit integer-key fast path; one obstacle far away -> knn_exact for every agent.
+    Both must produce the oracle's ordered lists (obstacle ids are reported as n + k and never appear here)."""
+    import torch
+    from oracle import oracle as orc
+    from sca_b200 import capi, scenarios
+    pos6, goal6, _ = scenarios.uniform_box_numpy(5000, 4.0 * 1.0e6 / 560.0 ** 3, seed=21)
+    pos, goal = pos6[:, :3], goal6[:, :3]
+    vel = np.random.default_rng(1).normal(0, 0.4, (len(pos), 3)).astype(np.float32)
+    w = orc.World(pos, goal, vel=vel)
+    w.policy_step('srvo3d', orc.NBR_KNN)
+    outs = []
+    for obs in (None, np.array([[1.0e5, 1.0e5, 1.0e5, 1.0]])):
+        sw = _swarm(pos, goal, obstacles=obs, vel=vel)
+        sw.stage_grid()
+        sw.stage_neighbors(capi.NBR_KNN)
+        torch.cuda.synchronize()
+        outs.append((sw.nbr_cnt.cpu().numpy(), sw.nbr_ids.cpu().numpy(), sw.nbr_dsq.cpu().numpy()))
+    for cnt, ids, dsq in outs:
+        assert np.array_equal(cnt, w.nbr_cnt)
+        assert np.array_equal(ids, w.nbr_ids)
+        assert np.array_equal(dsq, w.nbr_dsq)
+    assert (w.nbr_cnt == 16).mean() > 0.5
+
+
+def test_boundary_errors_are_reported_not_swallowed():
+    from sca_b200 import capi
+    from sca_b200.swarm import Swarm
+    sw = Swarm(8)
+    sw.set_state(np.zeros((8, 3)) + np.arange(8)[:, None] * 3.0, np.ones((8, 3)) * 50)
+    sw.fit_grid()
+    with pytest.raises(capi.ScabError, match='bad policy'):
+        sw.h.policy_step(99)
+    with pytest.raises(capi.ScabError, match='bad mode'):
+        sw.h.neighbors(7)
+    with pytest.raises(capi.ScabError, match='REF_COMPAT needs scab_kdtree_build'):
+        sw.h.neighbors(capi.NBR_REF_COMPAT)
+    with pytest.raises(capi.ScabError, match='exceeds capacity'):
+        sw._bind(9)
+    with pytest.raises(capi.ScabError, match='cell_size < neighbor_dist'):
+        sw.h.set_grid([0, 0, 0], 5.0, [4, 4, 4])
+    with pytest.raises(capi.ScabError, match='never enabled'):
+        sw.h.dubins_read(8)
