@@ -118,6 +118,13 @@ typedef struct {
     int64_t n_global;      /* total agents across all shards (0: n); obstacle ids are reported as n_global + k */
     /* Dubins v_pref provider (optional; see scab_dubins_enable) */
     const double *goal_heading; /* [n,3] goal_heading_frame = goal_pos[3:6] (agent.py:21); NULL: zeros           in */
+    /* Waypoint following (optional): agent.path of an external global planner + policy.now_goal, i.e. get_trajectory
+     * of rvo3dPolicy.py:71-86, srvo3dPolicy.py:71-86, orca3dPolicy.py:298-312, orca3dPolicyOfficial.py:302-316
+     * (SCA and RVO3D+Dubins define it but never call it).  NULL waypoints: v_pref aims at the goal. */
+    const double *waypoints;    /* [n, waypoint_stride, 3] in the reference's list order: pop() takes the LAST live entry in */
+    int32_t *waypoint_left;     /* [n] len(agent.path)                                                      in/out */
+    double *now_goal;           /* [n,3] policy.now_goal; NaN in [i,0] = None (not started)                 in/out */
+    int64_t waypoint_stride;    /* waypoint slots per agent */
 } scab_state_ptrs;
 
 /* Step counters, read back with scab_read_counters (device->host copy of 8 x int64). */

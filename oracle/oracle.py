@@ -38,7 +38,7 @@ class OrcWorld(C.Structure):
         'max_run_dist', 'is_zaxis', 'obs', 'vpref_ext', 'agent_perm', 'obst_perm',
         'ran', 'nbr_cnt', 'nbr_ids', 'nbr_dsq', 'coll_query', 'tag', 'n_suit', 'plane_fail', 'n_planes',
         'lp4_proj', 'lp4_inner_fail', 'vpref_in', 'vpref_store', 'action64', 'action',
-        'agent_nodes', 'obst_nodes')]
+        'agent_nodes', 'obst_nodes', 'waypoints', 'waypoint_left', 'now_goal')] + [('waypoint_stride', C.c_int32)]
 
 
 _lib = None
@@ -101,11 +101,24 @@ class World:
         self.action64 = np.zeros((n, 7))
         self.action = np.zeros((n, 7), np.float32)
         self._obst_built = False
+        self.waypoints = self.waypoint_left = self.now_goal = None
+        self.waypoint_stride = 0
+
+    def set_waypoints(self, waypoints, counts):
+        """agent.path for every agent: waypoints [n, P, 3] in the reference's list order (pop() takes the last live
+        entry), counts [n] = len(agent.path); resets policy.now_goal to None."""
+        wp = np.ascontiguousarray(np.nan_to_num(np.asarray(waypoints, 'float64')))
+        assert wp.shape[0] == self.n and wp.shape[2] == 3
+        self.waypoints = wp
+        self.waypoint_stride = int(wp.shape[1])
+        self.waypoint_left = np.ascontiguousarray(counts, np.int32).copy()
+        self.now_goal = np.full((self.n, 3), np.nan)
 
     def _struct(self):
         w = OrcWorld()
         w.n, w.m = self.n, self.m
-        for k, _ in OrcWorld._fields_[2:]:
+        w.waypoint_stride = self.waypoint_stride
+        for k, _ in OrcWorld._fields_[2:-1]:
             v = getattr(self, k)
             if v is None:
                 setattr(w, k, None)

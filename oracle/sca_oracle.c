@@ -71,6 +71,11 @@ typedef struct {
     /* scratch owned by the caller */
     KdNode *agent_nodes; /* [2n-1] */
     KdNode *obst_nodes;  /* [2m-1] */
+    /* waypoint following (agent.path / policy.now_goal, e.g. rvo3dPolicy.py:71-86); NULL: no paths */
+    double *waypoints;        /* [n, waypoint_stride, 3] in the reference's list order: pop() takes the LAST live entry */
+    int32_t *waypoint_left;   /* [n] len(agent.path)                                                    in/out */
+    double *now_goal;         /* [n,3] policy.now_goal, NaN = None                                      in/out */
+    int32_t waypoint_stride;
 } OrcWorld;
 
 /* ------------------------------------------------------------------ rounding conventions */
@@ -952,10 +957,38 @@ static void lp4(LPState *S, const Plane *planes, int np, int beginPlane, double 
 
 /* ------------------------------------------------------------------ v_pref, action */
 /* rvo3dPolicy.py:182-196 (use_distance=0) / orca3dPolicy*.py:345-359 (use_distance=1) */
-static void compute_v_pref_straight(const OrcWorld *w, int a, int use_distance, double *v_store, double *v_des)
+/* get_trajectory: rvo3dPolicy.py:71-86, srvo3dPolicy.py:71-86 (l3norm) / orca3dPolicy.py:298-312,
+ * orca3dPolicyOfficial.py:302-316 (distance).  Writes the target compute_v_pref aims at. */
+static void get_trajectory(OrcWorld *w, int a, int use_distance, double *target)
 {
-    double dif[3], zero[3] = { 0, 0, 0 };
-    for (int d = 0; d < 3; d++) dif[d] = w->goal[3 * a + d] - w->pos[3 * a + d];
+    const double *goal = &w->goal[3 * a], *pos = &w->pos[3 * a];
+    if (w->waypoints == NULL || w->waypoint_left[a] <= 0) {
+        for (int d = 0; d < 3; d++) target[d] = goal[d];
+        if (w->now_goal) for (int d = 0; d < 3; d++) w->now_goal[3 * a + d] = goal[d];
+        return;
+    }
+    double *ng = &w->now_goal[3 * a];
+    const double *wp = &w->waypoints[(size_t)a * w->waypoint_stride * 3];
+#define POP_WAYPOINT() do { int k_ = --w->waypoint_left[a]; ng[0] = wp[3 * k_]; ng[1] = wp[3 * k_ + 1]; ng[2] = wp[3 * k_ + 2]; } while (0)
+    if (isnan(ng[0])) POP_WAYPOINT();                     /* first */
+    double dis = use_distance ? distance_fn(pos, ng) : l3norm(pos, ng);
+    double d_ng_goal = use_distance ? distance_fn(ng, goal) : l3norm(ng, goal);
+    double d_pos_goal = use_distance ? distance_fn(pos, goal) : l3norm(pos, goal);
+    if (dis <= 1.0 * w->radius[a]) {                      /* update_now_goal_dist = 1.0 */
+        if (w->waypoint_left[a] > 0) POP_WAYPOINT();
+    } else if (d_ng_goal >= d_pos_goal) {
+        if (w->waypoint_left[a] > 0) POP_WAYPOINT();
+    }
+#undef POP_WAYPOINT
+    for (int d = 0; d < 3; d++) target[d] = ng[d];
+}
+
+static void compute_v_pref_straight(OrcWorld *w, int a, int use_distance, int follow_path, double *v_store, double *v_des)
+{
+    double dif[3], zero[3] = { 0, 0, 0 }, target[3];
+    if (follow_path) get_trajectory(w, a, use_distance, target);
+    else for (int d = 0; d < 3; d++) target[d] = w->goal[3 * a + d];
+    for (int d = 0; d < 3; d++) dif[d] = target[d] - w->pos[3 * a + d];
     double nrm = use_distance ? distance_fn(dif, zero) : l3norm(dif, zero);
     nrm = (trunc(nrm * 1e5) + 0.0) / 1e5;
     for (int d = 0; d < 3; d++) { volatile double q = dif[d] * w->pref_speed[a]; v_store[d] = q / nrm; }
@@ -990,7 +1023,8 @@ static void policy_one(OrcWorld *w, int a, int policy, int nbr_mode)
     if (ext_vpref) {
         for (int d = 0; d < 3; d++) v_des[d] = v_store[d] = w->vpref_ext[3 * a + d];
     } else {
-        compute_v_pref_straight(w, a, is_orca, v_store, v_des);
+        /* SCA / RVO3D+Dubins define get_trajectory but never call it (their v_pref is the Dubins tracker) */
+        compute_v_pref_straight(w, a, is_orca, policy != POL_SCA && policy != POL_RVO3D_DUBINS, v_store, v_des);
     }
     for (int d = 0; d < 3; d++) { w->vpref_in[3 * a + d] = v_des[d]; w->vpref_store[3 * a + d] = v_store[d]; }
     w->ran[a] = 1;

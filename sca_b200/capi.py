@@ -43,7 +43,8 @@ STATE_FIELDS = ['pos', 'vel', 'heading', 'goal', 'radius', 'pref_speed', 'status
 
 
 class StatePtrs(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in STATE_FIELDS] + [('n_global', C.c_int64), ('goal_heading', C.c_void_p)]
+    _fields_ = [(k, C.c_void_p) for k in STATE_FIELDS] + [('n_global', C.c_int64), ('goal_heading', C.c_void_p), ('waypoints', C.c_void_p),
+                                                               ('waypoint_left', C.c_void_p), ('now_goal', C.c_void_p), ('waypoint_stride', C.c_int64)]
 
 
 # mirror of DubState / Man2D in csrc/scab_dubins.cu (test hook only)

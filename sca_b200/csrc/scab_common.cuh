@@ -166,18 +166,50 @@ __device__ __forceinline__ Action7 cartesian2spherical(double vx, double vy, dou
     return r;
 }
 
-// rvo3dPolicy.py:182-196 (use_distance=false) / orca3dPolicy*.py:345-359 (use_distance=true)
-__device__ __forceinline__ void v_pref_straight(const double *g, double px, double py, double pz, double pref,
+__device__ __forceinline__ double distance_d(double ax, double ay, double az, double bx, double by, double bz)
+{  // util.py:140-142 distance(): round(norm + 1e-5, 5)
+    return py_round5(__dadd_rn(__dsqrt_rn(sumsq3(__dsub_rn(ax, bx), __dsub_rn(ay, by), __dsub_rn(az, bz))), 1e-5));
+}
+
+// get_trajectory (rvo3dPolicy.py:71-86, srvo3dPolicy.py:71-86 with l3norm; orca3dPolicy.py:298-312,
+// orca3dPolicyOfficial.py:302-316 with distance): the point compute_v_pref aims at.  Pops agent.path from its end.
+__device__ __forceinline__ void waypoint_target(const scab_state_ptrs &st, int id, double px, double py, double pz, bool use_distance,
+                                                double *target)
+{
+    const double *g = &st.goal[3 * id];
+    target[0] = g[0]; target[1] = g[1]; target[2] = g[2];
+    if (st.waypoints == nullptr) return;
+    double *ng = &st.now_goal[3 * id];
+    int left = st.waypoint_left[id];
+    if (left <= 0) { ng[0] = g[0]; ng[1] = g[1]; ng[2] = g[2]; return; }     // path exhausted: now_goal = goal
+    const double *wp = st.waypoints + (size_t)id * (size_t)st.waypoint_stride * 3;
+    double nx = ng[0], ny = ng[1], nz = ng[2];
+    if (isnan(nx)) { left--; nx = wp[3 * left]; ny = wp[3 * left + 1]; nz = wp[3 * left + 2]; }   // first
+    const double dis = use_distance ? distance_d(px, py, pz, nx, ny, nz) : l3norm_d(px, py, pz, nx, ny, nz);
+    const double d_ng_goal = use_distance ? distance_d(nx, ny, nz, g[0], g[1], g[2]) : l3norm_d(nx, ny, nz, g[0], g[1], g[2]);
+    const double d_pos_goal = use_distance ? distance_d(px, py, pz, g[0], g[1], g[2]) : l3norm_d(px, py, pz, g[0], g[1], g[2]);
+    if ((dis <= __dmul_rn(1.0, st.radius[id]) || d_ng_goal >= d_pos_goal) && left > 0) {   // update_now_goal_dist = 1.0
+        left--; nx = wp[3 * left]; ny = wp[3 * left + 1]; nz = wp[3 * left + 2];
+    }
+    st.waypoint_left[id] = left;
+    ng[0] = nx; ng[1] = ny; ng[2] = nz;
+    target[0] = nx; target[1] = ny; target[2] = nz;
+}
+
+// rvo3dPolicy.py:182-196 (use_distance=false) / orca3dPolicy*.py:345-359 (use_distance=true): aims at `t` (the goal or
+// the current waypoint); the at-goal zero tests the GLOBAL goal `g`
+__device__ __forceinline__ void v_pref_straight(const double *g, const double *t, double px, double py, double pz, double pref,
                                                 bool use_distance, double *v_store, double *v_des)
 {
-    double dx = __dsub_rn(g[0], px), dy = __dsub_rn(g[1], py), dz = __dsub_rn(g[2], pz);
+    double dx = __dsub_rn(t[0], px), dy = __dsub_rn(t[1], py), dz = __dsub_rn(t[2], pz);
     double nr = __dsqrt_rn(sumsq3(dx, dy, dz));
     double nrm = use_distance ? py_round5(__dadd_rn(nr, 1e-5)) : py_round5(nr);
     nrm = trunc5(nrm);
     v_store[0] = __ddiv_rn(__dmul_rn(dx, pref), nrm);
     v_store[1] = __ddiv_rn(__dmul_rn(dy, pref), nrm);
     v_store[2] = __ddiv_rn(__dmul_rn(dz, pref), nrm);
-    if (py_round5(nr) < 0.2) { v_store[0] = 0.0; v_store[1] = 0.0; v_store[2] = 0.0; }  // reached(), util.py:23
+    const double ng = __dsqrt_rn(sumsq3(__dsub_rn(g[0], px), __dsub_rn(g[1], py), __dsub_rn(g[2], pz)));
+    if (py_round5(ng) < 0.2) { v_store[0] = 0.0; v_store[1] = 0.0; v_store[2] = 0.0; }  // reached(), util.py:23
     v_des[0] = trunc5(v_store[0]); v_des[1] = trunc5(v_store[1]); v_des[2] = trunc5(v_store[2]);
 }
 

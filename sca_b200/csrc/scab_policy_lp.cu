@@ -215,7 +215,9 @@ __global__ void __launch_bounds__(LP_THREADS) k_policy_lp(StepArgs A)
         } else {
             ran = 1;
             double v_store[3], v_des[3];
-            v_pref_straight(&A.st.goal[3 * id], me.x, me.y, me.z, A.st.pref_speed[id], true, v_store, v_des);
+            double target[3];
+            waypoint_target(A.st, id, me.x, me.y, me.z, true, target);
+            v_pref_straight(&A.st.goal[3 * id], target, me.x, me.y, me.z, A.st.pref_speed[id], true, v_store, v_des);
             const double nv32 = __dsqrt_rn(sumsq_f32(mv.x, mv.y, mv.z));
             const bool first = py_round5(__dadd_rn(nv32, 1e-5)) <= 1e-5;   // :52 distance(vel, 0) <= 1e-5
             int tag = 0, plane_fail = -1, n_planes = -1, n_proj = 0;

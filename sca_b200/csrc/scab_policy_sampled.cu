@@ -146,7 +146,9 @@ __global__ void __launch_bounds__(256) k_vpref(StepArgs A)
     if (ALLOW_EXT && A.st.vpref_ext != nullptr) {
         for (int d = 0; d < 3; d++) v_des[d] = v_store[d] = A.st.vpref_ext[3 * id + d];
     } else {
-        v_pref_straight(&A.st.goal[3 * id], me.x, me.y, me.z, A.st.pref_speed[id], USE_DISTANCE, v_store, v_des);
+        double target[3] = {A.st.goal[3 * id], A.st.goal[3 * id + 1], A.st.goal[3 * id + 2]};
+        if (!ALLOW_EXT) waypoint_target(A.st, id, me.x, me.y, me.z, USE_DISTANCE, target);   // SCA / RVO3D+Dubins never follow agent.path
+        v_pref_straight(&A.st.goal[3 * id], target, me.x, me.y, me.z, A.st.pref_speed[id], USE_DISTANCE, v_store, v_des);
     }
     // first-step gate: l3norm(vA,0) <= 1e-5 (scaPolicy.py:34) / distance(vA,0) <= 1e-5 (orca3dPolicy.py:52)
     const double nv32 = __dsqrt_rn(sumsq_f32(mv.x, mv.y, mv.z));

@@ -25,7 +25,8 @@ class BatchedEnv(object):
         self.sw = None
         self.steps = 0
 
-    def set_agents(self, pos6, goal6, obstacles=None, radius=0.5, pref_speed=1.0, vel=None, margin=20.0):
+    def set_agents(self, pos6, goal6, obstacles=None, radius=0.5, pref_speed=1.0, vel=None, margin=20.0, paths=None):
+        """`paths`: optional per-agent waypoint lists (agent.path, popped from the end like the reference does)."""
         pos6, goal6 = np.asarray(pos6, 'float64'), np.asarray(goal6, 'float64')
         n = len(pos6)
         self.sw = Swarm(n, device=self.device, debug=self.debug)
@@ -37,6 +38,13 @@ class BatchedEnv(object):
         self.sw.fit_grid(lo, hi)
         if self.dubins:
             self.sw.enable_dubins(goal6[:, 3:6])
+        if paths is not None:
+            P = max(1, max(len(p) for p in paths))
+            wp = np.zeros((n, P, 3))
+            for i, p in enumerate(paths):
+                for k, w in enumerate(p):
+                    wp[i, k] = w[:3]
+            self.sw.set_waypoints(wp, [len(p) for p in paths])
         # agent.py:51-52 (metrics): straight_path_length = l3norm(start, goal) - 0.5, desire_steps
         d = np.round(np.sqrt(((pos6[:, :3] - goal6[:, :3]) ** 2).sum(1)), 5)
         self.straight_len = d - 0.5

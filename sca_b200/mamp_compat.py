@@ -56,6 +56,15 @@ class GPUKDTree(object):
         lo = np.minimum(pos.min(0), goal.min(0)) - 20.0
         hi = np.maximum(pos.max(0), goal.max(0)) + 20.0
         self.sw.fit_grid(lo, hi)
+        # agent.path of an external global planner (agent.py:44): followed on the device (scab_state_ptrs.waypoints)
+        self._has_paths = any(len(getattr(a, 'path', ()) or ()) for a in agents)
+        if self._has_paths:
+            P = max(len(a.path) for a in agents)
+            wp = np.zeros((n, P, 3))
+            for i, a in enumerate(agents):
+                for k, w in enumerate(a.path):
+                    wp[i, k] = np.asarray(w, 'float64')[:3]
+            self.sw.set_waypoints(wp, [len(a.path) for a in agents])
         if self.vpref_provider == 'device':
             # the Dubins tracker itself on the GPU (scab_dubins_enable) instead of the host-side reference tracker
             self.sw.enable_dubins(np.array([a.goal_pos for a in agents], 'float64')[:, 3:6])
@@ -107,6 +116,9 @@ class GPUKDTree(object):
         self._nbr_dsq = self.sw.nbr_dsq.cpu().numpy()
         self._status = self.sw.status.cpu().numpy()
         self._vpref = self.sw.vpref_out.cpu().numpy()
+        if self._has_paths:
+            self._path_left = self.sw.t['waypoint_left'].cpu().numpy()
+            self._now_goal = self.sw.t['now_goal'].cpu().numpy()
         self.step_ms = (time.time() - t0) * 1e3
 
     # The per-agent queries already ran inside buildAgentTree; kept for interface compatibility.
@@ -127,6 +139,10 @@ class GPUKDTree(object):
             agent.is_collision = True          # agent.py:83-85
         if self.vpref_provider is None:
             agent.v_pref = self._vpref[i].copy()
+        if self._has_paths:          # what get_trajectory leaves behind: the popped list and policy.now_goal
+            del agent.path[int(self._path_left[i]):]
+            if not np.isnan(self._now_goal[i, 0]):
+                agent.policy.now_goal = self._now_goal[i].copy()
 
 
 class _GPUPolicy(object):
@@ -144,7 +160,7 @@ class _GPUPolicy(object):
         if tree is None:
             raise capi.ScabError('GPU policy used without a GPUKDTree: set env.kdTree = GPUKDTree(agents, obstacles)')
         self.now_goal = agent.goal_global_frame
-        tree.backfill(agent)
+        tree.backfill(agent)      # (overrides now_goal while the agent still follows waypoints)
         agent.total_time += tree.step_ms * 1e-3 / max(1, len(tree.agents))
         return tree.action[agent.id]
 

@@ -61,6 +61,10 @@ class Swarm:
         p.n_global = int(getattr(self, 'n_global', 0))
         gh = self.t.get('goal_heading')
         p.goal_heading = gh.data_ptr() if gh is not None else None
+        wp = self.t.get('waypoints')
+        if wp is not None:
+            p.waypoints, p.waypoint_left, p.now_goal = wp.data_ptr(), self.t['waypoint_left'].data_ptr(), self.t['now_goal'].data_ptr()
+            p.waypoint_stride = int(wp.shape[1])
         self.h.bind_state(p, self.n)
 
     def set_global_ids(self, gid, n_global):
@@ -105,6 +109,26 @@ class Swarm:
             self.set_external_vpref(None)
             self._bind()
         self.h.dubins_enable(on, self._stream())
+        return self
+
+    def set_waypoints(self, waypoints, counts=None):
+        """agent.path of an external global planner (agent.py:44) for RVO3D / S-RVO3D / ORCA: `waypoints` [n, P, 3] in the
+        reference's list order (the policies pop() from the END, so the first waypoint to fly to is stored last),
+        `counts` [n] = len(agent.path) (default P).  Resets policy.now_goal to None.  None removes the paths."""
+        if waypoints is None:
+            for k in ('waypoints', 'waypoint_left', 'now_goal'):
+                self.t.pop(k, None)
+            self._bind()
+            return self
+        wp = np.nan_to_num(np.ascontiguousarray(waypoints, dtype='float64'))
+        n, P = wp.shape[0], max(1, wp.shape[1])
+        cnt = np.full(n, wp.shape[1], np.int32) if counts is None else np.ascontiguousarray(counts, np.int32)
+        self.t['waypoints'] = torch.zeros((self.capacity, P, 3), dtype=_F8, device=self.device)
+        self.t['waypoints'][:n, :wp.shape[1]].copy_(torch.from_numpy(wp))
+        self.t['waypoint_left'] = torch.zeros(self.capacity, dtype=_I4, device=self.device)
+        self.t['waypoint_left'][:n].copy_(torch.from_numpy(cnt))
+        self.t['now_goal'] = torch.full((self.capacity, 3), float('nan'), dtype=_F8, device=self.device)
+        self._bind()
         return self
 
     def dubins_states(self):

@@ -24,6 +24,21 @@ def dense(n, r, seed):
     return pos, goal, []
 
 
+def circle_with_waypoints(n=16, rad=10.0):
+    """the circle swap with a two-waypoint dog-leg per agent (agent.path as an external global planner
+    would fill it; the policies pop() from the end of the list, so the first waypoint is stored last)."""
+    pos, goal, obs = rh.scen_circle(n, rad)
+    paths = []
+    for j in range(n):
+        s, g = np.array(pos[j][:3], 'float64'), np.array(goal[j][:3], 'float64')
+        d = g - s
+        lat = np.array([-d[1], d[0], 0.0]) / max(np.hypot(d[0], d[1]), 1e-9)
+        wp1 = s + 0.35 * d + np.array([0.0, 0.0, 3.0 if j % 2 == 0 else -3.0])
+        wp2 = s + 0.70 * d + 2.0 * lat
+        paths.append([wp2.tolist(), wp1.tolist()] if j % 5 else [wp1.tolist()])     # some agents carry one waypoint only
+    return pos, goal, obs, paths
+
+
 CASES = {
     # name: (policy, scenario thunk, keep steps, run to completion?, max steps)
     'circle16_sca': ('sca', lambda: rh.scen_circle(16, 10.0), 130, False, 130),
@@ -45,13 +60,18 @@ CASES = {
     'dense40_rvo3d': ('rvo3d', lambda: dense(40, 4.0, 4), 12, False, 12),
     'dense40_orca_sampled': ('orca_sampled', lambda: dense(40, 4.0, 5), 12, False, 12),
     'dense60_orca_lp': ('orca_lp', lambda: dense(60, 3.5, 6), 30, False, 30),
+    'waypoints16_rvo3d': ('rvo3d', circle_with_waypoints, 160, False, 160),
+    'waypoints16_srvo3d': ('srvo3d', circle_with_waypoints, 160, False, 160),
+    'waypoints16_orca_sampled': ('orca_sampled', circle_with_waypoints, 160, False, 160),
+    'waypoints16_orca_lp': ('orca_lp', circle_with_waypoints, 200, False, 200),
 }
 
 
 def run_case(name):
     policy, scen, keep, full, max_steps = CASES[name]
-    pos, goal, obs = scen()
-    rec = rh.Recorder(policy, pos, goal, obs)
+    sc = scen()
+    pos, goal, obs = sc[:3]
+    rec = rh.Recorder(policy, pos, goal, obs, paths=sc[3] if len(sc) > 3 else None)
     t0 = time.time()
     steps = 0
     done = False

@@ -142,7 +142,7 @@ class _Proxy:
 class Recorder:
     """Builds a reference MACAEnv for (policy, scenario) and records per-step data."""
 
-    def __init__(self, policy, pos, goal, obstacles, radius=0.5, pref_speed=1.0):
+    def __init__(self, policy, pos, goal, obstacles, radius=0.5, pref_speed=1.0, paths=None):
         Agent = import_reference()
         from mamp.agents.obstacle import Obstacle
         from mamp.envs.mampenv import MACAEnv
@@ -153,6 +153,11 @@ class Recorder:
                              pref_speed=pref_speed, policy=cls, id=i, dt=0.1) for i in range(len(pos))]
         self.obstacles = [Obstacle(pos=o[:3], shape_dict={'shape': 'sphere', 'feature': o[3]}, id=i)
                           for i, o in enumerate(obstacles)]
+        # waypoint lists of an external global planner (agent.path, agent.py:44): the policies pop() from the END
+        self.paths = paths
+        if paths is not None:
+            for a, pth in zip(self.agents, paths):
+                a.path = [list(map(float, w)) for w in pth]
         self.env = MACAEnv()
         with contextlib.redirect_stdout(io.StringIO()):
             self.env.set_agents(self.agents, obstacles=self.obstacles)
@@ -265,6 +270,9 @@ class Recorder:
             total_dist=np.array([a.total_dist for a in ags], dtype='float64'),
             step_num=np.array([a.step_num for a in ags], dtype=np.int32),
             vpref_prev=np.array([np.asarray(a.v_pref, dtype='float64') for a in ags]),
+            path_left=np.array([len(a.path) for a in ags], dtype=np.int32),
+            now_goal=np.array([np.full(3, np.nan) if getattr(a.policy, 'now_goal', None) is None
+                               else np.asarray(a.policy.now_goal, dtype='float64') for a in ags]),
         )
 
     def step(self):
@@ -326,7 +334,18 @@ class Recorder:
             desire_steps=np.array([a.desire_steps for a in ags], dtype=np.int32),
             obstacles=np.array([[*o.pos_global_frame, o.radius] for o in self.obstacles],
                                dtype='float64').reshape(-1, 4),
+            **self._static_paths()
         )
+
+    def _static_paths(self):
+        if self.paths is None:
+            return {}
+        P = max(1, max(len(p) for p in self.paths))
+        wp = np.full((self.n, P, 3), np.nan)
+        for i, p in enumerate(self.paths):
+            for k, w in enumerate(p):
+                wp[i, k] = w
+        return dict(waypoints=wp, waypoint_count=np.array([len(p) for p in self.paths], dtype=np.int32))
 
     def metrics(self):
         """run_example/run_sca.py:228-250."""

@@ -15,6 +15,8 @@ def swarm_from_golden(g, debug=True, full_search=True):
                  pref_speed=g['pref_speed'], max_run_dist=g['max_run_dist'], initial_pos=g['initial_pos'],
                  goal_pos=g['goal_pos'])
     sw.set_obstacles(g['obstacles'])
+    if 'waypoints' in g:       # agent.path; the pop state then evolves on the device
+        sw.set_waypoints(g['waypoints'], g['waypoint_count'])
     lo = np.minimum(g['pos'].reshape(-1, 3).min(0), g['goal'].min(0)) - 5.0
     hi = np.maximum(g['pos'].reshape(-1, 3).max(0), g['goal'].max(0)) + 5.0
     sw.fit_grid(lo, hi)

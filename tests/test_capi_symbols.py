@@ -36,7 +36,7 @@ def test_struct_layouts_match_the_header():
     from sca_b200 import capi
     # scab_params: 5 doubles + 3 doubles + 1 double + 3 int32 + 1 int32
     assert ctypes.sizeof(capi.Params) == 9 * 8 + 16
-    assert ctypes.sizeof(capi.StatePtrs) == 8 * (len(capi.STATE_FIELDS) + 2)   # + n_global + goal_heading
+    assert ctypes.sizeof(capi.StatePtrs) == 8 * (len(capi.STATE_FIELDS) + 6)   # + n_global, goal_heading, waypoints, waypoint_left, now_goal, waypoint_stride
     assert ctypes.sizeof(capi.Counters) == 64
 
 

@@ -33,6 +33,12 @@ def _run_fixture(name, max_steps=None, full_search=True):
         out = G.policy_outputs(sw, s['status'])
         r = gu.compare_step(g, t, out, who='%s step %d' % (name, t), dsq_rtol=4e-16 if g['obstacles'].size else 0.0)
         r['perm_bad'] = int(not perm_ok)
+        if 'waypoints' in g and t + 1 < T:      # waypoint state after this step's get_trajectory == the reference's pre-state of t+1
+            left = sw.t['waypoint_left'][:sw.n].cpu().numpy()
+            ng = sw.t['now_goal'][:sw.n].cpu().numpy()
+            ref_ng = g['now_goal'][t + 1]
+            same = (np.isnan(ng) & np.isnan(ref_ng)) | (ng == ref_ng)
+            r['path_bad'] = int((left != g['path_left'][t + 1]).sum()) + int((~same).sum())
         sw.stage_status()
         post = G.post_state(sw)
         s2 = gu.state_at(g, t + 1)
@@ -57,7 +63,7 @@ def _run_fixture(name, max_steps=None, full_search=True):
 
 
 EXACT = ('tag', 'coll_query', 'nbr_cnt', 'nbr_ids', 'nbr_dsq', 'plane_fail', 'n_planes', 'lp4_proj', 'perm_bad',
-         'status_bad', 'stepnum_bad', 'active_bad', 'done_bad', 'n_suit')
+         'status_bad', 'stepnum_bad', 'active_bad', 'done_bad', 'n_suit', 'path_bad')
 
 
 @pytest.mark.parametrize('full_search', [True, False], ids=['full', 'lazy'])

@@ -15,9 +15,15 @@ def run_fixture(name):
     w = orc.World(g['pos'][0], g['goal'], heading=g['heading'][0], radius=g['radius'], pref_speed=g['pref_speed'],
                   obstacles=g['obstacles'], initial_pos=g['initial_pos'], goal_pos=g['goal_pos'])
     assert np.array_equal(w.max_run_dist, g['max_run_dist'])
+    if 'waypoints' in g:          # agent.path of an external planner; the pop state evolves in the oracle
+        w.set_waypoints(g['waypoints'], g['waypoint_count'])
     tot = {}
     for t in range(T):
         s = gu.state_at(g, t)
+        if 'waypoints' in g:
+            ng = g['now_goal'][t]
+            same = np.isnan(ng) & np.isnan(w.now_goal) | (ng == w.now_goal)
+            tot['path_bad'] = tot.get('path_bad', 0) + int((w.waypoint_left != g['path_left'][t]).sum()) + int((~same).sum())
         w.pos[:] = s['pos']
         w.vel[:] = s['vel'].astype(np.float32)
         w.heading[:] = s['heading']
