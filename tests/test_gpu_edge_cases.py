@@ -142,3 +142,29 @@ def test_boundary_errors_are_reported_not_swallowed():
         sw.h.set_grid([0, 0, 0], 5.0, [4, 4, 4])
     with pytest.raises(capi.ScabError, match='never enabled'):
         sw.h.dubins_read(8)
+
+
+def test_voxel_obstacle_field_at_scale_matches_oracle():
+    """every occupied voxel of a binvox map as an r = 0.2 sphere (~1.7e4 obstacles in the library's
+    static grid); agents fly past and over the field.  Ordered lists (obstacle ids included), tags and
+    velocities against the oracle."""
+    import io
+    import os
+    from sca_b200 import maps
+    from test_gpu_knn_oracle import _compare
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'map_synthetic.npz'))
+    obs = maps.obstacles_from_binvox(io.BytesIO(g['binvox'].tobytes()), center=(0.0, 0.0), above_every=1, floor_every=1)
+    assert len(obs) > 15000
+    c = obs[:, :3].mean(0)
+    n = 96
+    ang = 2 * np.pi * np.arange(n) / n
+    pos = np.zeros((n, 6)); goal = np.zeros((n, 6))
+    ring = 6.0 + 0.5 * (np.arange(n) % 3)
+    pos[:, 0], pos[:, 1], pos[:, 2] = c[0] + ring * np.cos(ang), c[1] + ring * np.sin(ang), c[2] + 1.5 + 0.6 * (np.arange(n) % 4)
+    goal[:, 0], goal[:, 1], goal[:, 2] = c[0] - ring * np.cos(ang), c[1] - ring * np.sin(ang), pos[:, 2]
+    pos[:, 3] = ang + np.pi
+    for policy in ('srvo3d', 'orca_lp'):
+        tot = _compare(pos, goal, obs, policy, steps=12)
+        print(policy, tot)
+        for k in ('nbr', 'tag', 'nsuit', 'vel', 'status', 'planes'):
+            assert tot[k] == 0, (policy, tot)
