@@ -14,12 +14,14 @@ from .swarm import Swarm
 
 
 class BatchedEnv(object):
-    def __init__(self, policy, nbr_mode=capi.NBR_KNN, device='cuda:0', debug=False, dubins=None):
+    def __init__(self, policy, nbr_mode=capi.NBR_KNN, device='cuda:0', debug=False, dubins=None, log_every=0,
+                 log_capacity=4096):
         """`dubins` (default: True for 'sca' and 'rvo3d_dubins', the two policies whose reference v_pref is the
         Dubins tracker of scaPolicy.py:264-338): run that tracker on the device; False = straight-line v_pref."""
         self.policy = policy
         self.dubins = (policy in ('sca', 'rvo3d_dubins')) if dubins is None else bool(dubins)
         self.nbr_mode = nbr_mode
+        self.log_every, self.log_capacity, self.traj = int(log_every), int(log_capacity), None   # trajectory log (logs.py)
         self.device = device
         self.debug = debug
         self.sw = None
@@ -50,12 +52,19 @@ class BatchedEnv(object):
         self.straight_len = d - 0.5
         self.desire_steps = (self.straight_len / (np.broadcast_to(pref_speed, (n,)) * 0.1)).astype(np.int64)
         self.steps = 0
+        self.obstacles = np.zeros((0, 4)) if obstacles is None else np.asarray(obstacles, 'float64').reshape(-1, 4)
+        self.goal6, self.radius = goal6, radius
+        if self.log_every > 0:
+            from .logs import TrajectoryLog
+            self.traj = TrajectoryLog(self.sw, self.log_capacity, self.log_every)
         return self
 
     def step(self, sync=True):
         """One MACAEnv.step.  With sync=False nothing is read back (returns None): call is_done() when needed."""
         self.sw.step(self.policy, self.nbr_mode)
         self.steps += 1
+        if self.traj is not None:
+            self.traj.record(self.steps)
         return self.sw.is_done() if sync else None
 
     def is_done(self):
@@ -70,3 +79,15 @@ class BatchedEnv(object):
 
     def metrics(self):
         return self.sw.metrics(self.straight_len, self.desire_steps)
+
+    def write_log(self, log_dir, compute_time=0.0):
+        """env_cfg.json in the reference's schema (run_sca.py:198-259) + the trajectory log, if one was kept."""
+        import os
+        from . import logs
+        d = self.sw.download(('status', 'total_dist', 'step_num'))
+        info = logs.rollout_info(d['status'], d['total_dist'], d['step_num'], self.straight_len, self.desire_steps, self.radius,
+                                 self.goal6, self.obstacles, compute_time)
+        logs.write_env_cfg(os.path.join(log_dir, 'env_cfg.json'), info)
+        if self.traj is not None:
+            self.traj.save(log_dir)
+        return info
