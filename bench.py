@@ -31,8 +31,12 @@ import numpy as np  # noqa: E402
 
 DENSITY = 1.0e6 / 560.0 ** 3          # agents per m^3 of BASELINE config 5
 ALGO_BYTES = {'grid': 168, 'neighbors': 116, 'policy': 660, 'status': 144}   # SURVEY.md 8(d), per agent-step
-KERNELS_PER_STEP = 11                 # k_cell_count, k_scan_tile_sums, k_scan_tiles, k_scan_apply, k_reorder, k_neighbors_knn, k_vpref, k_select_fast, k_select, k_integrate, k_status
-METRIC = 'agent-steps/sec (SCA, 1M UAVs)'
+# kernels launched per step: k_cell_count, k_scan_tile_sums, k_scan_tiles, k_scan_apply, k_reorder, k_neighbors_knn,
+# then k_vpref, k_select_fast, k_select, k_integrate (sampled policies) or k_policy_lp (ORCA LP), then k_status
+KERNELS_PER_STEP = {'orca_lp': 8}
+KERNELS_PER_STEP_SAMPLED = 11
+POLICY_KERNELS = {'orca_lp': 'k_policy_lp'}
+METRIC = 'agent-steps/sec (SCA, 1M UAVs)'      # --policy other than sca: the same workload under that policy (named in config)
 
 
 def measured_peak():
@@ -214,12 +218,13 @@ def run_ours(args):
         except Exception:
             pass
         roof = {'bound': 'hbm', 'kernel': {'grid': 'k_cell_count+k_scan_*+k_reorder', 'neighbors': 'k_neighbors_knn',
-                                           'policy': 'k_vpref+k_select_fast<SCA>+k_select<SCA>+k_integrate', 'status': 'k_status'}[dom],
+                                           'policy': POLICY_KERNELS.get(policy, 'k_vpref+k_select_fast<%s>+k_select<%s>+k_integrate' % (policy.upper(), policy.upper())),
+                                           'status': 'k_status'}[dom],
                 'achieved': round(achieved, 2), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 5),
                 'traffic': traffic, 'peak_source': how, 'algorithmic_bytes_per_agent_step': ALGO_BYTES[dom],
                 'units_per_launch': int(units), 'stage_ms': {k: round(v, 4) for k, v in stage_ms.items()},
                 'last_step_diag': {k: cdiag[k] for k in ('n_active', 'n_recheck', 'n_tier2', 'n_slow', 'n_collision')},
-                'note': 'SCA candidate search is fp32/fp64-ALU-bound (SURVEY.md 8d): HBM fraction is reported as asked, '
+                'note': 'the policy stage is ALU / instruction-issue bound (SURVEY.md 8d): HBM fraction is reported as asked, '
                         'stage_ms shows where the step goes'}
 
     # ---- end to end through host buffers (pinned H2D of the inputs, D2H of the results, every step)
@@ -268,7 +273,7 @@ def run_ours(args):
                                                                      % (n_total * 420 // 1000000),
                           'parallelism': 'spatial slabs x%d + halo exchange' % world if world > 1 else 'single GPU'},
                # + 5 halo kernels per step when sharded: k_halo_fill, k_halo_pack, k_halo_unpack, k_halo_pack_pos, k_halo_unpack_pos
-               'gpu_launches': (KERNELS_PER_STEP + (5 if world > 1 else 0)) * args.steps, 'clocks': clocks}
+               'gpu_launches': (KERNELS_PER_STEP.get(policy, KERNELS_PER_STEP_SAMPLED) + (5 if world > 1 else 0)) * args.steps, 'clocks': clocks}
         if roof:
             out['roofline'] = roof
         if e2e:

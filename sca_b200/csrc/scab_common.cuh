@@ -174,14 +174,14 @@ __device__ __forceinline__ double distance_d(double ax, double ay, double az, do
 // get_trajectory (rvo3dPolicy.py:71-86, srvo3dPolicy.py:71-86 with l3norm; orca3dPolicy.py:298-312,
 // orca3dPolicyOfficial.py:302-316 with distance): the point compute_v_pref aims at.  Pops agent.path from its end.
 __device__ __forceinline__ void waypoint_target(const scab_state_ptrs &st, int id, double px, double py, double pz, bool use_distance,
-                                                double *target)
-{
+                                                double *target, bool commit = true)
+{   // commit == false: compute the target only, leave agent.path / now_goal as they are (a later call commits)
     const double *g = &st.goal[3 * id];
     target[0] = g[0]; target[1] = g[1]; target[2] = g[2];
     if (st.waypoints == nullptr) return;
     double *ng = &st.now_goal[3 * id];
     int left = st.waypoint_left[id];
-    if (left <= 0) { ng[0] = g[0]; ng[1] = g[1]; ng[2] = g[2]; return; }     // path exhausted: now_goal = goal
+    if (left <= 0) { if (commit) { ng[0] = g[0]; ng[1] = g[1]; ng[2] = g[2]; } return; }     // path exhausted: now_goal = goal
     const double *wp = st.waypoints + (size_t)id * (size_t)st.waypoint_stride * 3;
     double nx = ng[0], ny = ng[1], nz = ng[2];
     if (isnan(nx)) { left--; nx = wp[3 * left]; ny = wp[3 * left + 1]; nz = wp[3 * left + 2]; }   // first
@@ -191,8 +191,10 @@ __device__ __forceinline__ void waypoint_target(const scab_state_ptrs &st, int i
     if ((dis <= __dmul_rn(1.0, st.radius[id]) || d_ng_goal >= d_pos_goal) && left > 0) {   // update_now_goal_dist = 1.0
         left--; nx = wp[3 * left]; ny = wp[3 * left + 1]; nz = wp[3 * left + 2];
     }
-    st.waypoint_left[id] = left;
-    ng[0] = nx; ng[1] = ny; ng[2] = nz;
+    if (commit) {
+        st.waypoint_left[id] = left;
+        ng[0] = nx; ng[1] = ny; ng[2] = nz;
+    }
     target[0] = nx; target[1] = ny; target[2] = nz;
 }
 

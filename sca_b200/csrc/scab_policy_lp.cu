@@ -11,6 +11,7 @@
 #include "scab_common.cuh"
 
 #define LP_THREADS 64
+#define LP_FAST_THREADS 128
 
 struct Planes {
     // [component][plane][thread] : consecutive threads -> consecutive 8-byte words (conflict-free)
@@ -186,25 +187,97 @@ __device__ void lp4(const PlaneView &P, const PlaneView &Q, int np, int beginPla
     }
 }
 
-__global__ void __launch_bounds__(LP_THREADS) k_policy_lp(StepArgs A)
+// ORCA plane of neighbour slot `e` for the agent (me, mv): orca3dPolicyOfficial.py:58-105.
+// point = vA + u/2 for every neighbour, static or not.
+__device__ __forceinline__ void orca_plane(const StepArgs &A, int e, const double4 &me, const float4 &mv, Vec3 &point, Vec3 &n)
+{
+    double4 o;
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (e < A.n) {
+        o = A.s_posr[e];
+        const float4 ov = A.s_vel[e];
+        ox = ov.x; oy = ov.y; oz = ov.z;
+    } else if (e < A.n + A.m) o = A.o_posr[e - A.n];
+    else o = A.o_posr_by_id[e - A.n - A.m];
+    const Vec3 rp{__dsub_rn(o.x, me.x), __dsub_rn(o.y, me.y), __dsub_rn(o.z, me.z)};
+    const Vec3 rv{(double)__fsub_rn(mv.x, ox), (double)__fsub_rn(mv.y, oy), (double)__fsub_rn(mv.z, oz)};
+    const double distSq = dotv(rp, rp);
+    const double R = __dadd_rn(__dadd_rn(me.w, 0.05), __dadd_rn(o.w, 0.05));
+    const double RSq = __dmul_rn(R, R);
+    Vec3 u;
+    if (distSq > RSq) {
+        const double invT = A.inv_time_horizon;
+        const Vec3 w{__dsub_rn(rv.x, __dmul_rn(invT, rp.x)), __dsub_rn(rv.y, __dmul_rn(invT, rp.y)),
+                     __dsub_rn(rv.z, __dmul_rn(invT, rp.z))};
+        const double wl2 = dotv(w, w);
+        const double dp = dotv(w, rp);
+        if (dp < 0.0 && __dmul_rn(dp, dp) > __dmul_rn(RSq, wl2)) {
+            const double wl = __dsqrt_rn(wl2);
+            n = Vec3{__ddiv_rn(w.x, wl), __ddiv_rn(w.y, wl), __ddiv_rn(w.z, wl)};
+            const double sc = __dsub_rn(__dmul_rn(R, invT), wl);
+            u = Vec3{__dmul_rn(sc, n.x), __dmul_rn(sc, n.y), __dmul_rn(sc, n.z)};
+        } else {
+            const double difSq = __dsub_rn(distSq, RSq);
+            const double dpr = dotv(rp, rv);
+            const Vec3 cr = crossv(rp, rv);
+            const double wwSq = __ddiv_rn(dotv(cr, cr), difSq);
+            const double pl = __dsqrt_rn(distSq);
+            const double t = __ddiv_rn(__dadd_rn(__ddiv_rn(dpr, pl), __dmul_rn(__dsqrt_rn(wwSq), __ddiv_rn(R, pl))), pl);
+            const Vec3 ww{__dsub_rn(rv.x, __dmul_rn(t, rp.x)), __dsub_rn(rv.y, __dmul_rn(t, rp.y)),
+                          __dsub_rn(rv.z, __dmul_rn(t, rp.z))};
+            const double wl = __dsqrt_rn(dotv(ww, ww));
+            n = Vec3{__ddiv_rn(ww.x, wl), __ddiv_rn(ww.y, wl), __ddiv_rn(ww.z, wl)};
+            const double sc = __dsub_rn(__dmul_rn(R, t), wl);
+            u = Vec3{__dmul_rn(sc, n.x), __dmul_rn(sc, n.y), __dmul_rn(sc, n.z)};
+        }
+    } else {
+        const double invDt = A.inv_time_step;
+        const Vec3 w{__dsub_rn(rv.x, __dmul_rn(invDt, rp.x)), __dsub_rn(rv.y, __dmul_rn(invDt, rp.y)),
+                     __dsub_rn(rv.z, __dmul_rn(invDt, rp.z))};
+        const double wl = __dsqrt_rn(dotv(w, w));
+        n = Vec3{__ddiv_rn(w.x, wl), __ddiv_rn(w.y, wl), __ddiv_rn(w.z, wl)};
+        const double sc = __dsub_rn(__dmul_rn(R, invDt), wl);
+        u = Vec3{__dmul_rn(sc, n.x), __dmul_rn(sc, n.y), __dmul_rn(sc, n.z)};
+    }
+    point = Vec3{__dadd_rn((double)mv.x, __dmul_rn(0.5, u.x)), __dadd_rn((double)mv.y, __dmul_rn(0.5, u.y)),
+                 __dadd_rn((double)mv.z, __dmul_rn(0.5, u.z))};
+}
+
+// linearProgram3's starting point (:240-250, dir_opt False): v_pref clamped to the maxSpeed sphere
+__device__ __forceinline__ Vec3 lp3_start(const Vec3 &vel_pref, double maxSpeed)
+{
+    if (dotv(vel_pref, vel_pref) > __dmul_rn(maxSpeed, maxSpeed)) {
+        const double nv = __dsqrt_rn(dotv(vel_pref, vel_pref));
+        return Vec3{__dmul_rn(__ddiv_rn(vel_pref.x, nv), maxSpeed), __dmul_rn(__ddiv_rn(vel_pref.y, nv), maxSpeed),
+                    __dmul_rn(__ddiv_rn(vel_pref.z, nv), maxSpeed)};
+    }
+    return vel_pref;
+}
+
+// MODE 0: every agent, planes in shared memory (SCAB_NO_FAST=1, the A/B switch).
+// MODE 1: fast path, no plane storage.  In linearProgram3 (:251-258) a plane is only ever re-read after SOME plane was
+//         violated by the running result; until then the result is the starting point.  So each plane is built in
+//         registers and tested against the starting point; if none is violated that IS the answer (planeFail == nc).
+//         The first violation appends the agent to A.slow_list and leaves every output untouched.
+// MODE 2: the agents on A.slow_list, planes in shared memory, full LP3 / LP4.
+template <int MODE>
+__global__ void __launch_bounds__(MODE == 1 ? LP_FAST_THREADS : LP_THREADS, MODE == 1 ? 6 : 1) k_policy_lp(StepArgs A)
 {
     extern __shared__ double lp_smem[];
-    Planes *PS = reinterpret_cast<Planes *>(lp_smem);
     const int tid = threadIdx.x;
-    double qloc[6 * KNBR];   // projected planes of linearProgram4: rare path, thread-local
-    PlaneView P{&PS[0].v[0][0][tid], LP_THREADS}, Q{qloc, 1};
-    const int s = blockIdx.x * blockDim.x + tid;
     unsigned long long ran = 0;
-    if (s < A.n) {
+    const int n_work = MODE == 2 ? min(*A.slow_count, A.n) : A.n;
+    if (MODE == 2 && blockIdx.x == 0 && tid == 0) A.counters[6] = (unsigned long long)n_work;
+    for (int wi = blockIdx.x * blockDim.x + tid; wi < n_work; wi += gridDim.x * blockDim.x) {
+        const int s = MODE == 2 ? A.slow_list[wi] : wi;
         const int id = A.s_id[s];
         const double4 me = A.s_posr[s];
         const float4 mv = A.s_vel[s];
         const int flags = __float_as_int(mv.w);
         Action7 act;
         double npx, npy, npz;
-        if (flags & SCAB_ST_GHOST) {
-            // halo copy: owned (and stepped) by another GPU
-        } else if (flags & FL_INACTIVE) {
+        if (flags & SCAB_ST_GHOST) continue;   // halo copy: owned (and stepped) by another GPU
+        if (flags & FL_INACTIVE) {
 #pragma unroll
             for (int k = 0; k < 7; k++) act.a[k] = 0.f;
             kinematic_update(A, id, act, me.x, me.y, me.z, &npx, &npy, &npz);
@@ -212,116 +285,104 @@ __global__ void __launch_bounds__(LP_THREADS) k_policy_lp(StepArgs A)
             if (A.st.plane_fail) A.st.plane_fail[id] = -1;
             if (A.st.n_planes) A.st.n_planes[id] = -1;
             if (A.st.lp4_proj) A.st.lp4_proj[id] = 0;
+            continue;
+        }
+        double v_store[3], v_des[3];
+        double target[3];
+        // the fast pass may still defer this agent: it only peeks at the waypoint state and commits the pop when it finishes
+        waypoint_target(A.st, id, me.x, me.y, me.z, true, target, MODE != 1);
+        v_pref_straight(&A.st.goal[3 * id], target, me.x, me.y, me.z, A.st.pref_speed[id], true, v_store, v_des);
+        const double nv32 = __dsqrt_rn(sumsq_f32(mv.x, mv.y, mv.z));
+        const bool first = py_round5(__dadd_rn(nv32, 1e-5)) <= 1e-5;   // :52 distance(vel, 0) <= 1e-5
+        int tag = 0, plane_fail = -1, n_planes = -1, n_proj = 0;
+        Vec3 res;
+        if (first) {
+            tag = SCAB_TAG_FIRST;
+            res = Vec3{__dmul_rn(0.3, v_des[0]), __dmul_rn(0.3, v_des[1]), __dmul_rn(0.3, v_des[2])};
         } else {
-            ran = 1;
-            double v_store[3], v_des[3];
-            double target[3];
-            waypoint_target(A.st, id, me.x, me.y, me.z, true, target);
-            v_pref_straight(&A.st.goal[3 * id], target, me.x, me.y, me.z, A.st.pref_speed[id], true, v_store, v_des);
-            const double nv32 = __dsqrt_rn(sumsq_f32(mv.x, mv.y, mv.z));
-            const bool first = py_round5(__dadd_rn(nv32, 1e-5)) <= 1e-5;   // :52 distance(vel, 0) <= 1e-5
-            int tag = 0, plane_fail = -1, n_planes = -1, n_proj = 0;
-            Vec3 res;
-            if (first) {
-                tag = SCAB_TAG_FIRST;
-                res = Vec3{__dmul_rn(0.3, v_des[0]), __dmul_rn(0.3, v_des[1]), __dmul_rn(0.3, v_des[2])};
+            const int nc = A.s_nbr_cnt[s];
+            const Vec3 vp{v_des[0], v_des[1], v_des[2]};
+            if (MODE == 1) {
+                res = lp3_start(vp, A.max_speed);
+                bool violated = false;
+                for (int k = 0; k < nc && !violated; k++) {
+                    Vec3 pt, n;
+                    orca_plane(A, A.s_nbr[(size_t)s * KNBR + k], me, mv, pt, n);
+                    violated = dotv(n, subv(pt, res)) > 0.0;            // :252
+                }
+                if (violated) {
+                    A.slow_list[atomicAdd(A.slow_count, 1)] = s;
+                    continue;
+                }
+                plane_fail = nc;
+                tag |= SCAB_TAG_LP3_OK;
             } else {
-                const int nc = A.s_nbr_cnt[s];
+                Planes *PS = reinterpret_cast<Planes *>(lp_smem);
+                double qloc[6 * KNBR];   // projected planes of linearProgram4: rare path, thread-local
+                PlaneView P{&PS[0].v[0][0][tid], LP_THREADS}, Q{qloc, 1};
                 for (int k = 0; k < nc; k++) {
-                    const int e = A.s_nbr[(size_t)s * KNBR + k];
-                    double4 o;
-                    float ox = 0.f, oy = 0.f, oz = 0.f;
-                    if (e < A.n) {
-                        o = A.s_posr[e];
-                        const float4 ov = A.s_vel[e];
-                        ox = ov.x; oy = ov.y; oz = ov.z;
-                    } else if (e < A.n + A.m) o = A.o_posr[e - A.n];
-                    else o = A.o_posr_by_id[e - A.n - A.m];
-                    // :58-105
-                    const Vec3 rp{__dsub_rn(o.x, me.x), __dsub_rn(o.y, me.y), __dsub_rn(o.z, me.z)};
-                    const Vec3 rv{(double)__fsub_rn(mv.x, ox), (double)__fsub_rn(mv.y, oy), (double)__fsub_rn(mv.z, oz)};
-                    const double distSq = dotv(rp, rp);
-                    const double R = __dadd_rn(__dadd_rn(me.w, 0.05), __dadd_rn(o.w, 0.05));
-                    const double RSq = __dmul_rn(R, R);
-                    Vec3 n, u;
-                    if (distSq > RSq) {
-                        const double invT = A.inv_time_horizon;
-                        const Vec3 w{__dsub_rn(rv.x, __dmul_rn(invT, rp.x)), __dsub_rn(rv.y, __dmul_rn(invT, rp.y)),
-                                     __dsub_rn(rv.z, __dmul_rn(invT, rp.z))};
-                        const double wl2 = dotv(w, w);
-                        const double dp = dotv(w, rp);
-                        if (dp < 0.0 && __dmul_rn(dp, dp) > __dmul_rn(RSq, wl2)) {
-                            const double wl = __dsqrt_rn(wl2);
-                            n = Vec3{__ddiv_rn(w.x, wl), __ddiv_rn(w.y, wl), __ddiv_rn(w.z, wl)};
-                            const double sc = __dsub_rn(__dmul_rn(R, invT), wl);
-                            u = Vec3{__dmul_rn(sc, n.x), __dmul_rn(sc, n.y), __dmul_rn(sc, n.z)};
-                        } else {
-                            const double difSq = __dsub_rn(distSq, RSq);
-                            const double dpr = dotv(rp, rv);
-                            const Vec3 cr = crossv(rp, rv);
-                            const double wwSq = __ddiv_rn(dotv(cr, cr), difSq);
-                            const double pl = __dsqrt_rn(distSq);
-                            const double t = __ddiv_rn(__dadd_rn(__ddiv_rn(dpr, pl), __dmul_rn(__dsqrt_rn(wwSq), __ddiv_rn(R, pl))), pl);
-                            const Vec3 ww{__dsub_rn(rv.x, __dmul_rn(t, rp.x)), __dsub_rn(rv.y, __dmul_rn(t, rp.y)),
-                                          __dsub_rn(rv.z, __dmul_rn(t, rp.z))};
-                            const double wl = __dsqrt_rn(dotv(ww, ww));
-                            n = Vec3{__ddiv_rn(ww.x, wl), __ddiv_rn(ww.y, wl), __ddiv_rn(ww.z, wl)};
-                            const double sc = __dsub_rn(__dmul_rn(R, t), wl);
-                            u = Vec3{__dmul_rn(sc, n.x), __dmul_rn(sc, n.y), __dmul_rn(sc, n.z)};
-                        }
-                    } else {
-                        const double invDt = A.inv_time_step;
-                        const Vec3 w{__dsub_rn(rv.x, __dmul_rn(invDt, rp.x)), __dsub_rn(rv.y, __dmul_rn(invDt, rp.y)),
-                                     __dsub_rn(rv.z, __dmul_rn(invDt, rp.z))};
-                        const double wl = __dsqrt_rn(dotv(w, w));
-                        n = Vec3{__ddiv_rn(w.x, wl), __ddiv_rn(w.y, wl), __ddiv_rn(w.z, wl)};
-                        const double sc = __dsub_rn(__dmul_rn(R, invDt), wl);
-                        u = Vec3{__dmul_rn(sc, n.x), __dmul_rn(sc, n.y), __dmul_rn(sc, n.z)};
-                    }
-                    P.at(0, k) = __dadd_rn((double)mv.x, __dmul_rn(0.5, u.x));
-                    P.at(1, k) = __dadd_rn((double)mv.y, __dmul_rn(0.5, u.y));
-                    P.at(2, k) = __dadd_rn((double)mv.z, __dmul_rn(0.5, u.z));
+                    Vec3 pt, n;
+                    orca_plane(A, A.s_nbr[(size_t)s * KNBR + k], me, mv, pt, n);
+                    P.at(0, k) = pt.x; P.at(1, k) = pt.y; P.at(2, k) = pt.z;
                     P.at(3, k) = n.x; P.at(4, k) = n.y; P.at(5, k) = n.z;
                 }
-                const Vec3 vp{v_des[0], v_des[1], v_des[2]};
                 plane_fail = lp3(P, nc, A.max_speed, vp, false, res);   // :108
-                n_planes = nc;
                 if (plane_fail == nc) tag |= SCAB_TAG_LP3_OK;
                 if (plane_fail < nc) {                                   // :110-111
                     tag |= SCAB_TAG_LP4;
                     lp4(P, Q, nc, plane_fail, A.max_speed, res, n_proj);
                 }
             }
-            act = cartesian2spherical(res.x, res.y, res.z, A.st.heading[3 * id], A.st.heading[3 * id + 1], true);
-            kinematic_update(A, id, act, me.x, me.y, me.z, &npx, &npy, &npz);
-            if (A.s_qcoll[s]) A.st.status[id] = flags | SCAB_ST_COLLISION;   // agent.py:83-85
-            if (A.st.vpref_out) { A.st.vpref_out[3 * id] = v_store[0]; A.st.vpref_out[3 * id + 1] = v_store[1]; A.st.vpref_out[3 * id + 2] = v_store[2]; }
-            if (A.st.tag) A.st.tag[id] = tag;
-            if (A.st.plane_fail) A.st.plane_fail[id] = plane_fail;
-            if (A.st.n_planes) A.st.n_planes[id] = n_planes;
-            if (A.st.lp4_proj) A.st.lp4_proj[id] = n_proj;
-            if (A.st.n_suit) A.st.n_suit[id] = 0;
+            n_planes = nc;
         }
+        ran++;
+        if (MODE == 1 && A.st.waypoints != nullptr) waypoint_target(A.st, id, me.x, me.y, me.z, true, target, true);
+        act = cartesian2spherical(res.x, res.y, res.z, A.st.heading[3 * id], A.st.heading[3 * id + 1], true);
+        kinematic_update(A, id, act, me.x, me.y, me.z, &npx, &npy, &npz);
+        if (A.s_qcoll[s]) A.st.status[id] = flags | SCAB_ST_COLLISION;   // agent.py:83-85
+        if (A.st.vpref_out) { A.st.vpref_out[3 * id] = v_store[0]; A.st.vpref_out[3 * id + 1] = v_store[1]; A.st.vpref_out[3 * id + 2] = v_store[2]; }
+        if (A.st.tag) A.st.tag[id] = tag;
+        if (A.st.plane_fail) A.st.plane_fail[id] = plane_fail;
+        if (A.st.n_planes) A.st.n_planes[id] = n_planes;
+        if (A.st.lp4_proj) A.st.lp4_proj[id] = n_proj;
+        if (A.st.n_suit) A.st.n_suit[id] = 0;
     }
-    // one counter update per warp
-    const unsigned act_mask = __ballot_sync(0xffffffffu, ran != 0);
-    if ((threadIdx.x & 31) == 0 && act_mask) {
-        atomicAdd(&A.counters[0], (unsigned long long)__popc(act_mask));
-        atomicAdd(&A.counters[4], (unsigned long long)__popc(act_mask));
+    // one counter update per warp (every thread of the warp leaves the loop before this point)
+    __syncwarp();
+    for (int o = 16; o; o >>= 1) ran += __shfl_xor_sync(0xffffffffu, ran, o);
+    if ((threadIdx.x & 31) == 0 && ran) {
+        atomicAdd(&A.counters[0], ran);
+        atomicAdd(&A.counters[4], ran);
     }
 }
 
 cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
 {
     if (A.n <= 0) return cudaSuccess;
-    static bool attr_set = false;
+    static int no_fast = -1, sms = 0, per_sm = 0;
     const size_t smem = sizeof(Planes);   // 6*16*64*8 = 49152 B
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_policy_lp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (no_fast < 0) {
+        cudaError_t e = cudaFuncSetAttribute(k_policy_lp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_policy_lp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_policy_lp<2>, LP_THREADS, smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (per_sm < 1) per_sm = 1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        const char *ev = getenv("SCAB_NO_FAST");   // A/B switch: every agent through the shared-memory kernel
+        no_fast = (ev && ev[0] == '1') ? 1 : 0;
     }
-    int nb = (A.n + LP_THREADS - 1) / LP_THREADS;
-    k_policy_lp<<<nb, LP_THREADS, smem, s>>>(A);
+    const int nb = (A.n + LP_THREADS - 1) / LP_THREADS;
+    if (no_fast) {
+        k_policy_lp<0><<<nb, LP_THREADS, smem, s>>>(A);
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaMemsetAsync(A.slow_count, 0, sizeof(int32_t), s);
+    if (e != cudaSuccess) return e;
+    k_policy_lp<1><<<(A.n + LP_FAST_THREADS - 1) / LP_FAST_THREADS, LP_FAST_THREADS, 0, s>>>(A);
+    // the agents with a violated plane: one resident wave, strided over the list
+    const int grid = nb < sms * per_sm ? nb : sms * per_sm;
+    k_policy_lp<2><<<grid, LP_THREADS, smem, s>>>(A);
     return cudaGetLastError();
 }
