@@ -89,3 +89,45 @@ def test_compat_equals_knn_when_lists_do_not_saturate():
     assert small.sum() > 50
     assert np.array_equal(np.sort(w1.nbr_ids[small], axis=1), np.sort(w2.nbr_ids[small], axis=1))
     assert np.array_equal(w1.nbr_dsq[small], w2.nbr_dsq[small])
+
+
+import pytest
+
+
+@pytest.mark.parametrize('policy', ['sca', 'orca_lp'])
+def test_locality_sub_box_reproduces_the_full_world(policy):
+    """The property the full-size GPU test relies on (tests/locality.py), checked on the oracle itself: stepping only
+    the agents of a box grown by > neighborDist reproduces, for the agents inside the box, the step of the whole world."""
+    import locality as loc
+    from sca_b200 import scenarios
+    n = 12000
+    dens = 2.0 * 1.0e6 / 560.0 ** 3
+    pos6, goal6, _ = scenarios.uniform_box_numpy(n, dens, seed=4)
+    L = (n / dens) ** (1.0 / 3.0)
+    orc.set_threads(8)
+    full = orc.World(pos6[:, :3], goal6[:, :3], heading=pos6[:, 3:6], initial_pos=pos6, goal_pos=goal6)
+    for _ in range(3):
+        full.step(policy, orc.NBR_KNN, fast=True)
+    pre = {k: getattr(full, k).copy() for k in loc.STATE_KEYS}
+    outer_idx, inner = loc.pick_box(pre['pos'], [L / 2, L / 2, L / 2 + 20.0], half_inner=22.0)
+    assert inner.sum() > 500 and len(outer_idx) < n // 2
+    sub = loc.make_subworld(orc, pre, pos6, goal6, outer_idx)
+    full.policy_step(policy, orc.NBR_KNN)
+    sub.policy_step(policy, orc.NBR_KNN)
+    out = {k: getattr(full, k).copy() for k in ('ran', 'nbr_cnt', 'nbr_ids', 'nbr_dsq', 'tag', 'n_suit', 'plane_fail',
+                                                  'lp4_proj', 'action')}
+    full.env_update(fast=True)
+    sub.env_update(fast=True)
+    post = {'status': full.status.copy(), 'pos': full.pos.copy()}
+    tot = loc.compare_inner(out, post, sub, outer_idx, inner, n, policy)
+    print(policy, tot)
+    assert tot['agents'] > 500 and tot['saturated'] > 0
+    for k in loc.EXACT:
+        assert tot.get(k, 0) == 0, (policy, k, tot)
+    assert tot['flips'] == 0
+    # the whole-swarm list invariants the full-size GPU test evaluates on the device
+    import torch
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    n_live = loc.list_invariants(t(out['nbr_cnt']), t(out['nbr_ids']), t(out['nbr_dsq']), t(out['ran'].astype(bool)),
+                                 t(pre['pos']), 10.0, sample_stride=7)
+    assert n_live > 10 * n
