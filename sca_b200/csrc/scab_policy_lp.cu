@@ -243,6 +243,71 @@ __device__ __forceinline__ void orca_plane(const StepArgs &A, int e, const doubl
                  __dadd_rn((double)mv.z, __dmul_rn(0.5, u.z))};
 }
 
+// fp32 pre-filter of the register-only pass.  That pass only needs the SIGN of m = n . (point - v0) per plane (:252),
+// and m = n . (vA - v0) + s / 2 with u = s n.  The sequence below is replayed in NumPy float32 against float64 by
+// tools/lp_prefilter_check.py on random and adversarial configurations: under the guards the largest |m32 - m64| seen is
+// 2.2e-5, so a margin below -LP_F32_EPS (~100x that) is trusted as "satisfied"; a margin above +LP_F32_EPS defers the agent
+// to the list pass (always exact); anything else -- inside the band, an ill-conditioned construction, a NaN -- is
+// re-evaluated with the reference's fp64 expressions.  No FMA contraction here (-fmad=false), IEEE div / sqrt.
+#define LP_F32_EPS 2e-3f
+#define LP_F32_WL_MIN 1e-2f
+#define LP_F32_DIF_MIN 5e-2f
+__device__ __forceinline__ float dot3f(float a0, float a1, float a2, float b0, float b1, float b2) { return (a0 * b0 + a1 * b1) + a2 * b2; }
+
+// 0: certainly satisfied, 1: certainly violated, 2: ask fp64.  (dx, dy, dz) = (float)(vA - v0)
+__device__ __forceinline__ int orca_margin_f32(const StepArgs &A, int e, const double4 &me, const float4 &mv, float dx, float dy, float dz)
+{
+    double4 o;
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (e < A.n) {
+        o = A.s_posr[e];
+        const float4 ov = A.s_vel[e];
+        ox = ov.x; oy = ov.y; oz = ov.z;
+    } else if (e < A.n + A.m) o = A.o_posr[e - A.n];
+    else o = A.o_posr_by_id[e - A.n - A.m];
+    const float px = (float)__dsub_rn(o.x, me.x), py = (float)__dsub_rn(o.y, me.y), pz = (float)__dsub_rn(o.z, me.z);
+    const float vx = mv.x - ox, vy = mv.y - oy, vz = mv.z - oz;
+    const float R = (float)__dadd_rn(__dadd_rn(me.w, 0.05), __dadd_rn(o.w, 0.05));
+    const float distSq = dot3f(px, py, pz, px, py, pz), RSq = R * R;
+    float nx, ny, nz, wl, sc;
+    bool ok;
+    if (distSq > RSq) {
+        const float invT = (float)A.inv_time_horizon;
+        const float wx = vx - invT * px, wy = vy - invT * py, wz = vz - invT * pz;
+        const float wl2 = dot3f(wx, wy, wz, wx, wy, wz), dp = dot3f(wx, wy, wz, px, py, pz);
+        if (dp < 0.f && dp * dp > RSq * wl2) {
+            wl = sqrtf(wl2);
+            nx = wx / wl; ny = wy / wl; nz = wz / wl;
+            sc = R * invT - wl;
+            ok = wl >= LP_F32_WL_MIN;
+        } else {
+            const float difSq = distSq - RSq;
+            const float cx = py * vz - pz * vy, cy = pz * vx - px * vz, cz = px * vy - py * vx;
+            const float crl = sqrtf(dot3f(cx, cy, cz, cx, cy, cz));
+            const float pl = sqrtf(distSq);
+            const float t = (dot3f(px, py, pz, vx, vy, vz) / pl + (crl / sqrtf(difSq)) * (R / pl)) / pl;
+            const float ax = vx - t * px, ay = vy - t * py, az = vz - t * pz;
+            wl = sqrtf(dot3f(ax, ay, az, ax, ay, az));
+            nx = ax / wl; ny = ay / wl; nz = az / wl;
+            sc = R * t - wl;
+            ok = wl >= LP_F32_WL_MIN;
+        }
+    } else {
+        const float invDt = (float)A.inv_time_step;
+        const float wx = vx - invDt * px, wy = vy - invDt * py, wz = vz - invDt * pz;
+        wl = sqrtf(dot3f(wx, wy, wz, wx, wy, wz));
+        nx = wx / wl; ny = wy / wl; nz = wz / wl;
+        sc = R * invDt - wl;
+        ok = wl >= LP_F32_WL_MIN;
+    }
+    // the collision / no-collision switch at |p| = R is a discontinuity of the construction: stay clear of it in every branch
+    ok = ok && fabsf(distSq - RSq) >= LP_F32_DIF_MIN;
+    const float m = dot3f(nx, ny, nz, dx, dy, dz) + 0.5f * sc;
+    if (ok && m < -LP_F32_EPS) return 0;      // a NaN fails both comparisons
+    if (ok && m > LP_F32_EPS) return 1;
+    return 2;
+}
+
 // linearProgram3's starting point (:240-250, dir_opt False): v_pref clamped to the maxSpeed sphere
 __device__ __forceinline__ Vec3 lp3_start(const Vec3 &vel_pref, double maxSpeed)
 {
@@ -259,9 +324,11 @@ __device__ __forceinline__ Vec3 lp3_start(const Vec3 &vel_pref, double maxSpeed)
 //         violated by the running result; until then the result is the starting point.  So each plane is built in
 //         registers and tested against the starting point; if none is violated that IS the answer (planeFail == nc).
 //         The first violation appends the agent to A.slow_list and leaves every output untouched.
+//         Each plane is first judged in fp32 (orca_margin_f32); only the undecided ones are built in fp64.
 // MODE 2: the agents on A.slow_list, planes in shared memory, full LP3 / LP4.
+// MODE 3: MODE 1 without the fp32 pre-filter (SCAB_LP_F64=1, the A/B switch for it).
 template <int MODE>
-__global__ void __launch_bounds__(MODE == 1 ? LP_FAST_THREADS : LP_THREADS, MODE == 1 ? 6 : 1) k_policy_lp(StepArgs A)
+__global__ void __launch_bounds__((MODE & 1) ? LP_FAST_THREADS : LP_THREADS, (MODE & 1) ? 6 : 1) k_policy_lp(StepArgs A)
 {
     extern __shared__ double lp_smem[];
     const int tid = threadIdx.x;
@@ -290,7 +357,7 @@ __global__ void __launch_bounds__(MODE == 1 ? LP_FAST_THREADS : LP_THREADS, MODE
         double v_store[3], v_des[3];
         double target[3];
         // the fast pass may still defer this agent: it only peeks at the waypoint state and commits the pop when it finishes
-        waypoint_target(A.st, id, me.x, me.y, me.z, true, target, MODE != 1);
+        waypoint_target(A.st, id, me.x, me.y, me.z, true, target, !(MODE & 1));
         v_pref_straight(&A.st.goal[3 * id], target, me.x, me.y, me.z, A.st.pref_speed[id], true, v_store, v_des);
         const double nv32 = __dsqrt_rn(sumsq_f32(mv.x, mv.y, mv.z));
         const bool first = py_round5(__dadd_rn(nv32, 1e-5)) <= 1e-5;   // :52 distance(vel, 0) <= 1e-5
@@ -302,10 +369,22 @@ __global__ void __launch_bounds__(MODE == 1 ? LP_FAST_THREADS : LP_THREADS, MODE
         } else {
             const int nc = A.s_nbr_cnt[s];
             const Vec3 vp{v_des[0], v_des[1], v_des[2]};
-            if (MODE == 1) {
+            if (MODE & 1) {
                 res = lp3_start(vp, A.max_speed);
                 bool violated = false;
-                for (int k = 0; k < nc && !violated; k++) {
+                unsigned ask = (MODE == 3) ? ((nc >= 32) ? 0xffffffffu : ((1u << nc) - 1u)) : 0u;   // planes to build in fp64
+                if (MODE == 1) {
+                    const float dx = (float)__dsub_rn((double)mv.x, res.x), dy = (float)__dsub_rn((double)mv.y, res.y),
+                                dz = (float)__dsub_rn((double)mv.z, res.z);
+                    for (int k = 0; k < nc && !violated; k++) {
+                        const int c = orca_margin_f32(A, A.s_nbr[(size_t)s * KNBR + k], me, mv, dx, dy, dz);
+                        violated = c == 1;
+                        if (c == 2) ask |= 1u << k;
+                    }
+                }
+                while (ask && !violated) {
+                    const int k = __ffs(ask) - 1;
+                    ask &= ask - 1u;
                     Vec3 pt, n;
                     orca_plane(A, A.s_nbr[(size_t)s * KNBR + k], me, mv, pt, n);
                     violated = dotv(n, subv(pt, res)) > 0.0;            // :252
@@ -336,7 +415,7 @@ __global__ void __launch_bounds__(MODE == 1 ? LP_FAST_THREADS : LP_THREADS, MODE
             n_planes = nc;
         }
         ran++;
-        if (MODE == 1 && A.st.waypoints != nullptr) waypoint_target(A.st, id, me.x, me.y, me.z, true, target, true);
+        if ((MODE & 1) && A.st.waypoints != nullptr) waypoint_target(A.st, id, me.x, me.y, me.z, true, target, true);
         act = cartesian2spherical(res.x, res.y, res.z, A.st.heading[3 * id], A.st.heading[3 * id + 1], true);
         kinematic_update(A, id, act, me.x, me.y, me.z, &npx, &npy, &npz);
         if (A.s_qcoll[s]) A.st.status[id] = flags | SCAB_ST_COLLISION;   // agent.py:83-85
@@ -359,7 +438,7 @@ __global__ void __launch_bounds__(MODE == 1 ? LP_FAST_THREADS : LP_THREADS, MODE
 cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
 {
     if (A.n <= 0) return cudaSuccess;
-    static int no_fast = -1, sms = 0, per_sm = 0;
+    static int no_fast = -1, sms = 0, per_sm = 0, f64_only = 0;
     const size_t smem = sizeof(Planes);   // 6*16*64*8 = 49152 B
     if (no_fast < 0) {
         cudaError_t e = cudaFuncSetAttribute(k_policy_lp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -371,6 +450,8 @@ cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
         const char *ev = getenv("SCAB_NO_FAST");   // A/B switch: every agent through the shared-memory kernel
+        const char *e64 = getenv("SCAB_LP_F64");   // A/B switch: register-only pass without the fp32 pre-filter
+        f64_only = (e64 && e64[0] == '1') ? 1 : 0;
         no_fast = (ev && ev[0] == '1') ? 1 : 0;
     }
     const int nb = (A.n + LP_THREADS - 1) / LP_THREADS;
@@ -380,7 +461,9 @@ cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
     }
     cudaError_t e = cudaMemsetAsync(A.slow_count, 0, sizeof(int32_t), s);
     if (e != cudaSuccess) return e;
-    k_policy_lp<1><<<(A.n + LP_FAST_THREADS - 1) / LP_FAST_THREADS, LP_FAST_THREADS, 0, s>>>(A);
+    const int nbf = (A.n + LP_FAST_THREADS - 1) / LP_FAST_THREADS;
+    if (f64_only) k_policy_lp<3><<<nbf, LP_FAST_THREADS, 0, s>>>(A);
+    else k_policy_lp<1><<<nbf, LP_FAST_THREADS, 0, s>>>(A);
     // the agents with a violated plane: one resident wave, strided over the list
     const int grid = nb < sms * per_sm ? nb : sms * per_sm;
     k_policy_lp<2><<<grid, LP_THREADS, smem, s>>>(A);
