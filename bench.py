@@ -32,8 +32,8 @@ import numpy as np  # noqa: E402
 DENSITY = 1.0e6 / 560.0 ** 3          # agents per m^3 of BASELINE config 5
 ALGO_BYTES = {'grid': 168, 'neighbors': 116, 'policy': 660, 'status': 144}   # SURVEY.md 8(d), per agent-step
 # kernels launched per step: k_cell_count, k_scan_tile_sums, k_scan_tiles, k_scan_apply, k_reorder, k_neighbors_knn,
-# then k_vpref, k_select_fast, k_select, k_integrate (sampled policies) or k_policy_lp (ORCA LP), then k_status
-KERNELS_PER_STEP = {'orca_lp': 8}
+# then k_vpref, k_select_fast, k_select, k_integrate (sampled policies) or k_policy_lp<1>, k_policy_lp<2> (ORCA LP), then k_status
+KERNELS_PER_STEP = {'orca_lp': 9}
 KERNELS_PER_STEP_SAMPLED = 11
 POLICY_KERNELS = {'orca_lp': 'k_policy_lp'}
 METRIC = 'agent-steps/sec (SCA, 1M UAVs)'      # --policy other than sca: the same workload under that policy (named in config)
