@@ -214,7 +214,7 @@ def run_ours(args):
         traffic = None
         try:
             with open(os.path.join(ROOT, 'profiles', 'dram_traffic.json')) as f:
-                traffic = json.load(f).get(dom)
+                traffic = json.load(f).get(dom if (dom != 'policy' or policy == 'sca') else 'policy_' + policy)   # ncu figures are per kernel
         except Exception:
             pass
         roof = {'bound': 'hbm', 'kernel': {'grid': 'k_cell_count+k_scan_*+k_reorder', 'neighbors': 'k_neighbors_knn',
