@@ -67,12 +67,11 @@ CASES = {
 }
 
 
-def run_case(name):
-    policy, scen, keep, full, max_steps = CASES[name]
-    sc = scen()
+def record(policy, sc, keep, full=False, max_steps=None, radius=0.5):
+    """Run the reference on scenario `sc` = (pos, goal, obstacles[, paths]) and return the fixture dict."""
+    max_steps = max_steps or keep
     pos, goal, obs = sc[:3]
-    rec = rh.Recorder(policy, pos, goal, obs, paths=sc[3] if len(sc) > 3 else None)
-    t0 = time.time()
+    rec = rh.Recorder(policy, pos, goal, obs, radius=radius, paths=sc[3] if len(sc) > 3 else None)
     steps = 0
     done = False
     while steps < max_steps and not done:
@@ -94,6 +93,13 @@ def run_case(name):
     d['rollout_steps'] = np.int32(steps)
     d['rollout_done'] = np.int32(done)
     d['full'] = np.int32(full)
+    return d, steps, done
+
+
+def run_case(name):
+    policy, scen, keep, full, max_steps = CASES[name]
+    t0 = time.time()
+    d, steps, done = record(policy, scen(), keep, full, max_steps)
     out = os.path.join(HERE, name + '.npz')
     np.savez_compressed(out, **d)
     print('%-26s steps=%d done=%d  %.1fs  %.0f kB  tags=%s' % (

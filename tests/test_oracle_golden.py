@@ -8,8 +8,8 @@ import golden_util as gu
 from oracle import oracle as orc
 
 
-def run_fixture(name):
-    g = gu.load(name)
+def run_fixture(name, g=None):
+    g = gu.load(name) if g is None else g
     pol = str(g['policy'])
     T = g['pos'].shape[0]
     w = orc.World(g['pos'][0], g['goal'], heading=g['heading'][0], radius=g['radius'], pref_speed=g['pref_speed'],
