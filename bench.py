@@ -311,6 +311,62 @@ def run_ours(args):
                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'steps': steps_e,
                'ms_per_step': round(dt / steps_e * 1e3, 3), 'copies': 'overlapped with the cell list / status kernels' if overlap else 'serial'}
 
+    elif os.environ.get('SCAB_BENCH_E2E_SHARDED', '1') == '1':
+        # sharded: every rank keeps the authoritative copy of its owned rows [0, own_cap) in pinned host memory; a step
+        # uploads them, replays the sharded step (halo exchange, migration and all) and downloads the rows + the action
+        # matrix.  Rows change owners on the device (migration), so the host copy is whatever came down last -- the
+        # upload restores exactly that.  Max over ranks of the wall time, sums of the agent-steps and of the bytes.
+        import torch.distributed as dist
+        keys_state = ('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')
+        ok, host, host_action, rows, st = 1.0, None, None, 0, None
+        try:
+            rows, st = int(sw.own_cap), sw.stream
+            host = {k: torch.empty((rows,) + tuple(sw.t[k].shape[1:]), dtype=sw.t[k].dtype).pin_memory() for k in keys_state}
+            host_action = torch.empty((rows, 7), dtype=sw.t['action'].dtype).pin_memory()
+            with torch.cuda.stream(st):
+                for k in keys_state:
+                    host[k].copy_(sw.t[k][:rows], non_blocking=True)
+            st.synchronize()
+        except Exception as e:       # never leave a peer alone inside a collective: agree on skipping instead
+            ok = 0.0
+            sys.stderr.write('rank %d: sharded e2e setup failed (%r); e2e omitted\n' % (rank, e))
+        flag = torch.tensor([ok], dtype=torch.float64, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag[0]) > 0:
+            try:
+                h2d = sum(v.numel() * v.element_size() for v in host.values())
+                d2h = h2d + host_action.numel() * host_action.element_size()
+                steps_e = max(3, min(args.steps, 20))
+
+                def one_sharded():
+                    with torch.cuda.stream(st):
+                        for k in keys_state:
+                            sw.t[k][:rows].copy_(host[k], non_blocking=True)
+                    sw.step(policy, capi.NBR_KNN)
+                    with torch.cuda.stream(st):
+                        for k in keys_state:
+                            host[k].copy_(sw.t[k][:rows], non_blocking=True)
+                        host_action.copy_(sw.t['action'][:rows], non_blocking=True)
+                    st.synchronize()          # the caller needs the results on the host before the next step
+                one_sharded()
+                a0 = sw.counters()['n_active_total']
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(steps_e):
+                    one_sharded()
+                barrier()
+                dt = time.perf_counter() - t0
+                tmax = torch.tensor([dt], dtype=torch.float64, device=device)
+                tsum = torch.tensor([float(sw.counters()['n_active_total'] - a0), float(h2d), float(d2h)], dtype=torch.float64, device=device)
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+                e2e = {'value': float(tsum[0]) / float(tmax[0]), 'unit': 'agent-steps/s', 'h2d_bytes_per_step': int(tsum[1]),
+                       'd2h_bytes_per_step': int(tsum[2]), 'steps': steps_e, 'ms_per_step': round(float(tmax[0]) / steps_e * 1e3, 3),
+                       'copies': 'per rank: owned rows up, sharded step, owned rows + actions down'}
+            except Exception as e:       # the same Python error hits every rank at the same point: all of them skip
+                e2e = None
+                sys.stderr.write('rank %d: sharded e2e failed (%r); e2e omitted\n' % (rank, e))
+
     cpu = None
     if world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args.cpu_agents, 1, policy, budget_s=12.0)
