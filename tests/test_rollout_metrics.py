@@ -34,6 +34,24 @@ def test_oracle_rollout_matches_reference(name):
     assert np.allclose(m[1:], g['metrics'][1:], rtol=0, atol=1e-6)
 
 
+def test_oracle_reproduces_the_100_agent_orca_rollout():
+    """BASELINE configs[0]-sized case for ORCA (run_orca.py circle, 100 agents, R = 18): the reference does not finish
+    within 2000 steps (49 agents collide or run out of distance budget) -- the oracle, free-running for the same 2000 steps,
+    ends in the reference's final state bit for bit and reproduces its four rollout metrics."""
+    from oracle import oracle as orc
+    g = gu.load('circle100_orca_lp')
+    w = orc.World(g['pos'][0], g['goal'], heading=g['heading'][0], radius=g['radius'], pref_speed=g['pref_speed'],
+                  obstacles=g['obstacles'], initial_pos=g['initial_pos'], goal_pos=g['goal_pos'])
+    done = False
+    for _ in range(int(g['rollout_steps'])):
+        done = w.step('orca_lp', orc.NBR_REF_COMPAT)
+    assert done == bool(g['rollout_done'])
+    assert np.array_equal(w.status & 15, g['final_status'] & 15) and np.array_equal(w.step_num, g['final_step_num'])
+    assert np.abs(w.pos - g['final_pos']).max() <= 1e-9 and np.abs(w.total_dist - g['final_total_dist']).max() <= 1e-9
+    m = _metrics(w.status, w.total_dist, w.step_num, g['straight_len'], g['desire_steps'], w.n)
+    assert m[0] == g['metrics'][0] == 0.51 and np.allclose(m[1:], g['metrics'][1:], rtol=0, atol=1e-6)
+
+
 DUBINS = ['circle16_sca', 'circle16_rvo3d_dubins', 'takeoff16_sca', 'dense40_sca', 'circle100_sca']
 
 
