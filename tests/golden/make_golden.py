@@ -67,6 +67,15 @@ CASES = {
 }
 
 
+# Reference rollouts run to COMPLETION, of which only the first two steps, the end state and the metrics are kept
+# (rollout_<name>.npz; excluded from the per-step fixture list): SCA with its Dubins tracker on the README scenarios.
+ROLLOUTS = {
+    'circle16_sca': ('sca', lambda: rh.scen_circle(16, 10.0), 3000),          # run_sca.py as shipped (R = 10, N = 16)
+    'takeoff16_sca': ('sca', lambda: rh.scen_takeoff_landing(16), 3000),      # run_sca.py:53-81 + the 8 exp2 obstacles
+    'circle100_sca': ('sca', lambda: rh.scen_circle(100, 18.0), 3000),        # BASELINE configs[0] (README, R = 18, N = 100)
+}
+
+
 def record(policy, sc, keep, full=False, max_steps=None, radius=0.5):
     """Run the reference on scenario `sc` = (pos, goal, obstacles[, paths]) and return the fixture dict."""
     max_steps = max_steps or keep
@@ -107,7 +116,19 @@ def run_case(name):
         np.unique(d['tag']).tolist()), flush=True)
 
 
+def run_rollout(name):
+    policy, scen, max_steps = ROLLOUTS[name]
+    t0 = time.time()
+    d, steps, done = record(policy, scen(), 2, True, max_steps)
+    out = os.path.join(HERE, 'rollout_' + name + '.npz')
+    np.savez_compressed(out, **d)
+    print('rollout_%-18s steps=%d done=%d  %.1fs  metrics=%s' % (name, steps, done, time.time() - t0, d['metrics']), flush=True)
+
+
 if __name__ == '__main__':
     names = sys.argv[1:] or list(CASES)
     for nm in names:
-        run_case(nm)
+        if nm.startswith('rollout_'):
+            run_rollout(nm[len('rollout_'):])
+        else:
+            run_case(nm)

@@ -13,9 +13,10 @@ K = 16
 
 
 def golden_names():
-    # rollout fixtures only (map_*.npz holds the binvox reader's golden vector)
+    # per-step fixtures only (map_*.npz holds the binvox reader's golden vector, rollout_*.npz the end state and metrics
+    # of reference rollouts run to completion -- tests/test_rollout_metrics.py)
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))
-                  if not os.path.basename(p).startswith('map_'))
+                  if not os.path.basename(p).startswith(('map_', 'rollout_')))
 
 
 def load(name):

@@ -76,6 +76,35 @@ def test_oracle_dubins_rollout_matches_reference(name):
     assert m[0] == g['metrics'][0] and np.allclose(m[1:], g['metrics'][1:], rtol=0, atol=1e-6)
 
 
+def _rollout_names():
+    import glob
+    import os
+    return sorted(os.path.basename(p)[len('rollout_'):-4] for p in glob.glob(os.path.join(gu.GOLDEN_DIR, 'rollout_*.npz')))
+
+
+@pytest.mark.parametrize('name', _rollout_names())
+def test_oracle_sca_rollout_to_completion_matches_reference(name):
+    """SCA with its Dubins tracker on the reference's README scenarios, run to COMPLETION by the unmodified reference
+    (tests/golden/make_golden.py rollout_<name>): the oracle, free-running, needs the same number of steps, ends in the
+    same final state bit for bit, and reproduces SuccessRate / ExtraTime / ExtraDistance / AverageSpeed."""
+    from oracle import oracle as orc
+    g = gu.load('rollout_' + name)
+    pol = str(g['policy'])
+    w = orc.World(g['pos'][0], g['goal'], heading=g['heading'][0], radius=g['radius'], pref_speed=g['pref_speed'],
+                  obstacles=g['obstacles'], initial_pos=g['initial_pos'], goal_pos=g['goal_pos'])
+    prov = orc.DubinsProvider(w.n)
+    done, steps = False, 0
+    while not done and steps < 4000:
+        done = w.step_dubins(pol, prov, g['goal_pos'][:, 3:6])
+        steps += 1
+    print(name, steps, int(g['rollout_steps']), np.abs(w.pos - g['final_pos']).max())
+    assert bool(g['rollout_done']) and done and steps == int(g['rollout_steps'])
+    assert np.array_equal(w.status & 15, g['final_status'] & 15) and np.array_equal(w.step_num, g['final_step_num'])
+    assert np.abs(w.pos - g['final_pos']).max() <= 1e-9
+    m = _metrics(w.status, w.total_dist, w.step_num, g['straight_len'], g['desire_steps'], w.n)
+    assert m[0] == g['metrics'][0] and np.allclose(m[1:], g['metrics'][1:], rtol=0, atol=1e-6)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', FULL)
 def test_gpu_rollout_matches_reference(name):
