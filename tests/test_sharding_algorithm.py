@@ -1,5 +1,6 @@
-"""CPU, world_size-2 gloo: the multi-GPU step PROTOCOL of sca_b200/sharding.py run end to end with the oracle as the
-per-rank stepper, against the single-process oracle run of the same swarm.
+"""CPU, world_size-2 and -4 gloo (at 4 ranks the inner slabs exchange on both faces at once): the multi-GPU step
+PROTOCOL of sca_b200/sharding.py run end to end with the oracle as the per-rank stepper, against the single-process
+oracle run of the same swarm.
 
 ShardedSwarm's per-step sequence (`_step_body`) is replayed on the host with the module's own building blocks --
 `SlabPlan` (equal-count slabs, halo width = neighborDist + 2 x drift), `pack_rows` / `unpack_rows` (full state rows),
@@ -126,8 +127,9 @@ def _worker(rank, world, port, q, policy, pos6, goal6, steps, migrate_every, exp
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('policy,steps', [('orca_lp', 26), ('sca', 12)])
-def test_two_slab_protocol_reproduces_the_single_world(policy, steps):
+@pytest.mark.parametrize('policy,steps,world', [('orca_lp', 26, 2), ('sca', 12, 2), ('orca_lp', 26, 4)],
+                         ids=['orca_lp-2', 'sca-2', 'orca_lp-4'])
+def test_slab_protocol_reproduces_the_single_world(policy, steps, world):
     from oracle import oracle as orc
     from sca_b200 import scenarios
     n, migrate_every = 2400, 8
@@ -141,8 +143,8 @@ def test_two_slab_protocol_reproduces_the_single_world(policy, steps):
     assert int(((expect['status'] & 2) != 0).sum()) > 0
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 31500 + (os.getpid() % 2000) + (7 if policy == 'sca' else 0)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, policy, pos6, goal6, steps, migrate_every, expect)) for r in range(2)]
+    port = 31500 + (os.getpid() % 2000) + (7 if policy == 'sca' else 0) + 13 * world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, policy, pos6, goal6, steps, migrate_every, expect)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=600) for _ in procs)
