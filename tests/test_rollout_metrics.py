@@ -126,3 +126,29 @@ def test_gpu_rollout_matches_reference(name):
     assert abs(m['ExtraTime'] - ref[1]) <= 0.05 + 0.01 * abs(ref[1])
     assert abs(m['ExtraDistance'] - ref[2]) <= 0.01 + 0.01 * abs(ref[2])
     assert abs(m['AverageSpeed'] - ref[3]) <= 0.005
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason='added after the round-1 GPU budget was spent: not yet run on hardware '
+                                        '(an XPASS in the log promotes it to a plain test in round 2)')
+@pytest.mark.parametrize('name', _rollout_names())
+def test_gpu_sca_rollout_to_completion_matches_reference(name):
+    """BatchedEnv('sca') with the device-side Dubins tracker, free-running to completion, against the reference rollouts run
+    to the end (rollout_<name>.npz).  Device libm differs from glibc in the last ulp and the rollouts are hundreds of steps
+    of mutually interacting agents, so the bar is the statistics bar of test_gpu_rollout_matches_reference."""
+    from sca_b200 import capi
+    from sca_b200.env import BatchedEnv
+    g = gu.load('rollout_' + name)
+    env = BatchedEnv(str(g['policy']), nbr_mode=capi.NBR_REF_COMPAT)
+    env.set_agents(g['initial_pos'], g['goal_pos'], g['obstacles'], radius=g['radius'], pref_speed=g['pref_speed'])
+    done = False
+    while not done and env.steps < 4000:
+        done = env.step()
+    m = env.metrics()
+    ref = g['metrics']
+    print(name, env.steps, int(g['rollout_steps']), m, ref)
+    assert done
+    assert abs(m['SuccessRate'] - ref[0]) <= 0.02
+    assert abs(m['ExtraTime'] - ref[1]) <= 0.3 + 0.05 * abs(ref[1])
+    assert abs(m['ExtraDistance'] - ref[2]) <= 0.3 + 0.05 * abs(ref[2])
+    assert abs(m['AverageSpeed'] - ref[3]) <= 0.01
