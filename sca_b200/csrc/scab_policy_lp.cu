@@ -435,6 +435,7 @@ __global__ void __launch_bounds__((MODE & 1) ? LP_FAST_THREADS : LP_THREADS, (MO
     }
 }
 
+#ifndef SCAB_HOSTSIM   // tests/hostsim compiles the device code above for the host (one thread at a time); no launcher there
 cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
 {
     if (A.n <= 0) return cudaSuccess;
@@ -469,3 +470,4 @@ cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
     k_policy_lp<2><<<grid, LP_THREADS, smem, s>>>(A);
     return cudaGetLastError();
 }
+#endif
