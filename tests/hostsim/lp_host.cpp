@@ -1,6 +1,7 @@
 // tests/hostsim/lp_host.cpp -- TEST INFRASTRUCTURE: the device code of sca_b200/csrc/scab_policy_lp.cu (ORCA planes, fp32
 // plane pre-filter, linearProgram1-4, action, kinematic update: every __device__ function and the kernel body itself),
 // compiled for the host and run one thread at a time.  tests/test_hostsim_lp.py drives it against the oracle.
+#define HOSTSIM_SINGLE_THREAD 1
 #include "cuda_host_shim.h"
 #define SCAB_HOSTSIM 1
 #include "../../sca_b200/csrc/scab_policy_lp.cu"
