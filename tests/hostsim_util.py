@@ -28,3 +28,23 @@ def activate(monkeypatch):
         orig_init(self, n, device='cpu', debug=debug, params=params, capacity=capacity)
     monkeypatch.setattr(swarm.Swarm, '__init__', init)
     return lib
+
+
+class _NoStream:
+    cuda_stream = 0
+
+    def synchronize(self):
+        pass
+
+    def wait_event(self, *a):
+        pass
+
+
+def activate_streams(monkeypatch):
+    """On top of activate(): CUDA streams / devices as no-ops, for code that manages its own stream (ShardedSwarm)."""
+    import contextlib
+    import torch
+    monkeypatch.setattr(torch.cuda, 'Stream', lambda *a, **k: _NoStream())
+    monkeypatch.setattr(torch.cuda, 'stream', lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a, **k: _NoStream())
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda *a, **k: None)

@@ -2,6 +2,9 @@
 kernels BIT FOR BIT (positions, velocities, headings, flags, counters), including across migrations.
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/sharding_check.py
+
+SHARD_HOSTSIM=1 runs the same check without GPUs: the kernels (halo pack / unpack, migration, the whole step) come from the
+host emulation build (tests/hostsim), the exchanges go over gloo, streams are no-ops and the step is launched eagerly.
 """
 import os
 import sys
@@ -23,10 +26,22 @@ def main():
     faulthandler.dump_traceback_later(int(os.environ.get('SHARD_WATCHDOG', '75')), exit=True)
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     local = int(os.environ.get('LOCAL_RANK', rank))
-    torch.cuda.set_device(local)
-    dev = 'cuda:%d' % local
     import datetime
-    dist.init_process_group('nccl', device_id=torch.device(dev), timeout=datetime.timedelta(seconds=90))
+    hostsim = os.environ.get('SHARD_HOSTSIM', '0') == '1'
+    if hostsim:
+        import pytest
+        sys.path.insert(0, os.path.join(ROOT, 'tests'))
+        import hostsim_util
+        mp = pytest.MonkeyPatch()
+        hostsim_util.activate(mp)
+        hostsim_util.activate_streams(mp)
+        os.environ['SCAB_NO_GRAPH'] = '1'
+        dev = 'cpu'
+        dist.init_process_group('gloo', timeout=datetime.timedelta(seconds=600))
+    else:
+        torch.cuda.set_device(local)
+        dev = 'cuda:%d' % local
+        dist.init_process_group('nccl', device_id=torch.device(dev), timeout=datetime.timedelta(seconds=90))
     n = int(os.environ.get('SHARD_N', '30000'))
     steps = int(os.environ.get('SHARD_STEPS', '40'))
     policy = os.environ.get('SHARD_POLICY', 'sca')
@@ -34,7 +49,7 @@ def main():
     pos, goal, _ = scenarios.uniform_box_numpy(n, density, seed=3)
     L = (n / density) ** (1 / 3)
     lo, hi = np.array([-20.0, -20.0, 0.0]), np.array([L + 20.0, L + 20.0, L + 40.0])
-    sh = ShardedSwarm(pos, goal, rank, world, dev, lo, hi, migrate_every=4)
+    sh = ShardedSwarm(pos, goal, rank, world, dev, lo, hi, migrate_every=4, mig_cap=int(os.environ.get('SHARD_MIG_CAP', '4096')))
     sh.warm_up(policy, capi.NBR_KNN)
     if os.environ.get('SHARD_DEBUG'):
         def _dbg(w):

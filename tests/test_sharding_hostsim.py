@@ -1,0 +1,28 @@
+"""CPU: the REAL multi-GPU path -- sca_b200.sharding.ShardedSwarm with the device-side halo pack / unpack and migration
+kernels of csrc/scab_halo.cu -- on the host emulation build of the kernels (tests/hostsim), one process per "GPU", the
+exchanges over gloo (tests/sharding_check.py with SHARD_HOSTSIM=1).  Same bar as tests/test_sharding_gpu.py holds the
+hardware run to: the sharded run equals the single-device run of the same kernels bit for bit, migrations included.
+(CUDA streams are no-ops and the step is launched eagerly here: the graph capture and NCCL are what only the GPU test sees.)"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('policy,world,n,steps', [('sca', 2, 2400, 10), ('orca_lp', 4, 6000, 10)], ids=['sca-2', 'orca_lp-4'])
+def test_sharded_swarm_on_emulated_devices_reproduces_the_single_device_run(policy, world, n, steps):
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'hostsim'))
+    import build as hostsim_build
+    hostsim_build.build()          # once, before the ranks race for it
+    env = dict(os.environ, SHARD_HOSTSIM='1', SHARD_POLICY=policy, SHARD_N=str(n), SHARD_STEPS=str(steps), SHARD_WATCHDOG='600',
+               OMP_NUM_THREADS='1')
+    port = 29700 + (os.getpid() % 200) + world
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world), '--master-addr',
+                        '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', 'sharding_check.py')],
+                       env=env, capture_output=True, text=True, timeout=900)
+    print(r.stdout[-1500:], r.stderr[-1500:])
+    assert r.returncode == 0
+    assert '-> OK' in r.stdout and 'migration-events 0 ' not in r.stdout
