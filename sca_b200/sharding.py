@@ -387,6 +387,20 @@ class ShardedSwarm:
         with torch.cuda.stream(self.stream):
             return self.sw.h.read_counters(self._stream())
 
+    def global_counters(self):
+        """Whole-swarm counters: one all-reduce (SUM) of the per-rank device counters (the done test)."""
+        c = self.counters()
+        keys = sorted(k for k, v in c.items() if isinstance(v, (int, np.integer)))
+        if self.world == 1:
+            return {k: int(c[k]) for k in keys}
+        t = torch.tensor([int(c[k]) for k in keys], dtype=torch.int64, device=self.sw.device)
+        torch.distributed.all_reduce(t)
+        return {k: int(v) for k, v in zip(keys, t.tolist())}
+
+    def is_done(self):
+        """MACAEnv.is_done (mampenv.py:51-59) over all slabs: every owned agent of every rank has finished."""
+        return self.global_counters()['n_not_done'] == 0
+
     def gather_state(self, keys=('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')):
         """Owned rows keyed by global id (host)."""
         self.stream.synchronize()

@@ -64,6 +64,8 @@ def main():
     gid, st = sh.gather_state()
     moved = len(set(gid.tolist()) - own0)          # agents this rank owns now but did not own at the start
     act = sh.counters()
+    glob = sh.global_counters()                      # one all-reduce: the whole-swarm counters (done test)
+    all_done = sh.is_done()                          # (collective: every rank calls it)
     gathered = [None] * world
     dist.gather_object((gid, st, act, moved), gathered if rank == 0 else None, dst=0)
     ok = True
@@ -89,7 +91,11 @@ def main():
         tot_active = sum(a['n_active_total'] for (_, _, a, _) in gathered)
         ref_active = ref.counters()['n_active_total']
         migrations = sum(mv for (_, _, _, mv) in gathered)
+        refc = ref.counters()
         ok = all(v == 0 for v in bad.values()) and tot_active == ref_active
+        for k in ('n_active_total', 'n_active', 'n_not_done', 'n_collision'):
+            ok = ok and glob[k] == refc[k]
+        ok = ok and all_done == ref.is_done()
         print('sharding_check world=%d n=%d steps=%d policy=%s mismatches=%s agent_steps %d vs %d  migration-events %d  '
               'collisions(ref)=%d  -> %s' % (world, n, steps, policy, bad, tot_active, ref_active, migrations,
                                              int((full['status'] & 2).astype(bool).sum()), 'OK' if ok else 'FAIL'), flush=True)
