@@ -227,6 +227,15 @@ int scab_migrate_pack(scab_handle *h, int64_t own_cap, int axis, double lo_face,
                       int32_t *cnt, void *stream);
 int scab_migrate_unpack(scab_handle *h, const void *in_lo, const void *in_hi, int32_t cap, int use_lo, int use_hi,
                         int32_t *free_list, int32_t *free_count, int32_t *cnt, void *stream);
+/* Per-agent state that lives outside the 128-byte row travels with a migrating agent in one extra row of
+ * scab_migrate_extra_row_doubles(h) doubles, same slot as its state row: the Dubins tracker (the library's tracker state,
+ * scab_state_ptrs.goal_heading; scaPolicy.py:264-338 keeps it on the Agent object) and the waypoint follower
+ * (waypoints, waypoint_left, now_goal; agent.path / policy.now_goal in the reference).  Call order per migration:
+ * scab_migrate_pack, scab_migrate_extra_pack (same cap, the same `cnt`), exchange both buffer pairs ([cap, row] f64,
+ * no header), scab_migrate_unpack, scab_migrate_extra_unpack.  Needs 2 * cap <= capacity. */
+int64_t scab_migrate_extra_row_doubles(scab_handle *h);
+int scab_migrate_extra_pack(scab_handle *h, double *out_lo, double *out_hi, int32_t cap, const int32_t *cnt, void *stream);
+int scab_migrate_extra_unpack(scab_handle *h, const double *in_lo, const double *in_hi, int32_t cap, void *stream);
 /* Blocking: how many agents the last scab_halo_pack selected per face (> cap means the buffers overflowed). */
 int scab_halo_counts(scab_handle *h, int32_t out_host[2], void *stream);
 

@@ -23,8 +23,8 @@ SYMBOLS = ['scab_version', 'scab_default_params', 'scab_set_option', 'scab_set_m
            'scab_bind_state', 'scab_set_obstacles', 'scab_kdtree_build', 'scab_kdtree_get_perm', 'scab_build_grid',
            'scab_neighbors', 'scab_policy_step', 'scab_status_step', 'scab_step', 'scab_read_counters',
            'scab_reset_counters', 'scab_halo_pack', 'scab_halo_unpack', 'scab_halo_pack_pos', 'scab_halo_unpack_pos',
-           'scab_halo_counts', 'scab_migrate_pack', 'scab_migrate_unpack', 'scab_dubins_enable', 'scab_dubins_state_size',
-           'scab_dubins_read']
+           'scab_halo_counts', 'scab_migrate_pack', 'scab_migrate_unpack', 'scab_migrate_extra_row_doubles', 'scab_migrate_extra_pack',
+           'scab_migrate_extra_unpack', 'scab_dubins_enable', 'scab_dubins_state_size', 'scab_dubins_read']
 
 
 class ScabError(RuntimeError):
@@ -106,6 +106,10 @@ def lib():
     L.scab_halo_counts.argtypes = [vp, C.POINTER(i32), vp]
     L.scab_migrate_pack.argtypes = [vp, i64, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), i32, i32, vp, vp, i32, vp, vp, vp, vp]
     L.scab_migrate_unpack.argtypes = [vp, vp, vp, i32, C.c_int, C.c_int, vp, vp, vp, vp]
+    L.scab_migrate_extra_row_doubles.restype = i64
+    L.scab_migrate_extra_row_doubles.argtypes = [vp]
+    L.scab_migrate_extra_pack.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.scab_migrate_extra_unpack.argtypes = [vp, vp, vp, i32, vp]
     _lib = L
     return L
 
@@ -232,6 +236,15 @@ class Handle:
 
     def migrate_unpack(self, in_lo, in_hi, cap, use_lo, use_hi, free_list, free_count, cnt, stream=0):
         self._ck(self._L.scab_migrate_unpack(self._h, in_lo, in_hi, int(cap), int(use_lo), int(use_hi), free_list, free_count, cnt, stream))
+
+    def migrate_extra_row_doubles(self):
+        return int(self._L.scab_migrate_extra_row_doubles(self._h))
+
+    def migrate_extra_pack(self, out_lo, out_hi, cap, cnt, stream=0):
+        self._ck(self._L.scab_migrate_extra_pack(self._h, out_lo, out_hi, int(cap), cnt, stream))
+
+    def migrate_extra_unpack(self, in_lo, in_hi, cap, stream=0):
+        self._ck(self._L.scab_migrate_extra_unpack(self._h, in_lo, in_hi, int(cap), stream))
 
     def halo_counts(self, stream=0):
         out = (C.c_int32 * 2)()

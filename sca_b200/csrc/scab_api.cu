@@ -39,6 +39,9 @@ struct scab_handle {
     bool kd_valid = false;
     // halo bookkeeping (which owned rows were packed for each face, and how many)
     int32_t *d_sent_lo = nullptr, *d_sent_hi = nullptr, *d_halo_cnt = nullptr;
+    // migration bookkeeping: rows vacated by the last scab_migrate_pack / rows given to the arrivals of the last unpack
+    int32_t *d_mig_sent_row = nullptr, *d_mig_recv_row = nullptr;
+    int32_t mig_cap = 0;
     // Dubins v_pref provider (allocated by the first scab_dubins_enable)
     void *d_dub_states = nullptr;
     double *d_dub_d0 = nullptr;
@@ -177,7 +180,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
                  o_cid = carve(cap * 4), o_cloc = carve(cap * 4), o_nbr = carve(cap * 4 * KNBR),
                  o_ncnt = carve(cap * 4), o_qc = carve(cap * 4), o_kdp = carve(cap * 4),
                  o_slo = carve(cap * 4), o_shi = carve(cap * 4), o_hcnt = carve(64),
-                 o_slow = carve(cap * 4), o_slowc = carve(64),
+                 o_slow = carve(cap * 4), o_slowc = carve(64), o_srow = carve(cap * 4), o_rrow = carve(cap * 4),
                  o_kdn = carve((2 * cap) * sizeof(KdNodeDev));
     e = cudaMalloc(&h->d_block, off);
     if (e != cudaSuccess) { delete h; return SCAB_ERR_NOMEM; }
@@ -189,6 +192,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     A.s_nbr = (int32_t *)(b + o_nbr); A.s_nbr_cnt = (int32_t *)(b + o_ncnt); A.s_qcoll = (int32_t *)(b + o_qc);
     h->d_kd_agent_perm = (int32_t *)(b + o_kdp); h->d_kd_agent = (KdNodeDev *)(b + o_kdn);
     A.slow_list = (int32_t *)(b + o_slow); A.slow_count = (int32_t *)(b + o_slowc);
+    h->d_mig_sent_row = (int32_t *)(b + o_srow); h->d_mig_recv_row = (int32_t *)(b + o_rrow);
     h->d_sent_lo = (int32_t *)(b + o_slo); h->d_sent_hi = (int32_t *)(b + o_shi); h->d_halo_cnt = (int32_t *)(b + o_hcnt);
     A.kd_agent = h->d_kd_agent; A.kd_agent_perm = h->d_kd_agent_perm;
     // candidate tables
@@ -537,8 +541,10 @@ extern "C" int scab_migrate_pack(scab_handle *h, int64_t own_cap, int axis, doub
     if (own_cap < 0 || own_cap > h->A.n || axis < 0 || axis > 2 || cap <= 0 || !park_geom || nx <= 0 || ny <= 0 || !out_lo || !out_hi ||
         !free_list || !free_count || !cnt)
         return fail(h, SCAB_ERR_INVALID, "scab_migrate_pack: bad argument");
+    // the vacated rows are remembered (when the scratch holds 2 * cap of them) for scab_migrate_extra_pack
+    h->mig_cap = (2 * (int64_t)cap <= h->capacity) ? cap : 0;
     CK(launch_migrate_pack(h->A, (int)own_cap, axis, lo_face, hi_face, park_geom, nx, ny, out_lo, out_hi, cap, free_list, free_count, cnt,
-                           (cudaStream_t)stream));
+                           h->mig_cap ? h->d_mig_sent_row : nullptr, (cudaStream_t)stream));
     return SCAB_OK;
 }
 
@@ -548,6 +554,33 @@ extern "C" int scab_migrate_unpack(scab_handle *h, const void *in_lo, const void
     int rc = check_ready(h, "scab_migrate_unpack");
     if (rc) return rc;
     if (cap <= 0 || !in_lo || !in_hi || !free_list || !free_count || !cnt) return fail(h, SCAB_ERR_INVALID, "scab_migrate_unpack: bad argument");
-    CK(launch_migrate_unpack(h->A, in_lo, in_hi, cap, use_lo, use_hi, free_list, free_count, cnt, (cudaStream_t)stream));
+    CK(launch_migrate_unpack(h->A, in_lo, in_hi, cap, use_lo, use_hi, free_list, free_count, cnt,
+                             (2 * (int64_t)cap <= h->capacity) ? h->d_mig_recv_row : nullptr, (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int64_t scab_migrate_extra_row_doubles(scab_handle *h)
+{
+    if (!h) return SCAB_ERR_INVALID;
+    return (int64_t)migrate_extra_row_doubles(h->A);
+}
+
+extern "C" int scab_migrate_extra_pack(scab_handle *h, double *out_lo, double *out_hi, int32_t cap, const int32_t *cnt, void *stream)
+{
+    int rc = check_ready(h, "scab_migrate_extra_pack");
+    if (rc) return rc;
+    if (cap <= 0 || !out_lo || !out_hi || !cnt || 2 * (int64_t)cap > h->capacity || h->mig_cap != cap)
+        return fail(h, SCAB_ERR_INVALID, "scab_migrate_extra_pack: call scab_migrate_pack with the same cap first (2 * cap <= capacity)");
+    CK(launch_migrate_extra_pack(h->A, h->d_mig_sent_row, cnt, cap, out_lo, out_hi, (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int scab_migrate_extra_unpack(scab_handle *h, const double *in_lo, const double *in_hi, int32_t cap, void *stream)
+{
+    int rc = check_ready(h, "scab_migrate_extra_unpack");
+    if (rc) return rc;
+    if (cap <= 0 || !in_lo || !in_hi || 2 * (int64_t)cap > h->capacity)
+        return fail(h, SCAB_ERR_INVALID, "scab_migrate_extra_unpack: bad argument");
+    CK(launch_migrate_extra_unpack(h->A, h->d_mig_recv_row, cap, in_lo, in_hi, (cudaStream_t)stream));
     return SCAB_OK;
 }

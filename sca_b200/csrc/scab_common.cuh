@@ -256,6 +256,12 @@ cudaError_t launch_halo_pack_pos(const StepArgs &A, const int32_t *sent_lo, cons
                                  double *out_lo, double *out_hi, const double park[3], cudaStream_t s);
 cudaError_t launch_halo_unpack_pos(const StepArgs &A, const double *p, int count, int row0, cudaStream_t s);
 cudaError_t launch_migrate_pack(const StepArgs &A, int own_cap, int axis, double lo_face, double hi_face, const double geom[4], int nx, int ny,
-                                void *out_lo, void *out_hi, int cap, int32_t *free_list, int32_t *free_count, int32_t *cnt, cudaStream_t s);
+                                void *out_lo, void *out_hi, int cap, int32_t *free_list, int32_t *free_count, int32_t *cnt, int32_t *sent_row,
+                                cudaStream_t s);
 cudaError_t launch_migrate_unpack(const StepArgs &A, const void *in_lo, const void *in_hi, int cap, int use_lo, int use_hi,
-                                  int32_t *free_list, int32_t *free_count, int32_t *cnt, cudaStream_t s);
+                                  int32_t *free_list, int32_t *free_count, int32_t *cnt, int32_t *recv_row, cudaStream_t s);
+int migrate_extra_row_doubles(const StepArgs &A);
+cudaError_t launch_migrate_extra_pack(const StepArgs &A, const int32_t *sent_row, const int32_t *cnt, int cap, double *out_lo, double *out_hi,
+                                      cudaStream_t s);
+cudaError_t launch_migrate_extra_unpack(const StepArgs &A, const int32_t *recv_row, int cap, const double *in_lo, const double *in_hi,
+                                        cudaStream_t s);

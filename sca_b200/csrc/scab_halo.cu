@@ -158,7 +158,7 @@ __device__ __forceinline__ void park_row(const StepArgs &A, int i, const ParkGeo
 
 __global__ void __launch_bounds__(256) k_migrate_pack(StepArgs A, int own_cap, int axis, double lo_face, double hi_face, ParkGeom P,
                                                       MigRow *out_lo, MigRow *out_hi, int cap, int32_t *free_list, int32_t *free_count,
-                                                      int32_t *cnt)
+                                                      int32_t *cnt, int32_t *sent_row)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= own_cap) return;
@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(256) k_migrate_pack(StepArgs A, int own_cap, i
     r.max_run_dist = A.st.max_run_dist[i];
     r.status = st; r.step_num = A.st.step_num[i]; r.gid = A.st.gid ? A.st.gid[i] : i;
     (side ? out_hi : out_lo)[1 + slot] = r;
+    if (sent_row) sent_row[side * cap + slot] = i;          // for k_migrate_extra_pack
     park_row(A, i, P);
     free_list[atomicAdd(free_count, 1)] = i;
 }
@@ -188,10 +189,11 @@ __global__ void k_migrate_header(MigRow *out_lo, MigRow *out_hi, int cap, const 
 }
 
 __global__ void __launch_bounds__(256) k_migrate_unpack(StepArgs A, const MigRow *in_lo, const MigRow *in_hi, int cap, int use_lo, int use_hi,
-                                                        int32_t *free_list, int32_t *free_count, int32_t *cnt)
+                                                        int32_t *free_list, int32_t *free_count, int32_t *cnt, int32_t *recv_row)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= 2 * cap) return;
+    if (recv_row) recv_row[k] = -1;                          // row given to arrival k (for k_migrate_extra_unpack); -1: none
     const int side = k / cap, slot = k - side * cap;
     if (side == 0 ? !use_lo : !use_hi) return;
     const MigRow *in = side ? in_hi : in_lo;
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(256) k_migrate_unpack(StepArgs A, const MigRow
     const int fi = atomicSub(free_count, 1) - 1;
     if (fi < 0) { atomicAdd(free_count, 1); atomicAdd(&cnt[3], 1); return; }   // no free row: counted as lost (never expected)
     const int i = free_list[fi];
+    if (recv_row) recv_row[k] = i;
     const MigRow r = in[1 + slot];
     for (int d = 0; d < 3; d++) {
         A.st.pos[3 * i + d] = r.pos[d]; A.st.heading[3 * i + d] = r.heading[d]; ((double *)A.st.goal)[3 * i + d] = r.goal[d];
@@ -212,23 +215,103 @@ __global__ void __launch_bounds__(256) k_migrate_unpack(StepArgs A, const MigRow
 }
 
 cudaError_t launch_migrate_pack(const StepArgs &A, int own_cap, int axis, double lo_face, double hi_face, const double geom[4], int nx, int ny,
-                                void *out_lo, void *out_hi, int cap, int32_t *free_list, int32_t *free_count, int32_t *cnt, cudaStream_t s)
+                                void *out_lo, void *out_hi, int cap, int32_t *free_list, int32_t *free_count, int32_t *cnt, int32_t *sent_row,
+                                cudaStream_t s)
 {
     cudaError_t e = cudaMemsetAsync(cnt, 0, 2 * sizeof(int32_t), s);    // cnt[2], cnt[3] (overflow / lost) accumulate
     if (e != cudaSuccess) return e;
     ParkGeom P{geom[0], geom[1], geom[2], geom[3], nx, ny};
     if (own_cap > 0)
         k_migrate_pack<<<(own_cap + 255) / 256, 256, 0, s>>>(A, own_cap, axis, lo_face, hi_face, P, (MigRow *)out_lo, (MigRow *)out_hi, cap,
-                                                            free_list, free_count, cnt);
+                                                            free_list, free_count, cnt, sent_row);
     k_migrate_header<<<1, 32, 0, s>>>((MigRow *)out_lo, (MigRow *)out_hi, cap, cnt);
     return cudaGetLastError();
 }
 
 cudaError_t launch_migrate_unpack(const StepArgs &A, const void *in_lo, const void *in_hi, int cap, int use_lo, int use_hi,
-                                  int32_t *free_list, int32_t *free_count, int32_t *cnt, cudaStream_t s)
+                                  int32_t *free_list, int32_t *free_count, int32_t *cnt, int32_t *recv_row, cudaStream_t s)
 {
     if (cap > 0)
         k_migrate_unpack<<<(2 * cap + 255) / 256, 256, 0, s>>>(A, (const MigRow *)in_lo, (const MigRow *)in_hi, cap, use_lo, use_hi, free_list,
-                                                              free_count, cnt);
+                                                              free_count, cnt, recv_row);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ per-agent state outside the 128-byte row
+// The Dubins tracker (library-owned DubState + this step's nearest-neighbour key, the caller's goal_heading)
+// and the waypoint follower (agent.path, its length, policy.now_goal) are row-indexed too, so they travel with
+// a migrating agent: one extra row of `row_doubles` doubles per migrated agent, same slot as its MigRow.
+//   [0, dub)  DubState   [dub] dub_d0   [+1..+3] goal_heading   [+4..+6] now_goal   [+7] waypoint_left   [+8 ...) waypoints
+__global__ void __launch_bounds__(128) k_migrate_extra_pack(StepArgs A, const int32_t *sent_row, const int32_t *cnt, int cap, double *out_lo,
+                                                            double *out_hi, int row_doubles, int dub_doubles)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * cap) return;
+    const int side = k / cap, slot = k - side * cap;
+    if (slot >= min(cnt[side], cap)) return;
+    const int i = sent_row[k];
+    double *o = (side ? out_hi : out_lo) + (size_t)slot * row_doubles;
+    int w = 0;
+    if (A.dub_states) {
+        const double *src = (const double *)((const char *)A.dub_states + (size_t)i * dub_doubles * sizeof(double));
+        for (int q = 0; q < dub_doubles; q++) o[q] = src[q];
+    } else for (int q = 0; q < dub_doubles; q++) o[q] = 0.0;
+    w = dub_doubles;
+    o[w++] = A.dub_d0 ? A.dub_d0[i] : 0.0;
+    for (int d = 0; d < 3; d++) o[w++] = A.st.goal_heading ? A.st.goal_heading[3 * i + d] : 0.0;
+    for (int d = 0; d < 3; d++) o[w++] = A.st.now_goal ? A.st.now_goal[3 * i + d] : 0.0;
+    o[w++] = A.st.waypoint_left ? (double)A.st.waypoint_left[i] : 0.0;
+    if (A.st.waypoints) {
+        const int nq = 3 * (int)A.st.waypoint_stride;
+        const double *src = A.st.waypoints + (size_t)i * nq;
+        for (int q = 0; q < nq; q++) o[w + q] = src[q];
+    }
+}
+
+__global__ void __launch_bounds__(128) k_migrate_extra_unpack(StepArgs A, const int32_t *recv_row, int cap, const double *in_lo,
+                                                              const double *in_hi, int row_doubles, int dub_doubles)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * cap) return;
+    const int i = recv_row[k];
+    if (i < 0) return;
+    const int side = k / cap, slot = k - side * cap;
+    const double *o = (side ? in_hi : in_lo) + (size_t)slot * row_doubles;
+    int w = dub_doubles;
+    if (A.dub_states) {
+        double *dst = (double *)((char *)A.dub_states + (size_t)i * dub_doubles * sizeof(double));
+        for (int q = 0; q < dub_doubles; q++) dst[q] = o[q];
+    }
+    if (A.dub_d0) A.dub_d0[i] = o[w];
+    w++;
+    for (int d = 0; d < 3; d++, w++) if (A.st.goal_heading) ((double *)A.st.goal_heading)[3 * i + d] = o[w];
+    for (int d = 0; d < 3; d++, w++) if (A.st.now_goal) A.st.now_goal[3 * i + d] = o[w];
+    if (A.st.waypoint_left) A.st.waypoint_left[i] = (int32_t)o[w];
+    w++;
+    if (A.st.waypoints) {
+        const int nq = 3 * (int)A.st.waypoint_stride;
+        double *dst = (double *)A.st.waypoints + (size_t)i * nq;
+        for (int q = 0; q < nq; q++) dst[q] = o[w + q];
+    }
+}
+
+int migrate_extra_row_doubles(const StepArgs &A)
+{
+    return (int)(scab_dubins_state_bytes() / sizeof(double)) + 8 + (A.st.waypoints ? 3 * (int)A.st.waypoint_stride : 0);
+}
+
+cudaError_t launch_migrate_extra_pack(const StepArgs &A, const int32_t *sent_row, const int32_t *cnt, int cap, double *out_lo, double *out_hi,
+                                      cudaStream_t s)
+{
+    const int dub = (int)(scab_dubins_state_bytes() / sizeof(double));
+    if (cap > 0) k_migrate_extra_pack<<<(2 * cap + 127) / 128, 128, 0, s>>>(A, sent_row, cnt, cap, out_lo, out_hi, migrate_extra_row_doubles(A), dub);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_migrate_extra_unpack(const StepArgs &A, const int32_t *recv_row, int cap, const double *in_lo, const double *in_hi,
+                                        cudaStream_t s)
+{
+    const int dub = (int)(scab_dubins_state_bytes() / sizeof(double));
+    if (cap > 0) k_migrate_extra_unpack<<<(2 * cap + 127) / 128, 128, 0, s>>>(A, recv_row, cap, in_lo, in_hi, migrate_extra_row_doubles(A), dub);
     return cudaGetLastError();
 }

@@ -137,6 +137,7 @@ class ShardedSwarm:
         from .scenarios import spatial_order
         mine = mine[spatial_order(pos6[mine, :3])]     # rows laid out cell by cell: coalesced gathers / scatters
         self.n_own = len(mine)
+        self._mine = mine
         # halo capacity per face: agents within `width` of a face, with head room
         # (the SAME value on every rank: the face buffers are exchanged as fixed-size messages)
         if halo_cap is None:
@@ -190,6 +191,7 @@ class ShardedSwarm:
         self.free_list[:nfree] = torch.arange(self.own_cap - 1, self.n_own - 1, -1, **i4)
         self.free_count = torch.tensor([nfree], **i4)
         self.mig_cnt = torch.zeros(4, **i4)
+        self._extra = None       # per-agent state outside the migration row (Dubins tracker / waypoints): see _enable_extra
         self.steps = 0
         self._fill_parked()
         self._park_rows(self.n_own, self.n_rows)
@@ -270,9 +272,16 @@ class ShardedSwarm:
         sw.h.migrate_pack(self.own_cap, self.plan.axis, lo_face, hi_face, (lo[0], lo[1], cell, self.park[2]), int(dim[0]), int(dim[1]),
                           self.msend_lo.data_ptr(), self.msend_hi.data_ptr(), self.mig_cap, self.free_list.data_ptr(),
                           self.free_count.data_ptr(), self.mig_cnt.data_ptr(), s)
+        x = self._extra
+        if x is not None:        # the Dubins tracker / waypoint state of the same agents, same slots
+            sw.h.migrate_extra_pack(x['send_lo'].data_ptr(), x['send_hi'].data_ptr(), self.mig_cap, self.mig_cnt.data_ptr(), s)
         exchange_with_neighbours(self.msend_lo, self.msend_hi, self.mrecv_lo, self.mrecv_hi, self.rank, self.world)
+        if x is not None:
+            exchange_with_neighbours(x['send_lo'], x['send_hi'], x['recv_lo'], x['recv_hi'], self.rank, self.world)
         sw.h.migrate_unpack(self.mrecv_lo.data_ptr(), self.mrecv_hi.data_ptr(), self.mig_cap, self.rank > 0, self.rank < self.world - 1,
                             self.free_list.data_ptr(), self.free_count.data_ptr(), self.mig_cnt.data_ptr(), s)
+        if x is not None:
+            sw.h.migrate_extra_unpack(x['recv_lo'].data_ptr(), x['recv_hi'].data_ptr(), self.mig_cap, s)
 
     def _step_body(self, pol, nbr_mode, with_migration=False):
         """One step: static shapes, static pointers -> capturable in a CUDA graph (two variants)."""
@@ -364,6 +373,50 @@ class ShardedSwarm:
             t = sw.t
             self._fill_parked()
             self.stream.synchronize()
+
+    # ------------------------------------------------------------------ state outside the 128-byte migration row
+    def _enable_extra(self):
+        """(Re)size the extra migration buffers: one row of scab_migrate_extra_row_doubles per migrated agent and face."""
+        if self.world == 1:
+            return
+        if 2 * self.mig_cap > self.n_rows:
+            raise capi.ScabError('sharded Dubins / waypoint state needs 2 * mig_cap <= rows per rank (%d > %d)' % (2 * self.mig_cap, self.n_rows))
+        row = self.sw.h.migrate_extra_row_doubles()
+        mk = lambda: torch.zeros((self.mig_cap, row), dtype=torch.float64, device=self.sw.device)
+        self._graphs.clear()            # captured steps do not know about the extra exchange
+        self._extra = {'send_lo': mk(), 'send_hi': mk(), 'recv_lo': mk(), 'recv_hi': mk(), 'row': row}
+
+    def enable_dubins(self, goal_heading, policy='sca'):
+        """SCA / RVO3D+Dubins on several GPUs: V_des from the device-side Dubins tracker (Swarm.enable_dubins); the tracker
+        state of an agent migrates with it.  `goal_heading` [n_global, 3] = goal_pos[3:6].  Call before the first step
+        (row r still holds the agent it was given at construction).  Collective-free."""
+        assert self.steps == 0, 'enable_dubins must be called before the first step'
+        gh = np.zeros((self.n_rows, 3))
+        gh[:len(self._mine)] = np.asarray(goal_heading, 'float64')[self._mine]
+        self.sw.enable_dubins(gh)
+        self.warm_up(policy)                     # load the tracker's kernels before any NCCL traffic ...
+        with torch.cuda.stream(self.stream):
+            self.sw.h.dubins_enable(True, self._stream())      # ... and start from fresh trackers again
+        self.stream.synchronize()
+        self._enable_extra()
+        return self
+
+    def set_waypoints(self, waypoints, counts=None):
+        """agent.path per GLOBAL agent ([n_global, P, 3], counts [n_global]); the lists and policy.now_goal migrate with
+        their agent.  Call before the first step."""
+        assert self.steps == 0, 'set_waypoints must be called before the first step'
+        wp = np.asarray(waypoints, 'float64')
+        cnt = np.full(len(wp), wp.shape[1], np.int32) if counts is None else np.asarray(counts, np.int32)
+        loc = np.zeros((self.n_rows,) + wp.shape[1:])
+        loc[:len(self._mine)] = wp[self._mine]
+        lc = np.zeros(self.n_rows, np.int32)
+        lc[:len(self._mine)] = cnt[self._mine]
+        n_live = self.sw.n
+        self.sw.n = self.n_rows                   # Swarm.set_waypoints sizes its tensors from capacity and copies n rows
+        self.sw.set_waypoints(loc, lc)
+        self.sw._bind(self.n_rows)
+        self._enable_extra()
+        return self
 
     # ------------------------------------------------------------------ diagnostics
     def check_overflow(self):

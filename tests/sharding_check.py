@@ -51,6 +51,25 @@ def main():
     lo, hi = np.array([-20.0, -20.0, 0.0]), np.array([L + 20.0, L + 20.0, L + 40.0])
     sh = ShardedSwarm(pos, goal, rank, world, dev, lo, hi, migrate_every=4, mig_cap=int(os.environ.get('SHARD_MIG_CAP', '4096')))
     sh.warm_up(policy, capi.NBR_KNN)
+    # optional per-agent state that lives outside the migration row and must travel with its agent
+    use_dubins = os.environ.get('SHARD_DUBINS', '0') == '1'        # device-side Dubins tracker (policy sca / rvo3d_dubins)
+    use_wp = os.environ.get('SHARD_WAYPOINTS', '0') == '1'         # two-waypoint dog-leg per agent (rvo3d / srvo3d / orca)
+    wp = wp_cnt = None
+    if use_wp:
+        rng = np.random.default_rng(5)
+        s0, g0 = pos[:, :3], goal[:, :3]
+        d0 = (g0 - s0) / np.linalg.norm(g0 - s0, axis=1, keepdims=True)
+        # list order = the reference's: pop() takes the LAST entry first -> [far, middle, near]; the near one (0.8 m ahead) is
+        # reached and popped within the run, after which the middle one is the target (left = 1, now_goal = middle) for the
+        # rest of it -- the state an agent must bring along when it changes slabs (an empty path means "fly to the goal")
+        wp = np.stack([s0 + 0.8 * (g0 - s0) + rng.normal(0, 1.0, (n, 3)), s0 + 0.5 * (g0 - s0) + rng.normal(0, 1.0, (n, 3)),
+                       s0 + 0.8 * d0 + rng.normal(0, 0.05, (n, 3))], 1)
+        wp_cnt = (3 - (np.arange(n) % 2)).astype(np.int32)
+        sh.set_waypoints(wp, wp_cnt)
+    if use_dubins:
+        sh.enable_dubins(goal[:, 3:6], policy)
+    if os.environ.get('SHARD_NO_EXTRA', '0') == '1':               # negative control: the extra rows stay behind
+        sh._extra = None
     if os.environ.get('SHARD_DEBUG'):
         def _dbg(w):
             sh.stream.synchronize()
@@ -61,7 +80,8 @@ def main():
     for _ in range(steps):
         sh.step(policy, capi.NBR_KNN)
     sh.check_overflow()
-    gid, st = sh.gather_state()
+    keys = ('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num') + (('waypoint_left', 'now_goal') if use_wp else ())
+    gid, st = sh.gather_state(keys)
     moved = len(set(gid.tolist()) - own0)          # agents this rank owns now but did not own at the start
     act = sh.counters()
     glob = sh.global_counters()                      # one all-reduce: the whole-swarm counters (done test)
@@ -73,10 +93,14 @@ def main():
         ref = Swarm(n, device=dev)
         ref.set_state(pos[:, :3], goal[:, :3], heading=pos[:, 3:6], initial_pos=pos, goal_pos=goal)
         ref.fit_grid(lo, hi)
+        if use_wp:
+            ref.set_waypoints(wp, wp_cnt)
+        if use_dubins:
+            ref.enable_dubins(goal[:, 3:6])
         for _ in range(steps):
             ref.step(policy, capi.NBR_KNN)
         torch.cuda.synchronize()
-        full = {k: ref.t[k][:n].cpu().numpy() for k in ('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')}
+        full = {k: ref.t[k][:n].cpu().numpy() for k in keys}
         seen = np.zeros(n, bool)
         bad = {}
         for (g, s, a, mv) in gathered:
@@ -86,6 +110,8 @@ def main():
                 a_, b_ = s[k], full[k][g]
                 if k == 'status':
                     a_, b_ = a_ & 15, b_ & 15
+                if k == 'now_goal':
+                    a_, b_ = np.nan_to_num(a_, nan=-1e9), np.nan_to_num(b_, nan=-1e9)
                 bad[k] = bad.get(k, 0) + int((a_ != b_).reshape(len(g), -1).any(1).sum())
         assert seen.all(), 'agents lost: %d' % int((~seen).sum())
         tot_active = sum(a['n_active_total'] for (_, _, a, _) in gathered)
@@ -96,6 +122,14 @@ def main():
         for k in ('n_active_total', 'n_active', 'n_not_done', 'n_collision'):
             ok = ok and glob[k] == refc[k]
         ok = ok and all_done == ref.is_done()
+        if use_wp:
+            popped = int((ref.t['waypoint_left'][:n].cpu().numpy() < wp_cnt).sum())
+            ok = ok and popped > 0
+            print('waypoints popped by %d agents' % popped)
+        if use_dubins:
+            replans = int(ref.dubins_states()['replans'].sum())
+            ok = ok and replans >= n
+            print('dubins plans made: %d' % replans)
         print('sharding_check world=%d n=%d steps=%d policy=%s mismatches=%s agent_steps %d vs %d  migration-events %d  '
               'collisions(ref)=%d  -> %s' % (world, n, steps, policy, bad, tot_active, ref_active, migrations,
                                              int((full['status'] & 2).astype(bool).sum()), 'OK' if ok else 'FAIL'), flush=True)

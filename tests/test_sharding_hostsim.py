@@ -12,13 +12,19 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize('policy,world,n,steps', [('sca', 2, 2400, 10), ('orca_lp', 4, 6000, 10)], ids=['sca-2', 'orca_lp-4'])
-def test_sharded_swarm_on_emulated_devices_reproduces_the_single_device_run(policy, world, n, steps):
+@pytest.mark.parametrize('policy,world,n,steps,extra', [('sca', 2, 2400, 10, {}), ('orca_lp', 4, 6000, 10, {}),
+                                                        ('rvo3d', 2, 2000, 12, {'SHARD_WAYPOINTS': '1'}),
+                                                        ('sca', 2, 1500, 12, {'SHARD_DUBINS': '1'})],
+                         ids=['sca-2', 'orca_lp-4', 'rvo3d-waypoints-2', 'sca-dubins-2'])
+def test_sharded_swarm_on_emulated_devices_reproduces_the_single_device_run(policy, world, n, steps, extra):
+    """`extra`: per-agent state that lives outside the 128-byte migration row -- the waypoint follower (agent.path,
+    policy.now_goal) and the device-side Dubins tracker -- must travel with an agent that changes slabs
+    (scab_migrate_extra_pack / _unpack); without it these two cases mismatch on ~30 agents (SHARD_NO_EXTRA=1)."""
     sys.path.insert(0, os.path.join(ROOT, 'tests', 'hostsim'))
     import build as hostsim_build
     hostsim_build.build()          # once, before the ranks race for it
     env = dict(os.environ, SHARD_HOSTSIM='1', SHARD_POLICY=policy, SHARD_N=str(n), SHARD_STEPS=str(steps), SHARD_WATCHDOG='600',
-               OMP_NUM_THREADS='1')
+               OMP_NUM_THREADS='1', **extra)
     port = 29700 + (os.getpid() % 200) + world
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world), '--master-addr',
                         '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', 'sharding_check.py')],
