@@ -39,7 +39,7 @@ def test_bench_two_devices_on_the_emulator():
     env = dict(os.environ, OMP_NUM_THREADS='1')
     port = 29750 + (os.getpid() % 200)
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
-                        '--master-port', str(port), RUNNER, '--gpus', '2', '--agents', '3000', '--steps', '3', '--warmup', '3'],
+                        '--master-port', str(port), RUNNER, '--gpus', '2', '--agents', '2000', '--steps', '3', '--warmup', '3'],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     d = _line(r.stdout)

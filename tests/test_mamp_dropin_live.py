@@ -115,8 +115,8 @@ def _nbr_ids(agents):
 
 
 # (policy, shim class, agents, box half-width, obstacles, steps, with waypoints)
-CASES = [('srvo3d', 'GPUSRVO3DPolicy', 14, 4.0, 2, 40, False),
-         ('rvo3d', 'GPURVO3DPolicy', 12, 4.0, 0, 40, True),
+CASES = [('srvo3d', 'GPUSRVO3DPolicy', 14, 4.0, 2, 24, False),
+         ('rvo3d', 'GPURVO3DPolicy', 12, 4.0, 0, 30, True),
          ('orca_lp', 'GPUORCA3DPolicyOfficial', 20, 3.0, 3, 40, False),
          ('orca_sampled', 'GPUORCA3DPolicy', 12, 4.0, 2, 30, True),
          ('sca', 'GPUSCAPolicy', 10, 5.0, 2, 30, False),

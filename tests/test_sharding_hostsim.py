@@ -12,9 +12,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize('policy,world,n,steps,extra', [('sca', 2, 2400, 10, {}), ('orca_lp', 4, 6000, 10, {}),
-                                                        ('rvo3d', 2, 2000, 12, {'SHARD_WAYPOINTS': '1'}),
-                                                        ('sca', 2, 1500, 12, {'SHARD_DUBINS': '1'})],
+@pytest.mark.parametrize('policy,world,n,steps,extra', [('sca', 2, 1600, 9, {}), ('orca_lp', 4, 3600, 9, {}),
+                                                        ('rvo3d', 2, 1400, 12, {'SHARD_WAYPOINTS': '1', 'SHARD_MIG_CAP': '512'}),
+                                                        ('sca', 2, 1000, 12, {'SHARD_DUBINS': '1', 'SHARD_MIG_CAP': '512'})],
                          ids=['sca-2', 'orca_lp-4', 'rvo3d-waypoints-2', 'sca-dubins-2'])
 def test_sharded_swarm_on_emulated_devices_reproduces_the_single_device_run(policy, world, n, steps, extra):
     """`extra`: per-agent state that lives outside the 128-byte migration row -- the waypoint follower (agent.path,
