@@ -32,6 +32,18 @@ struct PlaneView {
 
 struct Vec3 { double x, y, z; };
 
+// Compact planes (MODE 4, SCAB_LP_COMPACT=1): an ORCA plane is point = vA + u / 2 with u = s n (:104-105), so (n, s) -- 32 B
+// instead of 48 B -- determines it, and the point is rebuilt on every read with the roundings of the original construction
+// (s * n, * 0.5, + vA).  Two thirds of the shared memory per thread: 6-7 resident CTAs per SM instead of 4 in the list pass.
+struct PlanesC {
+    double v[4][KNBR][LP_THREADS];
+};
+struct PlaneViewC {
+    double *base;   // &P.v[0][0][tid], stride LP_THREADS
+    double vax, vay, vaz;
+    __device__ __forceinline__ double &at(int comp, int k) const { return base[(comp * KNBR + k) * LP_THREADS]; }
+};
+
 __device__ __forceinline__ double dotv(const Vec3 &a, const Vec3 &b) { return dot3(a.x, a.y, a.z, b.x, b.y, b.z); }
 __device__ __forceinline__ Vec3 crossv(const Vec3 &a, const Vec3 &b)
 {   // np.cross: products and differences rounded separately
@@ -43,6 +55,13 @@ __device__ __forceinline__ Vec3 crossv(const Vec3 &a, const Vec3 &b)
 }
 __device__ __forceinline__ Vec3 P_point(const PlaneView &P, int k) { return Vec3{P.px(k), P.py(k), P.pz(k)}; }
 __device__ __forceinline__ Vec3 P_normal(const PlaneView &P, int k) { return Vec3{P.nx(k), P.ny(k), P.nz(k)}; }
+__device__ __forceinline__ Vec3 P_normal(const PlaneViewC &P, int k) { return Vec3{P.at(0, k), P.at(1, k), P.at(2, k)}; }
+__device__ __forceinline__ Vec3 P_point(const PlaneViewC &P, int k)
+{
+    const double sc = P.at(3, k);
+    return Vec3{__dadd_rn(P.vax, __dmul_rn(0.5, __dmul_rn(sc, P.at(0, k)))), __dadd_rn(P.vay, __dmul_rn(0.5, __dmul_rn(sc, P.at(1, k)))),
+                __dadd_rn(P.vaz, __dmul_rn(0.5, __dmul_rn(sc, P.at(2, k))))};
+}
 __device__ __forceinline__ Vec3 subv(const Vec3 &a, const Vec3 &b) { return Vec3{__dsub_rn(a.x, b.x), __dsub_rn(a.y, b.y), __dsub_rn(a.z, b.z)}; }
 __device__ __forceinline__ Vec3 axpy(double s, const Vec3 &d, const Vec3 &p)
 {   // p + s * d with the product rounded first (NumPy ufunc order)
@@ -50,7 +69,8 @@ __device__ __forceinline__ Vec3 axpy(double s, const Vec3 &d, const Vec3 &p)
 }
 
 // orca3dPolicyOfficial.py:126-181
-__device__ bool lp1(const PlaneView &P, int planeNo, const Vec3 &lpoint, const Vec3 &ldir, double maxSpeed,
+template <class PV>
+__device__ bool lp1(const PV &P, int planeNo, const Vec3 &lpoint, const Vec3 &ldir, double maxSpeed,
                     const Vec3 &vel_pref, bool dir_opt, Vec3 &res)
 {
     const double dp = dotv(lpoint, ldir);
@@ -83,7 +103,8 @@ __device__ bool lp1(const PlaneView &P, int planeNo, const Vec3 &lpoint, const V
 }
 
 // orca3dPolicyOfficial.py:183-237
-__device__ bool lp2(const PlaneView &P, int planeNo, double maxSpeed, const Vec3 &vel_pref, bool dir_opt, Vec3 &res)
+template <class PV>
+__device__ bool lp2(const PV &P, int planeNo, double maxSpeed, const Vec3 &vel_pref, bool dir_opt, Vec3 &res)
 {
     const Vec3 pn = P_normal(P, planeNo), pp = P_point(P, planeNo);
     const double planeDist = dotv(pp, pn);
@@ -127,7 +148,8 @@ __device__ bool lp2(const PlaneView &P, int planeNo, double maxSpeed, const Vec3
 }
 
 // orca3dPolicyOfficial.py:239-259
-__device__ int lp3(const PlaneView &P, int np, double maxSpeed, const Vec3 &vel_pref, bool dir_opt, Vec3 &res)
+template <class PV>
+__device__ int lp3(const PV &P, int np, double maxSpeed, const Vec3 &vel_pref, bool dir_opt, Vec3 &res)
 {
     if (dir_opt) {
         res = Vec3{__dmul_rn(vel_pref.x, maxSpeed), __dmul_rn(vel_pref.y, maxSpeed), __dmul_rn(vel_pref.z, maxSpeed)};
@@ -151,7 +173,8 @@ __device__ int lp3(const PlaneView &P, int np, double maxSpeed, const Vec3 &vel_
 }
 
 // orca3dPolicyOfficial.py:261-300.  `Q` is a second plane set (the projected planes).
-__device__ void lp4(const PlaneView &P, const PlaneView &Q, int np, int beginPlane, double radius, Vec3 &res, int &n_proj)
+template <class PV>
+__device__ void lp4(const PV &P, const PlaneView &Q, int np, int beginPlane, double radius, Vec3 &res, int &n_proj)
 {
     for (int i = beginPlane; i < np; i++) {
         const Vec3 ni = P_normal(P, i), pi = P_point(P, i);
@@ -189,7 +212,8 @@ __device__ void lp4(const PlaneView &P, const PlaneView &Q, int np, int beginPla
 
 // ORCA plane of neighbour slot `e` for the agent (me, mv): orca3dPolicyOfficial.py:58-105.
 // point = vA + u/2 for every neighbour, static or not.
-__device__ __forceinline__ void orca_plane(const StepArgs &A, int e, const double4 &me, const float4 &mv, Vec3 &point, Vec3 &n)
+__device__ __forceinline__ void orca_plane(const StepArgs &A, int e, const double4 &me, const float4 &mv, Vec3 &point, Vec3 &n,
+                                           double *sc_out = nullptr)
 {
     double4 o;
     float ox = 0.f, oy = 0.f, oz = 0.f;
@@ -205,6 +229,7 @@ __device__ __forceinline__ void orca_plane(const StepArgs &A, int e, const doubl
     const double R = __dadd_rn(__dadd_rn(me.w, 0.05), __dadd_rn(o.w, 0.05));
     const double RSq = __dmul_rn(R, R);
     Vec3 u;
+    double scv;      // u = scv * n
     if (distSq > RSq) {
         const double invT = A.inv_time_horizon;
         const Vec3 w{__dsub_rn(rv.x, __dmul_rn(invT, rp.x)), __dsub_rn(rv.y, __dmul_rn(invT, rp.y)),
@@ -216,6 +241,7 @@ __device__ __forceinline__ void orca_plane(const StepArgs &A, int e, const doubl
             n = Vec3{__ddiv_rn(w.x, wl), __ddiv_rn(w.y, wl), __ddiv_rn(w.z, wl)};
             const double sc = __dsub_rn(__dmul_rn(R, invT), wl);
             u = Vec3{__dmul_rn(sc, n.x), __dmul_rn(sc, n.y), __dmul_rn(sc, n.z)};
+            scv = sc;
         } else {
             const double difSq = __dsub_rn(distSq, RSq);
             const double dpr = dotv(rp, rv);
@@ -229,6 +255,7 @@ __device__ __forceinline__ void orca_plane(const StepArgs &A, int e, const doubl
             n = Vec3{__ddiv_rn(ww.x, wl), __ddiv_rn(ww.y, wl), __ddiv_rn(ww.z, wl)};
             const double sc = __dsub_rn(__dmul_rn(R, t), wl);
             u = Vec3{__dmul_rn(sc, n.x), __dmul_rn(sc, n.y), __dmul_rn(sc, n.z)};
+            scv = sc;
         }
     } else {
         const double invDt = A.inv_time_step;
@@ -238,9 +265,11 @@ __device__ __forceinline__ void orca_plane(const StepArgs &A, int e, const doubl
         n = Vec3{__ddiv_rn(w.x, wl), __ddiv_rn(w.y, wl), __ddiv_rn(w.z, wl)};
         const double sc = __dsub_rn(__dmul_rn(R, invDt), wl);
         u = Vec3{__dmul_rn(sc, n.x), __dmul_rn(sc, n.y), __dmul_rn(sc, n.z)};
+            scv = sc;
     }
     point = Vec3{__dadd_rn((double)mv.x, __dmul_rn(0.5, u.x)), __dadd_rn((double)mv.y, __dmul_rn(0.5, u.y)),
                  __dadd_rn((double)mv.z, __dmul_rn(0.5, u.z))};
+    if (sc_out) *sc_out = scv;
 }
 
 // fp32 pre-filter of the register-only pass.  That pass only needs the SIGN of m = n . (point - v0) per plane (:252),
@@ -327,16 +356,18 @@ __device__ __forceinline__ Vec3 lp3_start(const Vec3 &vel_pref, double maxSpeed)
 //         Each plane is first judged in fp32 (orca_margin_f32); only the undecided ones are built in fp64.
 // MODE 2: the agents on A.slow_list, planes in shared memory, full LP3 / LP4.
 // MODE 3: MODE 1 without the fp32 pre-filter (SCAB_LP_F64=1, the A/B switch for it).
+// MODE 4: MODE 2 with compact planes (SCAB_LP_COMPACT=1; PlaneViewC) -- not the default until it has been timed on the GPU.
 template <int MODE>
 __global__ void __launch_bounds__((MODE & 1) ? LP_FAST_THREADS : LP_THREADS, (MODE & 1) ? 6 : 1) k_policy_lp(StepArgs A)
 {
     extern __shared__ double lp_smem[];
     const int tid = threadIdx.x;
     unsigned long long ran = 0;
-    const int n_work = MODE == 2 ? min(*A.slow_count, A.n) : A.n;
-    if (MODE == 2 && blockIdx.x == 0 && tid == 0) A.counters[6] = (unsigned long long)n_work;
+    constexpr bool LIST = (MODE == 2 || MODE == 4);
+    const int n_work = LIST ? min(*A.slow_count, A.n) : A.n;
+    if (LIST && blockIdx.x == 0 && tid == 0) A.counters[6] = (unsigned long long)n_work;
     for (int wi = blockIdx.x * blockDim.x + tid; wi < n_work; wi += gridDim.x * blockDim.x) {
-        const int s = MODE == 2 ? A.slow_list[wi] : wi;
+        const int s = LIST ? A.slow_list[wi] : wi;
         const int id = A.s_id[s];
         const double4 me = A.s_posr[s];
         const float4 mv = A.s_vel[s];
@@ -395,6 +426,23 @@ __global__ void __launch_bounds__((MODE & 1) ? LP_FAST_THREADS : LP_THREADS, (MO
                 }
                 plane_fail = nc;
                 tag |= SCAB_TAG_LP3_OK;
+            } else if (MODE == 4) {
+                PlanesC *PS = reinterpret_cast<PlanesC *>(lp_smem);
+                double qloc[6 * KNBR];   // projected planes of linearProgram4: rare path, thread-local
+                PlaneViewC P{&PS[0].v[0][0][tid], (double)mv.x, (double)mv.y, (double)mv.z};
+                PlaneView Q{qloc, 1};
+                for (int k = 0; k < nc; k++) {
+                    Vec3 pt, n;
+                    double sc;
+                    orca_plane(A, A.s_nbr[(size_t)s * KNBR + k], me, mv, pt, n, &sc);
+                    P.at(0, k) = n.x; P.at(1, k) = n.y; P.at(2, k) = n.z; P.at(3, k) = sc;
+                }
+                plane_fail = lp3(P, nc, A.max_speed, vp, false, res);   // :108
+                if (plane_fail == nc) tag |= SCAB_TAG_LP3_OK;
+                if (plane_fail < nc) {                                   // :110-111
+                    tag |= SCAB_TAG_LP4;
+                    lp4(P, Q, nc, plane_fail, A.max_speed, res, n_proj);
+                }
             } else {
                 Planes *PS = reinterpret_cast<Planes *>(lp_smem);
                 double qloc[6 * KNBR];   // projected planes of linearProgram4: rare path, thread-local
@@ -439,20 +487,25 @@ __global__ void __launch_bounds__((MODE & 1) ? LP_FAST_THREADS : LP_THREADS, (MO
 cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
 {
     if (A.n <= 0) return cudaSuccess;
-    static int no_fast = -1, sms = 0, per_sm = 0, f64_only = 0;
-    const size_t smem = sizeof(Planes);   // 6*16*64*8 = 49152 B
+    static int no_fast = -1, sms = 0, per_sm = 0, f64_only = 0, compact = 0, per_sm_c = 0;
+    const size_t smem = sizeof(Planes), smem_c = sizeof(PlanesC);   // 6*16*64*8 = 49152 B, 4*16*64*8 = 32768 B
     if (no_fast < 0) {
         cudaError_t e = cudaFuncSetAttribute(k_policy_lp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_policy_lp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_policy_lp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_policy_lp<2>, LP_THREADS, smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_policy_lp<4>, LP_THREADS, smem_c);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
+        if (per_sm_c < 1) per_sm_c = 1;
         int dev = 0;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
         const char *ev = getenv("SCAB_NO_FAST");   // A/B switch: every agent through the shared-memory kernel
         const char *e64 = getenv("SCAB_LP_F64");   // A/B switch: register-only pass without the fp32 pre-filter
         f64_only = (e64 && e64[0] == '1') ? 1 : 0;
+        const char *ec = getenv("SCAB_LP_COMPACT");   // A/B switch: list pass with 32-byte planes (more resident CTAs)
+        compact = (ec && ec[0] == '1') ? 1 : 0;
         no_fast = (ev && ev[0] == '1') ? 1 : 0;
     }
     const int nb = (A.n + LP_THREADS - 1) / LP_THREADS;
@@ -466,6 +519,11 @@ cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
     if (f64_only) k_policy_lp<3><<<nbf, LP_FAST_THREADS, 0, s>>>(A);
     else k_policy_lp<1><<<nbf, LP_FAST_THREADS, 0, s>>>(A);
     // the agents with a violated plane: one resident wave, strided over the list
+    if (compact) {
+        const int grid_c = nb < sms * per_sm_c ? nb : sms * per_sm_c;
+        k_policy_lp<4><<<grid_c, LP_THREADS, smem_c, s>>>(A);
+        return cudaGetLastError();
+    }
     const int grid = nb < sms * per_sm ? nb : sms * per_sm;
     k_policy_lp<2><<<grid, LP_THREADS, smem, s>>>(A);
     return cudaGetLastError();

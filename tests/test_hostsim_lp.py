@@ -3,10 +3,10 @@ pre-filter, linearProgram1-4, cartesian2spherical, the kinematic update and the 
 host by tests/hostsim (one thread at a time, -ffp-contract=off to mirror the device build's -fmad=false) and run against
 (a) the reference's recorded outputs on the ORCA-LP fixtures and (b) the oracle on dense random swarms with obstacles.
 
-All three launch configurations of `launch_policy_lp` are exercised: the register-only pass with the fp32 pre-filter + the
-work-list pass (default), the same without the pre-filter (SCAB_LP_F64=1) and the one-kernel version (SCAB_NO_FAST=1); they
-must agree with each other bit for bit.  This is not a substitute for the -m gpu parity tests (those run the compiled
-sm_100a code); it checks the kernel LOGIC on every CPU run and lets the LP kernels be edited without a GPU at hand.
+All four launch configurations of `launch_policy_lp` are exercised: the register-only pass with the fp32 pre-filter + the
+work-list pass (default), the same without the pre-filter (SCAB_LP_F64=1), the one-kernel version (SCAB_NO_FAST=1) and the
+work-list pass with compact 32-byte planes (SCAB_LP_COMPACT=1); they must agree with each other bit for bit.  This is not
+a substitute for the -m gpu parity tests (those run the compiled sm_100a code); it checks the kernel LOGIC on every CPU run and lets the LP kernels be edited without a GPU at hand.
 """
 import ctypes as C
 import os
@@ -88,7 +88,7 @@ def test_device_lp_source_matches_the_reference_fixtures(name):
         pre = _pre(w)
         w.policy_step('orca_lp', orc.NBR_REF_COMPAT)          # the reference's ordered neighbour lists (pinned elsewhere)
         ran = g['ran'][t].astype(bool)
-        outs = [run_device_source(mode, w, pre, w.nbr_cnt, w.nbr_ids, w.coll_query) for mode in (1, 3, 0)]
+        outs = [run_device_source(mode, w, pre, w.nbr_cnt, w.nbr_ids, w.coll_query) for mode in (1, 3, 0, 4)]
         for o in outs:
             assert o['n_ran'] == int(ran.sum())
             for k in ('tag', 'plane_fail', 'n_planes', 'lp4_proj'):
@@ -122,7 +122,7 @@ def test_device_lp_source_matches_the_oracle_on_dense_swarms(seed):
         pre = _pre(w)
         w.policy_step('orca_lp', orc.NBR_KNN)
         ran = w.ran.astype(bool)
-        outs = [run_device_source(mode, w, pre, w.nbr_cnt, w.nbr_ids, w.coll_query) for mode in (1, 3, 0)]
+        outs = [run_device_source(mode, w, pre, w.nbr_cnt, w.nbr_ids, w.coll_query) for mode in (1, 3, 0, 4)]
         ref = {k: getattr(w, k).copy() for k in ('tag', 'plane_fail', 'n_planes', 'lp4_proj', 'action', 'vpref_store')}
         w.env_update(fast=True)
         for o in outs:
