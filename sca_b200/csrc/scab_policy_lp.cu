@@ -356,9 +356,10 @@ __device__ __forceinline__ Vec3 lp3_start(const Vec3 &vel_pref, double maxSpeed)
 //         Each plane is first judged in fp32 (orca_margin_f32); only the undecided ones are built in fp64.
 // MODE 2: the agents on A.slow_list, planes in shared memory, full LP3 / LP4.
 // MODE 3: MODE 1 without the fp32 pre-filter (SCAB_LP_F64=1, the A/B switch for it).
+// MODE 5: MODE 1 compiled for 8 resident CTAs per SM (64 registers, a few spills; SCAB_LP_PASS1_CTAS8=1) -- to be timed.
 // MODE 4: MODE 2 with compact planes (SCAB_LP_COMPACT=1; PlaneViewC) -- not the default until it has been timed on the GPU.
 template <int MODE>
-__global__ void __launch_bounds__((MODE & 1) ? LP_FAST_THREADS : LP_THREADS, (MODE & 1) ? 6 : 1) k_policy_lp(StepArgs A)
+__global__ void __launch_bounds__((MODE & 1) ? LP_FAST_THREADS : LP_THREADS, (MODE == 5) ? 8 : ((MODE & 1) ? 6 : 1)) k_policy_lp(StepArgs A)
 {
     extern __shared__ double lp_smem[];
     const int tid = threadIdx.x;
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__((MODE & 1) ? LP_FAST_THREADS : LP_THREADS, (MO
                 res = lp3_start(vp, A.max_speed);
                 bool violated = false;
                 unsigned ask = (MODE == 3) ? ((nc >= 32) ? 0xffffffffu : ((1u << nc) - 1u)) : 0u;   // planes to build in fp64
-                if (MODE == 1) {
+                if (MODE == 1 || MODE == 5) {
                     const float dx = (float)__dsub_rn((double)mv.x, res.x), dy = (float)__dsub_rn((double)mv.y, res.y),
                                 dz = (float)__dsub_rn((double)mv.z, res.z);
                     for (int k = 0; k < nc && !violated; k++) {
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__((MODE & 1) ? LP_FAST_THREADS : LP_THREADS, (MO
 cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
 {
     if (A.n <= 0) return cudaSuccess;
-    static int no_fast = -1, sms = 0, per_sm = 0, f64_only = 0, compact = 0, per_sm_c = 0;
+    static int no_fast = -1, sms = 0, per_sm = 0, f64_only = 0, compact = 0, per_sm_c = 0, ctas8 = 0;
     const size_t smem = sizeof(Planes), smem_c = sizeof(PlanesC);   // 6*16*64*8 = 49152 B, 4*16*64*8 = 32768 B
     if (no_fast < 0) {
         cudaError_t e = cudaFuncSetAttribute(k_policy_lp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -506,6 +507,8 @@ cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
         f64_only = (e64 && e64[0] == '1') ? 1 : 0;
         const char *ec = getenv("SCAB_LP_COMPACT");   // A/B switch: list pass with 32-byte planes (more resident CTAs)
         compact = (ec && ec[0] == '1') ? 1 : 0;
+        const char *e8 = getenv("SCAB_LP_PASS1_CTAS8");   // A/B switch: register-only pass at 64 registers (8 CTAs per SM)
+        ctas8 = (e8 && e8[0] == '1') ? 1 : 0;
         no_fast = (ev && ev[0] == '1') ? 1 : 0;
     }
     const int nb = (A.n + LP_THREADS - 1) / LP_THREADS;
@@ -517,6 +520,7 @@ cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
     if (e != cudaSuccess) return e;
     const int nbf = (A.n + LP_FAST_THREADS - 1) / LP_FAST_THREADS;
     if (f64_only) k_policy_lp<3><<<nbf, LP_FAST_THREADS, 0, s>>>(A);
+    else if (ctas8) k_policy_lp<5><<<nbf, LP_FAST_THREADS, 0, s>>>(A);
     else k_policy_lp<1><<<nbf, LP_FAST_THREADS, 0, s>>>(A);
     // the agents with a violated plane: one resident wave, strided over the list
     if (compact) {

@@ -32,6 +32,7 @@ extern "C" int hostsim_policy_lp(int mode, const scab_state_ptrs *st, int n, int
     case 1: *slow_count = 0; k_policy_lp<1>(A); k_policy_lp<2>(A); break;     // what launch_policy_lp does by default
     case 3: *slow_count = 0; k_policy_lp<3>(A); k_policy_lp<2>(A); break;     // SCAB_LP_F64=1
     case 4: *slow_count = 0; k_policy_lp<1>(A); k_policy_lp<4>(A); break;     // SCAB_LP_COMPACT=1
+    case 5: *slow_count = 0; k_policy_lp<5>(A); k_policy_lp<2>(A); break;     // SCAB_LP_PASS1_CTAS8=1
     default: return -1;
     }
     return 0;

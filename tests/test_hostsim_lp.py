@@ -88,7 +88,7 @@ def test_device_lp_source_matches_the_reference_fixtures(name):
         pre = _pre(w)
         w.policy_step('orca_lp', orc.NBR_REF_COMPAT)          # the reference's ordered neighbour lists (pinned elsewhere)
         ran = g['ran'][t].astype(bool)
-        outs = [run_device_source(mode, w, pre, w.nbr_cnt, w.nbr_ids, w.coll_query) for mode in (1, 3, 0, 4)]
+        outs = [run_device_source(mode, w, pre, w.nbr_cnt, w.nbr_ids, w.coll_query) for mode in (1, 3, 0, 4, 5)]
         for o in outs:
             assert o['n_ran'] == int(ran.sum())
             for k in ('tag', 'plane_fail', 'n_planes', 'lp4_proj'):
@@ -122,7 +122,7 @@ def test_device_lp_source_matches_the_oracle_on_dense_swarms(seed):
         pre = _pre(w)
         w.policy_step('orca_lp', orc.NBR_KNN)
         ran = w.ran.astype(bool)
-        outs = [run_device_source(mode, w, pre, w.nbr_cnt, w.nbr_ids, w.coll_query) for mode in (1, 3, 0, 4)]
+        outs = [run_device_source(mode, w, pre, w.nbr_cnt, w.nbr_ids, w.coll_query) for mode in (1, 3, 0, 4, 5)]
         ref = {k: getattr(w, k).copy() for k in ('tag', 'plane_fail', 'n_planes', 'lp4_proj', 'action', 'vpref_store')}
         w.env_update(fast=True)
         for o in outs:
