@@ -245,23 +245,27 @@ class ShardedSwarm:
         if self.debug_phase is not None:
             self.debug_phase(what)
 
-    def _ghost_exchange_pre(self):
+    def _ghost_pre_pack(self):
         sw, cap = self.sw, self.cap
         lo_f, hi_f = self.plan.faces(self.rank)
         lo_face = lo_f if self.rank > 0 else -1e300            # no neighbour on that side: select nothing
         hi_face = hi_f if self.rank < self.world - 1 else 1e300
         sw.h.halo_pack(self.own_cap, self.plan.axis, lo_face, hi_face, self.plan.width, self.park,
                        self.send_lo.data_ptr(), self.send_hi.data_ptr(), cap, self._stream())
-        exchange_with_neighbours(self.send_lo, self.send_hi, self.recv[:cap], self.recv[cap:], self.rank, self.world)
-        sw.h.halo_unpack(self.recv.data_ptr(), 2 * cap, self.own_cap, self._stream())
+        return (self.send_lo, self.send_hi, self.recv[:cap], self.recv[cap:])
 
-    def _ghost_exchange_post(self):
+    def _ghost_pre_unpack(self):
+        self.sw.h.halo_unpack(self.recv.data_ptr(), 2 * self.cap, self.own_cap, self._stream())
+
+    def _ghost_post_pack(self):
         sw, cap = self.sw, self.cap
         sw.h.halo_pack_pos(self.psend_lo.data_ptr(), self.psend_hi.data_ptr(), cap, self.park, self._stream())
-        exchange_with_neighbours(self.psend_lo, self.psend_hi, self.precv[:cap], self.precv[cap:], self.rank, self.world)
-        sw.h.halo_unpack_pos(self.precv.data_ptr(), 2 * cap, self.own_cap, self._stream())
+        return (self.psend_lo, self.psend_hi, self.precv[:cap], self.precv[cap:])
 
-    def _migrate_device(self):
+    def _ghost_post_unpack(self):
+        self.sw.h.halo_unpack_pos(self.precv.data_ptr(), 2 * self.cap, self.own_cap, self._stream())
+
+    def _migrate_pack(self):
         """Agents that left the slab move to the neighbour rank -- on the device, fixed-size, no host sync."""
         sw = self.sw
         lo_f, hi_f = self.plan.faces(self.rank)
@@ -272,26 +276,34 @@ class ShardedSwarm:
         sw.h.migrate_pack(self.own_cap, self.plan.axis, lo_face, hi_face, (lo[0], lo[1], cell, self.park[2]), int(dim[0]), int(dim[1]),
                           self.msend_lo.data_ptr(), self.msend_hi.data_ptr(), self.mig_cap, self.free_list.data_ptr(),
                           self.free_count.data_ptr(), self.mig_cnt.data_ptr(), s)
+        out = [(self.msend_lo, self.msend_hi, self.mrecv_lo, self.mrecv_hi)]
         x = self._extra
         if x is not None:        # the Dubins tracker / waypoint state of the same agents, same slots
             sw.h.migrate_extra_pack(x['send_lo'].data_ptr(), x['send_hi'].data_ptr(), self.mig_cap, self.mig_cnt.data_ptr(), s)
-        exchange_with_neighbours(self.msend_lo, self.msend_hi, self.mrecv_lo, self.mrecv_hi, self.rank, self.world)
-        if x is not None:
-            exchange_with_neighbours(x['send_lo'], x['send_hi'], x['recv_lo'], x['recv_hi'], self.rank, self.world)
+            out.append((x['send_lo'], x['send_hi'], x['recv_lo'], x['recv_hi']))
+        return out
+
+    def _migrate_unpack(self):
+        sw, s, x = self.sw, self._stream(), self._extra
         sw.h.migrate_unpack(self.mrecv_lo.data_ptr(), self.mrecv_hi.data_ptr(), self.mig_cap, self.rank > 0, self.rank < self.world - 1,
                             self.free_list.data_ptr(), self.free_count.data_ptr(), self.mig_cnt.data_ptr(), s)
         if x is not None:
             sw.h.migrate_extra_unpack(x['recv_lo'].data_ptr(), x['recv_hi'].data_ptr(), self.mig_cap, s)
 
-    def _step_body(self, pol, nbr_mode, with_migration=False):
-        """One step: static shapes, static pointers -> capturable in a CUDA graph (two variants)."""
+    def _step_phases(self, pol, nbr_mode, with_migration=False):
+        """One step as a generator: static shapes, static pointers.  It yields at every exchange point the tuple
+        (send_lo, send_hi, recv_lo, recv_hi) the caller has to move between the slab neighbours -- NCCL send/recv for
+        one process per GPU (_step_body), plain device copies for several logical shards in one process (LogicalShards)."""
         sw = self.sw
         if self.world > 1:
             if with_migration:
                 self._mark('migrate')
-                self._migrate_device()
+                for x in self._migrate_pack():
+                    yield x
+                self._migrate_unpack()
             self._mark('pre-exchange')
-            self._ghost_exchange_pre()
+            yield self._ghost_pre_pack()
+            self._ghost_pre_unpack()
         s = self._stream()
         self._mark('grid')
         sw.h.build_grid(s)
@@ -301,15 +313,24 @@ class ShardedSwarm:
         sw.h.policy_step(pol, s)
         if self.world > 1:
             self._mark('post-exchange')
-            self._ghost_exchange_post()
+            yield self._ghost_post_pack()
+            self._ghost_post_unpack()
         self._mark('status')
         sw.h.status_step(s)
+
+    def _step_body(self, pol, nbr_mode, with_migration=False):
+        """One step with the exchanges over torch.distributed -> capturable in a CUDA graph (two variants)."""
+        for (s_lo, s_hi, r_lo, r_hi) in self._step_phases(pol, nbr_mode, with_migration):
+            exchange_with_neighbours(s_lo, s_hi, r_lo, r_hi, self.rank, self.world)
+
+    def _wants_migration(self):
+        # step 1 also migrates, so that both graph variants are exercised eagerly during any warm-up
+        return self.world > 1 and self.steps > 0 and (self.steps % self.plan.migrate_every == 0 or self.steps == 1)
 
     def step(self, policy, nbr_mode=capi.NBR_KNN):
         pol = capi.POLICIES[policy] if isinstance(policy, str) else int(policy)
         with torch.cuda.stream(self.stream):
-            # step 1 also migrates, so that both graph variants are exercised eagerly during any warm-up
-            mig = self.world > 1 and self.steps > 0 and (self.steps % self.plan.migrate_every == 0 or self.steps == 1)
+            mig = self._wants_migration()
             key = (pol, nbr_mode, mig)
             # the first steps run eagerly (NCCL creates its channels lazily on first use), then graphs replay
             if self.use_graph and self.debug_phase is None and self.steps >= 3:
@@ -462,3 +483,82 @@ class ShardedSwarm:
         own = torch.nonzero((t['status'][:self.own_cap] & capi.ST_GHOST) == 0)[:, 0]
         self.n_own = int(own.numel())
         return t['gid'][own].cpu().numpy(), {k: t[k][own].cpu().numpy() for k in keys}
+
+
+class LogicalShards:
+    """S slabs of one swarm as S ShardedSwarm objects in ONE process on ONE device: the same halo / migration kernels,
+    the same row layout and the same step sequence as the one-process-per-GPU run, with the NCCL send/recv of every
+    exchange point replaced by a device copy between the neighbours' buffers (all on one stream).  SURVEY 4(iii): the
+    sharded path can be held to "bit for bit equal to the single-device run" on a box with a single GPU."""
+
+    def __init__(self, pos6, goal6, shards, device, lo, hi, **kw):
+        self.world = int(shards)
+        kw.setdefault('use_graph', False)
+        self.shards = [ShardedSwarm(pos6, goal6, r, self.world, device, lo, hi, **kw) for r in range(self.world)]
+        self.stream = self.shards[0].stream
+        for sh in self.shards:
+            sh.stream = self.stream
+        self.n_global = self.shards[0].n_global
+
+    def enable_dubins(self, goal_heading, policy='sca'):
+        for sh in self.shards:
+            sh.enable_dubins(goal_heading, policy)
+        return self
+
+    def set_waypoints(self, waypoints, counts=None):
+        for sh in self.shards:
+            sh.set_waypoints(waypoints, counts)
+        return self
+
+    def step(self, policy, nbr_mode=capi.NBR_KNN):
+        pol = capi.POLICIES[policy] if isinstance(policy, str) else int(policy)
+        S = self.world
+        with torch.cuda.stream(self.stream):
+            mig = self.shards[0]._wants_migration()
+            gens = [sh._step_phases(pol, nbr_mode, mig) for sh in self.shards]
+            while True:
+                reqs = [next(g, None) for g in gens]          # every shard runs up to its next exchange point
+                if all(r is None for r in reqs):
+                    break
+                assert all(r is not None for r in reqs), 'logical shards fell out of lockstep'
+                for r in range(S):
+                    s_lo, s_hi = reqs[r][0], reqs[r][1]
+                    if r > 0:
+                        reqs[r - 1][3].copy_(s_lo)            # the lower neighbour's recv_hi
+                    if r < S - 1:
+                        reqs[r + 1][2].copy_(s_hi)            # the upper neighbour's recv_lo
+        for sh in self.shards:
+            sh.steps += 1
+
+    def check_overflow(self):
+        return [sh.check_overflow() for sh in self.shards]
+
+    def counters(self):
+        """Whole-swarm counters: the sum over the shards (what ShardedSwarm.global_counters all-reduces)."""
+        tot = {}
+        for sh in self.shards:
+            for k, v in sh.counters().items():
+                if isinstance(v, (int, np.integer)):
+                    tot[k] = tot.get(k, 0) + int(v)
+        return tot
+
+    def is_done(self):
+        return self.counters()['n_not_done'] == 0
+
+    def gather_state(self, keys=('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')):
+        """Owned rows of every shard keyed by global id (host); asserts that every agent has exactly one owner."""
+        gid = np.zeros(0, np.int64)
+        out = {k: [] for k in keys}
+        for sh in self.shards:
+            g, st = sh.gather_state(keys)
+            gid = np.concatenate([gid, g.astype(np.int64)])
+            for k in keys:
+                out[k].append(st[k])
+        assert len(np.unique(gid)) == len(gid) == self.n_global, 'an agent is owned by %s shards' % (
+            'no' if len(gid) < self.n_global else 'two')
+        order = np.argsort(gid)
+        return {k: np.concatenate(v)[order] for k, v in out.items()}
+
+    def close(self):
+        for sh in self.shards:
+            sh.close()
