@@ -136,8 +136,15 @@ typedef struct {
     int64_t n_active_total;/* cumulative n_active since scab_create / scab_reset_counters (agent-steps) */
     int64_t n_tier2;       /* diagnostics: agents whose lazy tier 1 did not pin the result (tier 2 examined) */
     int64_t n_slow;        /* diagnostics: agents handed to the general selection kernel */
-    int64_t reserved;
+    int64_t overflow;      /* STICKY bit mask (cleared only by scab_reset_counters); non-zero = results may be wrong:
+                              1 a halo face buffer was too small (records dropped), 2 a migration buffer was full (an agent
+                              stayed outside its slab), 4 an arriving agent found no free row (lost), 8 an agent moved farther
+                              in one step than scab_set_motion_bound allows (the collision stage's reach assumes the bound) */
 } scab_counters;
+#define SCAB_OVF_HALO 1
+#define SCAB_OVF_MIGRATION_DEFERRED 2
+#define SCAB_OVF_MIGRATION_LOST 4
+#define SCAB_OVF_MOTION 8
 
 const char *scab_version(void);
 void scab_default_params(scab_params *p);
@@ -157,6 +164,12 @@ int scab_set_option(scab_handle *h, int option, int value);
 /* Largest agent radius in the swarm (0 = unknown).  When known, the status stage reuses the step's neighbour
  * lists instead of re-scanning the cell list wherever those lists provably hold every possible collision partner. */
 int scab_set_max_radius(scab_handle *h, double r_max);
+
+/* Largest speed any agent can be commanded (max of max_speed, every pref_speed, 0.5 = the inner candidate shell, and the
+ * norm of any externally supplied V_des).  The collision stage (mampenv.py:61-80 is O(N^2) and has no such limit) only
+ * looks for partners within r_i + r_j + 2 v_max dt of an agent; the kinematic update checks every move against the bound
+ * and raises SCAB_OVF_MOTION in scab_counters.overflow if it is ever exceeded.  Default: 1.25 m per step. */
+int scab_set_motion_bound(scab_handle *h, double v_max);
 
 /* Replace the grid geometry (e.g. after the swarm's bounding box changed). */
 int scab_set_grid(scab_handle *h, const double origin[3], double cell_size, const int32_t dim[3]);

@@ -19,7 +19,12 @@ TAG_FIRST, TAG_SUITABLE, TAG_FALLBACK, TAG_LP3_OK, TAG_LP4 = 1, 2, 4, 8, 16
 # every symbol include/scab200.h declares (tests/test_capi_symbols.py checks the header against this)
 OPT_FULL_SEARCH = 1
 
-SYMBOLS = ['scab_version', 'scab_default_params', 'scab_set_option', 'scab_set_max_radius', 'scab_create', 'scab_destroy', 'scab_last_error', 'scab_set_grid',
+OVF_HALO, OVF_MIGRATION_DEFERRED, OVF_MIGRATION_LOST, OVF_MOTION = 1, 2, 4, 8
+OVF_TEXT = {1: 'a halo face buffer overflowed (ghost records dropped)', 2: 'a migration buffer was full (an agent stayed outside its slab)',
+            4: 'an arriving agent found no free row (agent lost)',
+            8: 'an agent moved farther in one step than the motion bound the collision stage relies on (scab_set_motion_bound)'}
+
+SYMBOLS = ['scab_version', 'scab_default_params', 'scab_set_option', 'scab_set_max_radius', 'scab_set_motion_bound', 'scab_create', 'scab_destroy', 'scab_last_error', 'scab_set_grid',
            'scab_bind_state', 'scab_set_obstacles', 'scab_kdtree_build', 'scab_kdtree_get_perm', 'scab_build_grid',
            'scab_neighbors', 'scab_policy_step', 'scab_status_step', 'scab_step', 'scab_read_counters',
            'scab_reset_counters', 'scab_halo_pack', 'scab_halo_unpack', 'scab_halo_pack_pos', 'scab_halo_unpack_pos',
@@ -57,7 +62,7 @@ DUBINS_STATE_DTYPE = [('in_use', '<i4'), ('n_points', '<i4'), ('cursor', '<i4'),
 class Counters(C.Structure):
     _fields_ = [('n_active', C.c_int64), ('n_not_done', C.c_int64), ('n_collision', C.c_int64),
                 ('n_recheck', C.c_int64), ('n_active_total', C.c_int64), ('n_tier2', C.c_int64), ('n_slow', C.c_int64),
-                ('reserved', C.c_int64)]
+                ('overflow', C.c_int64)]
 
 
 _lib = None
@@ -83,6 +88,7 @@ def lib():
     L.scab_set_grid.argtypes = [vp, C.POINTER(C.c_double), C.c_double, C.POINTER(i32)]
     L.scab_set_option.argtypes = [vp, C.c_int, C.c_int]
     L.scab_set_max_radius.argtypes = [vp, C.c_double]
+    L.scab_set_motion_bound.argtypes = [vp, C.c_double]
     L.scab_bind_state.argtypes = [vp, C.POINTER(StatePtrs), i64]
     L.scab_set_obstacles.argtypes = [vp, vp, i32]
     L.scab_kdtree_build.argtypes = [vp, vp, i64]
@@ -149,6 +155,9 @@ class Handle:
     def set_max_radius(self, r_max):
         self._ck(self._L.scab_set_max_radius(self._h, float(r_max)))
 
+    def set_motion_bound(self, v_max):
+        self._ck(self._L.scab_set_motion_bound(self._h, float(v_max)))
+
     def set_option(self, option, value):
         self._ck(self._L.scab_set_option(self._h, int(option), int(value)))
 
@@ -191,10 +200,13 @@ class Handle:
     def step(self, policy, nbr_mode, stream=0):
         self._ck(self._L.scab_step(self._h, policy, nbr_mode, stream))
 
-    def read_counters(self, stream=0):
+    def read_counters(self, stream=0, check=True):
+        """The step counters.  A non-zero sticky `overflow` mask means results may be wrong: raises unless check=False."""
         c = Counters()
         self._ck(self._L.scab_read_counters(self._h, C.byref(c), stream))
-        return {'n_active': c.n_active, 'n_not_done': c.n_not_done, 'n_collision': c.n_collision,
+        if check and c.overflow:
+            raise ScabError('libscab200 overflow flags %d: %s' % (c.overflow, '; '.join(t for b, t in OVF_TEXT.items() if c.overflow & b)))
+        return {'overflow': c.overflow, 'n_active': c.n_active, 'n_not_done': c.n_not_done, 'n_collision': c.n_collision,
                 'n_recheck': c.n_recheck, 'n_active_total': c.n_active_total, 'n_tier2': c.n_tier2, 'n_slow': c.n_slow}
 
     def reset_counters(self, stream=0):

@@ -17,6 +17,7 @@ struct scab_handle {
     int64_t capacity = 0;
     scab_params p{};
     StepArgs A{};
+    LaunchCfg cfg{};
     bool bound = false;
     std::string err;
     // library-owned device scratch
@@ -81,6 +82,14 @@ extern "C" int scab_set_max_radius(scab_handle *h, double r_max)
 {
     if (!h || !(r_max >= 0.0)) return fail(h, SCAB_ERR_INVALID, "scab_set_max_radius: bad argument");
     h->A.max_radius = r_max;
+    return SCAB_OK;
+}
+
+extern "C" int scab_set_motion_bound(scab_handle *h, double v_max)
+{
+    if (!h || !(v_max > 0.0) || !std::isfinite(v_max)) return fail(h, SCAB_ERR_INVALID, "scab_set_motion_bound: bad argument");
+    // 0.1 % slack: v_pref is dif * pref / trunc5(|dif|) (rvo3dPolicy.py:186-190), i.e. up to 5e-5 faster than pref near the goal
+    h->A.move_bound = v_max * h->p.time_step * 1.001 + 1e-9;
     return SCAB_OK;
 }
 
@@ -154,6 +163,13 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
 {
     if (!out || !p || capacity <= 0) return SCAB_ERR_INVALID;
     *out = nullptr;
+    // the 27-cell scans need cell_size >= neighbor_dist; the plane / integration arithmetic divides by these
+    const double chk[] = {p->neighbor_dist, p->time_step, p->time_horizon, p->max_speed, p->near_goal, p->cell_size,
+                          p->grid_origin[0], p->grid_origin[1], p->grid_origin[2]};
+    for (double v : chk) if (!std::isfinite(v)) return SCAB_ERR_INVALID;
+    if (!(p->neighbor_dist > 0.0) || !(p->time_step > 0.0) || !(p->time_horizon > 0.0) || !(p->max_speed > 0.0) ||
+        !(p->cell_size >= p->neighbor_dist) || p->grid_dim[0] < 1 || p->grid_dim[1] < 1 || p->grid_dim[2] < 1)
+        return SCAB_ERR_INVALID;
     scab_handle *h = new (std::nothrow) scab_handle();
     if (!h) return SCAB_ERR_NOMEM;
     h->device = device;
@@ -169,6 +185,19 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     A.max_speed = p->max_speed;
     A.near_goal = p->near_goal;
     A.tier_delta = TIER_DELTA_DEFAULT;
+    // until scab_set_motion_bound: no agent moves more than 1.25 m per step (12.5 m/s at the reference's dt)
+    A.move_bound = 1.25;
+    {   // launch configuration of THIS handle: its device's SM count, the A/B switches as they are set right now
+        LaunchCfg &c = h->cfg;
+        if (cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c.sms <= 0) c.sms = 148;
+        auto on = [](const char *name) { const char *v = getenv(name); return (v && v[0] == '1') ? 1 : 0; };
+        c.no_fast = on("SCAB_NO_FAST");        // every agent through the general kernels (sampled policies and ORCA-LP)
+        c.lp_f64 = on("SCAB_LP_F64");          // ORCA-LP register-only pass without the fp32 pre-filter
+        c.lp_compact = on("SCAB_LP_COMPACT");  // ORCA-LP list pass with 32-byte planes
+        c.lp_ctas8 = on("SCAB_LP_PASS1_CTAS8");// ORCA-LP register-only pass at 64 registers
+        c.knn_exact = on("SCAB_KNN_EXACT");    // 16-NN with fp64 total-order keys for every agent
+        A.cfg = &h->cfg;
+    }
     if (const char *td = getenv("SCAB_TIER_DELTA")) { float v = (float)atof(td); if (v > 0.f) A.tier_delta = v; }   // tuning knob
     // one block for all per-agent scratch
     const size_t cap = (size_t)capacity;
@@ -411,6 +440,9 @@ extern "C" int scab_status_step(scab_handle *h, void *stream)
 {
     int rc = check_ready(h, "scab_status_step");
     if (rc) return rc;
+    // every possible collision partner must lie in the 27-cell block around the agent's cell (mampenv.py:61-80 scans all agents)
+    if (2.0 * h->A.max_radius + 2.0 * h->A.move_bound + 1e-3 > 1.0 / h->A.g.inv_cs)
+        return fail(h, SCAB_ERR_INVALID, "scab_status_step: 2 r_max + 2 v_max dt exceeds the cell size (scab_set_grid with larger cells)");
     CK(launch_status(h->A, (cudaStream_t)stream));
     return SCAB_OK;
 }
@@ -472,6 +504,7 @@ extern "C" int scab_read_counters(scab_handle *h, scab_counters *out, void *stre
     out->n_active = (int64_t)v[0]; out->n_not_done = (int64_t)v[1]; out->n_collision = (int64_t)v[2]; out->n_recheck = (int64_t)v[3];
     out->n_active_total = (int64_t)v[4];
     out->n_tier2 = (int64_t)v[5]; out->n_slow = (int64_t)v[6];
+    out->overflow = (int64_t)v[7];
     return SCAB_OK;
 }
 

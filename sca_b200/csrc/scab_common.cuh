@@ -30,6 +30,21 @@ struct KdNodeDev {
     double mn[3], mx[3];
 };
 
+// Host only: launch configuration of ONE handle (its device's SM count, resident CTAs per SM of the persistent kernels on
+// that device, the A/B switches read from the environment by scab_create).  Kernels never dereference it.
+#define SCAB_OCC_SLOTS 24
+struct LaunchCfg {
+    int sms;
+    int no_fast, lp_f64, lp_compact, lp_ctas8, knn_exact;
+    int occ[SCAB_OCC_SLOTS];   // per kernel (slot constants next to each launcher); 0 = not queried on this device yet
+};
+
+// sticky bits of counters[7] (scab_counters.overflow): a result may be WRONG once one is set
+#define OVF_HALO 1ull        // k_halo_pack dropped records: a face buffer was too small
+#define OVF_MIG_DEFER 2ull   // k_migrate_pack could not send an agent (buffer full): it stays outside its slab
+#define OVF_MIG_LOST 4ull    // k_migrate_unpack found no free row for an arrival: the agent is gone
+#define OVF_MOTION 8ull      // an agent moved farther in one step than the bound the collision stage relies on
+
 // Everything a kernel needs; passed by value.
 struct StepArgs {
     scab_state_ptrs st;
@@ -55,6 +70,8 @@ struct StepArgs {
     int32_t *slow_list; // [n] agents the 8-lane fast selection kernel hands to the general kernel
     int32_t *slow_count;
     double max_radius;  // largest agent radius (0: unknown -> the status stage always scans the cell list)
+    double move_bound;  // no agent moves farther than this in one step (scab_set_motion_bound; kinematic_update checks it)
+    LaunchCfg *cfg;     // host pointer (the owning handle's launch configuration)
     int last_nbr_mode;  // mode of the neighbour lists currently in s_nbr
     float tier_delta;   // lazy tiers: tier 1 = candidates within this distance of the one closest to v_pref
     int full_search;    // SCAB_OPT_FULL_SEARCH: examine every candidate (exact n_suit) instead of the lazy tiers
@@ -231,6 +248,7 @@ __device__ __forceinline__ void kinematic_update(const StepArgs &A, int id, cons
     double dy = __dmul_rn(__dmul_rn(t, sa), A.time_step);
     double dz = __dmul_rn(__dmul_rn(speed, sb), A.time_step);
     double len = __dsqrt_rn(sumsq3(dx, dy, dz));
+    if (len > A.move_bound) atomicOr(&A.counters[7], OVF_MOTION);   // the collision stage's reach assumes the bound: be loud
     A.st.total_dist[id] = __dadd_rn(A.st.total_dist[id], len);
     *npx = __dadd_rn(px, dx); *npy = __dadd_rn(py, dy); *npz = __dadd_rn(pz, dz);
     A.st.pos[3 * id + 0] = *npx; A.st.pos[3 * id + 1] = *npy; A.st.pos[3 * id + 2] = *npz;

@@ -51,10 +51,12 @@ __global__ void __launch_bounds__(256) k_halo_pack(StepArgs A, int n_own, int ax
     if (to_lo) {
         const int slot = atomicAdd(&cnt[0], 1);
         if (slot < cap) { out_lo[slot] = r; sent_lo[slot] = i; }
+        else atomicOr(&A.counters[7], OVF_HALO);
     }
     if (to_hi) {
         const int slot = atomicAdd(&cnt[1], 1);
         if (slot < cap) { out_hi[slot] = r; sent_hi[slot] = i; }
+        else atomicOr(&A.counters[7], OVF_HALO);
     }
 }
 
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(256) k_migrate_pack(StepArgs A, int own_cap, i
     const int side = (c < lo_face) ? 0 : (c >= hi_face ? 1 : -1);
     if (side < 0) return;
     const int slot = atomicAdd(&cnt[side], 1);
-    if (slot >= cap) { atomicAdd(&cnt[2], 1); return; }      // overflow: the agent stays (and is counted)
+    if (slot >= cap) { atomicAdd(&cnt[2], 1); atomicOr(&A.counters[7], OVF_MIG_DEFER); return; }   // overflow: the agent stays (counted, sticky flag)
     MigRow r;
     for (int d = 0; d < 3; d++) {
         r.pos[d] = A.st.pos[3 * i + d]; r.heading[d] = A.st.heading[3 * i + d]; r.goal[d] = A.st.goal[3 * i + d];
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(256) k_migrate_unpack(StepArgs A, const MigRow
     const int count = min(max(in[0].gid, 0), cap);
     if (slot >= count) return;
     const int fi = atomicSub(free_count, 1) - 1;
-    if (fi < 0) { atomicAdd(free_count, 1); atomicAdd(&cnt[3], 1); return; }   // no free row: counted as lost (never expected)
+    if (fi < 0) { atomicAdd(free_count, 1); atomicAdd(&cnt[3], 1); atomicOr(&A.counters[7], OVF_MIG_LOST); return; }   // no free row: lost (sticky flag; scab_read_counters reports it)
     const int i = free_list[fi];
     if (recv_row) recv_row[k] = i;
     const MigRow r = in[1 + slot];

@@ -484,8 +484,7 @@ cudaError_t launch_neighbors(const StepArgs &A, int mode, cudaStream_t s)
     if (mode == SCAB_NBR_REF_COMPAT) k_neighbors_compat<<<nb, 128, 0, s>>>(A);
     else {
         // the integer-key fast path needs: no obstacles in the merged list, and distance keys below 2^24 units of 1e-5
-        static const bool no_fast = []() { const char *e = getenv("SCAB_KNN_EXACT"); return e && e[0] == '1'; }();   // A/B switch
-        const int fast_ok = (A.m == 0 && A.nbr_dist_sq * 1e5 < 16777215.0 && !no_fast) ? 1 : 0;
+        const int fast_ok = (A.m == 0 && A.nbr_dist_sq * 1e5 < 16777215.0 && !A.cfg->knn_exact) ? 1 : 0;   // SCAB_KNN_EXACT=1: A/B switch
         k_neighbors_knn<<<nb, 128, 0, s>>>(A, fast_ok);
     }
     return cudaGetLastError();

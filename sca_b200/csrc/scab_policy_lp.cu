@@ -488,9 +488,11 @@ __global__ void __launch_bounds__((MODE & 1) ? LP_FAST_THREADS : LP_THREADS, (MO
 cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
 {
     if (A.n <= 0) return cudaSuccess;
-    static int no_fast = -1, sms = 0, per_sm = 0, f64_only = 0, compact = 0, per_sm_c = 0, ctas8 = 0;
+    LaunchCfg &cfg = *A.cfg;      // this handle's device and switches (slots 12, 13: the two list-pass kernels)
+    int &per_sm = cfg.occ[12], &per_sm_c = cfg.occ[13];
+    const int no_fast = cfg.no_fast, sms = cfg.sms, f64_only = cfg.lp_f64, compact = cfg.lp_compact, ctas8 = cfg.lp_ctas8;
     const size_t smem = sizeof(Planes), smem_c = sizeof(PlanesC);   // 6*16*64*8 = 49152 B, 4*16*64*8 = 32768 B
-    if (no_fast < 0) {
+    if (per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(k_policy_lp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_policy_lp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_policy_lp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
@@ -499,17 +501,6 @@ cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
         if (per_sm_c < 1) per_sm_c = 1;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-        const char *ev = getenv("SCAB_NO_FAST");   // A/B switch: every agent through the shared-memory kernel
-        const char *e64 = getenv("SCAB_LP_F64");   // A/B switch: register-only pass without the fp32 pre-filter
-        f64_only = (e64 && e64[0] == '1') ? 1 : 0;
-        const char *ec = getenv("SCAB_LP_COMPACT");   // A/B switch: list pass with 32-byte planes (more resident CTAs)
-        compact = (ec && ec[0] == '1') ? 1 : 0;
-        const char *e8 = getenv("SCAB_LP_PASS1_CTAS8");   // A/B switch: register-only pass at 64 registers (8 CTAs per SM)
-        ctas8 = (e8 && e8[0] == '1') ? 1 : 0;
-        no_fast = (ev && ev[0] == '1') ? 1 : 0;
     }
     const int nb = (A.n + LP_THREADS - 1) / LP_THREADS;
     if (no_fast) {

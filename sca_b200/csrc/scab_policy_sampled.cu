@@ -656,7 +656,10 @@ __global__ void __launch_bounds__(256) k_integrate(StepArgs A)
 template <int POLICY>
 static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
 {
-    static int per_sm = 0, per_sm_fast = 0, no_fast = -1;
+    // resident CTAs per SM of the two persistent kernels on THIS handle's device (slots 2 * POLICY, 2 * POLICY + 1)
+    LaunchCfg &cfg = *A.cfg;
+    int &per_sm = cfg.occ[2 * POLICY], &per_sm_fast = cfg.occ[2 * POLICY + 1];
+    const int no_fast = cfg.no_fast;
     const size_t smem = sizeof(WarpSmem) * WARPS_PER_CTA, smem_fast = sizeof(GroupSmemT<POLICY == SCAB_POLICY_ORCA_SAMPLED>) * FG_WARPS * FG_PER_WARP + 384 * sizeof(float4);
     if (per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(k_select<POLICY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -667,8 +670,6 @@ static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
         if (per_sm_fast < 1) per_sm_fast = 1;
-        const char *ev = getenv("SCAB_NO_FAST");   // A/B switch: route every agent through the general kernel
-        no_fast = (ev && ev[0] == '1') ? 1 : 0;
     }
     // persistent kernels, exactly one resident wave each: grid = SMs x resident CTAs per SM
     const int need = (A.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
@@ -689,12 +690,7 @@ static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
 cudaError_t launch_policy_sampled(const StepArgs &A, int policy, cudaStream_t s)
 {
     if (A.n <= 0) return cudaSuccess;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
+    const int sms = A.cfg->sms;
     const int nb = (A.n + 255) / 256;
     const int grid = sms;   // launch_select multiplies by the resident CTAs per SM
     cudaError_t e;

@@ -49,12 +49,13 @@ __global__ void __launch_bounds__(128) k_status(StepArgs A)
             }
         }
         // agents (mampenv.py:68-75) through the pair rule
+        const double reach = 2.0 * A.move_bound + 1e-3;   // both partners move, plus slack for the 5-decimal rounding
         auto test_pair = [&](int j) {
             const double4 oo = A.s_posr[j];
-            // cheap reject on the old positions: both agents move < 1 m per step
+            // cheap reject on the old positions: each agent moves <= move_bound per step
             const double ex = oo.x - oldp.x, ey = oo.y - oldp.y, ez = oo.z - oldp.z;
             const double R = __dadd_rn(oldp.w, oo.w);
-            const double lim = R + 2.5;
+            const double lim = R + reach;
             if (ex * ex + ey * ey + ez * ez > lim * lim) return;
             const int jrow = A.s_id[j];
             const double4 on = make_double4(A.st.pos[3 * jrow], A.st.pos[3 * jrow + 1], A.st.pos[3 * jrow + 2], 0.0);
@@ -68,20 +69,22 @@ __global__ void __launch_bounds__(128) k_status(StepArgs A)
                       l3norm_d(on.x, on.y, on.z, newp.x, newp.y, newp.z) <= R;
             coll_agent |= hit;
         };
-        // Shortcut: this step's neighbour list already holds EVERY agent within reach when it is not
-        // saturated, or (true-KNN lists) when its farthest entry is an agent beyond r_i + r_max + 2.6 m.
+        // Shortcut: this step's neighbour list already holds EVERY agent within reach (r_i + r_max + `reach`) when it is
+        // not saturated and reach stays inside neighbor_dist, or (true-KNN lists) when its farthest entry is an agent
+        // beyond that reach.
         bool from_list = false;
         int ncnt = -1;
+        const double my_reach = oldp.w + A.max_radius + reach;
         if (A.max_radius > 0.0) {
             ncnt = A.s_nbr_cnt[s];
             if (ncnt >= 0 && !A.s_qcoll[s]) {
-                if (ncnt < KNBR) from_list = true;
+                if (ncnt < KNBR) from_list = (my_reach + 0.01) * (my_reach + 0.01) < A.nbr_dist_sq;
                 else if (A.last_nbr_mode == SCAB_NBR_KNN) {
                     const int e = A.s_nbr[(size_t)s * KNBR + KNBR - 1];
                     if (e < A.n) {
                         const double4 oo = A.s_posr[e];
                         const double ex = oo.x - oldp.x, ey = oo.y - oldp.y, ez = oo.z - oldp.z;
-                        const double lim = oldp.w + A.max_radius + 2.6;
+                        const double lim = my_reach + 0.1;
                         from_list = ex * ex + ey * ey + ez * ez > lim * lim;
                     }
                 }
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(128) k_status(StepArgs A)
         if (from_list) {
             // the list is sorted by distance (both modes insert in order): without obstacle entries mixed in, the
             // first agent beyond reach ends the walk -- typically after one or two entries
-            const double brk = oldp.w + A.max_radius + 2.51;
+            const double brk = my_reach + 0.01;
             const bool sorted_agents = (A.m == 0);
             for (int k = 0; k < ncnt; k++) {
                 const int e = A.s_nbr[(size_t)s * KNBR + k];

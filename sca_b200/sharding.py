@@ -126,12 +126,22 @@ class ShardedSwarm:
     """
 
     def __init__(self, pos6, goal6, rank, world, device, lo, hi, radius=0.5, pref_speed=1.0, migrate_every=8,
-                 halo_cap=None, debug=False, use_graph=True, mig_cap=4096):
+                 halo_cap=None, debug=False, use_graph=True, mig_cap=4096, params=None):
         from .swarm import Swarm
         pos6, goal6 = np.asarray(pos6, 'float64'), np.asarray(goal6, 'float64')
         n_global = len(pos6)
         self.rank, self.world, self.n_global = rank, world, n_global
-        self.plan = SlabPlan(pos6[:, 0], world, migrate_every=migrate_every)
+        from . import capi as _capi
+        prm = params if params is not None else _capi.default_params()
+        pref_g = np.broadcast_to(np.asarray(pref_speed, 'float64'), (n_global,))
+        v_bound = max(float(prm.max_speed), float(pref_g.max()) if n_global else 0.0, 0.5)    # == Swarm.v_bound over ALL shards
+        self.plan = SlabPlan(pos6[:, 0], world, neighbor_dist=float(prm.neighbor_dist), max_speed=v_bound, dt=float(prm.time_step),
+                             migrate_every=migrate_every)
+        # ghosts come from the two adjacent slabs only: an interior slab narrower than the halo width would hide
+        # neighbours (and collision partners) that live two slabs away
+        if self.plan.min_slab_width() < self.plan.width:
+            raise capi.ScabError('slab of width %.3f m is narrower than the halo width %.3f m: use fewer shards (or a smaller '
+                                 'migrate_every)' % (self.plan.min_slab_width(), self.plan.width))
         own_all = self.plan.owner(pos6[:, 0])
         mine = np.nonzero(own_all == rank)[0]
         from .scenarios import spatial_order
@@ -151,12 +161,13 @@ class ShardedSwarm:
         self.cap = int(halo_cap) if world > 1 else 0
         self.own_cap = int(self.n_own * 1.25) + 4096
         self.n_rows = self.own_cap + 2 * self.cap
-        sw = Swarm(self.n_own, device=device, debug=debug, capacity=self.n_rows)
+        sw = Swarm(self.n_own, device=device, debug=debug, capacity=self.n_rows, params=params)
         rad_g = np.broadcast_to(np.asarray(radius, 'float64'), (n_global,))
-        pref_g = np.broadcast_to(np.asarray(pref_speed, 'float64'), (n_global,))
         sw.set_state(pos6[mine, :3], goal6[mine, :3], heading=pos6[mine, 3:6], radius=rad_g[mine], pref_speed=pref_g[mine],
                      initial_pos=pos6[mine], goal_pos=goal6[mine])
-        sw.h.set_max_radius(float(rad_g.max()))      # ghosts included: the bound must hold across shards
+        sw.h.set_max_radius(float(rad_g.max()))      # ghosts included: the bounds must hold across shards
+        sw.v_bound = v_bound
+        sw.h.set_motion_bound(v_bound)
         sw.set_global_ids(mine.astype(np.int32), n_global)
         # two extra z layers: an empty buffer layer and the layer where unused slots are parked
         lo, hi = np.asarray(lo, 'float64').copy(), np.asarray(hi, 'float64').copy()
@@ -171,7 +182,9 @@ class ShardedSwarm:
             hi[ax] = min(hi[ax], hi_f + self.plan.width + 2 * cell)
         dim = np.maximum(1, np.ceil((hi - lo) / cell).astype(np.int64))
         self._park_geom = (lo.copy(), cell, dim.copy())
-        self.park = (float(lo[0] + 0.5 * cell), float(lo[1] + 0.5 * cell), float(lo[2] + (dim[2] + 1.5) * cell))
+        # physically remote (z = 1e9 clamps into the reserved top layer of the grid): an agent that climbs above the box is
+        # clamped into that layer too and scans the parked rows, but can never be within neighbor_dist of one
+        self.park = (float(lo[0] + 0.5 * cell), float(lo[1] + 0.5 * cell), 1.0e9)
         dim[2] += 2
         sw.h.set_grid(lo, cell, dim)
         self.sw = sw
@@ -457,19 +470,30 @@ class ShardedSwarm:
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ results
-    def counters(self):
+    def counters(self, check=True):
+        """This rank's counters (blocking).  Raises ScabError if a halo / migration buffer ever overflowed, an arrival was
+        lost or an agent outran the motion bound (sticky device flags: nothing is dropped silently)."""
         with torch.cuda.stream(self.stream):
-            return self.sw.h.read_counters(self._stream())
+            return self.sw.h.read_counters(self._stream(), check)
 
     def global_counters(self):
-        """Whole-swarm counters: one all-reduce (SUM) of the per-rank device counters (the done test)."""
-        c = self.counters()
-        keys = sorted(k for k, v in c.items() if isinstance(v, (int, np.integer)))
-        if self.world == 1:
-            return {k: int(c[k]) for k in keys}
-        t = torch.tensor([int(c[k]) for k in keys], dtype=torch.int64, device=self.sw.device)
-        torch.distributed.all_reduce(t)
-        return {k: int(v) for k, v in zip(keys, t.tolist())}
+        """Whole-swarm counters: one all-reduce (SUM) of the per-rank device counters (the done test).  The
+        overflow masks are OR-ed (as a per-bit sum), and every rank raises together if any rank's is set."""
+        c = self.counters(check=False)
+        keys = sorted(k for k, v in c.items() if isinstance(v, (int, np.integer)) and k != 'overflow')
+        ovf = [(int(c['overflow']) >> b) & 1 for b in range(4)]
+        if self.world > 1:
+            t = torch.tensor([int(c[k]) for k in keys] + ovf, dtype=torch.int64, device=self.sw.device)
+            torch.distributed.all_reduce(t)
+            vals = t.tolist()
+        else:
+            vals = [int(c[k]) for k in keys] + ovf
+        out = {k: int(v) for k, v in zip(keys, vals)}
+        out['overflow'] = sum((1 << b) for b in range(4) if vals[len(keys) + b])
+        if out['overflow']:
+            raise capi.ScabError('sharded run overflow flags %d: %s' % (out['overflow'], '; '.join(
+                t for b, t in capi.OVF_TEXT.items() if out['overflow'] & b)))
+        return out
 
     def is_done(self):
         """MACAEnv.is_done (mampenv.py:51-59) over all slabs: every owned agent of every rank has finished."""

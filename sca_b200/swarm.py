@@ -156,6 +156,10 @@ class Swarm:
             'max_run_dist': f8(max_run_dist, (n,)),
         }
         self.h.set_max_radius(float(np.max(host['radius'])) if n else 0.0)
+        # largest speed a policy can command: max_speed (the LP), pref_speed (outer candidate shell, |v_pref|), 0.5 (inner
+        # shell).  The collision stage's reach is derived from it; a move beyond it raises the sticky OVF_MOTION flag.
+        self.v_bound = max(float(self.params.max_speed), float(np.max(host['pref_speed'])) if n else 0.0, 0.5)
+        self.h.set_motion_bound(self.v_bound)
         self._zaxis = torch.zeros(self.capacity, dtype=_I4, device=self.device)
         self._zaxis[:n].copy_(torch.as_tensor(zaxis))
         for k, a in host.items():
@@ -227,8 +231,9 @@ class Swarm:
     def stage_status(self):
         self.h.status_step(self._stream())
 
-    def counters(self):
-        return self.h.read_counters(self._stream())
+    def counters(self, check=True):
+        """Step counters (blocking).  Raises ScabError if the sticky overflow mask is set (results may be wrong)."""
+        return self.h.read_counters(self._stream(), check)
 
     def is_done(self):
         return self.counters()['n_not_done'] == 0

@@ -70,6 +70,7 @@ template <typename T> static inline T __shfl_xor_sync(unsigned, T, int, int = 32
 static inline unsigned __ballot_sync(unsigned, int pred) { return pred ? 1u : 0u; }
 template <typename T> static inline T atomicAdd(T *p, T v) { T old = *p; *p = old + v; return old; }
 static inline int atomicAdd(int32_t *p, int v) { int old = *p; *p = old + v; return old; }
+static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { unsigned long long old = *p; *p = old | v; return old; }
 #else
 namespace hostsim {
 // all lanes named in `mask` deposit `v` and get everybody's deposits back (lanes that already left the kernel: 0)
@@ -151,4 +152,5 @@ static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __A
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicSub(int *p, int v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 #endif

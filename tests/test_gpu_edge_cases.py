@@ -168,3 +168,98 @@ def test_voxel_obstacle_field_at_scale_matches_oracle():
         print(policy, tot)
         for k in ('nbr', 'tag', 'nsuit', 'vel', 'status', 'planes'):
             assert tot[k] == 0, (policy, tot)
+
+
+def test_fast_agents_collision_flags_match_the_oracle():
+    """the collision stage's reach is derived from the motion bound (v_max dt), not from a fixed 1.25 m per
+    step.  pref_speed = 14 m/s moves an agent 1.4 m per step; the reference's O(N^2) check (mampenv.py:61-80) has no
+    reach limit, so the flags must still agree with the oracle's literal loop."""
+    import torch
+    from oracle import oracle as orc
+    from sca_b200 import capi
+    rng = np.random.default_rng(11)
+    n = 400
+    pos = rng.uniform(0, 28, (n, 3)) + [0, 0, 20]
+    keep = np.ones(n, bool)
+    for i in range(n):                      # >= 1.3 m apart at t = 0
+        if keep[i]:
+            d = np.linalg.norm(pos - pos[i], axis=1)
+            keep &= ~((d < 1.3) & (np.arange(n) > i))
+    pos = pos[keep]
+    n = len(pos)
+    goal = pos[rng.permutation(n)] + rng.normal(0, 2.0, (n, 3))
+    w = orc.World(pos, goal, pref_speed=14.0)
+    sw = _swarm(pos, goal, pref_speed=14.0)
+    assert sw.v_bound == 14.0
+    hits = 0
+    for t in range(6):
+        w.step('rvo3d', orc.NBR_KNN)         # fast=False: the literal sequential O(N^2) loop
+        sw.step('rvo3d', capi.NBR_KNN)
+        torch.cuda.synchronize()
+        st = sw.status.cpu().numpy()[:n] & 15
+        assert np.array_equal(st, w.status), (t, np.nonzero(st != w.status)[0][:10])
+        hits = int((st & 2).astype(bool).sum())
+    assert hits >= 4, 'the scenario must actually produce collisions (%d)' % hits
+    sw.counters()                            # no sticky flag
+
+
+def test_a_move_beyond_the_motion_bound_is_loud():
+    import torch
+    from sca_b200 import capi
+    rng = np.random.default_rng(3)
+    pos = rng.uniform(0, 40, (50, 3)) + [0, 0, 20]
+    sw = _swarm(pos, pos[::-1].copy())
+    sw.h.set_motion_bound(0.2)               # claims 0.02 m per step; the agents fly 0.1 m per step
+    sw.step('rvo3d', capi.NBR_KNN)
+    sw.step('rvo3d', capi.NBR_KNN)
+    torch.cuda.synchronize()
+    with pytest.raises(capi.ScabError, match='motion bound'):
+        sw.counters()
+    assert sw.counters(check=False)['overflow'] == capi.OVF_MOTION
+    sw.h.reset_counters()
+    sw.h.set_motion_bound(1.0)
+    sw.step('rvo3d', capi.NBR_KNN)
+    assert sw.counters()['overflow'] == 0
+
+
+def test_status_stage_refuses_a_reach_beyond_the_cell_size():
+    from sca_b200 import capi
+    pos = np.array([[0.0, 0.0, 20.0], [8.0, 0.0, 20.0]])
+    sw = _swarm(pos, pos[::-1].copy())
+    sw.h.set_motion_bound(60.0)              # 6 m per step: partners may sit outside the 27-cell block of 10 m cells
+    with pytest.raises(capi.ScabError, match='exceeds the cell size'):
+        sw.step('rvo3d', capi.NBR_KNN)
+    sw.fit_grid(pos.min(0) - 30, pos.max(0) + 30, cell=30.0)
+    sw.step('rvo3d', capi.NBR_KNN)
+
+
+def test_scab_create_validates_its_parameters():
+    from sca_b200 import capi
+    from sca_b200.swarm import Swarm
+    for field, bad in (('cell_size', 5.0), ('time_step', 0.0), ('time_horizon', -1.0), ('neighbor_dist', float('nan'))):
+        p = capi.default_params()
+        setattr(p, field, bad)
+        with pytest.raises(capi.ScabError, match='scab_create failed'):
+            Swarm(4, params=p)
+
+
+def test_halo_overflow_is_loud(request, monkeypatch):
+    """A halo face buffer that is too small drops ghost records: the sticky device flag turns that into an error at the next
+    counters() / is_done() instead of a quietly wrong rollout."""
+    device = 'cuda:0'
+    if request.config.getoption('--hostsim'):
+        import hostsim_util
+        hostsim_util.activate_streams(monkeypatch)
+        device = 'cpu'
+    from sca_b200 import capi, scenarios
+    from sca_b200.sharding import LogicalShards
+    n = 3000
+    density = 4.0e6 / 560.0 ** 3
+    pos, goal, _ = scenarios.uniform_box_numpy(n, density, seed=3)
+    L = (n / density) ** (1 / 3)
+    lo, hi = np.array([-20.0, -20.0, 0.0]), np.array([L + 20.0, L + 20.0, L + 40.0])
+    ls = LogicalShards(pos, goal, 2, device, lo, hi, halo_cap=16)
+    ls.step('rvo3d')
+    with pytest.raises(capi.ScabError, match='halo face buffer overflowed'):
+        ls.counters()
+    ls.close()

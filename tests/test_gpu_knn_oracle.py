@@ -13,7 +13,8 @@ def _compare(pos6, goal6, obstacles, policy, steps, lo=None, hi=None, full_searc
     from sca_b200.swarm import Swarm
     import gpu_util as G
     n = len(pos6)
-    orc.set_threads(8)
+    import os
+    orc.set_threads(max(8, min(32, os.cpu_count() or 8)))
     w = orc.World(pos6[:, :3], goal6[:, :3], heading=pos6[:, 3:6], obstacles=obstacles, initial_pos=pos6, goal_pos=goal6)
     sw = Swarm(n, debug=True)
     sw.h.set_option(capi.OPT_FULL_SEARCH, 1 if full_search else 0)
@@ -81,5 +82,33 @@ def test_dense_sphere_config4(policy):
     pos, goal, obs = scenarios.dense_sphere(4000)
     tot = _compare(pos, goal, obs, policy, steps=5)
     print(policy, tot)
+    for k in ('nbr', 'tag', 'nsuit', 'vel', 'status'):
+        assert tot[k] == 0, (policy, tot)
+
+
+# ---------------------------------------------------------------- BASELINE configs 3 and 4 at their NAMED sizes
+def test_takeoff_landing_config3_at_10000_uavs():
+    """BASELINE configs[2]: run_sca.py:53-81 take-off / landing pads with the 8 sphere obstacles of :139-150, tiled 25 x 25
+    (pitch 30 m) = 10 000 UAVs + 5 000 obstacles, SCA with the posture constraint (vertical start->goal: 2 x 128 + 1
+    candidates, scaPolicy.py:188-190).  EVERY agent of the whole world against the oracle, teacher-forced, 6 steps."""
+    from sca_b200 import scenarios
+    pos, goal, obs = scenarios.takeoff_landing_tiled(pads=625)
+    assert len(pos) == 10000 and len(obs) == 5000
+    tot = _compare(pos, goal, obs, 'sca', steps=6)
+    print(tot)
+    assert tot['agents'] >= 59000
+    for k in ('nbr', 'tag', 'nsuit', 'vel', 'status'):
+        assert tot[k] == 0, tot
+
+
+@pytest.mark.parametrize('policy', ['rvo3d', 'srvo3d'])
+def test_dense_sphere_config4_at_100000_agents(policy):
+    """BASELINE configs[3]: run_orca.py:36-54 Fibonacci sphere swap at 100 000 agents (R = 198 m, ~64 agents within
+    neighborDist of each: every 16-slot list saturates).  The whole world against the oracle, 3 steps."""
+    from sca_b200 import scenarios
+    pos, goal, obs = scenarios.dense_sphere(100000)
+    tot = _compare(pos, goal, obs, policy, steps=3, full_search=False)
+    print(policy, tot)
+    assert tot['agents'] == 300000
     for k in ('nbr', 'tag', 'nsuit', 'vel', 'status'):
         assert tot[k] == 0, (policy, tot)

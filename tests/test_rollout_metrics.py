@@ -128,9 +128,7 @@ def test_gpu_rollout_matches_reference(name):
     assert abs(m['AverageSpeed'] - ref[3]) <= 0.005
 
 
-@pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason='added after the round-1 GPU budget was spent: not yet run on hardware '
-                                        '(an XPASS in the log promotes it to a plain test in round 2)')
+@pytest.mark.gpu          # (XPASSed on the driver's B200 at the end of round 1, GPUTEST_r01.json: a plain test since round 2)
 @pytest.mark.parametrize('name', _rollout_names())
 def test_gpu_sca_rollout_to_completion_matches_reference(name):
     """BatchedEnv('sca') with the device-side Dubins tracker, free-running to completion, against the reference rollouts run

@@ -91,3 +91,18 @@ def test_neighbour_exchange_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True, True), (1, True, True)], res
+
+
+def test_a_slab_narrower_than_the_halo_is_refused():
+    """ghosts come from rank +- 1 only, so an interior slab must be at least as wide as the halo."""
+    import pytest
+    from sca_b200 import capi
+    from sca_b200.sharding import ShardedSwarm, SlabPlan
+    rng = np.random.default_rng(0)
+    pos = np.zeros((4000, 6)); pos[:, :3] = rng.uniform(0, 60, (4000, 3))
+    with pytest.raises(capi.ScabError, match='narrower than the halo width'):
+        ShardedSwarm(pos, pos, 1, 8, 'cpu', np.zeros(3), np.full(3, 60.0))        # 7.5 m slabs, 11.6 m halo
+    # faster agents and a larger neighbor_dist widen the halo
+    a = SlabPlan(pos[:, 0], 2, neighbor_dist=10.0, max_speed=1.0, dt=0.1, migrate_every=8)
+    b = SlabPlan(pos[:, 0], 2, neighbor_dist=15.0, max_speed=4.0, dt=0.1, migrate_every=8)
+    assert abs(a.width - 11.6) < 1e-5 and abs(b.width - (15.0 + 2 * 8 * 0.4)) < 1e-5

@@ -32,3 +32,18 @@ def test_sharded_swarm_on_emulated_devices_reproduces_the_single_device_run(poli
     print(r.stdout[-1500:], r.stderr[-1500:])
     assert r.returncode == 0
     assert '-> OK' in r.stdout and 'migration-events 0 ' not in r.stdout
+
+
+@pytest.mark.parametrize('policy,shards,n,steps,extra', [('sca', 3, 1500, 9, {}), ('orca_lp', 2, 1200, 9, {})], ids=['sca-3', 'orca_lp-2'])
+def test_logical_shards_on_the_emulated_device(monkeypatch, policy, shards, n, steps, extra):
+    """The one-process variant (sca_b200.sharding.LogicalShards, copies instead of send/recv) that the -m gpu suite runs on a
+    single real GPU (tests/test_gpu_logical_shards.py), here on the host emulation build."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import hostsim_util
+    hostsim_util.activate(monkeypatch)
+    hostsim_util.activate_streams(monkeypatch)
+    import logical_shards_check as lc
+    info = lc.run(policy, shards, n, steps, 'cpu', mig_cap=256, **extra)
+    print(info)
+    assert all(v == 0 for v in info['mismatches'].values()) and not info['counter_mismatches'], info
+    assert info['migrations'] > 0
