@@ -26,6 +26,7 @@ struct scab_handle {
     int64_t cell_cap = 0;
     double *d_dir256 = nullptr, *d_dir128 = nullptr;
     float4 *d_dir256f = nullptr, *d_dir128f = nullptr;
+    uint32_t *d_plut256 = nullptr, *d_plut128 = nullptr;
     unsigned long long *d_counters = nullptr;
     // obstacles
     int32_t m = 0;
@@ -121,6 +122,53 @@ static void make_dirs(int N, std::vector<double> &d64, std::vector<float4> &d32)
         d64[3 * (n - 1)] = x; d64[3 * (n - 1) + 1] = y; d64[3 * (n - 1) + 2] = z;
         d32[n - 1] = make_float4((float)x, (float)y, (float)z, 0.f);
     }
+}
+
+// Posture lookup table of k_select_fast (scab_select_fast.cuh posture_bin is the forward map).  For every bin of the
+// LUT_B x LUT_B octahedral map: c = direction of the bin centre, rho = largest angle between c and any direction of the bin
+// (sampled on a 9 x 9 lattice over the bin grown by 5 %, + 2 mrad for the lattice and for fp32 rounding in posture_bin).
+// Direction u passes util.py:6-20's angle test for EVERY vA of the bin if angle(u, c) <= pi/4 - rho - 1 mrad ("sure"), for
+// none if angle(u, c) >= pi/4 + rho + 1 mrad, and is tested by the kernel otherwise ("maybe").
+static void make_posture_lut(int N, const std::vector<double> &d64, std::vector<uint32_t> &lut)
+{
+    const int B = SCAB_POSTURE_LUT_B;
+    lut.assign((size_t)B * B * 16, 0u);
+    auto decode = [](double u, double v, double out[3]) {
+        double z = 1.0 - std::fabs(u) - std::fabs(v), x = u, y = v;
+        if (z < 0.0) {
+            x = (1.0 - std::fabs(v)) * (u >= 0.0 ? 1.0 : -1.0);
+            y = (1.0 - std::fabs(u)) * (v >= 0.0 ? 1.0 : -1.0);
+        }
+        const double l = std::sqrt(x * x + y * y + z * z);
+        out[0] = x / l; out[1] = y / l; out[2] = z / l;
+    };
+    const double quarter = 0.78539816339744831;
+    for (int iy = 0; iy < B; iy++)
+        for (int ix = 0; ix < B; ix++) {
+            const double u0 = -1.0 + 2.0 * ix / B, v0 = -1.0 + 2.0 * iy / B, w = 2.0 / B;
+            double c[3];
+            decode(u0 + 0.5 * w, v0 + 0.5 * w, c);
+            double rho = 0.0;
+            for (int a = 0; a <= 8; a++)
+                for (int b = 0; b <= 8; b++) {
+                    const double uu = std::min(1.0, std::max(-1.0, u0 + w * (-0.05 + 1.1 * a / 8.0)));
+                    const double vv = std::min(1.0, std::max(-1.0, v0 + w * (-0.05 + 1.1 * b / 8.0)));
+                    double q[3];
+                    decode(uu, vv, q);
+                    const double dt = std::min(1.0, std::max(-1.0, q[0] * c[0] + q[1] * c[1] + q[2] * c[2]));
+                    rho = std::max(rho, std::acos(dt));
+                }
+            rho += 2e-3;
+            const double cos_sure = std::cos(std::max(0.0, quarter - rho - 1e-3)), cos_never = std::cos(quarter + rho + 1e-3);
+            const bool no_sure = quarter - rho - 1e-3 <= 0.0;
+            uint32_t *row = &lut[((size_t)iy * B + ix) * 16];
+            for (int n = 0; n < N; n++) {
+                const double dt = d64[3 * n] * c[0] + d64[3 * n + 1] * c[1] + d64[3 * n + 2] * c[2];
+                const int lane = n & 7, bit = n >> 3;
+                if (!no_sure && dt >= cos_sure) row[lane] |= 1u << bit;
+                else if (dt > cos_never) row[8 + lane] |= 1u << bit;
+            }
+        }
 }
 
 static void set_geom(GridGeom &g, const double origin[3], double cs, const int32_t dim[3])
@@ -227,16 +275,24 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     // candidate tables
     std::vector<double> d64; std::vector<float4> d32;
     bool ok = true;
+    std::vector<uint32_t> lut;
     make_dirs(256, d64, d32);
-    ok &= cudaMalloc(&h->d_dir256, d64.size() * 8) == cudaSuccess && cudaMalloc(&h->d_dir256f, d32.size() * 16) == cudaSuccess;
-    if (ok) { cudaMemcpy(h->d_dir256, d64.data(), d64.size() * 8, cudaMemcpyHostToDevice); cudaMemcpy(h->d_dir256f, d32.data(), d32.size() * 16, cudaMemcpyHostToDevice); }
+    make_posture_lut(256, d64, lut);
+    ok &= cudaMalloc(&h->d_dir256, d64.size() * 8) == cudaSuccess && cudaMalloc(&h->d_dir256f, d32.size() * 16) == cudaSuccess &&
+          cudaMalloc(&h->d_plut256, lut.size() * 4) == cudaSuccess;
+    if (ok) { cudaMemcpy(h->d_dir256, d64.data(), d64.size() * 8, cudaMemcpyHostToDevice); cudaMemcpy(h->d_dir256f, d32.data(), d32.size() * 16, cudaMemcpyHostToDevice);
+              cudaMemcpy(h->d_plut256, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice); }
     make_dirs(128, d64, d32);
-    ok &= cudaMalloc(&h->d_dir128, d64.size() * 8) == cudaSuccess && cudaMalloc(&h->d_dir128f, d32.size() * 16) == cudaSuccess;
-    if (ok) { cudaMemcpy(h->d_dir128, d64.data(), d64.size() * 8, cudaMemcpyHostToDevice); cudaMemcpy(h->d_dir128f, d32.data(), d32.size() * 16, cudaMemcpyHostToDevice); }
+    make_posture_lut(128, d64, lut);
+    ok &= cudaMalloc(&h->d_dir128, d64.size() * 8) == cudaSuccess && cudaMalloc(&h->d_dir128f, d32.size() * 16) == cudaSuccess &&
+          cudaMalloc(&h->d_plut128, lut.size() * 4) == cudaSuccess;
+    if (ok) { cudaMemcpy(h->d_dir128, d64.data(), d64.size() * 8, cudaMemcpyHostToDevice); cudaMemcpy(h->d_dir128f, d32.data(), d32.size() * 16, cudaMemcpyHostToDevice);
+              cudaMemcpy(h->d_plut128, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice); }
     ok &= cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) { scab_destroy(h); return SCAB_ERR_NOMEM; }
     cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned long long));
     A.dir256 = h->d_dir256; A.dir128 = h->d_dir128; A.dir256f = h->d_dir256f; A.dir128f = h->d_dir128f;
+    A.plut256 = h->d_plut256; A.plut128 = h->d_plut128;
     A.counters = h->d_counters;
     set_geom(A.g, p->grid_origin, p->cell_size, p->grid_dim);
     int32_t one[3] = {1, 1, 1};
@@ -252,7 +308,7 @@ extern "C" int scab_destroy(scab_handle *h)
 {
     if (!h) return SCAB_ERR_INVALID;
     cudaSetDevice(h->device);
-    void *ptrs[] = {h->d_block, h->d_cell_count, h->d_cell_start, h->d_dir256, h->d_dir128, h->d_dir256f, h->d_dir128f,
+    void *ptrs[] = {h->d_block, h->d_cell_count, h->d_cell_start, h->d_dir256, h->d_dir128, h->d_dir256f, h->d_dir128f, h->d_plut256, h->d_plut128,
                     h->d_counters, h->d_o_posr, h->d_o_posr_by_id, h->d_o_id, h->d_o_cell_start, h->d_kd_obst_perm, h->d_kd_obst,
                     h->d_dub_states, h->d_dub_d0};
     for (void *q : ptrs) if (q) cudaFree(q);

@@ -12,6 +12,7 @@
 #include "../../include/scab200.h"
 
 #define KNBR SCAB_MAX_NEIGHBORS
+#define SCAB_POSTURE_LUT_B 64
 #define SCAB_PI 3.141592653589793
 #define RVO_EPS 1e-5  // mamp/configs/config.py:4
 
@@ -84,6 +85,10 @@ struct StepArgs {
     // candidate direction tables (host libm, uploaded once): unit Fibonacci-sphere directions
     const double *dir256, *dir128;   // [N,3] f64
     const float4 *dir256f, *dir128f; // [N] f32 (x y z 0)
+    // posture lookup tables (scab_api.cu make_posture_lut): per bin of an octahedral map of vA's direction, 8 words of
+    // directions that pass angle(vA, u) <= pi/4 for EVERY vA of the bin and 8 words of directions that may; lane l's word
+    // holds direction 8 i + l in bit i
+    const uint32_t *plut256, *plut128;   // [SCAB_POSTURE_LUT_B^2][16]
     unsigned long long *counters;    // scab_counters
     // Dubins v_pref provider (scab_dubins.cu); both NULL while it is disabled
     void *dub_states;                // [capacity] DubState, indexed by row

@@ -9,20 +9,24 @@
 // surviving directions than DIR_CAP, keys beyond 22 bits -- is appended to a work list and handled by the
 // general kernel k_select afterwards, so both kernels together cover every agent exactly once.
 //
-// Per group:  constraints (2 per lane) -> A: posture test per DIRECTION (both shells share cos(angle))
+// Per group:  constraints (2 per lane)
+//             -> A: posture test per DIRECTION (both shells share cos(angle)) from a lookup table over the direction of vA:
+//                   per bin of an octahedral map, the directions that pass for EVERY vA of the bin ("sure") and the ones
+//                   that may ("maybe"; only these ~10 of 256 are tested)
+//             -> tier 1: the candidates within tier_delta of the one closest to v_pref (squared fp32 distances)
 //             -> B: cone tests per direction, the two shells share the dot products p.u and h.u
 //             -> C: keys (fp64, decimal-rounded, packed key<<10|c) + REDUX selection / shunting.
+// If tier 1 does not pin the reference's answer (1 % of the agents) the agent goes to the work list as well: the general
+// kernel examines every candidate.
 #pragma once
 
 #define FG_LANES 8
 #define FG_PER_WARP 4
 #define FG_WARPS 4        // warps per CTA
 #define DIR_CAP 64        // surviving directions per agent (a pi/4 cap holds ~38 of 256)
+#define LUT_B SCAB_POSTURE_LUT_B
 #define LIVE_CAP 136      // 2 * DIR_CAP + v_pref, rounded up
 #define VPREF_ENTRY 0x3ff
-#ifndef FG_A_UNROLL
-#define FG_A_UNROLL 2   // posture loop; 4 is 230 instructions larger and measured 0.7 % slower (instruction-fetch bound)
-#endif
 #ifndef FG_MIN_CTAS
 #define FG_MIN_CTAS 4   // resident CTAs per SM the kernel is compiled for; 5 (<= 96 registers) spills and measured 2.6 % slower
 #endif
@@ -43,11 +47,10 @@ struct GroupSmemT : public std::conditional<WITH64, Exact64, NoExact64>::type {
     float4 ch[KNBR];
     float2 cg[KNBR];
     int cidx[KNBR];
-    unsigned short dirs[DIR_CAP];    // n | shell mask << 12 ; VPREF_ENTRY = v_pref itself
+    unsigned short act[DIR_CAP];     // tier-1 entries: n | shell mask << 12 ; n == VPREF_ENTRY = v_pref itself
     unsigned int kc[LIVE_CAP];       // live candidates: c, later key << 10 | c
     unsigned int dvu[LIVE_CAP];      // l3norm(v, vA) in units of 1e-5
-    unsigned char act[DIR_CAP];      // entries of the current tier: j | shell mask << 6
-    int pad[4];                      // sizeof % 128 == 80: the four groups of a warp start in different banks
+    int pad[4];                      // the four groups of a warp start in different banks
 };
 
 // the guard-band recheck of one cone (scaPolicy.py:47-60,180 + util.py:30-41) rebuilt from the neighbour record
@@ -82,6 +85,22 @@ __device__ __forceinline__ void push_slow(const StepArgs &A, int s)
 {
     const int w = atomicAdd(A.slow_count, 1);
     A.slow_list[w] = s;
+}
+
+// Bin of the posture lookup table for a (non-zero) vector: octahedral map of its direction, LUT_B x LUT_B bins.  The host
+// builds the table with the inverse map (scab_api.cu make_posture_lut) and a margin that covers fp32 rounding here.
+__device__ __forceinline__ int posture_bin(float x, float y, float z)
+{
+    const float inv = 1.f / (fabsf(x) + fabsf(y) + fabsf(z));
+    float ox = x * inv, oy = y * inv;
+    if (z < 0.f) {
+        const float tx = (1.f - fabsf(oy)) * (ox >= 0.f ? 1.f : -1.f);
+        oy = (1.f - fabsf(ox)) * (oy >= 0.f ? 1.f : -1.f);
+        ox = tx;
+    }
+    const int ix = min(max((int)((ox + 1.f) * (0.5f * LUT_B)), 0), LUT_B - 1);
+    const int iy = min(max((int)((oy + 1.f) * (0.5f * LUT_B)), 0), LUT_B - 1);
+    return iy * LUT_B + ix;
 }
 
 template <int POLICY>
@@ -147,6 +166,13 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
         const float fnvA = (float)a.nvA;
         const float ball_r = 0.70711f * vmaxf;
         const float bmx = ball_r * a.vx / fnvA, bmy = ball_r * a.vy / fnvA, bmz = ball_r * a.vz / fnvA;
+        // the posture table row of this agent: requested before the constraint gathers, consumed after them
+        const float4 *tab = zaxis ? s_dir128 : s_dir256;
+        unsigned sure = 0u, maybe = zaxis ? 0xffffu : 0xffffffffu;      // degenerate vA: test every direction
+        if (fnvA > 1e-30f) {
+            const unsigned *row = (zaxis ? A.plut128 : A.plut256) + (size_t)posture_bin(a.vx, a.vy, a.vz) * 16;
+            sure = row[l8]; maybe = row[8 + l8];
+        }
 
         // ------------------------------------------------------------ constraints: lane l8 builds k = l8, l8 + 8
         int nce = 0;
@@ -252,37 +278,20 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
         }
 
         // ------------------------------------------------------------ A: posture per direction
-        // Lane l8 owns directions n = 8 i + l8 and collects pass bits (bit i) for both shells; slots in the
-        // compacted list come from one 8-lane exclusive prefix of the pop-counts (no per-iteration ballots).
-        int ndir = 0;
+        // Lane l8 owns directions n = 8 i + l8 (bit i).  `sure` directions pass for every vA of the table bin; `maybe`
+        // directions get the fp32 test, and the reference's fp64 expression inside its 2e-6 guard band.
+        unsigned m0, m1;
         {
             const float thr = 0.70710678f * fnvA;
             const float band = 2e-6f * fnvA;
-            const double vmax = fmax(fmax(0.5, fabs(a.shell1)), fabs(a.vdz));
-            const bool near_ground = !(a.pz > A.time_step * vmax + 1e-9);
-            const float4 *tab = zaxis ? s_dir128 : s_dir256;
-            unsigned m0 = 0, m1 = 0;
-            constexpr int kAUnroll = FG_A_UNROLL;
-            const int iters = a.N / FG_LANES;
-            // The directions are a Fibonacci sphere, u_n.z = (2n - 1)/N - 1 increasing in n (scaPolicy.py:196-199), and
-            // a direction within pi/4 of vA has a polar angle within pi/4 of vA's: only that z band can pass.
-            int i_lo = 0, i_hi = iters;
-            {
-                // cos(theta -+ pi/4) = (hz +- sqrt(1 - hz^2)) / sqrt2, clamped at the poles
-                const float hz = fminf(fmaxf(a.vz / fnvA, -1.f), 1.f), sh = sqrtf(fmaxf(1.f - hz * hz, 0.f));
-                const float zhi = (hz >= 0.70710678f ? 1.f : 0.70710678f * (hz + sh)) + 0.02f;
-                const float zlo = (hz <= -0.70710678f ? -1.f : 0.70710678f * (hz - sh)) - 0.02f;
-                const float half = 0.5f * (float)a.N;
-                i_lo = max((int)floorf((zlo + 1.f) * half) / FG_LANES - 1, 0);
-                i_hi = min((int)ceilf((zhi + 1.f) * half) / FG_LANES + 2, iters);
-                if (!(fnvA > 0.f)) { i_lo = 0; i_hi = iters; }
-            }
-#pragma unroll kAUnroll
-            for (int i = i_lo; i < i_hi; i++) {
+            m0 = sure; m1 = sure;
+#pragma unroll 1
+            for (unsigned b = maybe; b; b &= b - 1) {
+                const int i = __ffs(b) - 1;
                 const float4 u = tab[FG_LANES * i + l8];
                 const float dt = fmaf(a.vz, u.z, fmaf(a.vy, u.y, a.vx * u.x));
                 bool p0 = dt >= thr, p1 = p0;
-                if (fabsf(dt - thr) <= band || near_ground) {
+                if (fabsf(dt - thr) <= band) {
                     double x, y, z;
                     cand64(a, FG_LANES * i + l8, x, y, z);
                     p0 = posture_ok(a, A.time_step, x, y, z);
@@ -292,200 +301,182 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
                 m0 |= (p0 ? 1u : 0u) << i;
                 m1 |= (p1 ? 1u : 0u) << i;
             }
-            unsigned bits = m0 | m1;
-            const int cnt = __popc(bits);
+            // altitude: pA.z + dt v.z >= 0 (util.py:19) can only fail within dt * max|v| of the ground
+            const double vmax = fmax(fmax(0.5, fabs(a.shell1)), fabs(a.vdz));
+            if (!(a.pz > A.time_step * vmax + 1e-9)) {
+#pragma unroll 1
+                for (unsigned b = m0 | m1; b; b &= b - 1) {
+                    const int i = __ffs(b) - 1;
+                    const double uz = a.dir[3 * (FG_LANES * i + l8) + 2];
+                    if (!(__dadd_rn(a.pz, __dmul_rn(A.time_step, __dmul_rn(0.5, uz))) >= 0.0)) m0 &= ~(1u << i);
+                    if (!(__dadd_rn(a.pz, __dmul_rn(A.time_step, __dmul_rn(a.shell1, uz))) >= 0.0)) m1 &= ~(1u << i);
+                }
+            }
+        }
+        const bool pv = posture_ok(a, A.time_step, a.vdx, a.vdy, a.vdz);    // v_pref itself, the last candidate (scaPolicy.py:206)
+        const int ndir = __reduce_add_sync(gmask, __popc(m0 | m1)) + (pv ? 1 : 0);
+        if (ndir >= DIR_CAP) {           // not the common case: leave it to the general kernel
+            if (l8 == 0) push_slow(A, s);
+            continue;
+        }
+
+        // ------------------------------------------------------------ tier 1
+        // The answer only depends on the head of the key-sorted suitable list and (with shunting) on the short prefix
+        // before the first element that breaks it, so only the candidates within tier_delta of the one closest to v_pref
+        // (APPROXIMATE fp32 distances) are examined.  If they pin the result -- head (and prefix-breaking element) found
+        // with exact keys below the tier boundary minus a margin covering the fp32 key error -- the other ~90 % never
+        // matter; otherwise the agent goes to the general kernel.  full_search (scab_set_option) examines everything
+        // and yields the exact n_suit of the reference.
+        const float vdx = (float)a.vdx, vdy = (float)a.vdy, vdz = (float)a.vdz;
+        const float vdvd = fmaf(vdz, vdz, fmaf(vdy, vdy, vdx * vdx));
+        float T1 = 3.0e38f;
+        if (!A.full_search) {
+            float kmin = pv ? 0.f : 3.0e38f;         // v_pref is at distance 0 from itself
+#pragma unroll 1
+            for (unsigned b = m0 | m1; b; b &= b - 1) {
+                const int i = __ffs(b) - 1;
+                const float4 u = tab[FG_LANES * i + l8];
+                const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x)), uv = fmaf(u.z, vdz, fmaf(u.y, vdy, u.x * vdx));
+                if ((m0 >> i) & 1u) kmin = fminf(kmin, fmaxf(fmaf(-1.f, uv, 0.25f * uu) + vdvd, 0.f));               // squared distances:
+                if ((m1 >> i) & 1u) kmin = fminf(kmin, fmaxf(fmaf(-2.f * r1f, uv, r1f * r1f * uu) + vdvd, 0.f));    // one sqrt after the min
+            }
+            kmin = sqrtf(__uint_as_float(__reduce_min_sync(gmask, __float_as_uint(kmin))));   // non-negative floats order as uints
+            T1 = kmin + A.tier_delta;
+        }
+        const float T1sq = T1 * T1;      // (+inf under full_search)
+        // exact keys strictly below this are certainly smaller than any key outside tier 1 (fp32 key error <= 1e-3)
+        const unsigned tier_units = A.full_search ? 0xffffffffu : (unsigned)fmaxf((T1 - 1.1e-3f) * 1.0e5f, 0.f);
+        int nact = 0;
+        {
+            unsigned a0 = 0, a1 = 0;             // per lane: direction 8 i + l8 -> bit i of the shell-0 / shell-1 masks
+#pragma unroll 1
+            for (unsigned b = m0 | m1; b; b &= b - 1) {
+                const int i = __ffs(b) - 1;
+                const float4 u = tab[FG_LANES * i + l8];
+                const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x)), uv = fmaf(u.z, vdz, fmaf(u.y, vdy, u.x * vdx));
+                const float k0 = fmaxf(fmaf(-1.f, uv, 0.25f * uu) + vdvd, 0.f);      // |v - v_pref|^2, fp32
+                const float k1 = fmaxf(fmaf(-2.f * r1f, uv, r1f * r1f * uu) + vdvd, 0.f);
+                if (k0 <= T1sq) a0 |= m0 & (1u << i);
+                if (k1 <= T1sq) a1 |= m1 & (1u << i);
+            }
+            unsigned ab = a0 | a1;
+            const int cnt = __popc(ab);
             int pre = cnt;
 #pragma unroll
             for (int o = 1; o < FG_LANES; o <<= 1) {
                 const int t = __shfl_up_sync(gmask, pre, o, FG_LANES);
                 if (l8 >= o) pre += t;
             }
-            ndir = __shfl_sync(gmask, pre, FG_LANES - 1, FG_LANES);
+            nact = __shfl_sync(gmask, pre, FG_LANES - 1, FG_LANES);
             int slot = pre - cnt;
-            if (ndir < DIR_CAP) {
-                while (bits) {
-                    const int i = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const int n = FG_LANES * i + l8;
-                    W.dirs[slot++] = (unsigned short)(n | (((m0 >> i) & 1u) | (((m1 >> i) & 1u) << 1)) << 12);
+            while (ab) {
+                const int i = __ffs(ab) - 1;
+                ab &= ab - 1;
+                W.act[slot++] = (unsigned short)((FG_LANES * i + l8) | ((((a0 >> i) & 1u) | (((a1 >> i) & 1u) << 1)) << 12));
+            }
+            if (pv) {
+                if (l8 == 0) W.act[nact] = (unsigned short)(VPREF_ENTRY | (1u << 12));
+                nact++;
+            }
+        }
+        __syncwarp(gmask);
+
+        // ---- B: cone tests per direction (the two shells share p.u and h.u)
+        int nlive = 0, best = -1;
+        unsigned kfail = 0xffffffffu;
+        bool overflow = false;
+        for (int jb = 0; jb < nact; jb += FG_LANES) {
+            const int ja = jb + l8;
+            bool s0 = false, s1 = false;
+            int n = 0;
+            if (ja < nact) {
+                const unsigned ae = W.act[ja];
+                n = ae & 0x3ff;
+                s0 = (ae >> 12) & 1; s1 = (ae >> 13) & 1;
+                const bool isv = (n == VPREF_ENTRY);
+                const float4 u = isv ? make_float4(vdx, vdy, vdz, 0.f) : tab[n];
+                const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x));
+                const float ra = isv ? 1.f : 0.5f, rb = r1f;
+                for (int kk = 0; kk < nce && (s0 || s1); kk++) {
+                    const float4 P = W.cp[kk];
+                    const float2 G = W.cg[kk];
+                    const float pa = fmaf(P.z, u.z, fmaf(P.y, u.y, P.x * u.x));
+                    float df0, df1, dt0, dt1;
+                    if (!IS_ORCA) {
+                        const float4 H = W.ch[kk];
+                        const float hb = fmaf(H.z, u.z, fmaf(H.y, u.y, H.x * u.x));
+                        dt0 = fmaf(ra, pa, -P.w); dt1 = fmaf(rb, pa, -P.w);
+                        const float vv0 = fmaf(-2.f * ra, hb, ra * ra * uu) + H.w, vv1 = fmaf(-2.f * rb, hb, rb * rb * uu) + H.w;
+                        df0 = fmaf(dt0, dt0, -vv0 * G.x); df1 = fmaf(dt1, dt1, -vv1 * G.x);
+                    } else {
+                        dt0 = 1.f; dt1 = 1.f;
+                        df0 = -(fmaf(ra, pa, -P.w)); df1 = -(fmaf(rb, pa, -P.w));   // violated iff n.v - n.q < 0
+                    }
+                    bool in0, in1;
+                    if (!IS_ORCA) { in0 = (dt0 > 0.f) && (df0 > 0.f); in1 = (dt1 > 0.f) && (df1 > 0.f); }
+                    else { in0 = !(-df0 >= 0.f); in1 = !(-df1 >= 0.f); }
+                    const bool un0 = s0 && fabsf(df0) <= G.y, un1 = s1 && fabsf(df1) <= G.y;
+                    if (un0 || un1) {
+                        const int k = W.cidx[kk];
+                        for (int sh = 0; sh < 2; sh++) {
+                            if (!(sh ? un1 : un0)) continue;
+                            n_recheck++;
+                            const int c = isv ? 2 * a.N : (sh ? a.N + n : n);
+                            double x, y, z;
+                            cand64(a, c, x, y, z);
+                            bool ins;
+                            if constexpr (!IS_ORCA) {
+                                ins = recheck_cone64(A, s, k, a, x, y, z);
+                            } else {
+                                double val = dot3(__dsub_rn(x, W.dpx[k]), __dsub_rn(y, W.dpy[k]), __dsub_rn(z, W.dpz[k]),
+                                                  W.dhx[k], W.dhy[k], W.dhz[k]);
+                                ins = !(val >= 0.0);
+                            }
+                            if (sh) in1 = ins; else in0 = ins;
+                        }
+                    }
+                    if (in0) s0 = false;
+                    if (in1) s1 = false;
                 }
-                if (posture_ok(a, A.time_step, a.vdx, a.vdy, a.vdz)) {   // v_pref itself, last (scaPolicy.py:206)
-                    if (l8 == 0) W.dirs[ndir] = (unsigned short)(VPREF_ENTRY | (1 << 12));
-                    ndir++;
+            }
+            // compact the surviving candidates of this round (generation index c) into the live list
+            const bool isv = (n == VPREF_ENTRY);
+            unsigned b0 = (__ballot_sync(gmask, s0) >> (8 * g)) & 0xffu;
+            if (s0) W.kc[nlive + __popc(b0 & lt8)] = isv ? 2 * a.N : n;
+            nlive += __popc(b0);
+            unsigned b1 = (__ballot_sync(gmask, s1) >> (8 * g)) & 0xffu;
+            if (s1) W.kc[nlive + __popc(b1 & lt8)] = a.N + n;
+            nlive += __popc(b1);
+        }
+        __syncwarp(gmask);
+
+        // ---- C: exact keys of the live candidates
+        for (int jb = 0; jb < nlive; jb += FG_LANES) {
+            const int j = jb + l8;
+            if (j < nlive) {
+                const int c = (int)W.kc[j];
+                double x, y, z;
+                cand64(a, c, x, y, z);
+                const double dist = __dsqrt_rn(sumsq3(__dsub_rn(x, a.vdx), __dsub_rn(y, a.vdy), __dsub_rn(z, a.vdz)));
+                const double ku = py_round5_units(dist);          // l3norm(v, v_pref) in units of 1e-5
+                if (!(ku < 4194304.0)) overflow = true;
+                W.kc[j] = ((unsigned)ku << 10) | (unsigned)c;
+                if (SHUNT) {
+                    const double dva = __dsqrt_rn(sumsq3(__dsub_rn(x, (double)a.vx), __dsub_rn(y, (double)a.vy), __dsub_rn(z, (double)a.vz)));
+                    W.dvu[j] = (unsigned int)py_round5_units(dva);
                 }
             }
         }
-        if (ndir >= DIR_CAP) {           // not the common case: leave it to the general kernel
-            if (l8 == 0) push_slow(A, s);
+        // keys beyond 22 bits, or nothing suitable in tier 1 (possibly "no suitable velocity" at all, scaPolicy.py:224-238)
+        if (__any_sync(gmask, overflow) || nlive == 0) {
+            if (l8 == 0) { push_slow(A, s); if (nlive == 0) n_tier2++; }
             continue;
         }
         __syncwarp(gmask);
 
-        // ------------------------------------------------------------ lazy tiers
-        // The answer only depends on the head of the key-sorted suitable list and (with shunting) on the
-        // short prefix before the first element that breaks it, so candidates are examined in two tiers of
-        // increasing APPROXIMATE distance to v_pref: tier 1 = within TIER_DELTA of the closest candidate.  If
-        // tier 1 already pins the result -- head (and prefix-breaking element) found with exact keys below the
-        // tier boundary minus a margin covering the fp32 key error -- tier 2 (the other ~90 %) is never tested.
-        // full_search (scab_set_option) disables the shortcut and yields the exact n_suit of the reference.
-        const float vdx = (float)a.vdx, vdy = (float)a.vdy, vdz = (float)a.vdz;
-        const float vdvd = fmaf(vdz, vdz, fmaf(vdy, vdy, vdx * vdx));
-        const float4 *tabB = zaxis ? s_dir128 : s_dir256;
-        float T1 = 3.0e38f;
-        if (!A.full_search) {
-            float kmin = 3.0e38f;
-#pragma unroll 1      // code size: the kernel is instruction-fetch bound (its hot path is larger than the 32 KB L1.5 I-cache)
-            for (int jb = 0; jb < ndir; jb += FG_LANES) {
-                const int j = jb + l8;
-                if (j < ndir) {
-                    const unsigned ent = W.dirs[j];
-                    const int n = ent & 0x3ff;
-                    const bool isv = (n == VPREF_ENTRY);
-                    const float4 u = isv ? make_float4(vdx, vdy, vdz, 0.f) : tabB[n];
-                    const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x)), uv = fmaf(u.z, vdz, fmaf(u.y, vdy, u.x * vdx));
-                    const float ra = isv ? 1.f : 0.5f;
-                    if (ent & (1u << 12)) kmin = fminf(kmin, fmaxf(fmaf(-2.f * ra, uv, ra * ra * uu) + vdvd, 0.f));     // squared distances:
-                    if (ent & (2u << 12)) kmin = fminf(kmin, fmaxf(fmaf(-2.f * r1f, uv, r1f * r1f * uu) + vdvd, 0.f));  // one sqrt after the min
-                }
-            }
-            kmin = sqrtf(__uint_as_float(__reduce_min_sync(gmask, __float_as_uint(kmin))));   // non-negative floats order as uints
-            T1 = kmin + A.tier_delta;
-        }
-        const float T1sq = T1 * T1;      // (+inf under full_search)
-        // exact keys strictly below this are certainly smaller than any key of tier 2 (fp32 key error <= 1e-3)
-        const unsigned tier_units = A.full_search ? 0xffffffffu : (unsigned)fmaxf((T1 - 1.1e-3f) * 1.0e5f, 0.f);
-
-        int nlive = 0, best = -1;
-        unsigned kfail = 0xffffffffu;
-        bool overflow = false, decided = false;
-        for (int pass = 0; pass < 2 && !decided; pass++) {
-            // ---- entries (and shells) of this tier, compacted: act[] = j | shell mask << 6
-            int nact = 0;
-            {
-                unsigned abits = 0, am = 0;          // per lane: entry l8 + 8 i -> bit i ; 2-bit masks packed in `am`
-#pragma unroll 1
-                for (int i = 0; FG_LANES * i + l8 < ndir; i++) {
-                    const int j = FG_LANES * i + l8;
-                    const unsigned ent = W.dirs[j];
-                    const int n = ent & 0x3ff;
-                    const bool isv = (n == VPREF_ENTRY);
-                    const float4 u = isv ? make_float4(vdx, vdy, vdz, 0.f) : tabB[n];
-                    const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x)), uv = fmaf(u.z, vdz, fmaf(u.y, vdy, u.x * vdx));
-                    const float ra = isv ? 1.f : 0.5f;
-                    const float k0 = fmaxf(fmaf(-2.f * ra, uv, ra * ra * uu) + vdvd, 0.f);      // |v - v_pref|^2, fp32
-                    const float k1 = fmaxf(fmaf(-2.f * r1f, uv, r1f * r1f * uu) + vdvd, 0.f);
-                    const unsigned t1 = (k0 <= T1sq ? 1u : 0u) | (k1 <= T1sq ? 2u : 0u);
-                    const unsigned m = ((ent >> 12) & 3u) & (pass == 0 ? t1 : ~t1);
-                    if (m) { abits |= 1u << i; am |= m << (2 * i); }
-                }
-                const int cnt = __popc(abits);
-                int pre = cnt;
-#pragma unroll
-                for (int o = 1; o < FG_LANES; o <<= 1) {
-                    const int t = __shfl_up_sync(gmask, pre, o, FG_LANES);
-                    if (l8 >= o) pre += t;
-                }
-                nact = __shfl_sync(gmask, pre, FG_LANES - 1, FG_LANES);
-                int slot = pre - cnt;
-                while (abits) {
-                    const int i = __ffs(abits) - 1;
-                    abits &= abits - 1;
-                    W.act[slot++] = (unsigned char)((FG_LANES * i + l8) | (((am >> (2 * i)) & 3u) << 6));
-                }
-            }
-            __syncwarp(gmask);
-            const int nlive_before = nlive;
-            if (pass == 1 && l8 == 0) n_tier2++;
-
-            // ---- B: cone tests per direction (the two shells share p.u and h.u)
-            for (int jb = 0; jb < nact; jb += FG_LANES) {
-                const int ja = jb + l8;
-                bool s0 = false, s1 = false;
-                int n = 0;
-                if (ja < nact) {
-                    const unsigned ae = W.act[ja];
-                    const unsigned ent = W.dirs[ae & 63u];
-                    n = ent & 0x3ff;
-                    s0 = (ae >> 6) & 1; s1 = (ae >> 7) & 1;
-                    const bool isv = (n == VPREF_ENTRY);
-                    const float4 u = isv ? make_float4(vdx, vdy, vdz, 0.f) : tabB[n];
-                    const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x));
-                    const float ra = isv ? 1.f : 0.5f, rb = r1f;
-                    for (int kk = 0; kk < nce && (s0 || s1); kk++) {
-                        const float4 P = W.cp[kk];
-                        const float2 G = W.cg[kk];
-                        const float pa = fmaf(P.z, u.z, fmaf(P.y, u.y, P.x * u.x));
-                        float df0, df1, dt0, dt1;
-                        if (!IS_ORCA) {
-                            const float4 H = W.ch[kk];
-                            const float hb = fmaf(H.z, u.z, fmaf(H.y, u.y, H.x * u.x));
-                            dt0 = fmaf(ra, pa, -P.w); dt1 = fmaf(rb, pa, -P.w);
-                            const float vv0 = fmaf(-2.f * ra, hb, ra * ra * uu) + H.w, vv1 = fmaf(-2.f * rb, hb, rb * rb * uu) + H.w;
-                            df0 = fmaf(dt0, dt0, -vv0 * G.x); df1 = fmaf(dt1, dt1, -vv1 * G.x);
-                        } else {
-                            dt0 = 1.f; dt1 = 1.f;
-                            df0 = -(fmaf(ra, pa, -P.w)); df1 = -(fmaf(rb, pa, -P.w));   // violated iff n.v - n.q < 0
-                        }
-                        bool in0, in1;
-                        if (!IS_ORCA) { in0 = (dt0 > 0.f) && (df0 > 0.f); in1 = (dt1 > 0.f) && (df1 > 0.f); }
-                        else { in0 = !(-df0 >= 0.f); in1 = !(-df1 >= 0.f); }
-                        const bool un0 = s0 && fabsf(df0) <= G.y, un1 = s1 && fabsf(df1) <= G.y;
-                        if (un0 || un1) {
-                            const int k = W.cidx[kk];
-                            for (int sh = 0; sh < 2; sh++) {
-                                if (!(sh ? un1 : un0)) continue;
-                                n_recheck++;
-                                const int c = isv ? 2 * a.N : (sh ? a.N + n : n);
-                                double x, y, z;
-                                cand64(a, c, x, y, z);
-                                bool ins;
-                                if constexpr (!IS_ORCA) {
-                                    ins = recheck_cone64(A, s, k, a, x, y, z);
-                                } else {
-                                    double val = dot3(__dsub_rn(x, W.dpx[k]), __dsub_rn(y, W.dpy[k]), __dsub_rn(z, W.dpz[k]),
-                                                      W.dhx[k], W.dhy[k], W.dhz[k]);
-                                    ins = !(val >= 0.0);
-                                }
-                                if (sh) in1 = ins; else in0 = ins;
-                            }
-                        }
-                        if (in0) s0 = false;
-                        if (in1) s1 = false;
-                    }
-                }
-                // compact the surviving candidates of this round (generation index c) into the live list
-                const bool isv = (n == VPREF_ENTRY);
-                unsigned m0 = (__ballot_sync(gmask, s0) >> (8 * g)) & 0xffu;
-                if (s0) W.kc[nlive + __popc(m0 & lt8)] = isv ? 2 * a.N : n;
-                nlive += __popc(m0);
-                unsigned m1 = (__ballot_sync(gmask, s1) >> (8 * g)) & 0xffu;
-                if (s1) W.kc[nlive + __popc(m1 & lt8)] = a.N + n;
-                nlive += __popc(m1);
-            }
-            __syncwarp(gmask);
-
-            // ---- C: exact keys of the new live candidates
-            for (int jb = nlive_before; jb < nlive; jb += FG_LANES) {
-                const int j = jb + l8;
-                if (j < nlive) {
-                    const int c = (int)W.kc[j];
-                    double x, y, z;
-                    cand64(a, c, x, y, z);
-                    const double dist = __dsqrt_rn(sumsq3(__dsub_rn(x, a.vdx), __dsub_rn(y, a.vdy), __dsub_rn(z, a.vdz)));
-                    const double ku = py_round5_units(dist);          // l3norm(v, v_pref) in units of 1e-5
-                    if (!(ku < 4194304.0)) overflow = true;
-                    W.kc[j] = ((unsigned)ku << 10) | (unsigned)c;
-                    if (SHUNT) {
-                        const double dva = __dsqrt_rn(sumsq3(__dsub_rn(x, (double)a.vx), __dsub_rn(y, (double)a.vy), __dsub_rn(z, (double)a.vz)));
-                        W.dvu[j] = (unsigned int)py_round5_units(dva);
-                    }
-                }
-            }
-            if (__any_sync(gmask, overflow)) break;
-            __syncwarp(gmask);
-            if (nlive == 0) continue;          // nothing suitable in this tier: look at the next one
-
-            // ---- head of the sorted list, and (shunting) the first element that breaks the prefix
+        // ---- head of the sorted list, and (shunting) the first element that breaks the prefix
+        bool decided;
+        {
             unsigned local_min = 0xffffffffu;
 #pragma unroll 1
             for (int j = l8; j < nlive; j += FG_LANES) local_min = min(local_min, W.kc[j]);
@@ -509,13 +500,13 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
                     if (!within) fmin_ = min(fmin_, W.kc[j]);
                 }
                 kfail = __reduce_min_sync(gmask, fmin_);
-                decided = (pass == 1) || (kfail != 0xffffffffu && (kfail >> 10) < tier_units);
+                decided = A.full_search || (kfail != 0xffffffffu && (kfail >> 10) < tier_units);
             } else {
-                decided = (pass == 1) || ((head >> 10) < tier_units);
+                decided = A.full_search || ((head >> 10) < tier_units);
             }
         }
-        if (overflow || nlive == 0) {     // keys beyond 22 bits, or "no suitable velocity" (scaPolicy.py:224-238): general kernel
-            if (l8 == 0) push_slow(A, s);
+        if (!decided) {                   // tier 1 does not pin the answer: every candidate, in the general kernel
+            if (l8 == 0) { push_slow(A, s); n_tier2++; }
             continue;
         }
         int nprefix = 0;

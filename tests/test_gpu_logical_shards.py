@@ -17,7 +17,7 @@ def test_logical_shards_reproduce_the_single_device_run(request, monkeypatch, po
     if request.config.getoption('--hostsim'):
         import hostsim_util
         hostsim_util.activate_streams(monkeypatch)
-        device, n, steps = 'cpu', max(800, n // 16), min(steps, 10)
+        device, n, steps = 'cpu', max(700 * shards, n // 16), min(steps, 10)      # (every slab wider than the halo)
         extra = dict(extra, mig_cap=min(extra.get('mig_cap', 4096), 256))
     import logical_shards_check as lc
     info = lc.run(policy, shards, n, steps, device, **extra)
