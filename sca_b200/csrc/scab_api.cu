@@ -253,7 +253,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_posr = carve(cap * sizeof(double4)), o_gid = carve(cap * 4),
                  o_vdes = carve(cap * sizeof(double4)), o_vpost = carve(cap * sizeof(double4)),
-                 o_vel = carve(cap * sizeof(float4)), o_id = carve(cap * 4), o_rank = carve(cap * 4),
+                 o_vel = carve(cap * sizeof(float4)), o_posf = carve(cap * sizeof(float4)), o_id = carve(cap * 4), o_rank = carve(cap * 4),
                  o_cid = carve(cap * 4), o_cloc = carve(cap * 4), o_nbr = carve(cap * 4 * KNBR),
                  o_ncnt = carve(cap * 4), o_qc = carve(cap * 4), o_kdp = carve(cap * 4),
                  o_slo = carve(cap * 4), o_shi = carve(cap * 4), o_hcnt = carve(64),
@@ -263,6 +263,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     if (e != cudaSuccess) { delete h; return SCAB_ERR_NOMEM; }
     char *b = (char *)h->d_block;
     A.s_posr = (double4 *)(b + o_posr); A.s_gid = (int32_t *)(b + o_gid); A.s_vel = (float4 *)(b + o_vel);
+    A.s_posf = (float4 *)(b + o_posf);
     A.s_vdes = (double4 *)(b + o_vdes); A.s_vpost = (double4 *)(b + o_vpost);
     A.s_id = (int32_t *)(b + o_id); A.rank = (int32_t *)(b + o_rank);
     A.cell_id = (int32_t *)(b + o_cid); A.cell_local = (int32_t *)(b + o_cloc);

@@ -58,6 +58,7 @@ struct StepArgs {
     // snapshot, sorted by cell
     double4 *s_posr;    // x y z r
     float4 *s_vel;      // vx vy vz, w = status bits
+    float4 *s_posf;     // fp32 copy of the position relative to the grid origin (x y z, w unused): the 16-NN tile scan's pre-filter
     int32_t *s_id;      // sorted idx -> row (local agent index)
     int32_t *s_gid;     // sorted idx -> global agent id (== row unless sharded)
     int obst_base;      // obstacle k is reported as obst_base + k in nbr_ids (n, or n_global when sharded)

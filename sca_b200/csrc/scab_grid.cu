@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(256) k_reorder(StepArgs A)
     v.x = A.st.vel[3 * i]; v.y = A.st.vel[3 * i + 1]; v.z = A.st.vel[3 * i + 2];
     v.w = __int_as_float(A.st.status[i]);
     A.s_posr[dst] = p;
+    A.s_posf[dst] = make_float4((float)(p.x - A.g.ox), (float)(p.y - A.g.oy), (float)(p.z - A.g.oz), 0.f);
     A.s_vel[dst] = v;
     A.s_id[dst] = i;
     A.s_gid[dst] = A.st.gid ? A.st.gid[i] : i;

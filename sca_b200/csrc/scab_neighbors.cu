@@ -71,70 +71,57 @@ __device__ __forceinline__ void write_lists(const StepArgs &A, int s, int id, in
     }
 }
 
-// Same list without the tie-break id in registers: ties on the decimal-rounded distance are rare, so the
-// id (obstacle id, or m + global agent id) is looked up only when two distances compare equal.
+// The sorted list of the general path.  It lives in local memory and is updated by a plain insertion loop: this path runs
+// for every agent only when obstacles share the 16 slots (the reference's own scenarios, N <= 10^4) and otherwise for the
+// rare agents with tied distance keys, so compact code matters more than speed (the register-resident, fully unrolled
+// version made every neighbour kernel 200 KB of SASS).  The tie-break id (obstacle id, or m + global agent id) is looked up
+// only when two distances compare equal.
 struct TopK2 {
     double d[KNBR];
     int s[KNBR];  // payload: sorted index (agents) or n + sorted obstacle index
     int cnt;
-    __device__ __forceinline__ void clear()
-    {
-#pragma unroll
-        for (int k = 0; k < KNBR; k++) { d[k] = DBL_MAX; s[k] = -1; }
-        cnt = 0;
-    }
+    __device__ __forceinline__ void clear() { cnt = 0; }
     static __device__ __forceinline__ int uid(const StepArgs &A, int sx)
     {
-        return sx < 0 ? INT_MAX : (sx >= A.n ? A.o_id[sx - A.n] : A.m + A.s_gid[sx]);
+        return sx >= A.n ? A.o_id[sx - A.n] : A.m + A.s_gid[sx];
     }
     static __device__ __forceinline__ bool less(const StepArgs &A, double d1, int s1, double d2, int s2)
     {
         if (d1 != d2) return d1 < d2;
         return uid(A, s1) < uid(A, s2);
     }
-    __device__ __forceinline__ void insert(const StepArgs &A, double nd, int ns)
+    __device__ __noinline__ void insert(const StepArgs &A, double nd, int ns)
     {
-        if (!less(A, nd, ns, d[KNBR - 1], s[KNBR - 1])) return;
-#pragma unroll
-        for (int k = KNBR - 1; k >= 1; k--) {
-            const bool lt_prev = less(A, nd, ns, d[k - 1], s[k - 1]);
-            const bool lt_here = less(A, nd, ns, d[k], s[k]);
-            if (lt_prev) { d[k] = d[k - 1]; s[k] = s[k - 1]; }
-            else if (lt_here) { d[k] = nd; s[k] = ns; }
-        }
-        if (less(A, nd, ns, d[0], s[0])) { d[0] = nd; s[0] = ns; }
+        if (cnt == KNBR && !less(A, nd, ns, d[KNBR - 1], s[KNBR - 1])) return;
+        int k = min(cnt, KNBR - 1);            // a full list drops its last entry
+#pragma unroll 1
+        while (k > 0 && less(A, nd, ns, d[k - 1], s[k - 1])) { d[k] = d[k - 1]; s[k] = s[k - 1]; k--; }
+        d[k] = nd; s[k] = ns;
         cnt = min(cnt + 1, KNBR);
     }
 };
 
-__device__ __forceinline__ void write_lists2(const StepArgs &A, int s, int id, const TopK2 &L, int qcoll)
+__device__ __noinline__ void write_lists2(const StepArgs &A, int s, int id, const TopK2 &L, int qcoll)
 {
     A.s_nbr_cnt[s] = L.cnt;
     A.s_qcoll[s] = qcoll;
     if (A.dub_d0) A.dub_d0[id] = L.cnt > 0 ? L.d[0] : -1.0;
-    int4 *dst = reinterpret_cast<int4 *>(A.s_nbr + (size_t)s * KNBR);
-#pragma unroll
-    for (int q = 0; q < KNBR / 4; q++) dst[q] = make_int4(L.s[4 * q], L.s[4 * q + 1], L.s[4 * q + 2], L.s[4 * q + 3]);
+#pragma unroll 1
+    for (int k = 0; k < KNBR; k++) {
+        const bool live = k < L.cnt;
+        const int sx = live ? L.s[k] : -1;
+        A.s_nbr[(size_t)s * KNBR + k] = sx;
+        if (A.st.nbr_ids) A.st.nbr_ids[(size_t)id * KNBR + k] = !live ? -1 : (sx >= A.n ? A.obst_base + A.o_id[sx - A.n] : A.s_gid[sx]);
+        if (A.st.nbr_dsq) A.st.nbr_dsq[(size_t)id * KNBR + k] = live ? L.d[k] : 0.0;
+    }
     if (A.st.nbr_cnt) A.st.nbr_cnt[id] = L.cnt;
-    if (A.st.nbr_ids) {
-#pragma unroll
-        for (int k = 0; k < KNBR; k++) {
-            int v = -1;
-            if (k < L.cnt) v = (L.s[k] >= A.n) ? A.obst_base + A.o_id[L.s[k] - A.n] : A.s_gid[L.s[k]];
-            A.st.nbr_ids[(size_t)id * KNBR + k] = v;
-        }
-    }
-    if (A.st.nbr_dsq) {
-#pragma unroll
-        for (int k = 0; k < KNBR; k++) A.st.nbr_dsq[(size_t)id * KNBR + k] = (k < L.cnt) ? L.d[k] : 0.0;
-    }
 }
 
 // ------------------------------------------------------------------ KNN over the cell list
 #define KNN_CAP 48
 // The exact general path (obstacles, ties on the decimal-rounded distance, more than KNN_CAP raw candidates):
-// fp64 keys + the (distSq, obstacles-before-agents, id) comparator, register-resident top-16 insertion.
-__device__ __noinline__ void knn_exact(const StepArgs &A, int s, int id, const double4 me, int (*buf)[128])
+// fp64 keys + the (distSq, obstacles-before-agents, id) comparator.
+__device__ __noinline__ void knn_exact(const StepArgs &A, int s, int id, const double4 me)
 {
     TopK2 L;
     L.clear();
@@ -145,40 +132,45 @@ __device__ __noinline__ void knn_exact(const StepArgs &A, int s, int id, const d
     if (A.m > 0) {
         int cx, cy, cz;
         cell_of(A.og, me.x, me.y, me.z, cx, cy, cz);
-        for (int dz = -1; dz <= 1; dz++) {
-            int z = cz + dz;
-            if (z < 0 || z >= A.og.nz) continue;
-            for (int dy = -1; dy <= 1; dy++) {
-                int y = cy + dy;
-                if (y < 0 || y >= A.og.ny) continue;
-                int row = (z * A.og.ny + y) * A.og.nx;
-                int beg = A.o_cell_start[row + max(cx - 1, 0)];
-                int end = A.o_cell_start[row + min(cx + 1, A.og.nx - 1) + 1];
-                for (int j = beg; j < end; j++) {
-                    const double4 o = A.o_posr[j];
-                    // agent.py:104-107
-                    double ss = sumsq3(__dsub_rn(me.x, o.x), __dsub_rn(me.y, o.y), __dsub_rn(me.z, o.z));
-                    double dsq1 = np_round5(ss);
-                    double t = __dsub_rn(py_round5(__dsqrt_rn(ss)), o.w);
-                    double dsq = __dmul_rn(t, t);
-                    double rr = __dadd_rn(me.w, o.w);
-                    bool is_c = dsq1 < __dmul_rn(rr, rr) && dsq < rangeSq;
-                    if (is_c && !coll) { coll = true; L.clear(); }
-                    if (coll ? is_c : (dsq < rangeSq)) L.insert(A, dsq, A.n + j);
-                }
+#pragma unroll 1
+        for (int r = 0; r < 9; r++) {
+            const int z = cz + r / 3 - 1, y = cy + r % 3 - 1;
+            if (z < 0 || z >= A.og.nz || y < 0 || y >= A.og.ny) continue;
+            const int row = (z * A.og.ny + y) * A.og.nx;
+            const int beg = A.o_cell_start[row + max(cx - 1, 0)];
+            const int end = A.o_cell_start[row + min(cx + 1, A.og.nx - 1) + 1];
+#pragma unroll 1
+            for (int j = beg; j < end; j++) {
+                const double4 o = A.o_posr[j];
+                // agent.py:104-107
+                double ss = sumsq3(__dsub_rn(me.x, o.x), __dsub_rn(me.y, o.y), __dsub_rn(me.z, o.z));
+                double dsq1 = np_round5(ss);
+                double t = __dsub_rn(py_round5(__dsqrt_rn(ss)), o.w);
+                double dsq = __dmul_rn(t, t);
+                double rr = __dadd_rn(me.w, o.w);
+                bool is_c = dsq1 < __dmul_rn(rr, rr) && dsq < rangeSq;
+                if (is_c && !coll) { coll = true; L.clear(); }
+                if (coll ? is_c : (dsq < rangeSq)) L.insert(A, dsq, A.n + j);
             }
         }
     }
-    // agents (scaPolicy.py:116).  Two phases keep the warp converged: (1) scan the 27 cells and only
-    // RECORD the candidates whose raw squared distance can be in range (a shared-memory column per
-    // thread); (2) walk the recorded candidates -- all lanes together -- with the exact decimal rounding
-    // and the register-resident top-16 insertion.  A full column is flushed through phase 2 and reused.
+    // agents (scaPolicy.py:116): the 27 cells, a cheap raw-distance reject, then the exact decimal rounding
     {
-        int nbuf = 0;
-        auto flush = [&]() {
-            for (int i = 0; i < nbuf; i++) {
-                const int j = buf[i][threadIdx.x];
+        int cx, cy, cz;
+        cell_of(A.g, me.x, me.y, me.z, cx, cy, cz);
+        const double lim = rangeSq + 1e-4;   // the 5-decimal rounding cannot bring anything beyond this back in range
+#pragma unroll 1
+        for (int r = 0; r < 9; r++) {
+            const int z = cz + r / 3 - 1, y = cy + r % 3 - 1;
+            if (z < 0 || z >= A.g.nz || y < 0 || y >= A.g.ny) continue;
+            const int row = (z * A.g.ny + y) * A.g.nx;
+            const int beg = A.cell_start[row + max(cx - 1, 0)];
+            const int end = A.cell_start[row + min(cx + 1, A.g.nx - 1) + 1];
+#pragma unroll 1
+            for (int j = beg; j < end; j++) {
                 const double4 o = A.s_posr[j];
+                const double ex = me.x - o.x, ey = me.y - o.y, ez = me.z - o.z;
+                if (ex * ex + ey * ey + ez * ez > lim || j == s) continue;
                 const double dsq = l3normsq_d(me.x, me.y, me.z, o.x, o.y, o.z);   // agent.py:81
                 if (!(dsq < rangeSq)) continue;
                 const double rr = __dadd_rn(me.w, o.w);
@@ -187,51 +179,197 @@ __device__ __noinline__ void knn_exact(const StepArgs &A, int s, int id, const d
                 if (coll && !is_c) continue;
                 L.insert(A, dsq, j);
             }
-            nbuf = 0;
-        };
-        int cx, cy, cz;
-        cell_of(A.g, me.x, me.y, me.z, cx, cy, cz);
-        const double lim = rangeSq + 1e-4;   // the 5-decimal rounding cannot bring anything beyond this back in range
-        for (int dz = -1; dz <= 1; dz++) {
-            int z = cz + dz;
-            if (z < 0 || z >= A.g.nz) continue;
-            for (int dy = -1; dy <= 1; dy++) {
-                int y = cy + dy;
-                if (y < 0 || y >= A.g.ny) continue;
-                int row = (z * A.g.ny + y) * A.g.nx;
-                int beg = A.cell_start[row + max(cx - 1, 0)];
-                int end = A.cell_start[row + min(cx + 1, A.g.nx - 1) + 1];
-                for (int j0 = beg; j0 < end; j0 += 4) {
-                    double4 o[4];          // four independent loads in flight per thread
-#pragma unroll
-                    for (int q = 0; q < 4; q++) o[q] = A.s_posr[min(j0 + q, end - 1)];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int j = j0 + q;
-                        const double ex = me.x - o[q].x, ey = me.y - o[q].y, ez = me.z - o[q].z;
-                        const double ss = ex * ex + ey * ey + ez * ez;
-                        if (j >= end || ss > lim || j == s) continue;
-                        if (nbuf == KNN_CAP) flush();
-                        buf[nbuf++][threadIdx.x] = j;
-                    }
-                }
-            }
         }
-        flush();
     }
     write_lists2(A, s, id, L, coll ? 1 : 0);
 }
 
 
-// Fast path of the common case (no obstacles, distinct distance keys): the decimal-rounded squared distance is an
-// exact integer number of 1e-5 units (< 2^24 for neighbor_dist < 12.9 m), so (units << 8 | candidate slot) is a
-// 32-bit sort key and inserting into the sorted top-16 is a branch-free min/max network on 16 registers:
-//     new[k] = min(old[k], max(old[k-1], x)).
-// A tie on the distance (the reference breaks it by agent id) is detected afterwards -- two equal neighbours in
-// the list, or the best rejected key equal to the last kept one -- and sends the agent to knn_exact.
-__global__ void __launch_bounds__(128, 6) k_neighbors_knn(const __grid_constant__ StepArgs A, int fast_ok)
+// ------------------------------------------------------------------ the scale path: tile-staged scan
+// Common case (no obstacles in the merged list, distinct distance keys).  One CTA per WORK ITEM = NT_W consecutive cells of
+// one x-row of the grid; its agents are a contiguous range of the cell-sorted snapshot, and everything they can see lies
+// in nine contiguous ranges (the 3 x 3 neighbouring x-rows, cells cx0-1 .. cx0+NT_W).  Those ranges are staged ONCE into
+// shared memory as fp32 float4 records (coalesced 128-bit loads of s_posf, the copy k_reorder writes) and every agent of
+// the item -- one thread each -- scans its own (trimmed) 27 cells out of the tile:
+//   phase 1  fp32 squared distance against rangeSq + a guard band that covers the fp32 error; survivors (their sorted index)
+//            go to a shared-memory column per thread, so that
+//   phase 2  all lanes walk their candidates together: the reference's fp64 distance with its decimal rounding
+//            (util.py:99-100) -- an exact integer number of 1e-5 units (< 2^24 for neighbor_dist < 12.9 m), so
+//            (units << 8 | candidate slot) is a 32-bit sort key and inserting into the sorted top-16 is a branch-free
+//            min/max network on 16 registers:  new[k] = min(old[k], max(old[k-1], x)).
+// A tie on the distance (the reference breaks it by agent id) is detected afterwards -- two equal neighbours in the list,
+// or the best rejected key equal to the last kept one -- and sends the agent to knn_exact, as does a full column.
+// A tile that does not fit (very dense cells) is scanned from global memory through the same code (generic pointer).
+#define NT_W 16
+#define NT_THREADS 128
+#define NT_TILE 1408   // static shared memory: tile + candidate columns + bounds < 48 KB
+
+__global__ void __launch_bounds__(NT_THREADS, 4) k_neighbors_tile(const __grid_constant__ StepArgs A, int segs)
 {
-    __shared__ int buf[KNN_CAP][128];
+    __shared__ float4 tile[NT_TILE];
+    __shared__ int buf[KNN_CAP][NT_THREADS];
+    __shared__ int cs[9][NT_W + 3];
+    __shared__ int rbase[9];
+    __shared__ int use_tile;
+    const int tid = threadIdx.x;
+    const int row = blockIdx.x / segs, cx0 = (blockIdx.x - row * segs) * NT_W;
+    const int nx = A.g.nx, ny = A.g.ny;
+    const int y0 = row % ny, z0 = row / ny;
+    const int a_beg = A.cell_start[row * nx + cx0], a_end = A.cell_start[row * nx + min(cx0 + NT_W, nx)];
+    if (a_beg == a_end) return;
+    {   // nothing to do for an item whose agents are all finished / ghosts (parked rows of a sharded run)
+        int act = 0;
+        for (int s = a_beg + tid; s < a_end; s += NT_THREADS) {
+            const bool inact = (__float_as_int(A.s_vel[s].w) & FL_INACTIVE) != 0;
+            if (inact) {
+                const int id = A.s_id[s];
+                A.s_nbr_cnt[s] = -1;
+                A.s_qcoll[s] = 0;
+                if (A.st.nbr_cnt) A.st.nbr_cnt[id] = -1;
+            } else act = 1;
+        }
+        if (!__syncthreads_or(act)) return;
+    }
+    // cell bounds of the nine x-rows: entry k <-> cell cx0 - 1 + k (clamped); rows outside the grid are empty
+    for (int t = tid; t < 9 * (NT_W + 3); t += NT_THREADS) {
+        const int r = t / (NT_W + 3), k = t - r * (NT_W + 3);
+        const int z = z0 + r / 3 - 1, y = y0 + r % 3 - 1;
+        int v = 0;
+        if (z >= 0 && z < A.g.nz && y >= 0 && y < ny) v = A.cell_start[(z * ny + y) * nx + min(max(cx0 - 1 + k, 0), nx)];
+        cs[r][k] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int r = 0; r < 9; r++) { rbase[r] = tot; tot += cs[r][NT_W + 2] - cs[r][0]; }
+        use_tile = tot <= NT_TILE;
+    }
+    __syncthreads();
+    const bool staged = use_tile != 0;
+    if (staged) {
+#pragma unroll 1
+        for (int r = 0; r < 9; r++) {
+            const int src = cs[r][0], len = cs[r][NT_W + 2] - src, dst = rbase[r];
+            for (int i = tid; i < len; i += NT_THREADS) tile[dst + i] = A.s_posf[src + i];
+        }
+    }
+    __syncthreads();
+
+    const double rangeSq = A.nbr_dist_sq;
+    const double cs_len = 1.0 / A.g.inv_cs;
+#pragma unroll 1
+    for (int s = a_beg + tid; s < a_end; s += NT_THREADS) {
+        const int flags = __float_as_int(A.s_vel[s].w);
+        if (flags & FL_INACTIVE) continue;
+        const int id = A.s_id[s];
+        const double4 me = A.s_posr[s];
+        // ---- phase 1: fp32 pre-filter over the (trimmed) 27 cells
+        int nbuf = 0;
+        bool overflow = false;
+        {
+            int cx, cy, cz;
+            cell_of(A.g, me.x, me.y, me.z, cx, cy, cz);
+            const double lim = rangeSq + 1e-4;   // the 5-decimal rounding cannot bring anything beyond this back in range
+            // Trim the 27-cell block to the cells the query ball actually reaches: (fx, fy, fz) is the offset inside
+            // the own cell, so the gap to a neighbouring slab is f or cs - f.  (Agents clamped into a border cell from
+            // outside the grid scan the full block; cell contents are never closer than their cell.)
+            const double fx = (me.x - A.g.ox) - cx * cs_len, fy = (me.y - A.g.oy) - cy * cs_len, fz = (me.z - A.g.oz) - cz * cs_len;
+            const bool trim = fx >= 0.0 && fx <= cs_len && fy >= 0.0 && fy <= cs_len && fz >= 0.0 && fz <= cs_len;
+            const double limt = lim + 1e-6;
+            const float mx = (float)(me.x - A.g.ox), my = (float)(me.y - A.g.oy), mz = (float)(me.z - A.g.oz);
+            // fp32 error of the squared distance of two points within ~10 m of each other at coordinates of magnitude S:
+            // <= 2 d (e_x + e_y + e_z) with e ~ 2^-23 (|c| + 10), i.e. < 2.5e-6 S + 2e-4
+            const float limf = (float)lim + 1e-3f + 4e-6f * (fabsf(mx) + fabsf(my) + fabsf(mz));
+#pragma unroll 1
+            for (int r = 0; r < 9; r++) {
+                const int dz = r / 3 - 1, dy = r % 3 - 1;
+                const double gz = dz == 0 ? 0.0 : (dz < 0 ? fz : cs_len - fz);
+                const double gy = dy == 0 ? 0.0 : (dy < 0 ? fy : cs_len - fy);
+                const double rem = limt - gz * gz - gy * gy;
+                if (trim && rem < 0.0) continue;
+                const int x0 = (trim && fx * fx > rem) ? cx : cx - 1, x1 = (trim && (cs_len - fx) * (cs_len - fx) > rem) ? cx : cx + 1;
+                const int beg = cs[r][max(x0, 0) - (cx0 - 1)], end = cs[r][min(x1, nx - 1) + 1 - (cx0 - 1)];
+                const float4 *rec = staged ? (tile + rbase[r] - cs[r][0]) : A.s_posf;
+#pragma unroll 2
+                for (int j = beg; j < end; j++) {
+                    const float4 o = rec[j];
+                    const float ex = mx - o.x, ey = my - o.y, ez = mz - o.z;
+                    const float ss = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                    if (ss <= limf && j != s) {
+                        if (nbuf < KNN_CAP) buf[nbuf++][tid] = j;
+                        else overflow = true;
+                    }
+                }
+            }
+        }
+        // ---- phase 2: exact keys, all lanes together
+        unsigned L[KNBR];
+#pragma unroll
+        for (int k = 0; k < KNBR; k++) L[k] = 0xffffffffu;
+        unsigned rej_min = 0xffffffffu;
+        int cnt = 0;
+        bool coll = false;
+#pragma unroll 1
+        for (int i0 = 0; i0 < nbuf; i0 += 4) {
+            double4 o4[4];             // four gathers in flight per thread (L1 / L2 hits)
+#pragma unroll
+            for (int q = 0; q < 4; q++) o4[q] = A.s_posr[buf[min(i0 + q, nbuf - 1)][tid]];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = i0 + q;
+                if (i >= nbuf) continue;
+                const double4 o = o4[q];
+                // l3normsq (util.py:99-100): round(sum, 5) = rint(sum * 1e5) / 1e5
+                const double units = rint(__dmul_rn(sumsq3(__dsub_rn(me.x, o.x), __dsub_rn(me.y, o.y), __dsub_rn(me.z, o.z)), 1e5));
+                const double dsq = __ddiv_rn(units, 1e5);
+                if (!(dsq < rangeSq)) continue;
+                const double rr = __dadd_rn(me.w, o.w);
+                const bool is_c = dsq < __dmul_rn(rr, rr);      // agent.py:83-85: from the first collider on, colliders only
+                if (is_c && !coll) {
+                    coll = true;
+#pragma unroll
+                    for (int k = 0; k < KNBR; k++) L[k] = 0xffffffffu;
+                    rej_min = 0xffffffffu;
+                    cnt = 0;
+                }
+                if (coll && !is_c) continue;
+                const unsigned x = ((unsigned)(int)units << 8) | (unsigned)i;
+                rej_min = min(rej_min, max(L[KNBR - 1], x));
+#pragma unroll
+                for (int k = KNBR - 1; k >= 1; k--) L[k] = min(L[k], max(L[k - 1], x));
+                L[0] = min(L[0], x);
+                cnt++;
+            }
+        }
+        const int n_in = min(cnt, KNBR);
+        bool tie = overflow || (cnt > KNBR && (rej_min >> 8) == (L[KNBR - 1] >> 8));
+#pragma unroll
+        for (int k = 1; k < KNBR; k++) tie |= (k < n_in) && ((L[k] >> 8) == (L[k - 1] >> 8));
+        if (tie) { knn_exact(A, s, id, me); continue; }
+        int sx[KNBR];
+#pragma unroll
+        for (int k = 0; k < KNBR; k++) sx[k] = (k < n_in) ? buf[L[k] & 0xffu][tid] : -1;
+        A.s_nbr_cnt[s] = n_in;
+        A.s_qcoll[s] = coll ? 1 : 0;
+        if (A.dub_d0) A.dub_d0[id] = n_in > 0 ? __ddiv_rn((double)(L[0] >> 8), 1e5) : -1.0;
+        int4 *dst = reinterpret_cast<int4 *>(A.s_nbr + (size_t)s * KNBR);
+#pragma unroll
+        for (int q = 0; q < KNBR / 4; q++) dst[q] = make_int4(sx[4 * q], sx[4 * q + 1], sx[4 * q + 2], sx[4 * q + 3]);
+        if (A.st.nbr_cnt) A.st.nbr_cnt[id] = n_in;
+        if (A.st.nbr_ids) {
+#pragma unroll
+            for (int k = 0; k < KNBR; k++) A.st.nbr_ids[(size_t)id * KNBR + k] = (k < n_in) ? A.s_gid[sx[k]] : -1;
+        }
+        if (A.st.nbr_dsq) {
+#pragma unroll
+            for (int k = 0; k < KNBR; k++) A.st.nbr_dsq[(size_t)id * KNBR + k] = (k < n_in) ? __ddiv_rn((double)(L[k] >> 8), 1e5) : 0.0;
+        }
+    }
+}
+
+// the general path for every agent (obstacles in the merged list, SCAB_KNN_EXACT=1, neighbor_dist >= 12.9 m): thread per agent
+__global__ void __launch_bounds__(128) k_neighbors_exact(const __grid_constant__ StepArgs A)
+{
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n) return;
     const int id = A.s_id[s];
@@ -242,118 +380,7 @@ __global__ void __launch_bounds__(128, 6) k_neighbors_knn(const __grid_constant_
         if (A.st.nbr_cnt) A.st.nbr_cnt[id] = -1;
         return;
     }
-    const double4 me = A.s_posr[s];
-    if (!fast_ok) { knn_exact(A, s, id, me, buf); return; }
-    const double rangeSq = A.nbr_dist_sq;
-    // phase 1: record the candidates whose raw squared distance can be in range (a shared-memory column per thread)
-    int nbuf = 0;
-    bool overflow = false;
-    {
-        int cx, cy, cz;
-        cell_of(A.g, me.x, me.y, me.z, cx, cy, cz);
-        const double lim = rangeSq + 1e-4;   // the 5-decimal rounding cannot bring anything beyond this back in range
-        // Trim the 27-cell block to the cells the query ball actually reaches: (fx, fy, fz) is the offset inside
-        // the own cell, so the gap to a neighbouring slab is f or cs - f.  (Agents clamped into a border cell from
-        // outside the grid scan the full block; cell contents are never closer than their cell.)
-        const double cs = 1.0 / A.g.inv_cs;
-        const double fx = (me.x - A.g.ox) - cx * cs, fy = (me.y - A.g.oy) - cy * cs, fz = (me.z - A.g.oz) - cz * cs;
-        const bool trim = fx >= 0.0 && fx <= cs && fy >= 0.0 && fy <= cs && fz >= 0.0 && fz <= cs;
-        const double limt = lim + 1e-6;
-        // the (up to) nine x-rows of the block: all their cell_start bounds are fetched before any row is scanned
-        int rbeg[9], rend[9];
-#pragma unroll
-        for (int r = 0; r < 9; r++) {
-            const int dz = r / 3 - 1, dy = r % 3 - 1;
-            const int z = cz + dz, y = cy + dy;
-            const double gz = dz == 0 ? 0.0 : (dz < 0 ? fz : cs - fz);
-            const double gy = dy == 0 ? 0.0 : (dy < 0 ? fy : cs - fy);
-            const double rem = limt - gz * gz - gy * gy;
-            const bool skip = z < 0 || z >= A.g.nz || y < 0 || y >= A.g.ny || (trim && rem < 0.0);
-            const int x0 = (trim && fx * fx > rem) ? cx : cx - 1, x1 = (trim && (cs - fx) * (cs - fx) > rem) ? cx : cx + 1;
-            const int row = (z * A.g.ny + y) * A.g.nx;
-            rbeg[r] = skip ? 0 : A.cell_start[row + max(x0, 0)];
-            rend[r] = skip ? 0 : A.cell_start[row + min(x1, A.g.nx - 1) + 1];
-        }
-#pragma unroll
-        for (int r = 0; r < 9; r++) {
-            const int beg = rbeg[r], end = rend[r];
-            for (int j0 = beg; j0 < end; j0 += 4) {
-                double4 o[4];          // four independent loads in flight per thread
-#pragma unroll
-                for (int q = 0; q < 4; q++) o[q] = A.s_posr[min(j0 + q, end - 1)];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int j = j0 + q;
-                    const double ex = me.x - o[q].x, ey = me.y - o[q].y, ez = me.z - o[q].z;
-                    const double ss = ex * ex + ey * ey + ez * ez;
-                    if (j >= end || ss > lim || j == s) continue;
-                    if (nbuf < KNN_CAP) buf[nbuf++][threadIdx.x] = j;
-                    else overflow = true;
-                }
-            }
-        }
-    }
-    // phase 2: exact keys, all lanes together
-    unsigned L[KNBR];
-#pragma unroll
-    for (int k = 0; k < KNBR; k++) L[k] = 0xffffffffu;
-    unsigned rej_min = 0xffffffffu;
-    int cnt = 0;
-    bool coll = false;
-    for (int i0 = 0; i0 < nbuf; i0 += 4) {
-        double4 o4[4];             // four gathers in flight per thread (the records were just read: L1 / L2 hits)
-#pragma unroll
-        for (int q = 0; q < 4; q++) o4[q] = A.s_posr[buf[min(i0 + q, nbuf - 1)][threadIdx.x]];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int i = i0 + q;
-            if (i >= nbuf) continue;
-            const double4 o = o4[q];
-            // l3normsq (util.py:99-100): round(sum, 5) = rint(sum * 1e5) / 1e5
-            const double units = rint(__dmul_rn(sumsq3(__dsub_rn(me.x, o.x), __dsub_rn(me.y, o.y), __dsub_rn(me.z, o.z)), 1e5));
-            const double dsq = __ddiv_rn(units, 1e5);
-            if (!(dsq < rangeSq)) continue;
-            const double rr = __dadd_rn(me.w, o.w);
-            const bool is_c = dsq < __dmul_rn(rr, rr);      // agent.py:83-85: from the first collider on, colliders only
-            if (is_c && !coll) {
-                coll = true;
-#pragma unroll
-                for (int k = 0; k < KNBR; k++) L[k] = 0xffffffffu;
-                rej_min = 0xffffffffu;
-                cnt = 0;
-            }
-            if (coll && !is_c) continue;
-            const unsigned x = ((unsigned)(int)units << 8) | (unsigned)i;
-            rej_min = min(rej_min, max(L[KNBR - 1], x));
-#pragma unroll
-            for (int k = KNBR - 1; k >= 1; k--) L[k] = min(L[k], max(L[k - 1], x));
-            L[0] = min(L[0], x);
-            cnt++;
-        }
-    }
-    const int n_in = min(cnt, KNBR);
-    bool tie = overflow || (cnt > KNBR && (rej_min >> 8) == (L[KNBR - 1] >> 8));
-#pragma unroll
-    for (int k = 1; k < KNBR; k++) tie |= (k < n_in) && ((L[k] >> 8) == (L[k - 1] >> 8));
-    if (tie) { knn_exact(A, s, id, me, buf); return; }
-    int sx[KNBR];
-#pragma unroll
-    for (int k = 0; k < KNBR; k++) sx[k] = (k < n_in) ? buf[L[k] & 0xffu][threadIdx.x] : -1;
-    A.s_nbr_cnt[s] = n_in;
-    A.s_qcoll[s] = coll ? 1 : 0;
-    if (A.dub_d0) A.dub_d0[id] = n_in > 0 ? __ddiv_rn((double)(L[0] >> 8), 1e5) : -1.0;
-    int4 *dst = reinterpret_cast<int4 *>(A.s_nbr + (size_t)s * KNBR);
-#pragma unroll
-    for (int q = 0; q < KNBR / 4; q++) dst[q] = make_int4(sx[4 * q], sx[4 * q + 1], sx[4 * q + 2], sx[4 * q + 3]);
-    if (A.st.nbr_cnt) A.st.nbr_cnt[id] = n_in;
-    if (A.st.nbr_ids) {
-#pragma unroll
-        for (int k = 0; k < KNBR; k++) A.st.nbr_ids[(size_t)id * KNBR + k] = (k < n_in) ? A.s_gid[sx[k]] : -1;
-    }
-    if (A.st.nbr_dsq) {
-#pragma unroll
-        for (int k = 0; k < KNBR; k++) A.st.nbr_dsq[(size_t)id * KNBR + k] = (k < n_in) ? __ddiv_rn((double)(L[k] >> 8), 1e5) : 0.0;
-    }
+    knn_exact(A, s, id, A.s_posr[s]);
 }
 
 // ------------------------------------------------------------------ REF_COMPAT: literal replay
@@ -484,8 +511,11 @@ cudaError_t launch_neighbors(const StepArgs &A, int mode, cudaStream_t s)
     if (mode == SCAB_NBR_REF_COMPAT) k_neighbors_compat<<<nb, 128, 0, s>>>(A);
     else {
         // the integer-key fast path needs: no obstacles in the merged list, and distance keys below 2^24 units of 1e-5
-        const int fast_ok = (A.m == 0 && A.nbr_dist_sq * 1e5 < 16777215.0 && !A.cfg->knn_exact) ? 1 : 0;   // SCAB_KNN_EXACT=1: A/B switch
-        k_neighbors_knn<<<nb, 128, 0, s>>>(A, fast_ok);
+        const bool fast_ok = A.m == 0 && A.nbr_dist_sq * 1e5 < 16777215.0 && !A.cfg->knn_exact;   // SCAB_KNN_EXACT=1: A/B switch
+        if (fast_ok) {
+            const int segs = (A.g.nx + NT_W - 1) / NT_W;
+            k_neighbors_tile<<<A.g.ny * A.g.nz * segs, NT_THREADS, 0, s>>>(A, segs);
+        } else k_neighbors_exact<<<nb, 128, 0, s>>>(A);
     }
     return cudaGetLastError();
 }

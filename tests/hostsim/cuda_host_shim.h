@@ -76,6 +76,7 @@ namespace hostsim {
 // all lanes named in `mask` deposit `v` and get everybody's deposits back (lanes that already left the kernel: 0)
 void warp_exchange(unsigned mask, unsigned long long v, unsigned long long out[32], unsigned *live_mask);
 void block_barrier();
+int block_or(int pred);
 struct Cfg { unsigned grid, block; size_t smem; };
 static inline Cfg cfg(unsigned g, unsigned b, size_t sm = 0, cudaStream_t = 0) { return Cfg{g, b, sm}; }
 void launch_impl(Cfg c, void (*thunk)(void *), void *ctx);
@@ -139,6 +140,7 @@ static inline int __reduce_max_sync(unsigned mask, int v)
     unsigned long long o[32]; unsigned live; hostsim::warp_exchange(mask, hostsim::to_bits(v), o, &live);
     int r = -0x7fffffff - 1; for (int l = 0; l < 32; l++) if ((live >> l) & 1u) r = std::max(r, hostsim::from_bits<int>(o[l])); return r;
 }
+static inline int __syncthreads_or(int pred) { return hostsim::block_or(pred); }
 static inline int __reduce_add_sync(unsigned mask, int v)
 {
     unsigned long long o[32]; unsigned live; hostsim::warp_exchange(mask, hostsim::to_bits(v), o, &live);

@@ -99,6 +99,18 @@ void block_barrier()
     bar_wait(block_bar, cur_bdim, [] { return block_exited.load(); });
 }
 
+int block_or(int pred)
+{
+    static std::atomic<int> acc{0};
+    if (pred) acc.store(1);
+    block_barrier();
+    const int v = acc.load();
+    block_barrier();
+    if (threadIdx.x == 0) acc.store(0);
+    block_barrier();
+    return v;
+}
+
 void warp_exchange(unsigned mask, unsigned long long v, unsigned long long out[32], unsigned *live_mask)
 {
     const unsigned tid = threadIdx.x, lane = tid & 31u;
