@@ -229,87 +229,30 @@ def run_ours(args):
 
     # ---- end to end through host buffers (pinned H2D of the inputs, D2H of the results, every step)
     e2e = None
-    if world == 1:
-        # host-resident state (pinned): every step uploads it, steps on the device, and downloads the new state
-        # straight back into the same pinned buffers plus the float32 action matrix the reference env consumes
-        keys_state = ('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')
-        host = {k: sw.t[k].cpu().pin_memory() for k in keys_state}
-        host_action = torch.empty_like(sw.t['action'], device='cpu').pin_memory()
-        h2d = sum(v.numel() * v.element_size() for v in host.values())
-        d2h = h2d + host_action.numel() * host_action.element_size()
+    if args.quick:
+        pass
+    elif world == 1:
+        # host-resident state (pinned): every step goes through the repo's public API for that case, Swarm.step_from_host --
+        # upload the step's inputs, the four stages, download the new state + the float32 action matrix the reference env
+        # consumes -- and returns when the results are on the host.  The velocity stays on the device (it is action[:3],
+        # mampenv.py:104).  SCAB_BENCH_E2E_OVERLAP=0 selects the serial copy schedule (same bytes, bit-identical results:
+        # tests/test_gpu_step_from_host.py).
+        host = sw.host_buffers()
+        h2d, d2h = sw.H2D_BYTES_PER_AGENT * sw.n, sw.D2H_BYTES_PER_AGENT * sw.n
         steps_e = max(3, min(args.steps, 20))
-
-        def one_plain():
-            sw.upload(host)
-            sw.step(policy, capi.NBR_KNN)
-            for k in keys_state:
-                host[k].copy_(sw.t[k], non_blocking=True)
-            host_action.copy_(sw.t['action'], non_blocking=True)
-            torch.cuda.synchronize()          # the caller needs the results on the host before the next step
-
-        # default (SCAB_BENCH_E2E_OVERLAP=0 selects the serial variant above): same bytes, same result -- checked bit for
-        # bit on the B200 with SCAB_BENCH_E2E_CHECK=1 -- but the inputs the cell list does not read (heading, total_dist,
-        # step_num: 36 of the 76 B) go up on a second stream while the cell list + 16-NN run, and everything k_status
-        # does not write comes back while k_status runs: 6.18 -> 5.48 ms per step at 10^6 agents
-        main_s = torch.cuda.current_stream()
-        copy_s = torch.cuda.Stream()
-        ev_in, ev_pol, ev_up = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-        first_up, late_up = ('pos', 'vel', 'status'), ('heading', 'total_dist', 'step_num')
-        early_down, late_down = ('pos', 'vel', 'heading', 'total_dist'), ('status', 'step_num')
-
-        def one_overlap():
-            nrow = host['pos'].shape[0]
-            for k in first_up:
-                sw.t[k][:nrow].copy_(host[k], non_blocking=True)
-            sw.t['status'].bitwise_or_(sw._zaxis)
-            ev_up.record(main_s)
-            with torch.cuda.stream(copy_s):
-                copy_s.wait_event(ev_up)          # (keeps the copy stream behind the previous step's downloads too)
-                for k in late_up:
-                    sw.t[k][:nrow].copy_(host[k], non_blocking=True)
-                ev_in.record(copy_s)
-            sw.stage_grid()
-            sw.stage_neighbors(capi.NBR_KNN)
-            main_s.wait_event(ev_in)
-            sw.stage_policy(policy)
-            ev_pol.record(main_s)
-            with torch.cuda.stream(copy_s):
-                copy_s.wait_event(ev_pol)
-                for k in early_down:
-                    host[k].copy_(sw.t[k], non_blocking=True)
-                host_action.copy_(sw.t['action'], non_blocking=True)
-            sw.stage_status()
-            for k in late_down:
-                host[k].copy_(sw.t[k], non_blocking=True)
-            torch.cuda.synchronize()
-
         overlap = os.environ.get('SCAB_BENCH_E2E_OVERLAP', '1') == '1'
-        one = one_overlap if overlap else one_plain
-        if os.environ.get('SCAB_BENCH_E2E_CHECK', '0') == '1':     # debug: both variants from the same host state, 3 steps each
-            keep = {k: v.clone() for k, v in host.items()}
-            res = []
-            for fn in (one_plain, one_overlap):
-                for k in keys_state:
-                    host[k].copy_(keep[k])
-                for _ in range(3):
-                    fn()
-                res.append({k: v.clone() for k, v in host.items()})
-                res[-1]['action'] = host_action.clone()
-            same = all(torch.equal(res[0][k], res[1][k]) for k in res[0])
-            sys.stderr.write('E2E_OVERLAP_CHECK %s\n' % ('identical' if same else 'MISMATCH'))
-            for k in keys_state:
-                host[k].copy_(keep[k])
-        one()
+        sw.step_from_host(host, policy, capi.NBR_KNN, overlap=overlap, upload_vel=True)
         a0 = sw.counters()['n_active_total']
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(steps_e):
-            one()
+            sw.step_from_host(host, policy, capi.NBR_KNN, overlap=overlap)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         e2e = {'value': (sw.counters()['n_active_total'] - a0) / dt, 'unit': 'agent-steps/s',
                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'steps': steps_e,
-               'ms_per_step': round(dt / steps_e * 1e3, 3), 'copies': 'overlapped with the cell list / status kernels' if overlap else 'serial'}
+               'ms_per_step': round(dt / steps_e * 1e3, 3), 'api': 'Swarm.step_from_host',
+               'copies': 'overlapped with the cell list / 16-NN / status kernels' if overlap else 'serial'}
 
     elif os.environ.get('SCAB_BENCH_E2E_SHARDED', '1') == '1':
         # sharded: every rank keeps the authoritative copy of its owned rows [0, own_cap) in pinned host memory; a step
@@ -368,7 +311,7 @@ def run_ours(args):
                 sys.stderr.write('rank %d: sharded e2e failed (%r); e2e omitted\n' % (rank, e))
 
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not args.quick:
         cpu = cpu_baseline(args.cpu_agents, 1, policy, budget_s=12.0)
 
     if rank == 0:
@@ -473,6 +416,7 @@ def main():
     ap.add_argument('--policy', default='sca')
     ap.add_argument('--cpu-agents', type=int, default=20000)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='A/B runs: device-timed value + stage times only (no e2e, no CPU baseline)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -118,7 +118,9 @@ __device__ __noinline__ void write_lists2(const StepArgs &A, int s, int id, cons
 }
 
 // ------------------------------------------------------------------ KNN over the cell list
+#ifndef KNN_CAP
 #define KNN_CAP 48
+#endif
 // The exact general path (obstacles, ties on the decimal-rounded distance, more than KNN_CAP raw candidates):
 // fp64 keys + the (distSq, obstacles-before-agents, id) comparator.
 __device__ __noinline__ void knn_exact(const StepArgs &A, int s, int id, const double4 me)
@@ -200,11 +202,16 @@ __device__ __noinline__ void knn_exact(const StepArgs &A, int s, int id, const d
 // A tie on the distance (the reference breaks it by agent id) is detected afterwards -- two equal neighbours in the list,
 // or the best rejected key equal to the last kept one -- and sends the agent to knn_exact, as does a full column.
 // A tile that does not fit (very dense cells) is scanned from global memory through the same code (generic pointer).
+#ifndef NT_W
 #define NT_W 16
 #define NT_THREADS 128
 #define NT_TILE 1408   // static shared memory: tile + candidate columns + bounds < 48 KB
+#endif
 
-__global__ void __launch_bounds__(NT_THREADS, 4) k_neighbors_tile(const __grid_constant__ StepArgs A, int segs)
+#ifndef NT_MIN_CTAS
+#define NT_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(NT_THREADS, NT_MIN_CTAS) k_neighbors_tile(const __grid_constant__ StepArgs A, int segs)
 {
     __shared__ float4 tile[NT_TILE];
     __shared__ int buf[KNN_CAP][NT_THREADS];

@@ -205,6 +205,85 @@ class Swarm:
     def download(self, keys=('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num', 'action')):
         return {k: self.t[k][:self.n].cpu().numpy() for k in keys if k in self.t}
 
+    # ------------------------------------------------------------------ host-resident state: one step end to end
+    HOST_STATE = ('pos', 'vel', 'heading', 'status', 'total_dist', 'step_num')
+
+    def host_buffers(self):
+        """Pinned host copies of the per-step state (+ the float32 action matrix the reference env consumes,
+        mampenv.py:31), initialised from the device.  The dict step_from_host() works on."""
+        n = self.n
+        host = {k: self.t[k][:n].to('cpu', copy=True).pin_memory() for k in self.HOST_STATE}
+        host['action'] = torch.zeros((n, 7), dtype=_F4).pin_memory()
+        return host
+
+    def step_from_host(self, host, policy, nbr_mode=capi.NBR_KNN, overlap=True, upload_vel=False):
+        """One MACAEnv.step for a caller whose state lives in HOST memory (what a mamp/envs drop-in pays per step): upload the
+        step's inputs from the pinned buffers of host_buffers(), run the four stages, download the new state and the action
+        matrix into the same buffers, and return once they are there.  Bytes per agent: 64 up (pos, heading, status,
+        total_dist, step_num), 92 down (the same + action).  The velocity is NOT moved in either direction unless
+        upload_vel=True: update_velocitie sets it to action[:3] (mampenv.py:104) and the device did exactly that in the
+        previous step, so its copy is current; host['vel'] is refreshed from the action rows on the host side lazily
+        by host_velocity().  overlap=True hides the part of the upload the cell list does not read behind the cell list +
+        16-NN (second stream) and the download of everything k_status does not write behind k_status; the result is
+        bit-identical to overlap=False (tests/test_gpu_step_from_host.py)."""
+        pol = capi.POLICIES[policy] if isinstance(policy, str) else int(policy)
+        n = self.n
+        t = self.t
+        first = ('pos', 'status') + (('vel',) if upload_vel else ())
+        late = ('heading', 'total_dist', 'step_num')
+        early_down, late_down = ('pos', 'heading', 'total_dist', 'action'), ('status', 'step_num')
+        main_s = torch.cuda.current_stream()
+        if not overlap:
+            for k in first + late:
+                t[k][:n].copy_(host[k], non_blocking=True)
+            t['status'].bitwise_or_(self._zaxis)
+            if nbr_mode == capi.NBR_REF_COMPAT:
+                self.h.kdtree_build(host['pos'].numpy())
+            self.h.step(pol, nbr_mode, self._stream())
+            for k in early_down + late_down:
+                host[k].copy_(t[k][:n], non_blocking=True)
+            main_s.synchronize()
+            return host
+        cs = self.__dict__.get('_copy_stream')
+        if cs is None:
+            cs = self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._ev = [torch.cuda.Event() for _ in range(3)]
+        ev_up, ev_in, ev_pol = self._ev
+        for k in first:
+            t[k][:n].copy_(host[k], non_blocking=True)
+        t['status'].bitwise_or_(self._zaxis)
+        ev_up.record(main_s)
+        with torch.cuda.stream(cs):
+            cs.wait_event(ev_up)              # (keeps the copy stream behind the previous step's downloads too)
+            for k in late:
+                t[k][:n].copy_(host[k], non_blocking=True)
+            ev_in.record(cs)
+        if nbr_mode == capi.NBR_REF_COMPAT:
+            self.h.kdtree_build(host['pos'].numpy())
+        self.h.build_grid(self._stream())
+        self.h.neighbors(nbr_mode, self._stream())
+        main_s.wait_event(ev_in)
+        self.h.policy_step(pol, self._stream())
+        ev_pol.record(main_s)
+        with torch.cuda.stream(cs):
+            cs.wait_event(ev_pol)
+            for k in early_down:
+                host[k].copy_(t[k][:n], non_blocking=True)
+        self.h.status_step(self._stream())
+        for k in late_down:
+            host[k].copy_(t[k][:n], non_blocking=True)
+        cs.synchronize()
+        main_s.synchronize()                  # the caller needs the results on the host before its next step
+        return host
+
+    @staticmethod
+    def host_velocity(host):
+        """vel_global_frame after the step = action[:3] (mampenv.py:104), as a host view of the downloaded action rows."""
+        return host['action'][:, :3]
+
+    H2D_BYTES_PER_AGENT = 24 + 24 + 4 + 8 + 4
+    D2H_BYTES_PER_AGENT = 24 + 24 + 4 + 8 + 4 + 28
+
     # ------------------------------------------------------------------ the step
     @staticmethod
     def _stream():

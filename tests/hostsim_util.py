@@ -40,6 +40,17 @@ class _NoStream:
         pass
 
 
+class _NoEvent:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a):
+        pass
+
+    def synchronize(self):
+        pass
+
+
 def activate_streams(monkeypatch):
     """On top of activate(): CUDA streams / devices as no-ops, for code that manages its own stream (ShardedSwarm)."""
     import contextlib
@@ -48,3 +59,4 @@ def activate_streams(monkeypatch):
     monkeypatch.setattr(torch.cuda, 'stream', lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a, **k: _NoStream())
     monkeypatch.setattr(torch.cuda, 'set_device', lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, 'Event', _NoEvent)
