@@ -32,7 +32,7 @@ def test_bench_single_device_on_the_emulator():
     assert d['n_gpus'] == 1 and d['value'] > 0 and d['config']['workload'].startswith('BASELINE configs[4]')
     assert d['e2e']['value'] > 0 and d['e2e']['h2d_bytes_per_step'] == 2500 * 64 and d['e2e']['d2h_bytes_per_step'] == 2500 * 92   # (the velocity stays on the device)
     assert set(d['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
-    assert 'E2E_OVERLAP_CHECK identical' in r.stderr           # overlapped copies == serial copies, bit for bit
+    assert d['e2e']['api'] == 'Swarm.step_from_host'      # (overlapped == serial, bit for bit: tests/test_gpu_step_from_host.py)
 
 
 def test_bench_two_devices_on_the_emulator():
