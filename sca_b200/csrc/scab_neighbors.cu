@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(NT_THREADS, NT_MIN_CTAS) k_neighbors_tile(cons
                 const double4 o = o4[q];
                 // l3normsq (util.py:99-100): round(sum, 5) = rint(sum * 1e5) / 1e5
                 const double units = rint(__dmul_rn(sumsq3(__dsub_rn(me.x, o.x), __dsub_rn(me.y, o.y), __dsub_rn(me.z, o.z)), 1e5));
-                const double dsq = __ddiv_rn(units, 1e5);
+                const double dsq = div1e5(units);
                 if (!(dsq < rangeSq)) continue;
                 const double rr = __dadd_rn(me.w, o.w);
                 const bool is_c = dsq < __dmul_rn(rr, rr);      // agent.py:83-85: from the first collider on, colliders only
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(NT_THREADS, NT_MIN_CTAS) k_neighbors_tile(cons
         for (int k = 0; k < KNBR; k++) sx[k] = (k < n_in) ? buf[L[k] & 0xffu][tid] : -1;
         A.s_nbr_cnt[s] = n_in;
         A.s_qcoll[s] = coll ? 1 : 0;
-        if (A.dub_d0) A.dub_d0[id] = n_in > 0 ? __ddiv_rn((double)(L[0] >> 8), 1e5) : -1.0;
+        if (A.dub_d0) A.dub_d0[id] = n_in > 0 ? div1e5((double)(L[0] >> 8)) : -1.0;
         int4 *dst = reinterpret_cast<int4 *>(A.s_nbr + (size_t)s * KNBR);
 #pragma unroll
         for (int q = 0; q < KNBR / 4; q++) dst[q] = make_int4(sx[4 * q], sx[4 * q + 1], sx[4 * q + 2], sx[4 * q + 3]);
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(NT_THREADS, NT_MIN_CTAS) k_neighbors_tile(cons
         }
         if (A.st.nbr_dsq) {
 #pragma unroll
-            for (int k = 0; k < KNBR; k++) A.st.nbr_dsq[(size_t)id * KNBR + k] = (k < n_in) ? __ddiv_rn((double)(L[k] >> 8), 1e5) : 0.0;
+            for (int k = 0; k < KNBR; k++) A.st.nbr_dsq[(size_t)id * KNBR + k] = (k < n_in) ? div1e5((double)(L[k] >> 8)) : 0.0;
         }
     }
 }

@@ -101,6 +101,10 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
 {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 
 // lexicographic warp arg-min over (a, b); lanes without a value pass a = ~0ull
 __device__ __forceinline__ void warp_lexmin(unsigned long long &a, unsigned &b)
@@ -550,7 +554,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
                 bool within;
                 if (du < thr_units - 1) within = true;
                 else if (du > thr_units + 1) within = false;
-                else within = fabs(__dsub_rn(__ddiv_rn((double)d0u, 1e5), __ddiv_rn((double)diu, 1e5))) < thr;
+                else within = fabs(__dsub_rn(div1e5((double)d0u), div1e5((double)diu))) < thr;
                 if (!within) {
                     const int c = slot_cand(j);
                     if (lex_less(W.key[j], (unsigned)c, fa, fb)) { fa = W.key[j]; fb = (unsigned)c; }
@@ -592,7 +596,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
                 pmin = (long long)gmin - 1000000;
                 pmax = (long long)gmax - 1000000;
             }
-            const double phi_min = __ddiv_rn((double)pmin, 1e5), phi_max = __ddiv_rn((double)pmax, 1e5);
+            const double phi_min = div1e5((double)pmin), phi_max = div1e5((double)pmax);
             best = (fabs(__dsub_rn(phi_max, phi_min)) <= SCAB_PI) ? (int)pmin_c : (int)pmax_c;
         }
         if (lane == 0) {

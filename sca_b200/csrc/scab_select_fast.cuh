@@ -165,116 +165,20 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
         const float vmaxf = 1.0001f * (float)fmax(fmax(0.5, fabs(a.shell1)), sqrt(a.vdx * a.vdx + a.vdy * a.vdy + a.vdz * a.vdz));
         const float fnvA = (float)a.nvA;
         const float ball_r = 0.70711f * vmaxf;
-        const float bmx = ball_r * a.vx / fnvA, bmy = ball_r * a.vy / fnvA, bmz = ball_r * a.vz / fnvA;
+        const float inv_nvA = 1.f / fnvA;
+        const float bmx = ball_r * a.vx * inv_nvA, bmy = ball_r * a.vy * inv_nvA, bmz = ball_r * a.vz * inv_nvA;
+        const float vdx = (float)a.vdx, vdy = (float)a.vdy, vdz = (float)a.vdz;
+        // my two neighbours (k = l8, l8 + 8): indices now, records towards L1 while the posture / tier phases run
+        const int e0 = (l8 < nc) ? A.s_nbr[(size_t)s * KNBR + l8] : -1;
+        const int e1 = (l8 + FG_LANES < nc) ? A.s_nbr[(size_t)s * KNBR + FG_LANES + l8] : -1;
+        if (e0 >= 0 && e0 < A.n) { prefetch_l1(&A.s_posr[e0]); prefetch_l1(&A.s_vel[e0]); }
+        if (e1 >= 0 && e1 < A.n) { prefetch_l1(&A.s_posr[e1]); prefetch_l1(&A.s_vel[e1]); }
         // the posture table row of this agent: requested before the constraint gathers, consumed after them
         const float4 *tab = zaxis ? s_dir128 : s_dir256;
         unsigned sure = 0u, maybe = zaxis ? 0xffffu : 0xffffffffu;      // degenerate vA: test every direction
         if (fnvA > 1e-30f) {
             const unsigned *row = (zaxis ? A.plut128 : A.plut256) + (size_t)posture_bin(a.vx, a.vy, a.vz) * 16;
             sure = row[l8]; maybe = row[8 + l8];
-        }
-
-        // ------------------------------------------------------------ constraints: lane l8 builds k = l8, l8 + 8
-        int nce = 0;
-        for (int kb = 0; kb < nc; kb += FG_LANES) {
-            const int k = kb + l8;
-            float4 cP = make_float4(0.f, 0.f, 0.f, 0.f), cH = cP;
-            float2 cG = make_float2(0.f, 0.f);
-            bool keep = false;
-            if (k < nc) {
-                const int e = A.s_nbr[(size_t)s * KNBR + k];
-                double4 o;
-                float ox = 0.f, oy = 0.f, oz = 0.f;
-                bool at_goal = true;
-                if (e < A.n) {
-                    o = A.s_posr[e];
-                    const float4 ov = A.s_vel[e];
-                    ox = ov.x; oy = ov.y; oz = ov.z;
-                    at_goal = (__float_as_int(ov.w) & SCAB_ST_AT_GOAL) != 0;
-                } else if (e < A.n + A.m) {
-                    o = A.o_posr[e - A.n];
-                } else {
-                    o = A.o_posr_by_id[e - A.n - A.m];
-                }
-                const double R = IS_ORCA ? __dadd_rn(__dadd_rn(a.r, 0.05), __dadd_rn(o.w, 0.05))
-                                         : __dadd_rn(__dadd_rn(o.w, 0.05), __dadd_rn(a.r, 0.05));
-                const double rx = __dsub_rn(o.x, a.px), ry = __dsub_rn(o.y, a.py), rz = __dsub_rn(o.z, a.pz);
-                if (!IS_ORCA) {   // scaPolicy.py:47-60
-                    float hx = 0.f, hy = 0.f, hz = 0.f;
-                    if (!at_goal) {
-                        hx = __fmul_rn(0.5f, __fadd_rn(ox, a.vx));
-                        hy = __fmul_rn(0.5f, __fadd_rn(oy, a.vy));
-                        hz = __fmul_rn(0.5f, __fadd_rn(oz, a.vz));
-                    }
-                    const double pp = dot3(rx, ry, rz, rx, ry, rz);
-                    const float fpx = (float)rx, fpy = (float)ry, fpz = (float)rz;
-                    const float hh = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
-                    cP = make_float4(fpx, fpy, fpz, fmaf(fpz, hz, fmaf(fpy, hy, fpx * hx)));
-                    cH = make_float4(hx, hy, hz, hh);
-                    const float vh_max = vmaxf + sqrtf(hh);
-                    const float c2f = (float)fmax(pp - R * R, 0.0);
-                    cG = make_float2(c2f, 2e-5f * (float)pp * vh_max * vh_max);
-                    const float d = sqrtf((float)pp), Rf = (float)R;
-                    const float qx = bmx - hx, qy = bmy - hy, qz = bmz - hz;
-                    const float qa = (qx * fpx + qy * fpy + qz * fpz) / d;
-                    const float qr = sqrtf(fmaxf(qx * qx + qy * qy + qz * qz - qa * qa, 0.f));
-                    const float sn = fminf(Rf / d, 1.f), cs = sqrtf(c2f) / d;
-                    keep = !(qr * cs - qa * sn > ball_r + 1e-2f) || !((float)pp > 1.02f * Rf * Rf);
-                } else {          // orca3dPolicy.py:57-107
-                    const double vrx = (double)__fsub_rn(a.vx, ox), vry = (double)__fsub_rn(a.vy, oy), vrz = (double)__fsub_rn(a.vz, oz);
-                    const double distSq = dot3(rx, ry, rz, rx, ry, rz);
-                    const double RSq = __dmul_rn(R, R);
-                    double nx, ny, nz, ux, uy, uz;
-                    if (distSq > RSq) {
-                        const double invT = A.inv_time_horizon;
-                        double wx = __dsub_rn(vrx, __dmul_rn(invT, rx)), wy = __dsub_rn(vry, __dmul_rn(invT, ry)), wz = __dsub_rn(vrz, __dmul_rn(invT, rz));
-                        double wl2 = dot3(wx, wy, wz, wx, wy, wz);
-                        double dp = dot3(wx, wy, wz, rx, ry, rz);
-                        if (dp < 0.0 && __dmul_rn(dp, dp) > __dmul_rn(RSq, wl2)) {
-                            double wl = __dsqrt_rn(wl2);
-                            nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
-                            double sc = __dsub_rn(__dmul_rn(R, invT), wl);
-                            ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
-                        } else {
-                            double difSq = __dsub_rn(distSq, RSq);
-                            double dpr = dot3(rx, ry, rz, vrx, vry, vrz);
-                            double cx = __dsub_rn(__dmul_rn(ry, vrz), __dmul_rn(rz, vry));
-                            double cy = __dsub_rn(__dmul_rn(rz, vrx), __dmul_rn(rx, vrz));
-                            double cz = __dsub_rn(__dmul_rn(rx, vry), __dmul_rn(ry, vrx));
-                            double wwSq = __ddiv_rn(dot3(cx, cy, cz, cx, cy, cz), difSq);
-                            double pl = __dsqrt_rn(distSq);
-                            double t = __ddiv_rn(__dadd_rn(__ddiv_rn(dpr, pl), __dmul_rn(__dsqrt_rn(wwSq), __ddiv_rn(R, pl))), pl);
-                            double wx = __dsub_rn(vrx, __dmul_rn(t, rx)), wy = __dsub_rn(vry, __dmul_rn(t, ry)), wz = __dsub_rn(vrz, __dmul_rn(t, rz));
-                            double wl = __dsqrt_rn(dot3(wx, wy, wz, wx, wy, wz));
-                            nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
-                            double sc = __dsub_rn(__dmul_rn(R, t), wl);
-                            ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
-                        }
-                    } else {
-                        const double invDt = A.inv_time_step;
-                        double wx = __dsub_rn(vrx, __dmul_rn(invDt, rx)), wy = __dsub_rn(vry, __dmul_rn(invDt, ry)), wz = __dsub_rn(vrz, __dmul_rn(invDt, rz));
-                        double wl = __dsqrt_rn(dot3(wx, wy, wz, wx, wy, wz));
-                        nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
-                        double sc = __dsub_rn(__dmul_rn(R, invDt), wl);
-                        ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
-                    }
-                    const double qx = __dadd_rn((double)a.vx, __dmul_rn(0.5, ux)), qy = __dadd_rn((double)a.vy, __dmul_rn(0.5, uy)),
-                                 qz = __dadd_rn((double)a.vz, __dmul_rn(0.5, uz));
-                    if constexpr (IS_ORCA) {
-                        W.dpx[k] = qx; W.dpy[k] = qy; W.dpz[k] = qz;
-                        W.dhx[k] = nx; W.dhy[k] = ny; W.dhz[k] = nz;
-                    }
-                    cP = make_float4((float)nx, (float)ny, (float)nz, (float)(nx * qx + ny * qy + nz * qz));
-                    cG = make_float2(0.f, 1e-5f * (vmaxf + (float)sqrt(qx * qx + qy * qy + qz * qz)));
-                    keep = !((cP.x * bmx + cP.y * bmy + cP.z * bmz) - ball_r - cP.w > 1e-2f);
-                }
-            }
-            const unsigned km = (__ballot_sync(gmask, keep) >> (8 * g)) & 0xffu;
-            if (keep) {
-                const int slot = nce + __popc(km & lt8);
-                W.cp[slot] = cP; W.ch[slot] = cH; W.cg[slot] = cG; W.cidx[slot] = k;
-            }
-            nce += __popc(km);
         }
 
         // ------------------------------------------------------------ A: posture per direction
@@ -327,20 +231,25 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
         // with exact keys below the tier boundary minus a margin covering the fp32 key error -- the other ~90 % never
         // matter; otherwise the agent goes to the general kernel.  full_search (scab_set_option) examines everything
         // and yields the exact n_suit of the reference.
-        const float vdx = (float)a.vdx, vdy = (float)a.vdy, vdz = (float)a.vdz;
+        // |r u - v_pref|^2 = r^2 - 2 r u.v_pref + |v_pref|^2 for a unit direction u (|u|^2 = 1 to 2e-7: these distances
+        // only order the candidates, to 1e-3)
         const float vdvd = fmaf(vdz, vdz, fmaf(vdy, vdy, vdx * vdx));
+        const float c0 = 0.25f + vdvd, c1 = fmaf(r1f, r1f, vdvd), r2 = 2.f * r1f;
         float T1 = 3.0e38f;
         if (!A.full_search) {
-            float kmin = pv ? 0.f : 3.0e38f;         // v_pref is at distance 0 from itself
+            float kmin = 0.f;                        // v_pref, when it passes the posture test, is at distance 0 from itself
+            if (!pv) {
+                kmin = 3.0e38f;
 #pragma unroll 1
-            for (unsigned b = m0 | m1; b; b &= b - 1) {
-                const int i = __ffs(b) - 1;
-                const float4 u = tab[FG_LANES * i + l8];
-                const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x)), uv = fmaf(u.z, vdz, fmaf(u.y, vdy, u.x * vdx));
-                if ((m0 >> i) & 1u) kmin = fminf(kmin, fmaxf(fmaf(-1.f, uv, 0.25f * uu) + vdvd, 0.f));               // squared distances:
-                if ((m1 >> i) & 1u) kmin = fminf(kmin, fmaxf(fmaf(-2.f * r1f, uv, r1f * r1f * uu) + vdvd, 0.f));    // one sqrt after the min
+                for (unsigned b = m0 | m1; b; b &= b - 1) {
+                    const int i = __ffs(b) - 1;
+                    const float4 u = tab[FG_LANES * i + l8];
+                    const float uv = fmaf(u.z, vdz, fmaf(u.y, vdy, u.x * vdx));
+                    if ((m0 >> i) & 1u) kmin = fminf(kmin, fmaxf(c0 - uv, 0.f));               // squared distances:
+                    if ((m1 >> i) & 1u) kmin = fminf(kmin, fmaxf(fmaf(-r2, uv, c1), 0.f));    // one sqrt after the min
+                }
+                kmin = sqrtf(__uint_as_float(__reduce_min_sync(gmask, __float_as_uint(kmin))));   // non-negative floats order as uints
             }
-            kmin = sqrtf(__uint_as_float(__reduce_min_sync(gmask, __float_as_uint(kmin))));   // non-negative floats order as uints
             T1 = kmin + A.tier_delta;
         }
         const float T1sq = T1 * T1;      // (+inf under full_search)
@@ -353,11 +262,9 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
             for (unsigned b = m0 | m1; b; b &= b - 1) {
                 const int i = __ffs(b) - 1;
                 const float4 u = tab[FG_LANES * i + l8];
-                const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x)), uv = fmaf(u.z, vdz, fmaf(u.y, vdy, u.x * vdx));
-                const float k0 = fmaxf(fmaf(-1.f, uv, 0.25f * uu) + vdvd, 0.f);      // |v - v_pref|^2, fp32
-                const float k1 = fmaxf(fmaf(-2.f * r1f, uv, r1f * r1f * uu) + vdvd, 0.f);
-                if (k0 <= T1sq) a0 |= m0 & (1u << i);
-                if (k1 <= T1sq) a1 |= m1 & (1u << i);
+                const float uv = fmaf(u.z, vdz, fmaf(u.y, vdy, u.x * vdx));
+                if (c0 - uv <= T1sq) a0 |= m0 & (1u << i);                 // |v - v_pref|^2, fp32
+                if (fmaf(-r2, uv, c1) <= T1sq) a1 |= m1 & (1u << i);
             }
             unsigned ab = a0 | a1;
             const int cnt = __popc(ab);
@@ -380,6 +287,122 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
             }
         }
         __syncwarp(gmask);
+
+        // ------------------------------------------------------------ constraints: lane l8 builds k = l8, l8 + 8
+        // A constraint is kept only if its forbidden region comes within 1e-2 of BOTH balls that enclose every candidate
+        // this kernel will test: the posture ball (all posture-feasible velocities) and the tier ball B(v_pref, T1).
+        int nce = 0;
+        const float rho_t = T1 + 2e-3f;          // fp32 tier distances are good to 1e-3 (+inf under full_search)
+        for (int kb = 0; kb < nc; kb += FG_LANES) {
+            const int k = kb + l8;
+            float4 cP = make_float4(0.f, 0.f, 0.f, 0.f), cH = cP;
+            float2 cG = make_float2(0.f, 0.f);
+            bool keep = false;
+            if (k < nc) {
+                const int e = kb ? e1 : e0;
+                double4 o;
+                float ox = 0.f, oy = 0.f, oz = 0.f;
+                bool at_goal = true;
+                if (e < A.n) {
+                    o = A.s_posr[e];
+                    const float4 ov = A.s_vel[e];
+                    ox = ov.x; oy = ov.y; oz = ov.z;
+                    at_goal = (__float_as_int(ov.w) & SCAB_ST_AT_GOAL) != 0;
+                } else if (e < A.n + A.m) {
+                    o = A.o_posr[e - A.n];
+                } else {
+                    o = A.o_posr_by_id[e - A.n - A.m];
+                }
+                const double R = IS_ORCA ? __dadd_rn(__dadd_rn(a.r, 0.05), __dadd_rn(o.w, 0.05))
+                                         : __dadd_rn(__dadd_rn(o.w, 0.05), __dadd_rn(a.r, 0.05));
+                const double rx = __dsub_rn(o.x, a.px), ry = __dsub_rn(o.y, a.py), rz = __dsub_rn(o.z, a.pz);
+                if (!IS_ORCA) {   // scaPolicy.py:47-60
+                    float hx = 0.f, hy = 0.f, hz = 0.f;
+                    if (!at_goal) {
+                        hx = __fmul_rn(0.5f, __fadd_rn(ox, a.vx));
+                        hy = __fmul_rn(0.5f, __fadd_rn(oy, a.vy));
+                        hz = __fmul_rn(0.5f, __fadd_rn(oz, a.vz));
+                    }
+                    const double pp = dot3(rx, ry, rz, rx, ry, rz);
+                    const float fpx = (float)rx, fpy = (float)ry, fpz = (float)rz;
+                    const float hh = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
+                    cP = make_float4(fpx, fpy, fpz, fmaf(fpz, hz, fmaf(fpy, hy, fpx * hx)));
+                    cH = make_float4(hx, hy, hz, hh);
+                    const float vh_max = vmaxf + sqrtf(hh);
+                    const float c2f = (float)fmax(pp - R * R, 0.0);
+                    cG = make_float2(c2f, 2e-5f * (float)pp * vh_max * vh_max);
+                    // distance from a ball centre (relative to the apex h) to the cone {w: p.w > |w| c} -- approximate
+                    // reciprocal square roots are fine here: the margin is 1e-2
+                    const float ppf = (float)pp, Rf = (float)R;
+                    const float invd = rsqrtf(ppf);
+                    const float sn = fminf(Rf * invd, 1.f), cs = (c2f > 0.f ? c2f * rsqrtf(c2f) : 0.f) * invd;
+                    auto clear_of = [&](float cx, float cy, float cz, float rad) {
+                        const float qx = cx - hx, qy = cy - hy, qz = cz - hz;
+                        const float qa = (qx * fpx + qy * fpy + qz * fpz) * invd;
+                        const float q2 = fmaxf(qx * qx + qy * qy + qz * qz - qa * qa, 0.f);
+                        const float qr = q2 > 0.f ? q2 * rsqrtf(q2) : 0.f;
+                        return qr * cs - qa * sn > rad + 1e-2f;
+                    };
+                    keep = !(ppf > 1.02f * Rf * Rf) || !(clear_of(bmx, bmy, bmz, ball_r) || clear_of(vdx, vdy, vdz, rho_t));
+                } else {          // orca3dPolicy.py:57-107
+                    const double vrx = (double)__fsub_rn(a.vx, ox), vry = (double)__fsub_rn(a.vy, oy), vrz = (double)__fsub_rn(a.vz, oz);
+                    const double distSq = dot3(rx, ry, rz, rx, ry, rz);
+                    const double RSq = __dmul_rn(R, R);
+                    double nx, ny, nz, ux, uy, uz;
+                    if (distSq > RSq) {
+                        const double invT = A.inv_time_horizon;
+                        double wx = __dsub_rn(vrx, __dmul_rn(invT, rx)), wy = __dsub_rn(vry, __dmul_rn(invT, ry)), wz = __dsub_rn(vrz, __dmul_rn(invT, rz));
+                        double wl2 = dot3(wx, wy, wz, wx, wy, wz);
+                        double dp = dot3(wx, wy, wz, rx, ry, rz);
+                        if (dp < 0.0 && __dmul_rn(dp, dp) > __dmul_rn(RSq, wl2)) {
+                            double wl = __dsqrt_rn(wl2);
+                            nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
+                            double sc = __dsub_rn(__dmul_rn(R, invT), wl);
+                            ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
+                        } else {
+                            double difSq = __dsub_rn(distSq, RSq);
+                            double dpr = dot3(rx, ry, rz, vrx, vry, vrz);
+                            double cx = __dsub_rn(__dmul_rn(ry, vrz), __dmul_rn(rz, vry));
+                            double cy = __dsub_rn(__dmul_rn(rz, vrx), __dmul_rn(rx, vrz));
+                            double cz = __dsub_rn(__dmul_rn(rx, vry), __dmul_rn(ry, vrx));
+                            double wwSq = __ddiv_rn(dot3(cx, cy, cz, cx, cy, cz), difSq);
+                            double pl = __dsqrt_rn(distSq);
+                            double t = __ddiv_rn(__dadd_rn(__ddiv_rn(dpr, pl), __dmul_rn(__dsqrt_rn(wwSq), __ddiv_rn(R, pl))), pl);
+                            double wx = __dsub_rn(vrx, __dmul_rn(t, rx)), wy = __dsub_rn(vry, __dmul_rn(t, ry)), wz = __dsub_rn(vrz, __dmul_rn(t, rz));
+                            double wl = __dsqrt_rn(dot3(wx, wy, wz, wx, wy, wz));
+                            nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
+                            double sc = __dsub_rn(__dmul_rn(R, t), wl);
+                            ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
+                        }
+                    } else {
+                        const double invDt = A.inv_time_step;
+                        double wx = __dsub_rn(vrx, __dmul_rn(invDt, rx)), wy = __dsub_rn(vry, __dmul_rn(invDt, ry)), wz = __dsub_rn(vrz, __dmul_rn(invDt, rz));
+                        double wl = __dsqrt_rn(dot3(wx, wy, wz, wx, wy, wz));
+                        nx = __ddiv_rn(wx, wl); ny = __ddiv_rn(wy, wl); nz = __ddiv_rn(wz, wl);
+                        double sc = __dsub_rn(__dmul_rn(R, invDt), wl);
+                        ux = __dmul_rn(sc, nx); uy = __dmul_rn(sc, ny); uz = __dmul_rn(sc, nz);
+                    }
+                    const double qx = __dadd_rn((double)a.vx, __dmul_rn(0.5, ux)), qy = __dadd_rn((double)a.vy, __dmul_rn(0.5, uy)),
+                                 qz = __dadd_rn((double)a.vz, __dmul_rn(0.5, uz));
+                    if constexpr (IS_ORCA) {
+                        W.dpx[k] = qx; W.dpy[k] = qy; W.dpz[k] = qz;
+                        W.dhx[k] = nx; W.dhy[k] = ny; W.dhz[k] = nz;
+                    }
+                    cP = make_float4((float)nx, (float)ny, (float)nz, (float)(nx * qx + ny * qy + nz * qz));
+                    cG = make_float2(0.f, 1e-5f * (vmaxf + (float)sqrt(qx * qx + qy * qy + qz * qz)));
+                    // half-space n.v >= n.point: the smallest n.v over a ball is n.centre - radius
+                    keep = !((cP.x * bmx + cP.y * bmy + cP.z * bmz) - ball_r - cP.w > 1e-2f ||
+                             (cP.x * vdx + cP.y * vdy + cP.z * vdz) - rho_t - cP.w > 1e-2f);
+                }
+            }
+            const unsigned km = (__ballot_sync(gmask, keep) >> (8 * g)) & 0xffu;
+            if (keep) {
+                const int slot = nce + __popc(km & lt8);
+                W.cp[slot] = cP; W.ch[slot] = cH; W.cg[slot] = cG; W.cidx[slot] = k;
+            }
+            nce += __popc(km);
+        }
+        __syncwarp(gmask);       // the packed constraints (and the tier-1 entries above) are read by every lane of the group
 
         // ---- B: cone tests per direction (the two shells share p.u and h.u)
         int nlive = 0, best = -1;
@@ -496,7 +519,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
                     bool within;
                     if (du < thr_units - 1) within = true;
                     else if (du > thr_units + 1) within = false;
-                    else within = fabs(__dsub_rn(__ddiv_rn((double)d0u, 1e5), __ddiv_rn((double)diu, 1e5))) < thr;
+                    else within = fabs(__dsub_rn(div1e5((double)d0u), div1e5((double)diu))) < thr;
                     if (!within) fmin_ = min(fmin_, W.kc[j]);
                 }
                 kfail = __reduce_min_sync(gmask, fmin_);
@@ -532,7 +555,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
             const unsigned gmin = __reduce_min_sync(gmask, umin), gmax = __reduce_max_sync(gmask, umax);
             const unsigned cmin = __reduce_min_sync(gmask, umin == gmin ? kmin_ : 0xffffffffu);
             const unsigned cmax = __reduce_min_sync(gmask, (umax == gmax && kmax_ != 0xffffffffu) ? kmax_ : 0xffffffffu);
-            const double phi_min = __ddiv_rn((double)((long long)gmin - 1000000), 1e5), phi_max = __ddiv_rn((double)((long long)gmax - 1000000), 1e5);
+            const double phi_min = div1e5((double)((long long)gmin - 1000000)), phi_max = div1e5((double)((long long)gmax - 1000000));
             best = (fabs(__dsub_rn(phi_max, phi_min)) <= SCAB_PI) ? (int)(cmin & 1023u) : (int)(cmax & 1023u);
         }
         if (l8 == 0) {

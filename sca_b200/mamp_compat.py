@@ -34,7 +34,12 @@ class GPUKDTree(object):
     """Same four methods as mamp/policies/kdTree.py:34 KDTree."""
 
     def __init__(self, agents, obstacles, policy=None, nbr_mode=capi.NBR_REF_COMPAT, device='cuda:0',
-                 vpref_provider=None):
+                 vpref_provider=None, backfill_neighbors=True):
+        """`vpref_provider`: where SCA / RVO3D+Dubins take V_des from -- 'device' (default of GPUSCAPolicy / GPURVO3dDubinsPolicy:
+        the Dubins tracker of scaPolicy.py:264-338 on the GPU), a callable agent -> V_des (e.g. reference_dubins_vpref, the
+        reference's own host-side tracker: 68 % of the reference's CPU time stays on the host then), or None (straight line).
+        `backfill_neighbors=False` skips rebuilding agent.neighbors as Python lists (the costliest part of the shim at scale)."""
+        self.backfill_neighbors = bool(backfill_neighbors)
         self.agents = agents
         self.obstacles = obstacles or []
         n = len(agents)
@@ -90,14 +95,15 @@ class GPUKDTree(object):
         ags, h = self.agents, self._host
         pos, vel, hd = h['pos'].numpy(), h['vel'].numpy(), h['heading'].numpy()
         st, td, sn = h['status'].numpy(), h['total_dist'].numpy(), h['step_num'].numpy()
-        for i, a in enumerate(ags):
-            pos[i] = a.pos_global_frame
-            vel[i] = a.vel_global_frame
-            hd[i] = a.heading_global_frame
-            st[i] = (capi.ST_AT_GOAL * bool(a.is_at_goal)) | (capi.ST_COLLISION * bool(a.is_collision)) | \
-                    (capi.ST_TIMEOUT * bool(a.is_out_of_max_time))
-            td[i] = a.total_dist
-            sn[i] = a.step_num
+        # Agent attributes -> structure of arrays: one pass per attribute (the objects are the reference's; reading them
+        # is the only per-agent Python left on this side of the boundary)
+        pos[:] = [a.pos_global_frame for a in ags]
+        vel[:] = [a.vel_global_frame for a in ags]
+        hd[:] = [a.heading_global_frame for a in ags]
+        flags = np.array([(a.is_at_goal, a.is_collision, a.is_out_of_max_time) for a in ags], dtype=bool).reshape(-1, 3)
+        st[:] = flags @ np.array([capi.ST_AT_GOAL, capi.ST_COLLISION, capi.ST_TIMEOUT], np.int32)
+        td[:] = [a.total_dist for a in ags]
+        sn[:] = [a.step_num for a in ags]
         if self.vpref_provider is not None:
             # upstream of the boundary: the reference's own stateful Dubins tracker (scaPolicy.py:264-338)
             vp = self._vp.numpy()
@@ -132,7 +138,7 @@ class GPUKDTree(object):
         i = agent.id
         n = len(self.agents)
         c = int(self._nbr_cnt[i])
-        if c >= 0:     # computeNeighbors ran for this agent (scaPolicy.py:107-116)
+        if c >= 0 and self.backfill_neighbors:     # computeNeighbors ran for this agent (scaPolicy.py:107-116)
             agent.neighbors = [((self.agents[j] if j < n else self.obstacles[j - n]), float(d))
                                for j, d in zip(self._nbr_ids[i, :c], self._nbr_dsq[i, :c])]
         if self._status[i] & capi.ST_COLLISION:
@@ -165,20 +171,31 @@ class _GPUPolicy(object):
         return tree.action[agent.id]
 
 
-def _reference_dubins_vpref(agent):
-    """The reference's own Dubins v_pref tracker, imported from the user's mamp installation."""
+def reference_dubins_vpref(agent):
+    """The reference's own Dubins v_pref tracker, imported from the user's mamp installation (host side, per agent)."""
     from mamp.policies.sca.scaPolicy import compute_v_pref
     return compute_v_pref(agent)
 
 
+_reference_dubins_vpref = reference_dubins_vpref
+
+
 class GPUSCAPolicy(_GPUPolicy):            # mamp/policies/sca/scaPolicy.py:18
     scab_policy = 'sca'
-    vpref_provider = staticmethod(_reference_dubins_vpref)
+    vpref_provider = 'device'              # the Dubins tracker on the GPU (k_dubins_track / k_dubins_replan)
 
 
 class GPURVO3dDubinsPolicy(_GPUPolicy):    # mamp/policies/sca/rvo3dDubinsPolicy.py:18
     scab_policy = 'rvo3d_dubins'
-    vpref_provider = staticmethod(_reference_dubins_vpref)
+    vpref_provider = 'device'
+
+
+class GPUSCAPolicyHostDubins(GPUSCAPolicy):                 # V_des from the reference's own host-side tracker instead
+    vpref_provider = staticmethod(reference_dubins_vpref)
+
+
+class GPURVO3dDubinsPolicyHostDubins(GPURVO3dDubinsPolicy):
+    vpref_provider = staticmethod(reference_dubins_vpref)
 
 
 class GPUSRVO3DPolicy(_GPUPolicy):         # mamp/policies/srvo3dPolicy.py:15

@@ -119,8 +119,8 @@ CASES = [('srvo3d', 'GPUSRVO3DPolicy', 14, 4.0, 2, 24, False),
          ('rvo3d', 'GPURVO3DPolicy', 12, 4.0, 0, 30, True),
          ('orca_lp', 'GPUORCA3DPolicyOfficial', 20, 3.0, 3, 40, False),
          ('orca_sampled', 'GPUORCA3DPolicy', 12, 4.0, 2, 30, True),
-         ('sca', 'GPUSCAPolicy', 10, 5.0, 2, 30, False),
-         ('rvo3d_dubins', 'GPURVO3dDubinsPolicy', 8, 5.0, 0, 25, False)]
+         ('sca', 'GPUSCAPolicyHostDubins', 10, 5.0, 2, 30, False),
+         ('rvo3d_dubins', 'GPURVO3dDubinsPolicyHostDubins', 8, 5.0, 0, 25, False)]
 
 
 @pytest.mark.parametrize('case', CASES, ids=lambda c: c[0])
