@@ -187,37 +187,151 @@ __device__ __noinline__ void knn_exact(const StepArgs &A, int s, int id, const d
 }
 
 
-// ------------------------------------------------------------------ the scale path: tile-staged scan
-// Common case (no obstacles in the merged list, distinct distance keys).  One CTA per WORK ITEM = NT_W consecutive cells of
-// one x-row of the grid; its agents are a contiguous range of the cell-sorted snapshot, and everything they can see lies
-// in nine contiguous ranges (the 3 x 3 neighbouring x-rows, cells cx0-1 .. cx0+NT_W).  Those ranges are staged ONCE into
-// shared memory as fp32 float4 records (coalesced 128-bit loads of s_posf, the copy k_reorder writes) and every agent of
-// the item -- one thread each -- scans its own (trimmed) 27 cells out of the tile:
-//   phase 1  fp32 squared distance against rangeSq + a guard band that covers the fp32 error; survivors (their sorted index)
-//            go to a shared-memory column per thread, so that
+// ------------------------------------------------------------------ the scale path
+// Common case (no obstacles in the merged list, distinct distance keys), two phases per agent (one thread each):
+//   phase 1  fp32 squared distance of every record of the (trimmed) 27 cells against rangeSq + a guard band that covers the
+//            fp32 error; survivors go to a shared-memory column per thread, so that
 //   phase 2  all lanes walk their candidates together: the reference's fp64 distance with its decimal rounding
 //            (util.py:99-100) -- an exact integer number of 1e-5 units (< 2^24 for neighbor_dist < 12.9 m), so
 //            (units << 8 | candidate slot) is a 32-bit sort key and inserting into the sorted top-16 is a branch-free
 //            min/max network on 16 registers:  new[k] = min(old[k], max(old[k-1], x)).
 // A tie on the distance (the reference breaks it by agent id) is detected afterwards -- two equal neighbours in the list,
 // or the best rejected key equal to the last kept one -- and sends the agent to knn_exact, as does a full column.
-// A tile that does not fit (very dense cells) is scanned from global memory through the same code (generic pointer).
+template <class GetJ>
+__device__ __forceinline__ void knn_phase2(const StepArgs &A, int s, int id, const double4 me, int nbuf, bool overflow, GetJ getj)
+{
+    const double rangeSq = A.nbr_dist_sq;
+    unsigned L[KNBR];
+#pragma unroll
+    for (int k = 0; k < KNBR; k++) L[k] = 0xffffffffu;
+    unsigned rej_min = 0xffffffffu;
+    int cnt = 0;
+    bool coll = false;
+#pragma unroll 1
+    for (int i0 = 0; i0 < nbuf; i0 += 4) {
+        double4 o4[4];             // four gathers in flight per thread (L1 / L2 hits)
+        int j4[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { j4[q] = getj(min(i0 + q, nbuf - 1)); o4[q] = A.s_posr[j4[q]]; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = i0 + q;
+            if (i >= nbuf || j4[q] == s) continue;
+            const double4 o = o4[q];
+            // l3normsq (util.py:99-100): round(sum, 5) = rint(sum * 1e5) / 1e5
+            const double units = rint(__dmul_rn(sumsq3(__dsub_rn(me.x, o.x), __dsub_rn(me.y, o.y), __dsub_rn(me.z, o.z)), 1e5));
+            const double dsq = div1e5(units);
+            if (!(dsq < rangeSq)) continue;
+            const double rr = __dadd_rn(me.w, o.w);
+            const bool is_c = dsq < __dmul_rn(rr, rr);      // agent.py:83-85: from the first collider on, colliders only
+            if (is_c && !coll) {
+                coll = true;
+#pragma unroll
+                for (int k = 0; k < KNBR; k++) L[k] = 0xffffffffu;
+                rej_min = 0xffffffffu;
+                cnt = 0;
+            }
+            if (coll && !is_c) continue;
+            const unsigned x = ((unsigned)(int)units << 8) | (unsigned)i;
+            rej_min = min(rej_min, max(L[KNBR - 1], x));
+#pragma unroll
+            for (int k = KNBR - 1; k >= 1; k--) L[k] = min(L[k], max(L[k - 1], x));
+            L[0] = min(L[0], x);
+            cnt++;
+        }
+    }
+    const int n_in = min(cnt, KNBR);
+    bool tie = overflow || (cnt > KNBR && (rej_min >> 8) == (L[KNBR - 1] >> 8));
+#pragma unroll
+    for (int k = 1; k < KNBR; k++) tie |= (k < n_in) && ((L[k] >> 8) == (L[k - 1] >> 8));
+    if (tie) { knn_exact(A, s, id, me); return; }
+    int sx[KNBR];
+#pragma unroll
+    for (int k = 0; k < KNBR; k++) sx[k] = (k < n_in) ? getj((int)(L[k] & 0xffu)) : -1;
+    A.s_nbr_cnt[s] = n_in;
+    A.s_qcoll[s] = coll ? 1 : 0;
+    if (A.dub_d0) A.dub_d0[id] = n_in > 0 ? div1e5((double)(L[0] >> 8)) : -1.0;
+    int4 *dst = reinterpret_cast<int4 *>(A.s_nbr + (size_t)s * KNBR);
+#pragma unroll
+    for (int q = 0; q < KNBR / 4; q++) dst[q] = make_int4(sx[4 * q], sx[4 * q + 1], sx[4 * q + 2], sx[4 * q + 3]);
+    if (A.st.nbr_cnt) A.st.nbr_cnt[id] = n_in;
+    if (A.st.nbr_ids) {
+#pragma unroll
+        for (int k = 0; k < KNBR; k++) A.st.nbr_ids[(size_t)id * KNBR + k] = (k < n_in) ? A.s_gid[sx[k]] : -1;
+    }
+    if (A.st.nbr_dsq) {
+#pragma unroll
+        for (int k = 0; k < KNBR; k++) A.st.nbr_dsq[(size_t)id * KNBR + k] = (k < n_in) ? div1e5((double)(L[k] >> 8)) : 0.0;
+    }
+}
+
+// The trimmed x-range of one of the nine x-rows around cell (cx, cy, cz) for a query ball of squared radius `limt`:
+// (fx, fy, fz) is the offset inside the own cell, so the gap to a neighbouring slab is f or cs - f.  Returns false when
+// the ball does not reach the row.  (Agents clamped into a border cell from outside the grid scan the full block; cell
+// contents are never closer than their cell.)
+struct RowTrim {
+    double fx, fy, fz, cs, limt;
+    bool trim;
+    __device__ __forceinline__ void init(const GridGeom &g, const double4 &me, int cx, int cy, int cz, double lim)
+    {
+        cs = 1.0 / g.inv_cs;
+        fx = (me.x - g.ox) - cx * cs; fy = (me.y - g.oy) - cy * cs; fz = (me.z - g.oz) - cz * cs;
+        trim = fx >= 0.0 && fx <= cs && fy >= 0.0 && fy <= cs && fz >= 0.0 && fz <= cs;
+        limt = lim + 1e-6;
+    }
+    __device__ __forceinline__ bool row(int r, int cx, int &x0, int &x1) const
+    {
+        const int dz = r / 3 - 1, dy = r % 3 - 1;
+        const double gz = dz == 0 ? 0.0 : (dz < 0 ? fz : cs - fz);
+        const double gy = dy == 0 ? 0.0 : (dy < 0 ? fy : cs - fy);
+        const double rem = limt - gz * gz - gy * gy;
+        if (trim && rem < 0.0) return false;
+        x0 = (trim && fx * fx > rem) ? cx : cx - 1;
+        x1 = (trim && (cs - fx) * (cs - fx) > rem) ? cx : cx + 1;
+        return true;
+    }
+};
+
+// fp32 error of the squared distance of two points within ~10 m of each other at (grid-relative) coordinates of magnitude S:
+// <= 2 d (e_x + e_y + e_z) with e ~ 2^-23 (|c| + 10), i.e. < 2.5e-6 S + 2e-4
+__device__ __forceinline__ float prefilter_limit(double lim, float mx, float my, float mz)
+{
+    return (float)lim + 1e-3f + 4e-6f * (fabsf(mx) + fabsf(my) + fabsf(mz));
+}
+
+#ifndef KNN_VARIANT
+#define KNN_VARIANT 1      // 0: tile-staged scan (k_neighbors_tile)   1: records straight from L1 / L2 (k_neighbors_direct)
+#endif
+#ifndef KNN_UNROLL
+#define KNN_UNROLL 4       // records loaded per inner iteration of the direct scan (must divide 32)
+#endif
+#ifndef KNN_DIRECT_CTAS
+#define KNN_DIRECT_CTAS 5
+#endif
+
+// ---- variant 0: one CTA per WORK ITEM = NT_W consecutive cells of one x-row of the grid.  Its agents are a contiguous range
+// of the cell-sorted snapshot, and everything they can see lies in nine contiguous ranges (the 3 x 3 neighbouring x-rows,
+// cells cx0-1 .. cx0+NT_W): those are staged ONCE into shared memory as fp32 float4 records (coalesced 128-bit loads of
+// s_posf, the copy k_reorder writes) and every agent of the item scans its own 27 cells out of the tile.  Candidates are
+// recorded as 16-bit (row << 11 | offset in the row's range).  An item whose ranges do not fit the tile (very dense cells)
+// sends its agents through knn_exact.
 #ifndef NT_W
 #define NT_W 16
 #define NT_THREADS 128
-#define NT_TILE 1408   // static shared memory: tile + candidate columns + bounds < 48 KB
+#define NT_TILE 1408
+#endif
+#ifndef NT_MIN_CTAS
+#define NT_MIN_CTAS 5
 #endif
 
-#ifndef NT_MIN_CTAS
-#define NT_MIN_CTAS 4
-#endif
 __global__ void __launch_bounds__(NT_THREADS, NT_MIN_CTAS) k_neighbors_tile(const __grid_constant__ StepArgs A, int segs)
 {
     __shared__ float4 tile[NT_TILE];
-    __shared__ int buf[KNN_CAP][NT_THREADS];
+    __shared__ unsigned short buf[KNN_CAP][NT_THREADS];
     __shared__ int cs[9][NT_W + 3];
     __shared__ int rbase[9];
     __shared__ int use_tile;
+    static_assert(NT_TILE <= 2048, "candidate codes hold an 11-bit offset");
     const int tid = threadIdx.x;
     const int row = blockIdx.x / segs, cx0 = (blockIdx.x - row * segs) * NT_W;
     const int nx = A.g.nx, ny = A.g.ny;
@@ -262,116 +376,119 @@ __global__ void __launch_bounds__(NT_THREADS, NT_MIN_CTAS) k_neighbors_tile(cons
     }
     __syncthreads();
 
-    const double rangeSq = A.nbr_dist_sq;
-    const double cs_len = 1.0 / A.g.inv_cs;
 #pragma unroll 1
     for (int s = a_beg + tid; s < a_end; s += NT_THREADS) {
         const int flags = __float_as_int(A.s_vel[s].w);
         if (flags & FL_INACTIVE) continue;
         const int id = A.s_id[s];
         const double4 me = A.s_posr[s];
-        // ---- phase 1: fp32 pre-filter over the (trimmed) 27 cells
+        if (!staged) { knn_exact(A, s, id, me); continue; }
+        // ---- phase 1: fp32 pre-filter over the (trimmed) 27 cells, out of the tile
         int nbuf = 0;
         bool overflow = false;
-        {
-            int cx, cy, cz;
-            cell_of(A.g, me.x, me.y, me.z, cx, cy, cz);
-            const double lim = rangeSq + 1e-4;   // the 5-decimal rounding cannot bring anything beyond this back in range
-            // Trim the 27-cell block to the cells the query ball actually reaches: (fx, fy, fz) is the offset inside
-            // the own cell, so the gap to a neighbouring slab is f or cs - f.  (Agents clamped into a border cell from
-            // outside the grid scan the full block; cell contents are never closer than their cell.)
-            const double fx = (me.x - A.g.ox) - cx * cs_len, fy = (me.y - A.g.oy) - cy * cs_len, fz = (me.z - A.g.oz) - cz * cs_len;
-            const bool trim = fx >= 0.0 && fx <= cs_len && fy >= 0.0 && fy <= cs_len && fz >= 0.0 && fz <= cs_len;
-            const double limt = lim + 1e-6;
-            const float mx = (float)(me.x - A.g.ox), my = (float)(me.y - A.g.oy), mz = (float)(me.z - A.g.oz);
-            // fp32 error of the squared distance of two points within ~10 m of each other at coordinates of magnitude S:
-            // <= 2 d (e_x + e_y + e_z) with e ~ 2^-23 (|c| + 10), i.e. < 2.5e-6 S + 2e-4
-            const float limf = (float)lim + 1e-3f + 4e-6f * (fabsf(mx) + fabsf(my) + fabsf(mz));
+        int cx, cy, cz;
+        cell_of(A.g, me.x, me.y, me.z, cx, cy, cz);
+        const double lim = A.nbr_dist_sq + 1e-4;   // the 5-decimal rounding cannot bring anything beyond this back in range
+        RowTrim T;
+        T.init(A.g, me, cx, cy, cz, lim);
+        const float mx = (float)(me.x - A.g.ox), my = (float)(me.y - A.g.oy), mz = (float)(me.z - A.g.oz);
+        const float limf = prefilter_limit(lim, mx, my, mz);
 #pragma unroll 1
-            for (int r = 0; r < 9; r++) {
-                const int dz = r / 3 - 1, dy = r % 3 - 1;
-                const double gz = dz == 0 ? 0.0 : (dz < 0 ? fz : cs_len - fz);
-                const double gy = dy == 0 ? 0.0 : (dy < 0 ? fy : cs_len - fy);
-                const double rem = limt - gz * gz - gy * gy;
-                if (trim && rem < 0.0) continue;
-                const int x0 = (trim && fx * fx > rem) ? cx : cx - 1, x1 = (trim && (cs_len - fx) * (cs_len - fx) > rem) ? cx : cx + 1;
-                const int beg = cs[r][max(x0, 0) - (cx0 - 1)], end = cs[r][min(x1, nx - 1) + 1 - (cx0 - 1)];
-                const float4 *rec = staged ? (tile + rbase[r] - cs[r][0]) : A.s_posf;
-#pragma unroll 2
-                for (int j = beg; j < end; j++) {
-                    const float4 o = rec[j];
-                    const float ex = mx - o.x, ey = my - o.y, ez = mz - o.z;
+        for (int r = 0; r < 9; r++) {
+            int x0, x1;
+            if (!T.row(r, cx, x0, x1)) continue;
+            const int r0 = cs[r][0];
+            const int beg = cs[r][max(x0, 0) - (cx0 - 1)] - r0, end = cs[r][min(x1, nx - 1) + 1 - (cx0 - 1)] - r0;   // offsets in the row's range
+            const float4 *rec = tile + rbase[r];
+            const unsigned code = (unsigned)r << 11;
+#pragma unroll 1
+            for (int j0 = beg; j0 < end; j0 += 4) {
+                float4 o[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) o[q] = rec[min(j0 + q, end - 1)];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float ex = mx - o[q].x, ey = my - o[q].y, ez = mz - o[q].z;
                     const float ss = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-                    if (ss <= limf && j != s) {
-                        if (nbuf < KNN_CAP) buf[nbuf++][tid] = j;
+                    if (ss <= limf && j0 + q < end) {           // (the agent itself included: phase 2 drops it)
+                        if (nbuf < KNN_CAP) buf[nbuf++][tid] = (unsigned short)(code | (unsigned)(j0 + q));
                         else overflow = true;
                     }
                 }
             }
         }
-        // ---- phase 2: exact keys, all lanes together
-        unsigned L[KNBR];
+        knn_phase2(A, s, id, me, nbuf, overflow, [&](int i) { const unsigned c = buf[i][tid]; return cs[c >> 11][0] + (int)(c & 2047u); });
+    }
+}
+
+// ---- variant 1: thread per agent, records straight from global memory (s_posf: 16-byte fp32 records, L1 / L2 hits)
+__global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const __grid_constant__ StepArgs A)
+{
+    __shared__ int buf[KNN_CAP][128];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, tid = threadIdx.x;
+    if (s >= A.n) return;
+    const int id = A.s_id[s];
+    const int flags = __float_as_int(A.s_vel[s].w);
+    if (flags & FL_INACTIVE) {
+        A.s_nbr_cnt[s] = -1;
+        A.s_qcoll[s] = 0;
+        if (A.st.nbr_cnt) A.st.nbr_cnt[id] = -1;
+        return;
+    }
+    const double4 me = A.s_posr[s];
+    int nbuf = 0;
+    bool overflow = false;
+    int cx, cy, cz;
+    cell_of(A.g, me.x, me.y, me.z, cx, cy, cz);
+    const double lim = A.nbr_dist_sq + 1e-4;
+    RowTrim T;
+    T.init(A.g, me, cx, cy, cz, lim);
+    const float mx = (float)(me.x - A.g.ox), my = (float)(me.y - A.g.oy), mz = (float)(me.z - A.g.oz);
+    const float limf = prefilter_limit(lim, mx, my, mz);
+    // the (up to) nine x-rows of the block: all their cell_start bounds are fetched before any row is scanned
+    int rbeg[9], rend[9];
 #pragma unroll
-        for (int k = 0; k < KNBR; k++) L[k] = 0xffffffffu;
-        unsigned rej_min = 0xffffffffu;
-        int cnt = 0;
-        bool coll = false;
+    for (int r = 0; r < 9; r++) {
+        const int z = cz + r / 3 - 1, y = cy + r % 3 - 1;
+        int x0, x1;
+        const bool ok = z >= 0 && z < A.g.nz && y >= 0 && y < A.g.ny && T.row(r, cx, x0, x1);
+        const int rowi = (z * A.g.ny + y) * A.g.nx;
+        rbeg[r] = ok ? A.cell_start[rowi + max(x0, 0)] : 0;
+        rend[r] = ok ? A.cell_start[rowi + min(x1, A.g.nx - 1) + 1] : 0;
+    }
+    // Per row, the hits of up to 32 consecutive records are collected as a bit mask (one instruction per record instead of
+    // a predicated store sequence) and then drained into the thread's shared-memory column.
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+        const int end = rend[r];
 #pragma unroll 1
-        for (int i0 = 0; i0 < nbuf; i0 += 4) {
-            double4 o4[4];             // four gathers in flight per thread (L1 / L2 hits)
+        for (int c0 = rbeg[r]; c0 < end; c0 += 32) {
+            const int n = min(32, end - c0);
+            unsigned m = 0u;
+#pragma unroll 1
+            for (int j0 = 0; j0 < n; j0 += KNN_UNROLL) {
+                float4 o[KNN_UNROLL];          // independent loads in flight per thread
 #pragma unroll
-            for (int q = 0; q < 4; q++) o4[q] = A.s_posr[buf[min(i0 + q, nbuf - 1)][tid]];
+                for (int q = 0; q < KNN_UNROLL; q++) o[q] = __ldg(&A.s_posf[min(c0 + j0 + q, end - 1)]);
+                unsigned mq = 0u;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int i = i0 + q;
-                if (i >= nbuf) continue;
-                const double4 o = o4[q];
-                // l3normsq (util.py:99-100): round(sum, 5) = rint(sum * 1e5) / 1e5
-                const double units = rint(__dmul_rn(sumsq3(__dsub_rn(me.x, o.x), __dsub_rn(me.y, o.y), __dsub_rn(me.z, o.z)), 1e5));
-                const double dsq = div1e5(units);
-                if (!(dsq < rangeSq)) continue;
-                const double rr = __dadd_rn(me.w, o.w);
-                const bool is_c = dsq < __dmul_rn(rr, rr);      // agent.py:83-85: from the first collider on, colliders only
-                if (is_c && !coll) {
-                    coll = true;
-#pragma unroll
-                    for (int k = 0; k < KNBR; k++) L[k] = 0xffffffffu;
-                    rej_min = 0xffffffffu;
-                    cnt = 0;
+                for (int q = 0; q < KNN_UNROLL; q++) {
+                    const float ex = mx - o[q].x, ey = my - o[q].y, ez = mz - o[q].z;
+                    const float ss = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                    mq |= (ss <= limf ? 1u : 0u) << q;           // (the agent itself included: phase 2 drops it)
                 }
-                if (coll && !is_c) continue;
-                const unsigned x = ((unsigned)(int)units << 8) | (unsigned)i;
-                rej_min = min(rej_min, max(L[KNBR - 1], x));
-#pragma unroll
-                for (int k = KNBR - 1; k >= 1; k--) L[k] = min(L[k], max(L[k - 1], x));
-                L[0] = min(L[0], x);
-                cnt++;
+                m |= mq << j0;
+            }
+            if (n < 32) m &= (1u << n) - 1u;                      // the clamped tail loads repeat the last record
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                if (nbuf < KNN_CAP) buf[nbuf++][tid] = c0 + b;
+                else overflow = true;
             }
         }
-        const int n_in = min(cnt, KNBR);
-        bool tie = overflow || (cnt > KNBR && (rej_min >> 8) == (L[KNBR - 1] >> 8));
-#pragma unroll
-        for (int k = 1; k < KNBR; k++) tie |= (k < n_in) && ((L[k] >> 8) == (L[k - 1] >> 8));
-        if (tie) { knn_exact(A, s, id, me); continue; }
-        int sx[KNBR];
-#pragma unroll
-        for (int k = 0; k < KNBR; k++) sx[k] = (k < n_in) ? buf[L[k] & 0xffu][tid] : -1;
-        A.s_nbr_cnt[s] = n_in;
-        A.s_qcoll[s] = coll ? 1 : 0;
-        if (A.dub_d0) A.dub_d0[id] = n_in > 0 ? div1e5((double)(L[0] >> 8)) : -1.0;
-        int4 *dst = reinterpret_cast<int4 *>(A.s_nbr + (size_t)s * KNBR);
-#pragma unroll
-        for (int q = 0; q < KNBR / 4; q++) dst[q] = make_int4(sx[4 * q], sx[4 * q + 1], sx[4 * q + 2], sx[4 * q + 3]);
-        if (A.st.nbr_cnt) A.st.nbr_cnt[id] = n_in;
-        if (A.st.nbr_ids) {
-#pragma unroll
-            for (int k = 0; k < KNBR; k++) A.st.nbr_ids[(size_t)id * KNBR + k] = (k < n_in) ? A.s_gid[sx[k]] : -1;
-        }
-        if (A.st.nbr_dsq) {
-#pragma unroll
-            for (int k = 0; k < KNBR; k++) A.st.nbr_dsq[(size_t)id * KNBR + k] = (k < n_in) ? div1e5((double)(L[k] >> 8)) : 0.0;
-        }
     }
+    knn_phase2(A, s, id, me, nbuf, overflow, [&](int i) { return buf[i][tid]; });
 }
 
 // the general path for every agent (obstacles in the merged list, SCAB_KNN_EXACT=1, neighbor_dist >= 12.9 m): thread per agent
@@ -519,10 +636,11 @@ cudaError_t launch_neighbors(const StepArgs &A, int mode, cudaStream_t s)
     else {
         // the integer-key fast path needs: no obstacles in the merged list, and distance keys below 2^24 units of 1e-5
         const bool fast_ok = A.m == 0 && A.nbr_dist_sq * 1e5 < 16777215.0 && !A.cfg->knn_exact;   // SCAB_KNN_EXACT=1: A/B switch
-        if (fast_ok) {
+        if (fast_ok && KNN_VARIANT == 0) {
             const int segs = (A.g.nx + NT_W - 1) / NT_W;
             k_neighbors_tile<<<A.g.ny * A.g.nz * segs, NT_THREADS, 0, s>>>(A, segs);
-        } else k_neighbors_exact<<<nb, 128, 0, s>>>(A);
+        } else if (fast_ok) k_neighbors_direct<<<nb, 128, 0, s>>>(A);
+        else k_neighbors_exact<<<nb, 128, 0, s>>>(A);
     }
     return cudaGetLastError();
 }

@@ -47,7 +47,7 @@ struct GroupSmemT : public std::conditional<WITH64, Exact64, NoExact64>::type {
     float4 ch[KNBR];
     float2 cg[KNBR];
     int cidx[KNBR];
-    unsigned short act[DIR_CAP];     // tier-1 entries: n | shell mask << 12 ; n == VPREF_ENTRY = v_pref itself
+    unsigned short act[LIVE_CAP];    // tier-1 candidates: n | shell << 12 ; n == VPREF_ENTRY = v_pref itself
     unsigned int kc[LIVE_CAP];       // live candidates: c, later key << 10 | c
     unsigned int dvu[LIVE_CAP];      // l3norm(v, vA) in units of 1e-5
     int pad[4];                      // the four groups of a warp start in different banks
@@ -266,8 +266,9 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
                 if (c0 - uv <= T1sq) a0 |= m0 & (1u << i);                 // |v - v_pref|^2, fp32
                 if (fmaf(-r2, uv, c1) <= T1sq) a1 |= m1 & (1u << i);
             }
-            unsigned ab = a0 | a1;
-            const int cnt = __popc(ab);
+            // one entry per CANDIDATE (tier 1 around a v_pref of length pref_speed is almost all outer shell: testing the
+            // two shells of a direction together would do half of its arithmetic for nothing)
+            const int cnt = __popc(a0) + __popc(a1);
             int pre = cnt;
 #pragma unroll
             for (int o = 1; o < FG_LANES; o <<= 1) {
@@ -276,13 +277,18 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
             }
             nact = __shfl_sync(gmask, pre, FG_LANES - 1, FG_LANES);
             int slot = pre - cnt;
-            while (ab) {
-                const int i = __ffs(ab) - 1;
-                ab &= ab - 1;
-                W.act[slot++] = (unsigned short)((FG_LANES * i + l8) | ((((a0 >> i) & 1u) | (((a1 >> i) & 1u) << 1)) << 12));
+            while (a0) {
+                const int i = __ffs(a0) - 1;
+                a0 &= a0 - 1;
+                W.act[slot++] = (unsigned short)(FG_LANES * i + l8);
+            }
+            while (a1) {
+                const int i = __ffs(a1) - 1;
+                a1 &= a1 - 1;
+                W.act[slot++] = (unsigned short)((FG_LANES * i + l8) | (1u << 12));
             }
             if (pv) {
-                if (l8 == 0) W.act[nact] = (unsigned short)(VPREF_ENTRY | (1u << 12));
+                if (l8 == 0) W.act[nact] = (unsigned short)VPREF_ENTRY;
                 nact++;
             }
         }
@@ -404,72 +410,60 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
         }
         __syncwarp(gmask);       // the packed constraints (and the tier-1 entries above) are read by every lane of the group
 
-        // ---- B: cone tests per direction (the two shells share p.u and h.u)
+        // ---- B: cone tests, one candidate per lane and round
         int nlive = 0, best = -1;
         unsigned kfail = 0xffffffffu;
         bool overflow = false;
         for (int jb = 0; jb < nact; jb += FG_LANES) {
             const int ja = jb + l8;
-            bool s0 = false, s1 = false;
-            int n = 0;
+            bool ok = false;
+            int c = 0;
             if (ja < nact) {
                 const unsigned ae = W.act[ja];
-                n = ae & 0x3ff;
-                s0 = (ae >> 12) & 1; s1 = (ae >> 13) & 1;
-                const bool isv = (n == VPREF_ENTRY);
+                const int n = ae & 0x3ff;
+                const bool isv = (n == VPREF_ENTRY), outer = (ae >> 12) != 0;
                 const float4 u = isv ? make_float4(vdx, vdy, vdz, 0.f) : tab[n];
                 const float uu = fmaf(u.z, u.z, fmaf(u.y, u.y, u.x * u.x));
-                const float ra = isv ? 1.f : 0.5f, rb = r1f;
-                for (int kk = 0; kk < nce && (s0 || s1); kk++) {
+                const float ra = isv ? 1.f : (outer ? r1f : 0.5f);
+                c = isv ? 2 * a.N : (outer ? a.N + n : n);
+                ok = true;
+                for (int kk = 0; kk < nce && ok; kk++) {
                     const float4 P = W.cp[kk];
                     const float2 G = W.cg[kk];
                     const float pa = fmaf(P.z, u.z, fmaf(P.y, u.y, P.x * u.x));
-                    float df0, df1, dt0, dt1;
+                    float df;
+                    bool in;
                     if (!IS_ORCA) {
                         const float4 H = W.ch[kk];
                         const float hb = fmaf(H.z, u.z, fmaf(H.y, u.y, H.x * u.x));
-                        dt0 = fmaf(ra, pa, -P.w); dt1 = fmaf(rb, pa, -P.w);
-                        const float vv0 = fmaf(-2.f * ra, hb, ra * ra * uu) + H.w, vv1 = fmaf(-2.f * rb, hb, rb * rb * uu) + H.w;
-                        df0 = fmaf(dt0, dt0, -vv0 * G.x); df1 = fmaf(dt1, dt1, -vv1 * G.x);
+                        const float dt = fmaf(ra, pa, -P.w);
+                        const float vv = fmaf(-2.f * ra, hb, ra * ra * uu) + H.w;
+                        df = fmaf(dt, dt, -vv * G.x);
+                        in = (dt > 0.f) && (df > 0.f);
                     } else {
-                        dt0 = 1.f; dt1 = 1.f;
-                        df0 = -(fmaf(ra, pa, -P.w)); df1 = -(fmaf(rb, pa, -P.w));   // violated iff n.v - n.q < 0
+                        df = fmaf(ra, pa, -P.w);          // n.v - n.q: violated iff negative
+                        in = !(df >= 0.f);
                     }
-                    bool in0, in1;
-                    if (!IS_ORCA) { in0 = (dt0 > 0.f) && (df0 > 0.f); in1 = (dt1 > 0.f) && (df1 > 0.f); }
-                    else { in0 = !(-df0 >= 0.f); in1 = !(-df1 >= 0.f); }
-                    const bool un0 = s0 && fabsf(df0) <= G.y, un1 = s1 && fabsf(df1) <= G.y;
-                    if (un0 || un1) {
+                    if (fabsf(df) <= G.y) {              // inside the fp32 guard band: the reference's fp64 expression
                         const int k = W.cidx[kk];
-                        for (int sh = 0; sh < 2; sh++) {
-                            if (!(sh ? un1 : un0)) continue;
-                            n_recheck++;
-                            const int c = isv ? 2 * a.N : (sh ? a.N + n : n);
-                            double x, y, z;
-                            cand64(a, c, x, y, z);
-                            bool ins;
-                            if constexpr (!IS_ORCA) {
-                                ins = recheck_cone64(A, s, k, a, x, y, z);
-                            } else {
-                                double val = dot3(__dsub_rn(x, W.dpx[k]), __dsub_rn(y, W.dpy[k]), __dsub_rn(z, W.dpz[k]),
-                                                  W.dhx[k], W.dhy[k], W.dhz[k]);
-                                ins = !(val >= 0.0);
-                            }
-                            if (sh) in1 = ins; else in0 = ins;
+                        n_recheck++;
+                        double x, y, z;
+                        cand64(a, c, x, y, z);
+                        if constexpr (!IS_ORCA) {
+                            in = recheck_cone64(A, s, k, a, x, y, z);
+                        } else {
+                            double val = dot3(__dsub_rn(x, W.dpx[k]), __dsub_rn(y, W.dpy[k]), __dsub_rn(z, W.dpz[k]),
+                                              W.dhx[k], W.dhy[k], W.dhz[k]);
+                            in = !(val >= 0.0);
                         }
                     }
-                    if (in0) s0 = false;
-                    if (in1) s1 = false;
+                    if (in) ok = false;
                 }
             }
             // compact the surviving candidates of this round (generation index c) into the live list
-            const bool isv = (n == VPREF_ENTRY);
-            unsigned b0 = (__ballot_sync(gmask, s0) >> (8 * g)) & 0xffu;
-            if (s0) W.kc[nlive + __popc(b0 & lt8)] = isv ? 2 * a.N : n;
+            const unsigned b0 = (__ballot_sync(gmask, ok) >> (8 * g)) & 0xffu;
+            if (ok) W.kc[nlive + __popc(b0 & lt8)] = c;
             nlive += __popc(b0);
-            unsigned b1 = (__ballot_sync(gmask, s1) >> (8 * g)) & 0xffu;
-            if (s1) W.kc[nlive + __popc(b1 & lt8)] = a.N + n;
-            nlive += __popc(b1);
         }
         __syncwarp(gmask);
 

@@ -59,6 +59,7 @@ static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4
 static inline long long __double_as_longlong(double d) { long long i; std::memcpy(&i, &d, 8); return i; }
 static inline double __longlong_as_double(long long i) { double d; std::memcpy(&d, &i, 8); return d; }
 static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
+template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
