@@ -31,12 +31,40 @@ import numpy as np  # noqa: E402
 
 DENSITY = 1.0e6 / 560.0 ** 3          # agents per m^3 of BASELINE config 5
 ALGO_BYTES = {'grid': 168, 'neighbors': 116, 'policy': 660, 'status': 144}   # SURVEY.md 8(d), per agent-step
-# kernels launched per step: k_cell_count, k_scan_tile_sums, k_scan_tiles, k_scan_apply, k_reorder, k_neighbors_knn,
+# kernels launched per step: k_cell_count, k_scan_tile_sums, k_scan_tiles, k_scan_apply, k_reorder, k_neighbors_direct,
 # then k_vpref, k_select_fast, k_select, k_integrate (sampled policies) or k_policy_lp<1>, k_policy_lp<2> (ORCA LP), then k_status
 KERNELS_PER_STEP = {'orca_lp': 9}
 KERNELS_PER_STEP_SAMPLED = 11
 POLICY_KERNELS = {'orca_lp': 'k_policy_lp'}
 METRIC = 'agent-steps/sec (SCA, 1M UAVs)'      # --policy other than sca: the same workload under that policy (named in config)
+
+# BASELINE.json configs[0..4] as --config 1..5 (5 = the headline workload and the default).  `cpu`: the bounded sample the
+# CPU legs run (the whole scenario where the oracle finishes it in seconds).
+CONFIGS = {
+    1: dict(workload='BASELINE configs[0]: run_sca.py circle scenario (R = 18 m), 100 fixed-wing UAVs, SCA with its Dubins v_pref '
+                     'tracker on the device, REF_COMPAT neighbour lists (the reference\'s own kd-tree order)',
+            policy='sca', nbr='compat', dubins=True, gen=lambda sc: sc.circle(100, 18.0), cpu=lambda sc: sc.circle(100, 18.0)),
+    2: dict(workload='BASELINE configs[1]: run_orca.py random box (r = 15 m, seed 0), 1,000 agents, ORCA3D with linearProgram3 / '
+                     'linearProgram4 (orca3dPolicyOfficial), REF_COMPAT neighbour lists',
+            policy='orca_lp', nbr='compat', dubins=False, gen=lambda sc: sc.random_box(1000, 15.0, seed=0),
+            cpu=lambda sc: sc.random_box(1000, 15.0, seed=0)),
+    3: dict(workload='BASELINE configs[2]: SCA take-off / landing pads (run_sca.py:53-81 + the 8 obstacles of :139-150) tiled 25 x 25 at '
+                     '30 m pitch: 10,000 UAVs + 5,000 obstacles, posture constraint, Dubins tracker on the device, KNN neighbour mode',
+            policy='sca', nbr='knn', dubins=True, gen=lambda sc: sc.takeoff_landing_tiled(625), cpu=lambda sc: sc.takeoff_landing_tiled(64)),
+    4: dict(workload='BASELINE configs[3]: dense Fibonacci-sphere swap (run_orca.py:36-54 scaled, R = 198 m), 100,000 agents, KNN neighbour mode',
+            policy='rvo3d', nbr='knn', dubins=False, gen=lambda sc: sc.dense_sphere(100000), cpu=lambda sc: sc.dense_sphere(100000)),
+}
+
+
+def config_of(args):
+    """-> (cfg dict or None for the default workload, policy, neighbour mode name)."""
+    if args.config == 5:
+        return None, args.policy or 'sca', 'knn'
+    cfg = CONFIGS[args.config]
+    pol = args.policy or cfg['policy']
+    if args.config == 4 and pol not in ('rvo3d', 'srvo3d'):
+        raise SystemExit('--config 4 is the RVO3D / S-RVO3D workload: --policy rvo3d|srvo3d')
+    return cfg, pol, cfg['nbr']
 
 
 def measured_peak():
@@ -90,6 +118,23 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def make_config_swarm(cfg, device):
+    """BASELINE configs[0..3]: the reference's own scenario geometry on one GPU."""
+    from sca_b200 import scenarios
+    from sca_b200.swarm import Swarm
+    pos, goal, obs = cfg['gen'](scenarios)
+    n = len(pos)
+    sw = Swarm(n, device=device, debug=False)
+    sw.set_state(pos[:, :3], goal[:, :3], heading=pos[:, 3:6], initial_pos=pos, goal_pos=goal)
+    sw.set_obstacles(obs)
+    lo = np.minimum(pos[:, :3].min(0), goal[:, :3].min(0)) - 20.0
+    hi = np.maximum(pos[:, :3].max(0), goal[:, :3].max(0)) + 20.0
+    sw.fit_grid(lo, hi)
+    if cfg['dubins']:
+        sw.enable_dubins(goal[:, 3:6])
+    return sw
+
+
 def make_swarm(n_total, rank, world, device, seed=0):
     from sca_b200 import scenarios
     from sca_b200.swarm import Swarm
@@ -123,9 +168,18 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device(device))
     from sca_b200 import capi
-    n_total = args.agents
-    sw = make_swarm(n_total, rank, world, device)
-    policy = args.policy
+    cfg, policy, nbr_name = config_of(args)
+    NBR = capi.NBR_REF_COMPAT if nbr_name == 'compat' else capi.NBR_KNN
+    if cfg is not None and world > 1:
+        raise SystemExit('--config 1-4 are single-GPU workloads (below the size where sharding pays off, SURVEY 8e)')
+    if cfg is None:
+        n_total = args.agents
+        sw = make_swarm(n_total, rank, world, device)
+    else:
+        sw = make_config_swarm(cfg, device)
+        n_total = sw.n
+    for _ in range(args.skip_steps):          # a later part of the rollout (conflicts have developed), untimed
+        sw.step(policy, NBR)
 
     def barrier():
         if world > 1:
@@ -133,17 +187,17 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     if world > 1:
-        sw.warm_up(policy, capi.NBR_KNN)     # load every kernel before the first NCCL exchange
+        sw.warm_up(policy, NBR)     # load every kernel before the first NCCL exchange
         torch.distributed.barrier()
     tstream = getattr(sw, 'stream', None) or torch.cuda.current_stream()   # the stream the kernels are launched on
     for _ in range(max(args.warmup, 3)):
-        sw.step(policy, capi.NBR_KNN)
+        sw.step(policy, NBR)
     barrier()
     if os.environ.get('SCAB_BENCH_TRACE'):        # debug: per-step wall times (synchronised), not part of the measurement
         tr = []
         for _ in range(args.steps):
             t0 = time.perf_counter()
-            sw.step(policy, capi.NBR_KNN)
+            sw.step(policy, NBR)
             tstream.synchronize()
             tr.append(round((time.perf_counter() - t0) * 1e3, 2))
         if rank == 0:
@@ -158,7 +212,7 @@ def run_ours(args):
         acc = {}
         for _ in range(args.steps):
             del marks[:]
-            sw.step(policy, capi.NBR_KNN)
+            sw.step(policy, NBR)
             with torch.cuda.stream(sw.stream):
                 mark('end')
             sw.stream.synchronize()
@@ -175,7 +229,7 @@ def run_ours(args):
     t_wall0 = time.time()
     ev0.record(tstream)
     for _ in range(args.steps):
-        sw.step(policy, capi.NBR_KNN)
+        sw.step(policy, NBR)
     ev1.record(tstream)
     barrier()
     t_wall1 = time.time()
@@ -198,7 +252,7 @@ def run_ours(args):
         act0 = sw.counters()['n_active_total']
         for k in range(args.steps):
             evs[k][0].record(); sw.stage_grid()
-            evs[k][1].record(); sw.stage_neighbors(capi.NBR_KNN)
+            evs[k][1].record(); sw.stage_neighbors(NBR)
             evs[k][2].record(); sw.stage_policy(policy)
             evs[k][3].record(); sw.stage_status()
             evs[k][4].record()
@@ -207,6 +261,9 @@ def run_ours(args):
         act = (cdiag['n_active_total'] - act0) / args.steps
         stage_ms = {nm: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)]))
                     for i, nm in enumerate(names)}
+        # the reference's own cost metric: AverageCost = 1000 * sum(agent.total_time) / sum(step_num) (run_sca.py:250), i.e.
+        # POLICY milliseconds per agent-step (neighbour query + velocity selection; kd-tree build and env update excluded)
+        average_cost = (stage_ms['neighbors'] + stage_ms['policy']) / max(act, 1.0)
         dom = max(stage_ms, key=stage_ms.get)
         peak, how = measured_peak()
         units = n_total if dom in ('grid', 'status') else act     # grid/status touch every agent, the others the active ones
@@ -217,12 +274,13 @@ def run_ours(args):
                 traffic = json.load(f).get(dom if (dom != 'policy' or policy == 'sca') else 'policy_' + policy)   # ncu figures are per kernel
         except Exception:
             pass
-        roof = {'bound': 'hbm', 'kernel': {'grid': 'k_cell_count+k_scan_*+k_reorder', 'neighbors': 'k_neighbors_knn',
+        roof = {'bound': 'hbm', 'kernel': {'grid': 'k_cell_count+k_scan_*+k_reorder', 'neighbors': 'k_neighbors_compat' if nbr_name == 'compat' else 'k_neighbors_direct',
                                            'policy': POLICY_KERNELS.get(policy, 'k_vpref+k_select_fast<%s>+k_select<%s>+k_integrate' % (policy.upper(), policy.upper())),
                                            'status': 'k_status'}[dom],
                 'achieved': round(achieved, 2), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 5),
                 'traffic': traffic, 'peak_source': how, 'algorithmic_bytes_per_agent_step': ALGO_BYTES[dom],
                 'units_per_launch': int(units), 'stage_ms': {k: round(v, 4) for k, v in stage_ms.items()},
+                'average_cost_ms_per_agent_step': average_cost,
                 'last_step_diag': {k: cdiag[k] for k in ('n_active', 'n_recheck', 'n_tier2', 'n_slow', 'n_collision')},
                 'note': 'the policy stage is ALU / instruction-issue bound (SURVEY.md 8d): HBM fraction is reported as asked, '
                         'stage_ms shows where the step goes'}
@@ -285,7 +343,7 @@ def run_ours(args):
                     with torch.cuda.stream(st):
                         for k in keys_state:
                             sw.t[k][:rows].copy_(host[k], non_blocking=True)
-                    sw.step(policy, capi.NBR_KNN)
+                    sw.step(policy, NBR)
                     with torch.cuda.stream(st):
                         for k in keys_state:
                             host[k].copy_(sw.t[k][:rows], non_blocking=True)
@@ -312,18 +370,30 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu and not args.quick:
-        cpu = cpu_baseline(args.cpu_agents, 1, policy, budget_s=12.0)
+        cpu = cpu_baseline(args.cpu_agents, 1, policy, budget_s=12.0, cfg=cfg)
 
     if rank == 0:
-        out = {'metric': METRIC, 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': args.steps,
+        if cfg is None:
+            metric = METRIC
+            conf = {'workload': 'BASELINE configs[4]: SCA synthetic uniform-random swarm, %d UAVs, density 1e6/(560 m)^3, '
+                                'straight-line v_pref, KNN neighbour mode' % n_total,
+                    'policy': policy, 'agents': n_total, 'neighbour_mode': 'KNN (true 16 nearest; NOT the reference\'s traversal-order '
+                    'lists, SURVEY fact 3 -- REF_COMPAT reproduces those and is what --config 1 / 2 run)',
+                    'l2': 'per-step working set (~%d MB) exceeds the 126 MB L2' % (n_total * 420 // 1000000),
+                    'parallelism': 'spatial slabs x%d + halo exchange' % world if world > 1 else 'single GPU'}
+        else:
+            metric = 'agent-steps/sec (%s, %d agents)' % (policy.upper(), n_total)
+            conf = {'workload': cfg['workload'], 'policy': policy, 'agents': n_total,
+                    'neighbour_mode': 'REF_COMPAT (kd-tree rebuilt on the host every step, as mampenv.py:28 does)' if nbr_name == 'compat' else 'KNN',
+                    'l2': 'working set fits the 126 MB L2: the step is launch / latency bound at this size' if n_total < 200000 else '',
+                    'parallelism': 'single GPU'}
+        if args.skip_steps:
+            conf['rollout_window'] = 'steps %d..%d of the rollout' % (args.skip_steps + max(args.warmup, 3), args.skip_steps + max(args.warmup, 3) + args.steps)
+        out = {'metric': metric, 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': args.steps,
                'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
                'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32 candidate tests + f64 decision scalars',
                'data': 'synthetic',
-               'config': {'workload': 'BASELINE configs[4]: SCA synthetic uniform-random swarm, %d UAVs, density 1e6/(560 m)^3, '
-                                      'straight-line v_pref, KNN neighbour mode' % n_total,
-                          'policy': policy, 'agents': n_total, 'l2': 'per-step working set (~%d MB) exceeds the 126 MB L2'
-                                                                     % (n_total * 420 // 1000000),
-                          'parallelism': 'spatial slabs x%d + halo exchange' % world if world > 1 else 'single GPU'},
+               'config': conf,
                # + 5 halo kernels per step when sharded: k_halo_fill, k_halo_pack, k_halo_unpack, k_halo_pack_pos, k_halo_unpack_pos
                'gpu_launches': (KERNELS_PER_STEP.get(policy, KERNELS_PER_STEP_SAMPLED) + (5 if world > 1 else 0)) * args.steps, 'clocks': clocks}
         if roof:
@@ -342,28 +412,58 @@ def run_ours(args):
         os._exit(0)
 
 
-def cpu_baseline(n_agents, threads, policy, budget_s=15.0, steps=None):
-    """The CPU oracle port of the reference (oracle/sca_oracle.c) on a bounded sample of the same workload:
-    the same density and policy, n_agents agents.  Returns the cpu_baseline object of the bench contract."""
+def oracle_world(n_agents, policy, cfg):
+    """The oracle's world for a CPU leg: the default workload at `n_agents` agents, or a --config scenario.
+    -> (world, stepper(), sample description, neighbour mode)"""
     from oracle import oracle as orc
     from sca_b200 import scenarios
+    if cfg is None:
+        pos, goal, obs = scenarios.uniform_box_numpy(n_agents, DENSITY, seed=1)
+        what, mode, dub = '%d agents at the workload density' % n_agents, orc.NBR_KNN, False
+    else:
+        pos, goal, obs = cfg['cpu'](scenarios)
+        what, mode, dub = 'the scenario at %d agents' % len(pos), (orc.NBR_REF_COMPAT if cfg['nbr'] == 'compat' else orc.NBR_KNN), cfg['dubins']
+    w = orc.World(pos[:, :3], goal[:, :3], heading=pos[:, 3:6], obstacles=obs, initial_pos=pos, goal_pos=goal)
+    timing = {'policy': 0.0}
+    if dub:
+        prov = orc.DubinsProvider(len(pos))
+        gh = np.ascontiguousarray(goal[:, 3:6])
+
+        def one():
+            t0 = time.perf_counter()
+            w.step_dubins(policy, prov, gh, mode)
+            timing['policy'] += time.perf_counter() - t0      # (includes the env update of step_dubins: small next to the tracker)
+    else:
+        def one():
+            t0 = time.perf_counter()
+            w.policy_step(policy, mode)
+            timing['policy'] += time.perf_counter() - t0
+            w.env_update(fast=True)
+    return w, one, what, ('REF_COMPAT' if mode == orc.NBR_REF_COMPAT else 'KNN'), timing
+
+
+def cpu_baseline(n_agents, threads, policy, budget_s=15.0, steps=None, cfg=None):
+    """The CPU oracle port of the reference (oracle/sca_oracle.c) on a bounded sample of the same workload:
+    the same density (or scenario) and policy.  Returns the cpu_baseline object of the bench contract."""
+    from oracle import oracle as orc
     orc.set_threads(threads)
-    pos, goal, _ = scenarios.uniform_box_numpy(n_agents, DENSITY, seed=1)
-    w = orc.World(pos[:, :3], goal[:, :3], heading=pos[:, 3:])
+    w, one, what, mode, timing = oracle_world(n_agents, policy, cfg)
     for _ in range(2):                      # leave the zero-velocity shortcut (step 0)
-        w.step(policy, orc.NBR_KNN, fast=True)
+        one()
+    timing['policy'] = 0.0
     done_steps, agent_steps = 0, 0
     t0 = time.perf_counter()
     while True:
-        w.step(policy, orc.NBR_KNN, fast=True)
+        one()
         agent_steps += int(w.ran.sum())
         done_steps += 1
         el = time.perf_counter() - t0
         if (steps and done_steps >= steps) or (not steps and (el > budget_s or done_steps >= 200)):
             break
     return {'value': agent_steps / el, 'unit': 'agent-steps/s', 'cores': threads, 'kind': 'port',
-            'sample': '%d agents at the workload density, %d steps, %s policy, KNN neighbour mode, %.1f s' % (
-                n_agents, done_steps, policy, el), 'ms_per_step': el / done_steps * 1e3, 'steps': done_steps}
+            'sample': '%s, %d steps, %s policy, %s neighbour mode, %.1f s' % (what, done_steps, policy, mode, el),
+            'ms_per_step': el / done_steps * 1e3, 'steps': done_steps,
+            'average_cost_ms_per_agent_step': 1e3 * timing['policy'] / max(agent_steps, 1)}
 
 
 def run_reference(args):
@@ -375,28 +475,28 @@ def run_reference(args):
     total_agent_steps, total_t = 0, 0.0
     # each "step" of this arm is one oracle step over the bounded sample
     from oracle import oracle as orc
-    from sca_b200 import scenarios
     orc.set_threads(threads)
-    n = args.cpu_agents
-    pos, goal, _ = scenarios.uniform_box_numpy(n, DENSITY, seed=1)
-    w = orc.World(pos[:, :3], goal[:, :3], heading=pos[:, 3:])
+    cfg, policy, _ = config_of(args)
+    args.policy = policy
+    w, one, what, mode, timing = oracle_world(args.cpu_agents, policy, cfg)
+    n = w.n
     for _ in range(max(args.warmup, 2)):
-        w.step(args.policy, orc.NBR_KNN, fast=True)
+        one()
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        w.step(args.policy, orc.NBR_KNN, fast=True)
+        one()
         dt = time.perf_counter() - t0
         per_step.append(dt)
         total_agent_steps += int(w.ran.sum())
         total_t += dt
     value = total_agent_steps / total_t
-    sample = '%d agents at the workload density per step (bounded sample of the 1M workload), %s policy' % (n, args.policy)
-    out = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'agent-steps/s',
+    sample = '%s per step (bounded sample), %s policy, %s neighbour mode' % (what, args.policy, mode)
+    out = {'impl': 'reference', 'metric': METRIC if cfg is None else 'agent-steps/sec (%s, %d agents)' % (policy.upper(), len(cfg['gen'](__import__('sca_b200.scenarios', fromlist=['x']))[0])), 'value': value, 'unit': 'agent-steps/s',
            'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': args.steps, 'warmup': max(args.warmup, 2),
            'ms_per_step': total_t / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
            'dtype': 'f64', 'data': 'synthetic',
-           'config': {'workload': 'BASELINE configs[4]: SCA synthetic uniform-random swarm (bounded sample: %d UAVs at the '
-                                  '1M-UAV density), straight-line v_pref, KNN neighbour mode' % n,
+           'config': {'workload': ('BASELINE configs[4]: SCA synthetic uniform-random swarm (bounded sample: %d UAVs at the '
+                                   '1M-UAV density), straight-line v_pref, KNN neighbour mode' % n) if cfg is None else cfg['workload'] + ' (CPU sample: %s)' % what,
                       'policy': args.policy, 'agents': n,
                       'note': 'the Python reference runs ~40 agent-steps/s single-threaded (BASELINE.md); this arm times its C '
                               'restatement (oracle/sca_oracle.c), which is pinned to the reference by the golden fixtures'},
@@ -413,7 +513,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--agents', type=int, default=1000000)
-    ap.add_argument('--policy', default='sca')
+    ap.add_argument('--policy', default=None, help='default: the policy of the chosen --config (sca for the headline workload)')
+    ap.add_argument('--config', type=int, default=5, choices=[1, 2, 3, 4, 5], help='BASELINE.json configs[N-1]; 5 = the headline workload (default)')
+    ap.add_argument('--skip-steps', type=int, default=0, help='untimed steps before the warm-up: sample a later part of the rollout')
     ap.add_argument('--cpu-agents', type=int, default=20000)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--quick', action='store_true', help='A/B runs: device-timed value + stage times only (no e2e, no CPU baseline)')

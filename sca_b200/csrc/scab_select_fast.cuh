@@ -28,7 +28,7 @@
 #define LIVE_CAP 136      // 2 * DIR_CAP + v_pref, rounded up
 #define VPREF_ENTRY 0x3ff
 #ifndef FG_MIN_CTAS
-#define FG_MIN_CTAS 4   // resident CTAs per SM the kernel is compiled for; 5 (<= 96 registers) spills and measured 2.6 % slower
+#define FG_MIN_CTAS 5   // resident CTAs per SM the kernel is compiled for (96 registers): 1.39 -> 1.27 ms for the policy stage on B200; 6 spills
 #endif
 // tier 1 = candidates within StepArgs::tier_delta (default 0.3, SCAB_TIER_DELTA) of the one closest to v_pref
 
