@@ -154,7 +154,8 @@ def make_swarm(n_total, rank, world, device, seed=0):
         sw.fit_grid(lo, hi)
         return sw
     from sca_b200.sharding import ShardedSwarm
-    return ShardedSwarm(pos, goal, rank, world, device, lo, hi)
+    # SCAB_TRANSPORT=nccl: pack -> ncclSend/ncclRecv -> unpack instead of the direct NVLink writes (A/B switch)
+    return ShardedSwarm(pos, goal, rank, world, device, lo, hi, transport=os.environ.get('SCAB_TRANSPORT', 'p2p'))
 
 
 def run_ours(args):

@@ -249,6 +249,22 @@ int scab_migrate_unpack(scab_handle *h, const void *in_lo, const void *in_hi, in
 int64_t scab_migrate_extra_row_doubles(scab_handle *h);
 int scab_migrate_extra_pack(scab_handle *h, double *out_lo, double *out_hi, int32_t cap, const int32_t *cnt, void *stream);
 int scab_migrate_extra_unpack(scab_handle *h, const double *in_lo, const double *in_hi, int32_t cap, void *stream);
+/* ---- The same exchanges WITHOUT a communication library: peer-to-peer over NVLink.  The out_lo / out_hi arguments of
+ * scab_halo_pack, scab_halo_pack_pos, scab_migrate_pack and scab_migrate_extra_pack may be PEER memory: the slab neighbour's
+ * receive buffers.  scab_p2p_alloc allocates a zeroed device buffer that another process of the node can map
+ * (handle_out: SCAB_IPC_HANDLE_BYTES bytes to hand to the peer; NULL = no handle wanted), scab_p2p_open maps a peer's
+ * buffer from its handle; both are released by scab_destroy.  After its pack kernels a rank calls scab_p2p_signal:
+ * seq = ++*local_seq, then (system-scope fence) *peer_flag_lo = *peer_flag_hi = seq (NULL = no neighbour on that side);
+ * before its unpack kernels it calls scab_p2p_wait: e = ++*local_expect, spin until both flags >= e.  All four are
+ * uint64 words in device memory (the flags inside a scab_p2p_alloc'ed buffer, written by the peers).  Asynchronous on `stream`,
+ * capturable in a CUDA graph.  A wait that is not satisfied within ~2 s gives up and sets SCAB_OVF_P2P_TIMEOUT. */
+#define SCAB_IPC_HANDLE_BYTES 64
+#define SCAB_OVF_P2P_TIMEOUT 16
+int scab_p2p_alloc(scab_handle *h, int64_t bytes, void **dev_ptr, unsigned char *handle_out);
+int scab_p2p_open(scab_handle *h, const unsigned char *handle, void **dev_ptr);
+int scab_p2p_signal(scab_handle *h, void *local_seq, void *peer_flag_lo, void *peer_flag_hi, void *stream);
+int scab_p2p_wait(scab_handle *h, void *local_expect, const void *flag_from_lo, const void *flag_from_hi, void *stream);
+
 /* Blocking: how many agents the last scab_halo_pack selected per face (> cap means the buffers overflowed). */
 int scab_halo_counts(scab_handle *h, int32_t out_host[2], void *stream);
 

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libscab200.so')
 SOURCES = ['scab_api.cu', 'scab_grid.cu', 'scab_neighbors.cu', 'scab_policy_sampled.cu', 'scab_policy_lp.cu',
-           'scab_status.cu', 'scab_halo.cu', 'scab_dubins.cu']
+           'scab_status.cu', 'scab_halo.cu', 'scab_p2p.cu', 'scab_dubins.cu']
 # -fmad=false: the reference's decision scalars are reproduced op by op in fp64; the only fused
 # multiply-adds are the explicit ones (NumPy's 3-element dot, the fp32 candidate loop).
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-fmad=false',

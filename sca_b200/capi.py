@@ -19,17 +19,19 @@ TAG_FIRST, TAG_SUITABLE, TAG_FALLBACK, TAG_LP3_OK, TAG_LP4 = 1, 2, 4, 8, 16
 # every symbol include/scab200.h declares (tests/test_capi_symbols.py checks the header against this)
 OPT_FULL_SEARCH = 1
 
-OVF_HALO, OVF_MIGRATION_DEFERRED, OVF_MIGRATION_LOST, OVF_MOTION = 1, 2, 4, 8
+OVF_HALO, OVF_MIGRATION_DEFERRED, OVF_MIGRATION_LOST, OVF_MOTION, OVF_P2P_TIMEOUT = 1, 2, 4, 8, 16
+IPC_HANDLE_BYTES = 64
 OVF_TEXT = {1: 'a halo face buffer overflowed (ghost records dropped)', 2: 'a migration buffer was full (an agent stayed outside its slab)',
             4: 'an arriving agent found no free row (agent lost)',
-            8: 'an agent moved farther in one step than the motion bound the collision stage relies on (scab_set_motion_bound)'}
+            8: 'an agent moved farther in one step than the motion bound the collision stage relies on (scab_set_motion_bound)',
+            16: 'a peer-to-peer halo wait timed out (the neighbour rank never published its data)'}
 
 SYMBOLS = ['scab_version', 'scab_default_params', 'scab_set_option', 'scab_set_max_radius', 'scab_set_motion_bound', 'scab_create', 'scab_destroy', 'scab_last_error', 'scab_set_grid',
            'scab_bind_state', 'scab_set_obstacles', 'scab_kdtree_build', 'scab_kdtree_get_perm', 'scab_build_grid',
            'scab_neighbors', 'scab_policy_step', 'scab_status_step', 'scab_step', 'scab_read_counters',
            'scab_reset_counters', 'scab_halo_pack', 'scab_halo_unpack', 'scab_halo_pack_pos', 'scab_halo_unpack_pos',
            'scab_halo_counts', 'scab_migrate_pack', 'scab_migrate_unpack', 'scab_migrate_extra_row_doubles', 'scab_migrate_extra_pack',
-           'scab_migrate_extra_unpack', 'scab_dubins_enable', 'scab_dubins_state_size', 'scab_dubins_read']
+           'scab_migrate_extra_unpack', 'scab_p2p_alloc', 'scab_p2p_open', 'scab_p2p_signal', 'scab_p2p_wait', 'scab_dubins_enable', 'scab_dubins_state_size', 'scab_dubins_read']
 
 
 class ScabError(RuntimeError):
@@ -116,6 +118,10 @@ def lib():
     L.scab_migrate_extra_row_doubles.argtypes = [vp]
     L.scab_migrate_extra_pack.argtypes = [vp, vp, vp, i32, vp, vp]
     L.scab_migrate_extra_unpack.argtypes = [vp, vp, vp, i32, vp]
+    L.scab_p2p_alloc.argtypes = [vp, i64, C.POINTER(vp), vp]
+    L.scab_p2p_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.scab_p2p_signal.argtypes = [vp, vp, vp, vp, vp]
+    L.scab_p2p_wait.argtypes = [vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -257,6 +263,26 @@ class Handle:
 
     def migrate_extra_unpack(self, in_lo, in_hi, cap, stream=0):
         self._ck(self._L.scab_migrate_extra_unpack(self._h, in_lo, in_hi, int(cap), stream))
+
+    # ---- peer-to-peer exchange (NVLink, CUDA IPC)
+    def p2p_alloc(self, nbytes, want_handle=True):
+        """-> (device pointer, IPC handle bytes or None).  Zeroed; released by scab_destroy."""
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * IPC_HANDLE_BYTES)() if want_handle else None
+        self._ck(self._L.scab_p2p_alloc(self._h, int(nbytes), C.byref(ptr), C.cast(buf, C.c_void_p) if want_handle else None))
+        return int(ptr.value), (bytes(buf) if want_handle else None)
+
+    def p2p_open(self, handle):
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        self._ck(self._L.scab_p2p_open(self._h, C.cast(buf, C.c_void_p), C.byref(ptr)))
+        return int(ptr.value)
+
+    def p2p_signal(self, local_seq, peer_flag_lo, peer_flag_hi, stream=0):
+        self._ck(self._L.scab_p2p_signal(self._h, local_seq, peer_flag_lo or None, peer_flag_hi or None, stream))
+
+    def p2p_wait(self, local_expect, flag_from_lo, flag_from_hi, stream=0):
+        self._ck(self._L.scab_p2p_wait(self._h, local_expect, flag_from_lo or None, flag_from_hi or None, stream))
 
     def halo_counts(self, stream=0):
         out = (C.c_int32 * 2)()

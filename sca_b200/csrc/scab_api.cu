@@ -44,6 +44,8 @@ struct scab_handle {
     // migration bookkeeping: rows vacated by the last scab_migrate_pack / rows given to the arrivals of the last unpack
     int32_t *d_mig_sent_row = nullptr, *d_mig_recv_row = nullptr;
     int32_t mig_cap = 0;
+    // peer-to-peer exchange buffers (scab_p2p_alloc) and peer mappings (scab_p2p_open)
+    std::vector<void *> p2p_own, p2p_peer;
     // Dubins v_pref provider (allocated by the first scab_dubins_enable)
     void *d_dub_states = nullptr;
     double *d_dub_d0 = nullptr;
@@ -315,6 +317,8 @@ extern "C" int scab_destroy(scab_handle *h)
                     h->d_counters, h->d_o_posr, h->d_o_posr_by_id, h->d_o_id, h->d_o_cell_start, h->d_kd_obst_perm, h->d_kd_obst,
                     h->d_dub_states, h->d_dub_d0};
     for (void *q : ptrs) if (q) cudaFree(q);
+    for (void *q : h->p2p_peer) cudaIpcCloseMemHandle(q);
+    for (void *q : h->p2p_own) cudaFree(q);
     delete h;
     return SCAB_OK;
 }
@@ -674,5 +678,56 @@ extern "C" int scab_migrate_extra_unpack(scab_handle *h, const double *in_lo, co
     if (cap <= 0 || !in_lo || !in_hi || 2 * (int64_t)cap > h->capacity)
         return fail(h, SCAB_ERR_INVALID, "scab_migrate_extra_unpack: bad argument");
     CK(launch_migrate_extra_unpack(h->A, h->d_mig_recv_row, cap, in_lo, in_hi, (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+
+// ------------------------------------------------------------------ peer-to-peer exchange (scab_p2p.cu)
+static_assert(sizeof(cudaIpcMemHandle_t) == SCAB_IPC_HANDLE_BYTES, "scab200.h: SCAB_IPC_HANDLE_BYTES");
+
+extern "C" int scab_p2p_alloc(scab_handle *h, int64_t bytes, void **dev_ptr, unsigned char *handle_out)
+{
+    if (!h || bytes <= 0 || !dev_ptr) return fail(h, SCAB_ERR_INVALID, "scab_p2p_alloc: bad argument");
+    CK(cudaSetDevice(h->device));
+    void *p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) { (void)cudaGetLastError(); return fail(h, SCAB_ERR_NOMEM, "scab_p2p_alloc: out of device memory"); }
+    CK(cudaMemset(p, 0, (size_t)bytes));
+    h->p2p_own.push_back(p);
+    *dev_ptr = p;
+    if (handle_out) {     // NULL: the buffer is only shared inside this process (logical shards on one device)
+        cudaIpcMemHandle_t ih;
+        CK(cudaIpcGetMemHandle(&ih, p));
+        memcpy(handle_out, &ih, sizeof(ih));
+    }
+    return SCAB_OK;
+}
+
+extern "C" int scab_p2p_open(scab_handle *h, const unsigned char *handle, void **dev_ptr)
+{
+    if (!h || !handle || !dev_ptr) return fail(h, SCAB_ERR_INVALID, "scab_p2p_open: bad argument");
+    CK(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, handle, sizeof(ih));
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+    h->p2p_peer.push_back(p);
+    *dev_ptr = p;
+    return SCAB_OK;
+}
+
+extern "C" int scab_p2p_signal(scab_handle *h, void *local_seq, void *peer_flag_lo, void *peer_flag_hi, void *stream)
+{
+    if (!h || !local_seq) return fail(h, SCAB_ERR_INVALID, "scab_p2p_signal: bad argument");
+    CK(cudaSetDevice(h->device));
+    CK(launch_p2p_signal((unsigned long long *)local_seq, (unsigned long long *)peer_flag_lo, (unsigned long long *)peer_flag_hi, (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int scab_p2p_wait(scab_handle *h, void *local_expect, const void *flag_from_lo, const void *flag_from_hi, void *stream)
+{
+    if (!h || !local_expect) return fail(h, SCAB_ERR_INVALID, "scab_p2p_wait: bad argument");
+    CK(cudaSetDevice(h->device));
+    CK(launch_p2p_wait(h->A, (unsigned long long *)local_expect, (const unsigned long long *)flag_from_lo, (const unsigned long long *)flag_from_hi,
+                       (cudaStream_t)stream));
     return SCAB_OK;
 }

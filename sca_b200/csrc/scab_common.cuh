@@ -45,6 +45,7 @@ struct LaunchCfg {
 #define OVF_MIG_DEFER 2ull   // k_migrate_pack could not send an agent (buffer full): it stays outside its slab
 #define OVF_MIG_LOST 4ull    // k_migrate_unpack found no free row for an arrival: the agent is gone
 #define OVF_MOTION 8ull      // an agent moved farther in one step than the bound the collision stage relies on
+#define OVF_P2P_TIMEOUT 16ull // a peer-to-peer halo wait gave up after ~2 s (the neighbour rank never published its data)
 
 // Everything a kernel needs; passed by value.
 struct StepArgs {
@@ -295,6 +296,9 @@ cudaError_t launch_migrate_pack(const StepArgs &A, int own_cap, int axis, double
 cudaError_t launch_migrate_unpack(const StepArgs &A, const void *in_lo, const void *in_hi, int cap, int use_lo, int use_hi,
                                   int32_t *free_list, int32_t *free_count, int32_t *cnt, int32_t *recv_row, cudaStream_t s);
 int migrate_extra_row_doubles(const StepArgs &A);
+cudaError_t launch_p2p_signal(unsigned long long *local_seq, unsigned long long *peer_flag_lo, unsigned long long *peer_flag_hi, cudaStream_t s);
+cudaError_t launch_p2p_wait(const StepArgs &A, unsigned long long *local_expect, const unsigned long long *flag_from_lo,
+                            const unsigned long long *flag_from_hi, cudaStream_t s);
 cudaError_t launch_migrate_extra_pack(const StepArgs &A, const int32_t *sent_row, const int32_t *cnt, int cap, double *out_lo, double *out_hi,
                                       cudaStream_t s);
 cudaError_t launch_migrate_extra_unpack(const StepArgs &A, const int32_t *recv_row, int cap, const double *in_lo, const double *in_hi,

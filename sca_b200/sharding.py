@@ -21,6 +21,23 @@ import torch
 from . import capi
 
 REC_DOUBLES = 8          # 64-byte halo record
+KIND_HALO, KIND_POS, KIND_MIG, KIND_MIGX = 0, 1, 2, 3      # peer-to-peer exchange kinds (flag / sequence words of the control block)
+
+
+def _view(ptr, shape, dtype, device):
+    """A torch tensor over raw library-owned memory (scab_p2p_alloc): device memory through __cuda_array_interface__, host
+    memory (the emulation build of the tests) through ctypes."""
+    import ctypes as C
+    n = int(np.prod(shape))
+    if torch.device(device).type == 'cpu':
+        ct = {torch.float64: C.c_double, torch.int64: C.c_int64, torch.int32: C.c_int32}[dtype]
+        return torch.from_numpy(np.ctypeslib.as_array((ct * n).from_address(ptr))).view(*shape)
+    ts = {torch.float64: '<f8', torch.int64: '<i8', torch.int32: '<i4'}[dtype]
+
+    class _Raw:
+        __cuda_array_interface__ = {'shape': tuple(int(x) for x in shape), 'typestr': ts, 'data': (int(ptr), False), 'version': 2}
+    return torch.as_tensor(_Raw(), device=device)
+
 ROW_COLS = 22            # full state row used for migration (19 used + 3 spare)
 
 
@@ -126,7 +143,14 @@ class ShardedSwarm:
     """
 
     def __init__(self, pos6, goal6, rank, world, device, lo, hi, radius=0.5, pref_speed=1.0, migrate_every=8,
-                 halo_cap=None, debug=False, use_graph=True, mig_cap=4096, params=None):
+                 halo_cap=None, debug=False, use_graph=True, mig_cap=4096, params=None, transport='nccl', own_slack=0.1):
+        """`transport`: how the halo / migration buffers reach the slab neighbours --
+        'nccl'  pack -> torch.distributed send/recv -> unpack (any backend; gloo in the CPU tests);
+        'p2p'   the pack kernels write straight into the neighbour's receive buffers over NVLink (CUDA IPC between the ranks of
+                one node) and a flag kernel publishes them: no communication library in the step (scab_p2p.cu);
+        'local' the same direct writes between logical shards of ONE process (LogicalShards wires the pointers)."""
+        assert transport in ('nccl', 'p2p', 'local')
+        self.transport = transport if world > 1 else 'nccl'
         from .swarm import Swarm
         pos6, goal6 = np.asarray(pos6, 'float64'), np.asarray(goal6, 'float64')
         n_global = len(pos6)
@@ -157,9 +181,10 @@ class ShardedSwarm:
                 x = pos6[own_all == r, 0]
                 near = max(near, int((x < lo_f + self.plan.width).sum()) if r > 0 else 0,
                            int((x >= hi_f - self.plan.width).sum()) if r < world - 1 else 0)
-            halo_cap = int(near * 1.5) + 1024
+            halo_cap = int(near * 1.25) + 1024      # unused slots are parked ghost rows every per-row kernel still visits: keep it tight
+                                                    # (an overflow is loud: the sticky OVF_HALO flag)
         self.cap = int(halo_cap) if world > 1 else 0
-        self.own_cap = int(self.n_own * 1.25) + 4096
+        self.own_cap = int(self.n_own * (1.0 + own_slack)) + 4096     # free rows for arrivals (an arrival without one is loud: OVF_MIGRATION_LOST)
         self.n_rows = self.own_cap + 2 * self.cap
         sw = Swarm(self.n_own, device=device, debug=debug, capacity=self.n_rows, params=params)
         rad_g = np.broadcast_to(np.asarray(radius, 'float64'), (n_global,))
@@ -191,13 +216,17 @@ class ShardedSwarm:
         dev = sw.device
         f8 = dict(dtype=torch.float64, device=dev)
         self.send_lo, self.send_hi = torch.zeros((self.cap, REC_DOUBLES), **f8), torch.zeros((self.cap, REC_DOUBLES), **f8)
-        self.recv = torch.zeros((2 * self.cap, REC_DOUBLES), **f8)
         self.psend_lo, self.psend_hi = torch.zeros((self.cap, 3), **f8), torch.zeros((self.cap, 3), **f8)
-        self.precv = torch.zeros((2 * self.cap, 3), **f8)
         # device-side migration: 128-byte full-state rows, 1 header row + mig_cap rows per face, and the free list
         self.mig_cap = int(mig_cap)
         mk = lambda: torch.zeros((self.mig_cap + 1, 16), **f8)
-        self.msend_lo, self.msend_hi, self.mrecv_lo, self.mrecv_hi = mk(), mk(), mk(), mk()
+        self.msend_lo, self.msend_hi = mk(), mk()
+        if self.transport == 'nccl':
+            self.recv = torch.zeros((2 * self.cap, REC_DOUBLES), **f8)
+            self.precv = torch.zeros((2 * self.cap, 3), **f8)
+            self.mrecv_lo, self.mrecv_hi = mk(), mk()
+        else:
+            self._p2p_setup(dev)
         i4 = dict(dtype=torch.int32, device=dev)
         self.free_list = torch.zeros(self.own_cap, **i4)
         nfree = self.own_cap - self.n_own
@@ -217,6 +246,56 @@ class ShardedSwarm:
         self._graphs = {}
         sw._bind(self.n_rows)
         torch.cuda.synchronize(dev)
+
+    # ------------------------------------------------------------------ peer-to-peer transport
+    def _p2p_setup(self, dev):
+        """One library-owned arena per rank that the neighbours can write: [control block | halo records | new positions |
+        migration rows from below | from above]; the same offsets on every rank (cap and mig_cap are global)."""
+        cap, mc = self.cap, self.mig_cap
+        off, sizes = {}, (('ctl', 32 * 8), ('recv', 2 * cap * REC_DOUBLES * 8), ('precv', 2 * cap * 3 * 8),
+                          ('mrecv_lo', (mc + 1) * 128), ('mrecv_hi', (mc + 1) * 128))
+        total = 0
+        for k, b in sizes:
+            off[k] = total
+            total += (b + 255) // 256 * 256
+        self._off = off
+        ipc = self.transport == 'p2p'
+        self._arena, handle = self.sw.h.p2p_alloc(total, want_handle=ipc)
+        a = self._arena
+        self.ctl = _view(a + off['ctl'], (32,), torch.int64, dev)
+        self.recv = _view(a + off['recv'], (2 * cap, REC_DOUBLES), torch.float64, dev)
+        self.precv = _view(a + off['precv'], (2 * cap, 3), torch.float64, dev)
+        self.mrecv_lo = _view(a + off['mrecv_lo'], (mc + 1, 16), torch.float64, dev)
+        self.mrecv_hi = _view(a + off['mrecv_hi'], (mc + 1, 16), torch.float64, dev)
+        self._peer = {'lo': 0, 'hi': 0}          # base of the neighbours' arenas in THIS process's address space (0: none)
+        self._xarena, self._xpeer = 0, {'lo': 0, 'hi': 0}
+        if ipc:
+            lo_b, hi_b = self._open_neighbours(handle)
+            self._peer = {'lo': lo_b, 'hi': hi_b}
+
+    def _open_neighbours(self, handle):
+        """Collective: every rank publishes the IPC handle of its arena and maps its slab neighbours'."""
+        handles = [None] * self.world
+        torch.distributed.all_gather_object(handles, handle)
+        lo_b = self.sw.h.p2p_open(handles[self.rank - 1]) if self.rank > 0 else 0
+        hi_b = self.sw.h.p2p_open(handles[self.rank + 1]) if self.rank < self.world - 1 else 0
+        return lo_b, hi_b
+
+    def _remote(self, side, offset, fallback):
+        """Address of byte `offset` of the `side` ('lo' / 'hi') neighbour's arena; a local scratch tensor on a side without one."""
+        has = self.rank > 0 if side == 'lo' else self.rank < self.world - 1
+        return self._peer[side] + offset if has else fallback.data_ptr()
+
+    def _signal(self, kind):
+        c = self.ctl.data_ptr()
+        lo = self._peer['lo'] + self._off['ctl'] + 8 * (2 * kind + 1) if self.rank > 0 else 0             # I am its upper neighbour
+        hi = self._peer['hi'] + self._off['ctl'] + 8 * (2 * kind) if self.rank < self.world - 1 else 0   # I am its lower neighbour
+        self.sw.h.p2p_signal(c + 8 * (8 + kind), lo, hi, self._stream())
+
+    def _wait(self, kind):
+        c = self.ctl.data_ptr()
+        self.sw.h.p2p_wait(c + 8 * (12 + kind), c + 8 * (2 * kind) if self.rank > 0 else 0,
+                           c + 8 * (2 * kind + 1) if self.rank < self.world - 1 else 0, self._stream())
 
     # ------------------------------------------------------------------
     def _park_rows(self, r0, r1):
@@ -263,6 +342,13 @@ class ShardedSwarm:
         lo_f, hi_f = self.plan.faces(self.rank)
         lo_face = lo_f if self.rank > 0 else -1e300            # no neighbour on that side: select nothing
         hi_face = hi_f if self.rank < self.world - 1 else 1e300
+        if self.transport != 'nccl':      # straight into the neighbours' receive buffers
+            # the lower neighbour's "from above" half, the upper neighbour's "from below" half
+            out_lo = self._remote('lo', self._off['recv'] + cap * REC_DOUBLES * 8, self.send_lo)
+            out_hi = self._remote('hi', self._off['recv'], self.send_hi)
+            sw.h.halo_pack(self.own_cap, self.plan.axis, lo_face, hi_face, self.plan.width, self.park, out_lo, out_hi, cap, self._stream())
+            self._signal(KIND_HALO)
+            return KIND_HALO
         sw.h.halo_pack(self.own_cap, self.plan.axis, lo_face, hi_face, self.plan.width, self.park,
                        self.send_lo.data_ptr(), self.send_hi.data_ptr(), cap, self._stream())
         return (self.send_lo, self.send_hi, self.recv[:cap], self.recv[cap:])
@@ -272,6 +358,12 @@ class ShardedSwarm:
 
     def _ghost_post_pack(self):
         sw, cap = self.sw, self.cap
+        if self.transport != 'nccl':
+            out_lo = self._remote('lo', self._off['precv'] + cap * 3 * 8, self.psend_lo)
+            out_hi = self._remote('hi', self._off['precv'], self.psend_hi)
+            sw.h.halo_pack_pos(out_lo, out_hi, cap, self.park, self._stream())
+            self._signal(KIND_POS)
+            return KIND_POS
         sw.h.halo_pack_pos(self.psend_lo.data_ptr(), self.psend_hi.data_ptr(), cap, self.park, self._stream())
         return (self.psend_lo, self.psend_hi, self.precv[:cap], self.precv[cap:])
 
@@ -286,11 +378,22 @@ class ShardedSwarm:
         hi_face = hi_f if self.rank < self.world - 1 else 1e300
         lo, cell, dim = self._park_geom
         s = self._stream()
+        x = self._extra
+        if self.transport != 'nccl':
+            out_lo = self._remote('lo', self._off['mrecv_hi'], self.msend_lo)
+            out_hi = self._remote('hi', self._off['mrecv_lo'], self.msend_hi)
+            sw.h.migrate_pack(self.own_cap, self.plan.axis, lo_face, hi_face, (lo[0], lo[1], cell, self.park[2]), int(dim[0]), int(dim[1]),
+                              out_lo, out_hi, self.mig_cap, self.free_list.data_ptr(), self.free_count.data_ptr(), self.mig_cnt.data_ptr(), s)
+            if x is not None:
+                xlo = self._xpeer['lo'] + self._xoff['recv_hi'] if self.rank > 0 else x['send_lo'].data_ptr()
+                xhi = self._xpeer['hi'] + self._xoff['recv_lo'] if self.rank < self.world - 1 else x['send_hi'].data_ptr()
+                sw.h.migrate_extra_pack(xlo, xhi, self.mig_cap, self.mig_cnt.data_ptr(), s)
+            self._signal(KIND_MIG)
+            return [KIND_MIG]
         sw.h.migrate_pack(self.own_cap, self.plan.axis, lo_face, hi_face, (lo[0], lo[1], cell, self.park[2]), int(dim[0]), int(dim[1]),
                           self.msend_lo.data_ptr(), self.msend_hi.data_ptr(), self.mig_cap, self.free_list.data_ptr(),
                           self.free_count.data_ptr(), self.mig_cnt.data_ptr(), s)
         out = [(self.msend_lo, self.msend_hi, self.mrecv_lo, self.mrecv_hi)]
-        x = self._extra
         if x is not None:        # the Dubins tracker / waypoint state of the same agents, same slots
             sw.h.migrate_extra_pack(x['send_lo'].data_ptr(), x['send_hi'].data_ptr(), self.mig_cap, self.mig_cnt.data_ptr(), s)
             out.append((x['send_lo'], x['send_hi'], x['recv_lo'], x['recv_hi']))
@@ -313,9 +416,14 @@ class ShardedSwarm:
                 self._mark('migrate')
                 for x in self._migrate_pack():
                     yield x
+                    if isinstance(x, int):
+                        self._wait(x)
                 self._migrate_unpack()
             self._mark('pre-exchange')
-            yield self._ghost_pre_pack()
+            x = self._ghost_pre_pack()
+            yield x
+            if isinstance(x, int):
+                self._wait(x)
             self._ghost_pre_unpack()
         s = self._stream()
         self._mark('grid')
@@ -326,15 +434,20 @@ class ShardedSwarm:
         sw.h.policy_step(pol, s)
         if self.world > 1:
             self._mark('post-exchange')
-            yield self._ghost_post_pack()
+            x = self._ghost_post_pack()
+            yield x
+            if isinstance(x, int):
+                self._wait(x)
             self._ghost_post_unpack()
         self._mark('status')
         sw.h.status_step(s)
 
     def _step_body(self, pol, nbr_mode, with_migration=False):
-        """One step with the exchanges over torch.distributed -> capturable in a CUDA graph (two variants)."""
-        for (s_lo, s_hi, r_lo, r_hi) in self._step_phases(pol, nbr_mode, with_migration):
-            exchange_with_neighbours(s_lo, s_hi, r_lo, r_hi, self.rank, self.world)
+        """One step -> capturable in a CUDA graph (two variants).  Exchange points: torch.distributed send/recv ('nccl'), or
+        nothing at all ('p2p': the data is already in the neighbours' buffers, the flag kernels order it)."""
+        for x in self._step_phases(pol, nbr_mode, with_migration):
+            if not isinstance(x, int):
+                exchange_with_neighbours(x[0], x[1], x[2], x[3], self.rank, self.world)
 
     def _wants_migration(self):
         # step 1 also migrates, so that both graph variants are exercised eagerly during any warm-up
@@ -418,7 +531,20 @@ class ShardedSwarm:
         row = self.sw.h.migrate_extra_row_doubles()
         mk = lambda: torch.zeros((self.mig_cap, row), dtype=torch.float64, device=self.sw.device)
         self._graphs.clear()            # captured steps do not know about the extra exchange
-        self._extra = {'send_lo': mk(), 'send_hi': mk(), 'recv_lo': mk(), 'recv_hi': mk(), 'row': row}
+        if self.transport == 'nccl':
+            self._extra = {'send_lo': mk(), 'send_hi': mk(), 'recv_lo': mk(), 'recv_hi': mk(), 'row': row}
+            return
+        # peer-to-peer: a second neighbour-writable arena [rows from below | rows from above] (collective for 'p2p')
+        half = (self.mig_cap * row * 8 + 255) // 256 * 256
+        self._xoff = {'recv_lo': 0, 'recv_hi': half}
+        self._xarena, handle = self.sw.h.p2p_alloc(2 * half, want_handle=self.transport == 'p2p')
+        dev = self.sw.device
+        self._extra = {'send_lo': mk(), 'send_hi': mk(), 'row': row,
+                       'recv_lo': _view(self._xarena, (self.mig_cap, row), torch.float64, dev),
+                       'recv_hi': _view(self._xarena + half, (self.mig_cap, row), torch.float64, dev)}
+        if self.transport == 'p2p':
+            lo_b, hi_b = self._open_neighbours(handle)
+            self._xpeer = {'lo': lo_b, 'hi': hi_b}
 
     def enable_dubins(self, goal_heading, policy='sca'):
         """SCA / RVO3D+Dubins on several GPUs: V_des from the device-side Dubins tracker (Swarm.enable_dubins); the tracker
@@ -481,7 +607,7 @@ class ShardedSwarm:
         overflow masks are OR-ed (as a per-bit sum), and every rank raises together if any rank's is set."""
         c = self.counters(check=False)
         keys = sorted(k for k, v in c.items() if isinstance(v, (int, np.integer)) and k != 'overflow')
-        ovf = [(int(c['overflow']) >> b) & 1 for b in range(4)]
+        ovf = [(int(c['overflow']) >> b) & 1 for b in range(5)]
         if self.world > 1:
             t = torch.tensor([int(c[k]) for k in keys] + ovf, dtype=torch.int64, device=self.sw.device)
             torch.distributed.all_reduce(t)
@@ -489,7 +615,7 @@ class ShardedSwarm:
         else:
             vals = [int(c[k]) for k in keys] + ovf
         out = {k: int(v) for k, v in zip(keys, vals)}
-        out['overflow'] = sum((1 << b) for b in range(4) if vals[len(keys) + b])
+        out['overflow'] = sum((1 << b) for b in range(5) if vals[len(keys) + b])
         if out['overflow']:
             raise capi.ScabError('sharded run overflow flags %d: %s' % (out['overflow'], '; '.join(
                 t for b, t in capi.OVF_TEXT.items() if out['overflow'] & b)))
@@ -518,20 +644,33 @@ class LogicalShards:
     def __init__(self, pos6, goal6, shards, device, lo, hi, **kw):
         self.world = int(shards)
         kw.setdefault('use_graph', False)
+        kw.setdefault('transport', 'local')      # 'local': direct writes into the neighbour shard's buffers; 'nccl': staged copies
         self.shards = [ShardedSwarm(pos6, goal6, r, self.world, device, lo, hi, **kw) for r in range(self.world)]
         self.stream = self.shards[0].stream
         for sh in self.shards:
             sh.stream = self.stream
+        self._wire()
         self.n_global = self.shards[0].n_global
+
+    def _wire(self):
+        """'local' transport: the neighbours' arenas are ordinary pointers of this process."""
+        for r, sh in enumerate(self.shards):
+            if sh.transport != 'local':
+                continue
+            lo, hi = (self.shards[r - 1] if r > 0 else None), (self.shards[r + 1] if r < self.world - 1 else None)
+            sh._peer = {'lo': lo._arena if lo else 0, 'hi': hi._arena if hi else 0}
+            sh._xpeer = {'lo': lo._xarena if lo else 0, 'hi': hi._xarena if hi else 0}
 
     def enable_dubins(self, goal_heading, policy='sca'):
         for sh in self.shards:
             sh.enable_dubins(goal_heading, policy)
+        self._wire()
         return self
 
     def set_waypoints(self, waypoints, counts=None):
         for sh in self.shards:
             sh.set_waypoints(waypoints, counts)
+        self._wire()
         return self
 
     def step(self, policy, nbr_mode=capi.NBR_KNN):
@@ -546,6 +685,8 @@ class LogicalShards:
                     break
                 assert all(r is not None for r in reqs), 'logical shards fell out of lockstep'
                 for r in range(S):
+                    if isinstance(reqs[r], int):              # direct-write transport: the data is already there
+                        continue
                     s_lo, s_hi = reqs[r][0], reqs[r][1]
                     if r > 0:
                         reqs[r - 1][3].copy_(s_lo)            # the lower neighbour's recv_hi

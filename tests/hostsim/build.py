@@ -18,7 +18,7 @@ CSRC = os.path.join(ROOT, 'sca_b200', 'csrc')
 GEN = os.path.join(HERE, '_gen')
 LIB = os.path.join(HERE, 'libscab200_hostsim.so')
 SOURCES = ['scab_api.cu', 'scab_grid.cu', 'scab_neighbors.cu', 'scab_policy_sampled.cu', 'scab_policy_lp.cu', 'scab_status.cu',
-           'scab_halo.cu', 'scab_dubins.cu']
+           'scab_halo.cu', 'scab_p2p.cu', 'scab_dubins.cu']
 LAUNCH = re.compile(r'([A-Za-z_]\w*(?:<[^<>;(){}]*>)?)\s*<<<(.*?)>>>\s*\((.*?)\);', re.S)
 FLAGS = ['-O1', '-g', '-std=c++17', '-ffp-contract=off', '-fPIC', '-w', '-pthread', '-D_GNU_SOURCE', '-I/usr/local/cuda/include',
          '-I' + CSRC, '-I' + HERE, '-include', os.path.join(HERE, 'cuda_host_shim.h')]

@@ -61,6 +61,9 @@ static inline double __longlong_as_double(long long i) { double d; std::memcpy(&
 static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline long long clock64() { return 0; }
+static inline void __nanosleep(unsigned) {}
+static inline void __threadfence_system() { __sync_synchronize(); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }

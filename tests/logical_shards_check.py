@@ -8,12 +8,12 @@ from sca_b200.sharding import LogicalShards
 from sca_b200.swarm import Swarm
 
 
-def run(policy, shards, n, steps, device, dubins=False, waypoints=False, migrate_every=4, mig_cap=4096, density_x=4.0):
+def run(policy, shards, n, steps, device, dubins=False, waypoints=False, migrate_every=4, mig_cap=4096, density_x=4.0, transport='local'):
     density = density_x * 1.0e6 / 560.0 ** 3          # denser than config 5: more interaction across the faces
     pos, goal, _ = scenarios.uniform_box_numpy(n, density, seed=3)
     L = (n / density) ** (1 / 3)
     lo, hi = np.array([-20.0, -20.0, 0.0]), np.array([L + 20.0, L + 20.0, L + 40.0])
-    ls = LogicalShards(pos, goal, shards, device, lo, hi, migrate_every=migrate_every, mig_cap=mig_cap)
+    ls = LogicalShards(pos, goal, shards, device, lo, hi, migrate_every=migrate_every, mig_cap=mig_cap, transport=transport)
     wp = wp_cnt = None
     if waypoints:
         rng = np.random.default_rng(5)

@@ -49,7 +49,10 @@ def main():
     pos, goal, _ = scenarios.uniform_box_numpy(n, density, seed=3)
     L = (n / density) ** (1 / 3)
     lo, hi = np.array([-20.0, -20.0, 0.0]), np.array([L + 20.0, L + 20.0, L + 40.0])
-    sh = ShardedSwarm(pos, goal, rank, world, dev, lo, hi, migrate_every=4, mig_cap=int(os.environ.get('SHARD_MIG_CAP', '4096')))
+    # transport: peer-to-peer direct writes over NVLink on real GPUs, staged send / recv (gloo) between the emulated devices
+    transport = os.environ.get('SHARD_TRANSPORT', 'nccl' if hostsim else 'p2p')
+    sh = ShardedSwarm(pos, goal, rank, world, dev, lo, hi, migrate_every=4, mig_cap=int(os.environ.get('SHARD_MIG_CAP', '4096')),
+                      transport=transport)
     sh.warm_up(policy, capi.NBR_KNN)
     # optional per-agent state that lives outside the migration row and must travel with its agent
     use_dubins = os.environ.get('SHARD_DUBINS', '0') == '1'        # device-side Dubins tracker (policy sca / rvo3d_dubins)
@@ -130,8 +133,8 @@ def main():
             replans = int(ref.dubins_states()['replans'].sum())
             ok = ok and replans >= n
             print('dubins plans made: %d' % replans)
-        print('sharding_check world=%d n=%d steps=%d policy=%s mismatches=%s agent_steps %d vs %d  migration-events %d  '
-              'collisions(ref)=%d  -> %s' % (world, n, steps, policy, bad, tot_active, ref_active, migrations,
+        print('sharding_check transport=%s world=%d n=%d steps=%d policy=%s mismatches=%s agent_steps %d vs %d  migration-events %d  '
+              'collisions(ref)=%d  -> %s' % (transport, world, n, steps, policy, bad, tot_active, ref_active, migrations,
                                              int((full['status'] & 2).astype(bool).sum()), 'OK' if ok else 'FAIL'), flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)

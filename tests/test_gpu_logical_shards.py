@@ -7,8 +7,11 @@ pytestmark = pytest.mark.gpu
 CASES = [('sca', 2, 20000, 30, {}), ('sca', 4, 30000, 24, {}), ('orca_lp', 2, 20000, 30, {}), ('orca_lp', 4, 30000, 24, {}),
          ('srvo3d', 3, 12000, 16, {}),
          ('rvo3d', 2, 6000, 16, {'waypoints': True, 'mig_cap': 1024}), ('sca', 2, 4000, 16, {'dubins': True, 'mig_cap': 1024}),
-         ('sca', 4, 6000, 12, {'dubins': True, 'mig_cap': 512})]
-IDS = ['sca-2', 'sca-4', 'orca_lp-2', 'orca_lp-4', 'srvo3d-3', 'rvo3d-waypoints-2', 'sca-dubins-2', 'sca-dubins-4']
+         ('sca', 4, 6000, 12, {'dubins': True, 'mig_cap': 512}),
+         # the staged path (pack -> copy -> unpack: what the NCCL transport does between processes)
+         ('sca', 2, 12000, 16, {'transport': 'nccl'}), ('rvo3d', 2, 6000, 16, {'waypoints': True, 'mig_cap': 1024, 'transport': 'nccl'})]
+IDS = ['sca-2', 'sca-4', 'orca_lp-2', 'orca_lp-4', 'srvo3d-3', 'rvo3d-waypoints-2', 'sca-dubins-2', 'sca-dubins-4', 'sca-2-staged',
+       'rvo3d-waypoints-2-staged']
 
 
 @pytest.mark.parametrize('policy,shards,n,steps,extra', CASES, ids=IDS)
