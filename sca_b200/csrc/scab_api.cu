@@ -317,6 +317,7 @@ extern "C" int scab_destroy(scab_handle *h)
                     h->d_counters, h->d_o_posr, h->d_o_posr_by_id, h->d_o_id, h->d_o_cell_start, h->d_kd_obst_perm, h->d_kd_obst,
                     h->d_dub_states, h->d_dub_d0};
     for (void *q : ptrs) if (q) cudaFree(q);
+    if (h->cfg.aux) { cudaStreamDestroy(h->cfg.aux); cudaEventDestroy(h->cfg.ev_fork); cudaEventDestroy(h->cfg.ev_join); }
     for (void *q : h->p2p_peer) cudaIpcCloseMemHandle(q);
     for (void *q : h->p2p_own) cudaFree(q);
     delete h;

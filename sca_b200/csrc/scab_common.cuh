@@ -38,7 +38,13 @@ struct LaunchCfg {
     int sms;
     int no_fast, lp_f64, lp_compact, lp_ctas8, knn_exact;
     int occ[SCAB_OCC_SLOTS];   // per kernel (slot constants next to each launcher); 0 = not queried on this device yet
+    // fork / join inside a stage (e.g. the work-list kernel of the sampled policies next to the kinematic update of
+    // everybody else): an auxiliary non-blocking stream and two timing-less events, created on first use
+    cudaStream_t aux;
+    cudaEvent_t ev_fork, ev_join;
 };
+#define SCAB_TAG_PENDING 0x40   // internal: s_vpost of an agent that waits on the work list (k_integrate's first pass skips it)
+#define SCAB_TAG_LISTED 0x80    // internal: s_vpost written by the work-list kernel (the two k_integrate passes may overlap in time)
 
 // sticky bits of counters[7] (scab_counters.overflow): a result may be WRONG once one is set
 #define OVF_HALO 1ull        // k_halo_pack dropped records: a face buffer was too small

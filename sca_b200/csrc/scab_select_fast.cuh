@@ -85,6 +85,7 @@ __device__ __forceinline__ void push_slow(const StepArgs &A, int s)
 {
     const int w = atomicAdd(A.slow_count, 1);
     A.slow_list[w] = s;
+    A.s_vpost[s].w = __longlong_as_double((long long)SCAB_TAG_PENDING);   // its result comes from the general kernel
 }
 
 // Bin of the posture lookup table for a (non-zero) vector: octahedral map of its direction, LUT_B x LUT_B bins.  The host
