@@ -248,6 +248,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
         c.lp_compact = off("SCAB_LP_COMPACT");     // ORCA-LP list pass with 32-byte planes (7 resident CTAs instead of 4); =0: 48-byte planes
         c.lp_ctas8 = off("SCAB_LP_PASS1_CTAS8");   // ORCA-LP register-only pass at 64 registers (8 resident CTAs); =0: 80 registers
         c.knn_exact = on("SCAB_KNN_EXACT");    // 16-NN with fp64 total-order keys for every agent
+        c.no_fork = getenv("SCAB_NO_FORK") ? atoi(getenv("SCAB_NO_FORK")) : 0;   // 1: work-list kernel on the caller's stream (serial); 2: fork, main pass launched first
         A.cfg = &h->cfg;
     }
     if (const char *td = getenv("SCAB_TIER_DELTA")) { float v = (float)atof(td); if (v > 0.f) A.tier_delta = v; }   // tuning knob

@@ -36,7 +36,7 @@ struct KdNodeDev {
 #define SCAB_OCC_SLOTS 24
 struct LaunchCfg {
     int sms;
-    int no_fast, lp_f64, lp_compact, lp_ctas8, knn_exact;
+    int no_fast, lp_f64, lp_compact, lp_ctas8, knn_exact, no_fork;
     int occ[SCAB_OCC_SLOTS];   // per kernel (slot constants next to each launcher); 0 = not queried on this device yet
     // fork / join inside a stage (e.g. the work-list kernel of the sampled policies next to the kinematic update of
     // everybody else): an auxiliary non-blocking stream and two timing-less events, created on first use

@@ -119,7 +119,7 @@ __device__ __noinline__ void write_lists2(const StepArgs &A, int s, int id, cons
 
 // ------------------------------------------------------------------ KNN over the cell list
 #ifndef KNN_CAP
-#define KNN_CAP 48
+#define KNN_CAP 64      // candidate slots per agent (in range + pre-filter guard); 128 threads x 64 x 4 B = 32 KB per CTA
 #endif
 // The exact general path (obstacles, ties on the decimal-rounded distance, more than KNN_CAP raw candidates):
 // fp64 keys + the (distSq, obstacles-before-agents, id) comparator.
@@ -197,10 +197,12 @@ __device__ __noinline__ void knn_exact(const StepArgs &A, int s, int id, const d
 //            min/max network on 16 registers:  new[k] = min(old[k], max(old[k-1], x)).
 // A tie on the distance (the reference breaks it by agent id) is detected afterwards -- two equal neighbours in the list,
 // or the best rejected key equal to the last kept one -- and sends the agent to knn_exact, as does a full column.
+// `rangeSq`: the squared query radius the candidates were collected for -- neighbor_dist^2, or less when a dense
+// neighbourhood overflowed the candidate column and the scan was repeated with a smaller ball (the 16 nearest are then
+// certainly inside it, provided it still holds 16 agents: checked here).
 template <class GetJ>
-__device__ __forceinline__ void knn_phase2(const StepArgs &A, int s, int id, const double4 me, int nbuf, bool overflow, GetJ getj)
+__device__ __forceinline__ void knn_phase2(const StepArgs &A, int s, int id, const double4 me, int nbuf, bool overflow, double rangeSq, GetJ getj)
 {
-    const double rangeSq = A.nbr_dist_sq;
     unsigned L[KNBR];
 #pragma unroll
     for (int k = 0; k < KNBR; k++) L[k] = 0xffffffffu;
@@ -241,7 +243,7 @@ __device__ __forceinline__ void knn_phase2(const StepArgs &A, int s, int id, con
         }
     }
     const int n_in = min(cnt, KNBR);
-    bool tie = overflow || (cnt > KNBR && (rej_min >> 8) == (L[KNBR - 1] >> 8));
+    bool tie = overflow || (cnt > KNBR && (rej_min >> 8) == (L[KNBR - 1] >> 8)) || (rangeSq < A.nbr_dist_sq && !coll && cnt < KNBR);
 #pragma unroll
     for (int k = 1; k < KNBR; k++) tie |= (k < n_in) && ((L[k] >> 8) == (L[k - 1] >> 8));
     if (tie) { knn_exact(A, s, id, me); return; }
@@ -417,16 +419,24 @@ __global__ void __launch_bounds__(NT_THREADS, NT_MIN_CTAS) k_neighbors_tile(cons
                 }
             }
         }
-        knn_phase2(A, s, id, me, nbuf, overflow, [&](int i) { const unsigned c = buf[i][tid]; return cs[c >> 11][0] + (int)(c & 2047u); });
+        knn_phase2(A, s, id, me, nbuf, overflow, A.nbr_dist_sq, [&](int i) { const unsigned c = buf[i][tid]; return cs[c >> 11][0] + (int)(c & 2047u); });
     }
 }
 
-// ---- variant 1: thread per agent, records straight from global memory (s_posf: 16-byte fp32 records, L1 / L2 hits)
+// ---- variant 1: thread per agent, records straight from global memory (s_posf: 16-byte fp32 records, L1 / L2 hits).
+// DENSE = false: every agent, one scan; an agent with more than KNN_CAP candidates in range is appended to a work list.
+// DENSE = true: the agents of that list, scanned again with half the squared radius until the column holds them (the 16
+// nearest of a crowded neighbourhood are certainly inside a smaller ball).  Keeping the retry out of the first kernel keeps
+// a warp from re-scanning for one crowded lane (BASELINE config 4 has ~64 agents in range of each other; the uniform
+// workload gets there locally late in a rollout).
+template <bool DENSE>
 __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const __grid_constant__ StepArgs A)
 {
     __shared__ int buf[KNN_CAP][128];
-    const int s = blockIdx.x * blockDim.x + threadIdx.x, tid = threadIdx.x;
-    if (s >= A.n) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, tid = threadIdx.x;
+    const int n_work = DENSE ? min(*A.slow_count, A.n) : A.n;
+    if (t >= n_work) return;
+    const int s = DENSE ? A.slow_list[t] : t;
     const int id = A.s_id[s];
     const int flags = __float_as_int(A.s_vel[s].w);
     if (flags & FL_INACTIVE) {
@@ -444,7 +454,8 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
     RowTrim T;
     T.init(A.g, me, cx, cy, cz, lim);
     const float mx = (float)(me.x - A.g.ox), my = (float)(me.y - A.g.oy), mz = (float)(me.z - A.g.oz);
-    const float limf = prefilter_limit(lim, mx, my, mz);
+    double range_used = DENSE ? 0.5 * A.nbr_dist_sq : A.nbr_dist_sq;
+    float limf = prefilter_limit(range_used + 1e-4, mx, my, mz);
     // the (up to) nine x-rows of the block: all their cell_start bounds are fetched before any row is scanned
     int rbeg[9], rend[9];
 #pragma unroll
@@ -457,7 +468,12 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
         rend[r] = ok ? A.cell_start[rowi + min(x1, A.g.nx - 1) + 1] : 0;
     }
     // Per row, the hits of up to 32 consecutive records are collected as a bit mask (one instruction per record instead of
-    // a predicated store sequence) and then drained into the thread's shared-memory column.
+    // a predicated store sequence) and then drained into the thread's shared-memory column.  A neighbourhood too dense for
+    // the column (> KNN_CAP agents in range: BASELINE config 4 has ~64) is scanned again with half the squared radius.
+#pragma unroll 1
+    for (int attempt = 0; attempt < (DENSE ? 5 : 1); attempt++) {
+    nbuf = 0;
+    overflow = false;
 #pragma unroll
     for (int r = 0; r < 9; r++) {
         const int end = rend[r];
@@ -488,7 +504,12 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
             }
         }
     }
-    knn_phase2(A, s, id, me, nbuf, overflow, [&](int i) { return buf[i][tid]; });
+    if (!DENSE || !overflow) break;
+    range_used *= 0.5;
+    limf = prefilter_limit(range_used + 1e-4, mx, my, mz);
+    }
+    if (!DENSE && overflow) { A.slow_list[atomicAdd(A.slow_count, 1)] = s; return; }      // (the policy stage resets the list for its own use)
+    knn_phase2(A, s, id, me, nbuf, overflow, range_used, [&](int i) { return buf[i][tid]; });
 }
 
 // the general path for every agent (obstacles in the merged list, SCAB_KNN_EXACT=1, neighbor_dist >= 12.9 m): thread per agent
@@ -639,7 +660,12 @@ cudaError_t launch_neighbors(const StepArgs &A, int mode, cudaStream_t s)
         if (fast_ok && KNN_VARIANT == 0) {
             const int segs = (A.g.nx + NT_W - 1) / NT_W;
             k_neighbors_tile<<<A.g.ny * A.g.nz * segs, NT_THREADS, 0, s>>>(A, segs);
-        } else if (fast_ok) k_neighbors_direct<<<nb, 128, 0, s>>>(A);
+        } else if (fast_ok) {
+            cudaError_t e = cudaMemsetAsync(A.slow_count, 0, sizeof(int32_t), s);
+            if (e != cudaSuccess) return e;
+            k_neighbors_direct<false><<<nb, 128, 0, s>>>(A);
+            k_neighbors_direct<true><<<nb, 128, 0, s>>>(A);       // the crowded agents (usually none: the blocks exit at once)
+        }
         else k_neighbors_exact<<<nb, 128, 0, s>>>(A);
     }
     return cudaGetLastError();

@@ -704,14 +704,21 @@ static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
     // fork: the agents the fast kernel deferred (general kernel, then their kinematic update) on the auxiliary stream, next to
     // the kinematic update of everybody else -- the general kernel is one warp's latency per agent (~35 us even for a
     // handful of agents), which this hides; join before the stage ends.  (Capturable: the fork / join become graph edges.)
+    if (cfg.no_fork == 1) {      // A/B switch: everything on the caller's stream
+        k_select<POLICY, true><<<grid, WARPS_PER_CTA * 32, smem, s>>>(A);
+        k_integrate<IS_ORCA, true><<<nb256, 256, 0, s>>>(A);
+        k_integrate<IS_ORCA, false><<<nb256, 256, 0, s>>>(A);
+        return cudaGetLastError();
+    }
     e = cudaEventRecord(cfg.ev_fork, s);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(cfg.aux, cfg.ev_fork, 0);
     if (e != cudaSuccess) return e;
+    if (cfg.no_fork == 2) k_integrate<IS_ORCA, false><<<nb256, 256, 0, s>>>(A);
     k_select<POLICY, true><<<grid, WARPS_PER_CTA * 32, smem, cfg.aux>>>(A);
     k_integrate<IS_ORCA, true><<<nb256, 256, 0, cfg.aux>>>(A);
     e = cudaEventRecord(cfg.ev_join, cfg.aux);
     if (e != cudaSuccess) return e;
-    k_integrate<IS_ORCA, false><<<nb256, 256, 0, s>>>(A);
+    if (cfg.no_fork != 2) k_integrate<IS_ORCA, false><<<nb256, 256, 0, s>>>(A);
     e = cudaStreamWaitEvent(s, cfg.ev_join, 0);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
