@@ -169,6 +169,8 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device(device))
     from sca_b200 import capi
+    if os.environ.get('SCAB_BENCH_SIDE_STREAM', '0') == '1':      # debug: everything on a non-default (non-blocking) stream
+        torch.cuda.set_stream(torch.cuda.Stream())
     cfg, policy, nbr_name = config_of(args)
     NBR = capi.NBR_REF_COMPAT if nbr_name == 'compat' else capi.NBR_KNN
     if cfg is not None and world > 1:

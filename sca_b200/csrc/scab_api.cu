@@ -248,7 +248,6 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
         c.lp_compact = off("SCAB_LP_COMPACT");     // ORCA-LP list pass with 32-byte planes (7 resident CTAs instead of 4); =0: 48-byte planes
         c.lp_ctas8 = off("SCAB_LP_PASS1_CTAS8");   // ORCA-LP register-only pass at 64 registers (8 resident CTAs); =0: 80 registers
         c.knn_exact = on("SCAB_KNN_EXACT");    // 16-NN with fp64 total-order keys for every agent
-        c.no_fork = getenv("SCAB_NO_FORK") ? atoi(getenv("SCAB_NO_FORK")) : 0;   // 1: work-list kernel on the caller's stream (serial); 2: fork, main pass launched first
         A.cfg = &h->cfg;
     }
     if (const char *td = getenv("SCAB_TIER_DELTA")) { float v = (float)atof(td); if (v > 0.f) A.tier_delta = v; }   // tuning knob
@@ -262,7 +261,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
                  o_cid = carve(cap * 4), o_cloc = carve(cap * 4), o_nbr = carve(cap * 4 * KNBR),
                  o_ncnt = carve(cap * 4), o_qc = carve(cap * 4), o_kdp = carve(cap * 4),
                  o_slo = carve(cap * 4), o_shi = carve(cap * 4), o_hcnt = carve(64),
-                 o_slow = carve(cap * 4), o_slowc = carve(64), o_srow = carve(cap * 4), o_rrow = carve(cap * 4),
+                 o_slow = carve(cap * 4), o_slowc = carve(64), o_slow2 = carve(cap * 4), o_slowc2 = carve(64), o_srow = carve(cap * 4), o_rrow = carve(cap * 4),
                  o_kdn = carve((2 * cap) * sizeof(KdNodeDev));
     e = cudaMalloc(&h->d_block, off);
     if (e != cudaSuccess) { delete h; return SCAB_ERR_NOMEM; }
@@ -275,6 +274,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     A.s_nbr = (int32_t *)(b + o_nbr); A.s_nbr_cnt = (int32_t *)(b + o_ncnt); A.s_qcoll = (int32_t *)(b + o_qc);
     h->d_kd_agent_perm = (int32_t *)(b + o_kdp); h->d_kd_agent = (KdNodeDev *)(b + o_kdn);
     A.slow_list = (int32_t *)(b + o_slow); A.slow_count = (int32_t *)(b + o_slowc);
+    A.slow_list2 = (int32_t *)(b + o_slow2); A.slow_count2 = (int32_t *)(b + o_slowc2);
     h->d_mig_sent_row = (int32_t *)(b + o_srow); h->d_mig_recv_row = (int32_t *)(b + o_rrow);
     h->d_sent_lo = (int32_t *)(b + o_slo); h->d_sent_hi = (int32_t *)(b + o_shi); h->d_halo_cnt = (int32_t *)(b + o_hcnt);
     A.kd_agent = h->d_kd_agent; A.kd_agent_perm = h->d_kd_agent_perm;
@@ -318,7 +318,6 @@ extern "C" int scab_destroy(scab_handle *h)
                     h->d_counters, h->d_o_posr, h->d_o_posr_by_id, h->d_o_id, h->d_o_cell_start, h->d_kd_obst_perm, h->d_kd_obst,
                     h->d_dub_states, h->d_dub_d0};
     for (void *q : ptrs) if (q) cudaFree(q);
-    if (h->cfg.aux) { cudaStreamDestroy(h->cfg.aux); cudaEventDestroy(h->cfg.ev_fork); cudaEventDestroy(h->cfg.ev_join); }
     for (void *q : h->p2p_peer) cudaIpcCloseMemHandle(q);
     for (void *q : h->p2p_own) cudaFree(q);
     delete h;

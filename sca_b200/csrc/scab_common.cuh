@@ -36,15 +36,9 @@ struct KdNodeDev {
 #define SCAB_OCC_SLOTS 24
 struct LaunchCfg {
     int sms;
-    int no_fast, lp_f64, lp_compact, lp_ctas8, knn_exact, no_fork;
+    int no_fast, lp_f64, lp_compact, lp_ctas8, knn_exact;
     int occ[SCAB_OCC_SLOTS];   // per kernel (slot constants next to each launcher); 0 = not queried on this device yet
-    // fork / join inside a stage (e.g. the work-list kernel of the sampled policies next to the kinematic update of
-    // everybody else): an auxiliary non-blocking stream and two timing-less events, created on first use
-    cudaStream_t aux;
-    cudaEvent_t ev_fork, ev_join;
 };
-#define SCAB_TAG_PENDING 0x40   // internal: s_vpost of an agent that waits on the work list (k_integrate's first pass skips it)
-#define SCAB_TAG_LISTED 0x80    // internal: s_vpost written by the work-list kernel (the two k_integrate passes may overlap in time)
 
 // sticky bits of counters[7] (scab_counters.overflow): a result may be WRONG once one is set
 #define OVF_HALO 1ull        // k_halo_pack dropped records: a face buffer was too small
@@ -78,6 +72,7 @@ struct StepArgs {
     int32_t *s_qcoll;   // [n] collision flag raised by the neighbour query (agent.py:83-85)
     int32_t *slow_list; // [n] agents the 8-lane fast selection kernel hands to the general kernel
     int32_t *slow_count;
+    int32_t *slow_list2, *slow_count2;   // agents the second (every-candidate) fast pass hands to the general kernel
     double max_radius;  // largest agent radius (0: unknown -> the status stage always scans the cell list)
     double move_bound;  // no agent moves farther than this in one step (scab_set_motion_bound; kinematic_update checks it)
     LaunchCfg *cfg;     // host pointer (the owning handle's launch configuration)

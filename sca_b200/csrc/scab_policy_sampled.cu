@@ -181,10 +181,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
     const int warps_total = gridDim.x * WARPS_PER_CTA;
     unsigned long long n_recheck = 0;
 
-    const int n_work = USE_LIST ? min(*A.slow_count, A.n) : A.n;
+    const int n_work = USE_LIST ? min(*A.slow_count2, A.n) : A.n;       // (the list the second fast pass leaves)
     if (USE_LIST && blockIdx.x == 0 && threadIdx.x == 0) A.counters[6] = (unsigned long long)n_work;
     for (int wi = blockIdx.x * WARPS_PER_CTA + wid; wi < n_work; wi += warps_total) {
-        const int s = USE_LIST ? A.slow_list[wi] : wi;
+        const int s = USE_LIST ? A.slow_list2[wi] : wi;
         const float4 mv = A.s_vel[s];
         const int flags = __float_as_int(mv.w);
         if (flags & FL_INACTIVE) continue;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
         if (vd.w < 0.0) {   // zero-velocity shortcut: vA_post = 0.3 v_pref (scaPolicy.py:38)
             if (lane == 0)
                 A.s_vpost[s] = make_double4(__dmul_rn(0.3, vd.x), __dmul_rn(0.3, vd.y), __dmul_rn(0.3, vd.z),
-                                            __longlong_as_double((long long)(SCAB_TAG_FIRST | (USE_LIST ? SCAB_TAG_LISTED : 0))));
+                                            __longlong_as_double((long long)SCAB_TAG_FIRST));
             continue;
         }
         const double4 me = A.s_posr[s];
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
             cand64(a, best, bx, by, bz);
             // scaPolicy.py:239 truncation; w packs tag | n_suit << 8
             A.s_vpost[s] = make_double4(trunc5(bx), trunc5(by), trunc5(bz),
-                                        __longlong_as_double((long long)(tag | (USE_LIST ? SCAB_TAG_LISTED : 0)) | ((long long)n_suit << 8)));
+                                        __longlong_as_double((long long)tag | ((long long)n_suit << 8)));
         }
         __syncwarp();
     }
@@ -614,17 +614,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
 }
 
 // ------------------------------------------------------------------ k_integrate (thread per agent)
-// USE_LIST = false: every agent except the ones still waiting on the work list (SCAB_TAG_PENDING); USE_LIST = true: exactly
-// those, after the general kernel has produced their velocity -- the two passes run on two streams (launch_select).
-template <bool IS_ORCA, bool USE_LIST>
+template <bool IS_ORCA>
 __global__ void __launch_bounds__(256) k_integrate(StepArgs A)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n_work = USE_LIST ? min(*A.slow_count, A.n) : A.n;
-    const int s = (t < n_work) ? (USE_LIST ? A.slow_list[t] : t) : A.n;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
     bool ran = false;
-    if (s < A.n && (USE_LIST || !(__double_as_longlong(A.s_vpost[s].w) & (SCAB_TAG_PENDING | SCAB_TAG_LISTED)) ||
-                    (__float_as_int(A.s_vel[s].w) & FL_INACTIVE))) {
+    if (s < A.n) {
         const int id = A.s_id[s];
         const double4 me = A.s_posr[s];
         const int flags = __float_as_int(A.s_vel[s].w);
@@ -643,7 +638,7 @@ __global__ void __launch_bounds__(256) k_integrate(StepArgs A)
             ran = true;
             const double4 vp = A.s_vpost[s];
             const long long bits = __double_as_longlong(vp.w);
-            const int tag = (int)(bits & 0x3f), n_suit = (int)(bits >> 8);
+            const int tag = (int)(bits & 0xff), n_suit = (int)(bits >> 8);
             act = cartesian2spherical(vp.x, vp.y, vp.z, A.st.heading[3 * id], A.st.heading[3 * id + 1], false);
             kinematic_update(A, id, act, me.x, me.y, me.z, &npx, &npy, &npz);
             // RVO family: computeNeighbors is not called on the zero-velocity shortcut (scaPolicy.py:34-45);
@@ -675,9 +670,10 @@ static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
     if (per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(k_select<POLICY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select<POLICY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select_fast<POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select_fast<POLICY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select_fast<POLICY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_select<POLICY, true>, WARPS_PER_CTA * 32, smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fast, k_select_fast<POLICY>, FG_WARPS * 32, smem_fast);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fast, k_select_fast<POLICY, false>, FG_WARPS * 32, smem_fast);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
         if (per_sm_fast < 1) per_sm_fast = 1;
@@ -687,40 +683,22 @@ static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
     const int grid = need < sms * per_sm ? need : sms * per_sm;
     if (no_fast) {
         k_select<POLICY, false><<<grid, WARPS_PER_CTA * 32, smem, s>>>(A);
-        k_integrate<IS_ORCA, false><<<nb256, 256, 0, s>>>(A);
+        k_integrate<IS_ORCA><<<nb256, 256, 0, s>>>(A);
         return cudaGetLastError();
-    }
-    if (!cfg.aux) {
-        cudaError_t e = cudaStreamCreateWithFlags(&cfg.aux, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&cfg.ev_fork, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&cfg.ev_join, cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
     }
     cudaError_t e = cudaMemsetAsync(A.slow_count, 0, sizeof(int32_t), s);
     if (e != cudaSuccess) return e;
     const int need_f = (A.n + FG_WARPS * FG_PER_WARP - 1) / (FG_WARPS * FG_PER_WARP);
     const int grid_f = need_f < sms * per_sm_fast ? need_f : sms * per_sm_fast;
-    k_select_fast<POLICY><<<grid_f, FG_WARPS * 32, smem_fast, s>>>(A);
-    // fork: the agents the fast kernel deferred (general kernel, then their kinematic update) on the auxiliary stream, next to
-    // the kinematic update of everybody else -- the general kernel is one warp's latency per agent (~35 us even for a
-    // handful of agents), which this hides; join before the stage ends.  (Capturable: the fork / join become graph edges.)
-    if (cfg.no_fork == 1) {      // A/B switch: everything on the caller's stream
-        k_select<POLICY, true><<<grid, WARPS_PER_CTA * 32, smem, s>>>(A);
-        k_integrate<IS_ORCA, true><<<nb256, 256, 0, s>>>(A);
-        k_integrate<IS_ORCA, false><<<nb256, 256, 0, s>>>(A);
-        return cudaGetLastError();
-    }
-    e = cudaEventRecord(cfg.ev_fork, s);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(cfg.aux, cfg.ev_fork, 0);
+    if (e == cudaSuccess) e = cudaMemsetAsync(A.slow_count2, 0, sizeof(int32_t), s);
     if (e != cudaSuccess) return e;
-    if (cfg.no_fork == 2) k_integrate<IS_ORCA, false><<<nb256, 256, 0, s>>>(A);
-    k_select<POLICY, true><<<grid, WARPS_PER_CTA * 32, smem, cfg.aux>>>(A);
-    k_integrate<IS_ORCA, true><<<nb256, 256, 0, cfg.aux>>>(A);
-    e = cudaEventRecord(cfg.ev_join, cfg.aux);
-    if (e != cudaSuccess) return e;
-    if (cfg.no_fork != 2) k_integrate<IS_ORCA, false><<<nb256, 256, 0, s>>>(A);
-    e = cudaStreamWaitEvent(s, cfg.ev_join, 0);
-    if (e != cudaSuccess) return e;
+    k_select_fast<POLICY, false><<<grid_f, FG_WARPS * 32, smem_fast, s>>>(A);
+    // pass 2: the agents tier 1 did not pin (~1 %), eight lanes each again but examining EVERY candidate; what that cannot
+    // handle either (no suitable velocity at all, > 63 surviving directions) goes on to the general kernel, one warp per
+    // agent (usually nobody: the launch is then one warp's look at an empty list)
+    k_select_fast<POLICY, true><<<grid_f, FG_WARPS * 32, smem_fast, s>>>(A);
+    k_select<POLICY, true><<<grid, WARPS_PER_CTA * 32, smem, s>>>(A);
+    k_integrate<IS_ORCA><<<nb256, 256, 0, s>>>(A);
     return cudaGetLastError();
 }
 

@@ -81,11 +81,11 @@ __device__ __noinline__ bool recheck_cone64(const StepArgs &A, int s, int k, con
     return is_intersect64_fast(__dsub_rn(o.x, a.px), __dsub_rn(o.y, a.py), __dsub_rn(o.z, a.pz), R, dx, dy, dz);
 }
 
+template <bool LIST>
 __device__ __forceinline__ void push_slow(const StepArgs &A, int s)
-{
-    const int w = atomicAdd(A.slow_count, 1);
-    A.slow_list[w] = s;
-    A.s_vpost[s].w = __longlong_as_double((long long)SCAB_TAG_PENDING);   // its result comes from the general kernel
+{   // first pass -> the list of the second pass; second pass -> the list of the general kernel
+    const int w = atomicAdd(LIST ? A.slow_count2 : A.slow_count, 1);
+    (LIST ? A.slow_list2 : A.slow_list)[w] = s;
 }
 
 // Bin of the posture lookup table for a (non-zero) vector: octahedral map of its direction, LUT_B x LUT_B bins.  The host
@@ -104,9 +104,11 @@ __device__ __forceinline__ int posture_bin(float x, float y, float z)
     return iy * LUT_B + ix;
 }
 
-template <int POLICY>
+// LIST = false: every agent, tier 1 only.  LIST = true: the agents the first pass could not pin, every candidate.
+template <int POLICY, bool LIST>
 __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAMPLED) ? 4 : FG_MIN_CTAS) k_select_fast(const __grid_constant__ StepArgs A)
 {
+    const bool full_search = LIST || A.full_search != 0;
     constexpr bool IS_ORCA = (POLICY == SCAB_POLICY_ORCA_SAMPLED);
     constexpr bool SHUNT = (POLICY == SCAB_POLICY_SCA || POLICY == SCAB_POLICY_SRVO3D);
     typedef GroupSmemT<IS_ORCA> GroupSmem;
@@ -125,10 +127,12 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
     for (int i = threadIdx.x; i < 128; i += blockDim.x) s_dir128[i] = A.dir128f[i];
     __syncthreads();
 
-    for (int s = (blockIdx.x * FG_WARPS + wid) * FG_PER_WARP + g; s < A.n; s += groups_total) {
+    const int n_work = LIST ? min(*A.slow_count, A.n) : A.n;
+    for (int wi = (blockIdx.x * FG_WARPS + wid) * FG_PER_WARP + g; wi < n_work; wi += groups_total) {
+        const int s = LIST ? A.slow_list[wi] : wi;
         const float4 mv = A.s_vel[s];
         const int flags = __float_as_int(mv.w);
-        {   // L2 prefetch of this group's next agent (header lines) and of its neighbour records
+        if (!LIST) {   // L2 prefetch of this group's next agent (header lines) and of its neighbour records
             const int s1 = s + groups_total;
             if (s1 < A.n) {
                 if (l8 == 0) prefetch_l2(&A.s_vel[s1]);
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
         const bool pv = posture_ok(a, A.time_step, a.vdx, a.vdy, a.vdz);    // v_pref itself, the last candidate (scaPolicy.py:206)
         const int ndir = __reduce_add_sync(gmask, __popc(m0 | m1)) + (pv ? 1 : 0);
         if (ndir >= DIR_CAP) {           // not the common case: leave it to the general kernel
-            if (l8 == 0) push_slow(A, s);
+            if (l8 == 0) push_slow<LIST>(A, s);
             continue;
         }
 
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
         const float vdvd = fmaf(vdz, vdz, fmaf(vdy, vdy, vdx * vdx));
         const float c0 = 0.25f + vdvd, c1 = fmaf(r1f, r1f, vdvd), r2 = 2.f * r1f;
         float T1 = 3.0e38f;
-        if (!A.full_search) {
+        if (!full_search) {
             float kmin = 0.f;                        // v_pref, when it passes the posture test, is at distance 0 from itself
             if (!pv) {
                 kmin = 3.0e38f;
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
         }
         const float T1sq = T1 * T1;      // (+inf under full_search)
         // exact keys strictly below this are certainly smaller than any key outside tier 1 (fp32 key error <= 1e-3)
-        const unsigned tier_units = A.full_search ? 0xffffffffu : (unsigned)fmaxf((T1 - 1.1e-3f) * 1.0e5f, 0.f);
+        const unsigned tier_units = full_search ? 0xffffffffu : (unsigned)fmaxf((T1 - 1.1e-3f) * 1.0e5f, 0.f);
         int nact = 0;
         {
             unsigned a0 = 0, a1 = 0;             // per lane: direction 8 i + l8 -> bit i of the shell-0 / shell-1 masks
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
         }
         // keys beyond 22 bits, or nothing suitable in tier 1 (possibly "no suitable velocity" at all, scaPolicy.py:224-238)
         if (__any_sync(gmask, overflow) || nlive == 0) {
-            if (l8 == 0) { push_slow(A, s); if (nlive == 0) n_tier2++; }
+            if (l8 == 0) { push_slow<LIST>(A, s); if (nlive == 0 && !LIST) n_tier2++; }
             continue;
         }
         __syncwarp(gmask);
@@ -518,13 +522,13 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
                     if (!within) fmin_ = min(fmin_, W.kc[j]);
                 }
                 kfail = __reduce_min_sync(gmask, fmin_);
-                decided = A.full_search || (kfail != 0xffffffffu && (kfail >> 10) < tier_units);
+                decided = full_search || (kfail != 0xffffffffu && (kfail >> 10) < tier_units);
             } else {
-                decided = A.full_search || ((head >> 10) < tier_units);
+                decided = full_search || ((head >> 10) < tier_units);
             }
         }
         if (!decided) {                   // tier 1 does not pin the answer: every candidate, in the general kernel
-            if (l8 == 0) { push_slow(A, s); n_tier2++; }
+            if (l8 == 0) { push_slow<LIST>(A, s); if (!LIST) n_tier2++; }
             continue;
         }
         int nprefix = 0;
@@ -557,7 +561,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
             double bx, by, bz;
             cand64(a, best, bx, by, bz);
             // n_suit is only known when every candidate was examined (full_search); otherwise report -1
-            const long long ns = A.full_search ? (long long)nlive : -1ll;
+            const long long ns = full_search ? (long long)nlive : -1ll;
             A.s_vpost[s] = make_double4(trunc5(bx), trunc5(by), trunc5(bz),
                                         __longlong_as_double((long long)SCAB_TAG_SUITABLE | (ns << 8)));
         }
