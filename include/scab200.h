@@ -264,6 +264,11 @@ int scab_p2p_alloc(scab_handle *h, int64_t bytes, void **dev_ptr, unsigned char 
 int scab_p2p_open(scab_handle *h, const unsigned char *handle, void **dev_ptr);
 int scab_p2p_signal(scab_handle *h, void *local_seq, void *peer_flag_lo, void *peer_flag_hi, void *stream);
 int scab_p2p_wait(scab_handle *h, void *local_expect, const void *flag_from_lo, const void *flag_from_hi, void *stream);
+/* The same wait WITHOUT a kernel of its own: folded into the next scab_halo_unpack / scab_halo_unpack_pos / scab_migrate_unpack
+ * launch of this handle (every block's first thread spins, then the block proceeds).  The expected value is read from
+ * *local_seq at run time: this rank's own sequence number of that exchange -- both sides signal once per exchange, so the
+ * peers' numbers match it.  Call scab_p2p_signal for the exchange first. */
+int scab_p2p_wait_next(scab_handle *h, const void *local_seq, const void *flag_from_lo, const void *flag_from_hi);
 
 /* Blocking: how many agents the last scab_halo_pack selected per face (> cap means the buffers overflowed). */
 int scab_halo_counts(scab_handle *h, int32_t out_host[2], void *stream);

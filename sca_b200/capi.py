@@ -31,7 +31,7 @@ SYMBOLS = ['scab_version', 'scab_default_params', 'scab_set_option', 'scab_set_m
            'scab_neighbors', 'scab_policy_step', 'scab_status_step', 'scab_step', 'scab_read_counters',
            'scab_reset_counters', 'scab_halo_pack', 'scab_halo_unpack', 'scab_halo_pack_pos', 'scab_halo_unpack_pos',
            'scab_halo_counts', 'scab_migrate_pack', 'scab_migrate_unpack', 'scab_migrate_extra_row_doubles', 'scab_migrate_extra_pack',
-           'scab_migrate_extra_unpack', 'scab_p2p_alloc', 'scab_p2p_open', 'scab_p2p_signal', 'scab_p2p_wait', 'scab_dubins_enable', 'scab_dubins_state_size', 'scab_dubins_read']
+           'scab_migrate_extra_unpack', 'scab_p2p_alloc', 'scab_p2p_open', 'scab_p2p_signal', 'scab_p2p_wait', 'scab_p2p_wait_next', 'scab_dubins_enable', 'scab_dubins_state_size', 'scab_dubins_read']
 
 
 class ScabError(RuntimeError):
@@ -122,6 +122,7 @@ def lib():
     L.scab_p2p_open.argtypes = [vp, vp, C.POINTER(vp)]
     L.scab_p2p_signal.argtypes = [vp, vp, vp, vp, vp]
     L.scab_p2p_wait.argtypes = [vp, vp, vp, vp, vp]
+    L.scab_p2p_wait_next.argtypes = [vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -283,6 +284,9 @@ class Handle:
 
     def p2p_wait(self, local_expect, flag_from_lo, flag_from_hi, stream=0):
         self._ck(self._L.scab_p2p_wait(self._h, local_expect, flag_from_lo or None, flag_from_hi or None, stream))
+
+    def p2p_wait_next(self, local_seq, flag_from_lo, flag_from_hi):
+        self._ck(self._L.scab_p2p_wait_next(self._h, local_seq, flag_from_lo or None, flag_from_hi or None))
 
     def halo_counts(self, stream=0):
         out = (C.c_int32 * 2)()

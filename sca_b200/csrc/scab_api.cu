@@ -46,6 +46,7 @@ struct scab_handle {
     int32_t mig_cap = 0;
     // peer-to-peer exchange buffers (scab_p2p_alloc) and peer mappings (scab_p2p_open)
     std::vector<void *> p2p_own, p2p_peer;
+    P2PWait pending_wait{nullptr, nullptr, nullptr};      // scab_p2p_wait_next: consumed by the next unpack launch
     // Dubins v_pref provider (allocated by the first scab_dubins_enable)
     void *d_dub_states = nullptr;
     double *d_dub_d0 = nullptr;
@@ -261,7 +262,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
                  o_cid = carve(cap * 4), o_cloc = carve(cap * 4), o_nbr = carve(cap * 4 * KNBR),
                  o_ncnt = carve(cap * 4), o_qc = carve(cap * 4), o_kdp = carve(cap * 4),
                  o_slo = carve(cap * 4), o_shi = carve(cap * 4), o_hcnt = carve(64),
-                 o_slow = carve(cap * 4), o_slowc = carve(64), o_slow2 = carve(cap * 4), o_slowc2 = carve(64), o_srow = carve(cap * 4), o_rrow = carve(cap * 4),
+                 o_slow = carve(cap * 4), o_slowc = carve(64), o_slow2 = carve(cap * 4), o_srow = carve(cap * 4), o_rrow = carve(cap * 4),
                  o_kdn = carve((2 * cap) * sizeof(KdNodeDev));
     e = cudaMalloc(&h->d_block, off);
     if (e != cudaSuccess) { delete h; return SCAB_ERR_NOMEM; }
@@ -274,7 +275,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     A.s_nbr = (int32_t *)(b + o_nbr); A.s_nbr_cnt = (int32_t *)(b + o_ncnt); A.s_qcoll = (int32_t *)(b + o_qc);
     h->d_kd_agent_perm = (int32_t *)(b + o_kdp); h->d_kd_agent = (KdNodeDev *)(b + o_kdn);
     A.slow_list = (int32_t *)(b + o_slow); A.slow_count = (int32_t *)(b + o_slowc);
-    A.slow_list2 = (int32_t *)(b + o_slow2); A.slow_count2 = (int32_t *)(b + o_slowc2);
+    A.slow_list2 = (int32_t *)(b + o_slow2); A.slow_count2 = A.slow_count + 1;      // adjacent: one memset resets both
     h->d_mig_sent_row = (int32_t *)(b + o_srow); h->d_mig_recv_row = (int32_t *)(b + o_rrow);
     h->d_sent_lo = (int32_t *)(b + o_slo); h->d_sent_hi = (int32_t *)(b + o_shi); h->d_halo_cnt = (int32_t *)(b + o_hcnt);
     A.kd_agent = h->d_kd_agent; A.kd_agent_perm = h->d_kd_agent_perm;
@@ -598,7 +599,8 @@ extern "C" int scab_halo_unpack(scab_handle *h, const void *recs, int32_t count,
     int rc = check_ready(h, "scab_halo_unpack");
     if (rc) return rc;
     if (count < 0 || row0 < 0 || row0 + count > h->capacity || (count > 0 && !recs)) return fail(h, SCAB_ERR_INVALID, "scab_halo_unpack: bad argument");
-    CK(launch_halo_unpack(h->A, recs, count, (int)row0, (cudaStream_t)stream));
+    CK(launch_halo_unpack(h->A, recs, count, (int)row0, (cudaStream_t)stream, h->pending_wait));
+    h->pending_wait = P2PWait{nullptr, nullptr, nullptr};
     return SCAB_OK;
 }
 
@@ -616,7 +618,8 @@ extern "C" int scab_halo_unpack_pos(scab_handle *h, const double *pos, int32_t c
     int rc = check_ready(h, "scab_halo_unpack_pos");
     if (rc) return rc;
     if (count < 0 || row0 < 0 || row0 + count > h->capacity || (count > 0 && !pos)) return fail(h, SCAB_ERR_INVALID, "scab_halo_unpack_pos: bad argument");
-    CK(launch_halo_unpack_pos(h->A, pos, count, (int)row0, (cudaStream_t)stream));
+    CK(launch_halo_unpack_pos(h->A, pos, count, (int)row0, (cudaStream_t)stream, h->pending_wait));
+    h->pending_wait = P2PWait{nullptr, nullptr, nullptr};
     return SCAB_OK;
 }
 
@@ -652,7 +655,8 @@ extern "C" int scab_migrate_unpack(scab_handle *h, const void *in_lo, const void
     if (rc) return rc;
     if (cap <= 0 || !in_lo || !in_hi || !free_list || !free_count || !cnt) return fail(h, SCAB_ERR_INVALID, "scab_migrate_unpack: bad argument");
     CK(launch_migrate_unpack(h->A, in_lo, in_hi, cap, use_lo, use_hi, free_list, free_count, cnt,
-                             (2 * (int64_t)cap <= h->capacity) ? h->d_mig_recv_row : nullptr, (cudaStream_t)stream));
+                             (2 * (int64_t)cap <= h->capacity) ? h->d_mig_recv_row : nullptr, (cudaStream_t)stream, h->pending_wait));
+    h->pending_wait = P2PWait{nullptr, nullptr, nullptr};
     return SCAB_OK;
 }
 
@@ -730,5 +734,12 @@ extern "C" int scab_p2p_wait(scab_handle *h, void *local_expect, const void *fla
     CK(cudaSetDevice(h->device));
     CK(launch_p2p_wait(h->A, (unsigned long long *)local_expect, (const unsigned long long *)flag_from_lo, (const unsigned long long *)flag_from_hi,
                        (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int scab_p2p_wait_next(scab_handle *h, const void *local_seq, const void *flag_from_lo, const void *flag_from_hi)
+{
+    if (!h || !local_seq) return fail(h, SCAB_ERR_INVALID, "scab_p2p_wait_next: bad argument");
+    h->pending_wait = P2PWait{(const unsigned long long *)local_seq, (const unsigned long long *)flag_from_lo, (const unsigned long long *)flag_from_hi};
     return SCAB_OK;
 }

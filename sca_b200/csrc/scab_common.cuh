@@ -276,6 +276,26 @@ __device__ __forceinline__ void kinematic_update(const StepArgs &A, int id, cons
     for (int k = 0; k < 7; k++) A.st.action[7 * id + k] = act.a[k];
 }
 
+// the spin of a folded peer-to-peer wait (see P2PWait); call with every thread of the block, before any early return
+__device__ __forceinline__ void p2p_block_wait(const unsigned long long *seq, const unsigned long long *flag_lo,
+                                               const unsigned long long *flag_hi, unsigned long long *counters)
+{
+    if (seq == nullptr) return;          // (uniform across the block)
+    if (threadIdx.x == 0) {
+        const unsigned long long e = *seq;
+        const long long t0 = clock64();
+        for (;;) {
+            const bool lo_ok = !flag_lo || *(volatile const unsigned long long *)flag_lo >= e;
+            const bool hi_ok = !flag_hi || *(volatile const unsigned long long *)flag_hi >= e;
+            if (lo_ok && hi_ok) break;
+            if (clock64() - t0 > 8000000000ll) { atomicOr(&counters[7], OVF_P2P_TIMEOUT); break; }
+            __nanosleep(40);
+        }
+        __threadfence_system();          // acquire: the rest of the block reads what the peers wrote
+    }
+    __syncthreads();
+}
+
 // kernels' host-side launchers (one translation unit per stage)
 cudaError_t launch_grid_build(const StepArgs &A, cudaStream_t s);
 cudaError_t launch_neighbors(const StepArgs &A, int mode, cudaStream_t s);
@@ -287,15 +307,19 @@ size_t scab_dubins_state_bytes();
 cudaError_t launch_halo_pack(const StepArgs &A, int n_own, int axis, double lo_face, double hi_face, double width,
                              const double park[3], void *out_lo, void *out_hi, int cap, int32_t *sent_lo, int32_t *sent_hi,
                              int32_t *cnt, cudaStream_t s);
-cudaError_t launch_halo_unpack(const StepArgs &A, const void *recs, int count, int row0, cudaStream_t s);
+// a peer-to-peer wait folded into the next unpack kernel (scab_p2p_wait_next): every block's first thread spins until both
+// neighbours' flags reach this rank's own sequence number of that exchange, then the block proceeds
+struct P2PWait { const unsigned long long *seq, *flag_lo, *flag_hi; };
+cudaError_t launch_halo_unpack(const StepArgs &A, const void *recs, int count, int row0, cudaStream_t s, P2PWait w = P2PWait{nullptr, nullptr, nullptr});
 cudaError_t launch_halo_pack_pos(const StepArgs &A, const int32_t *sent_lo, const int32_t *sent_hi, const int32_t *cnt, int cap,
                                  double *out_lo, double *out_hi, const double park[3], cudaStream_t s);
-cudaError_t launch_halo_unpack_pos(const StepArgs &A, const double *p, int count, int row0, cudaStream_t s);
+cudaError_t launch_halo_unpack_pos(const StepArgs &A, const double *p, int count, int row0, cudaStream_t s, P2PWait w = P2PWait{nullptr, nullptr, nullptr});
 cudaError_t launch_migrate_pack(const StepArgs &A, int own_cap, int axis, double lo_face, double hi_face, const double geom[4], int nx, int ny,
                                 void *out_lo, void *out_hi, int cap, int32_t *free_list, int32_t *free_count, int32_t *cnt, int32_t *sent_row,
                                 cudaStream_t s);
 cudaError_t launch_migrate_unpack(const StepArgs &A, const void *in_lo, const void *in_hi, int cap, int use_lo, int use_hi,
-                                  int32_t *free_list, int32_t *free_count, int32_t *cnt, int32_t *recv_row, cudaStream_t s);
+                                  int32_t *free_list, int32_t *free_count, int32_t *cnt, int32_t *recv_row, cudaStream_t s,
+                                  P2PWait w = P2PWait{nullptr, nullptr, nullptr});
 int migrate_extra_row_doubles(const StepArgs &A);
 cudaError_t launch_p2p_signal(unsigned long long *local_seq, unsigned long long *peer_flag_lo, unsigned long long *peer_flag_hi, cudaStream_t s);
 cudaError_t launch_p2p_wait(const StepArgs &A, unsigned long long *local_expect, const unsigned long long *flag_from_lo,

@@ -11,6 +11,10 @@
 __global__ void __launch_bounds__(256) k_cell_count(StepArgs A)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {     // per-step counters [0..3] and diagnostics [5..6] (nothing accumulates into them before this stage ends)
+        A.counters[0] = A.counters[1] = A.counters[2] = A.counters[3] = 0ull;
+        A.counters[5] = A.counters[6] = 0ull;
+    }
     if (i >= A.n) return;
     int cx, cy, cz;
     int c = cell_of(A.g, A.st.pos[3 * i], A.st.pos[3 * i + 1], A.st.pos[3 * i + 2], cx, cy, cz);
@@ -121,10 +125,12 @@ cudaError_t launch_grid_build(const StepArgs &A, cudaStream_t s)
 {
     cudaError_t e = cudaMemsetAsync(A.cell_count, 0, sizeof(int32_t) * A.g.ncell, s);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(A.counters, 0, sizeof(unsigned long long) * 4, s);     // per-step counters [0..3]
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(A.counters + 5, 0, sizeof(unsigned long long) * 2, s); // per-step diagnostics [5..6]
-    if (e != cudaSuccess) return e;
+    if (A.n <= 0) {     // (otherwise k_cell_count zeroes them)
+        e = cudaMemsetAsync(A.counters, 0, sizeof(unsigned long long) * 4, s);     // per-step counters [0..3]
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(A.counters + 5, 0, sizeof(unsigned long long) * 2, s); // per-step diagnostics [5..6]
+        if (e != cudaSuccess) return e;
+    }
     if (A.n > 0) {
         int nb = (A.n + 255) / 256;
         k_cell_count<<<nb, 256, 0, s>>>(A);

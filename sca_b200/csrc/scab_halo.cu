@@ -18,9 +18,10 @@ struct HaloRec {       // 64 B
     int32_t pad[3];
 };
 
-__global__ void __launch_bounds__(256) k_halo_fill(HaloRec *lo, HaloRec *hi, int cap, double px, double py, double pz)
+__global__ void __launch_bounds__(256) k_halo_fill(HaloRec *lo, HaloRec *hi, int cap, double px, double py, double pz, int32_t *cnt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { cnt[0] = 0; cnt[1] = 0; }      // the per-face counters of the pack kernel that follows
     if (i >= cap) return;
     HaloRec r;
     r.x = px; r.y = py; r.z = pz; r.r = 0.0;
@@ -60,8 +61,9 @@ __global__ void __launch_bounds__(256) k_halo_pack(StepArgs A, int n_own, int ax
     }
 }
 
-__global__ void __launch_bounds__(256) k_halo_unpack(StepArgs A, const HaloRec *recs, int count, int row0)
+__global__ void __launch_bounds__(256) k_halo_unpack(StepArgs A, const HaloRec *recs, int count, int row0, P2PWait w)
 {
+    p2p_block_wait(w.seq, w.flag_lo, w.flag_hi, A.counters);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     const HaloRec r = recs[k];
@@ -90,8 +92,9 @@ __global__ void __launch_bounds__(256) k_halo_pack_pos(StepArgs A, const int32_t
     }
 }
 
-__global__ void __launch_bounds__(256) k_halo_unpack_pos(StepArgs A, const double *p, int count, int row0)
+__global__ void __launch_bounds__(256) k_halo_unpack_pos(StepArgs A, const double *p, int count, int row0, P2PWait w)
 {
+    p2p_block_wait(w.seq, w.flag_lo, w.flag_hi, A.counters);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     const int i = row0 + k;
@@ -102,18 +105,20 @@ cudaError_t launch_halo_pack(const StepArgs &A, int n_own, int axis, double lo_f
                              const double park[3], void *out_lo, void *out_hi, int cap, int32_t *sent_lo, int32_t *sent_hi,
                              int32_t *cnt, cudaStream_t s)
 {
-    cudaError_t e = cudaMemsetAsync(cnt, 0, 2 * sizeof(int32_t), s);
-    if (e != cudaSuccess) return e;
-    if (cap > 0) k_halo_fill<<<(cap + 255) / 256, 256, 0, s>>>((HaloRec *)out_lo, (HaloRec *)out_hi, cap, park[0], park[1], park[2]);
+    if (cap > 0) k_halo_fill<<<(cap + 255) / 256, 256, 0, s>>>((HaloRec *)out_lo, (HaloRec *)out_hi, cap, park[0], park[1], park[2], cnt);
+    else {
+        cudaError_t e = cudaMemsetAsync(cnt, 0, 2 * sizeof(int32_t), s);
+        if (e != cudaSuccess) return e;
+    }
     if (n_own > 0)
         k_halo_pack<<<(n_own + 255) / 256, 256, 0, s>>>(A, n_own, axis, lo_face, hi_face, width, (HaloRec *)out_lo, (HaloRec *)out_hi,
                                                        cap, sent_lo, sent_hi, cnt);
     return cudaGetLastError();
 }
 
-cudaError_t launch_halo_unpack(const StepArgs &A, const void *recs, int count, int row0, cudaStream_t s)
+cudaError_t launch_halo_unpack(const StepArgs &A, const void *recs, int count, int row0, cudaStream_t s, P2PWait w)
 {
-    if (count > 0) k_halo_unpack<<<(count + 255) / 256, 256, 0, s>>>(A, (const HaloRec *)recs, count, row0);
+    if (count > 0) k_halo_unpack<<<(count + 255) / 256, 256, 0, s>>>(A, (const HaloRec *)recs, count, row0, w);
     return cudaGetLastError();
 }
 
@@ -125,9 +130,9 @@ cudaError_t launch_halo_pack_pos(const StepArgs &A, const int32_t *sent_lo, cons
     return cudaGetLastError();
 }
 
-cudaError_t launch_halo_unpack_pos(const StepArgs &A, const double *p, int count, int row0, cudaStream_t s)
+cudaError_t launch_halo_unpack_pos(const StepArgs &A, const double *p, int count, int row0, cudaStream_t s, P2PWait w)
 {
-    if (count > 0) k_halo_unpack_pos<<<(count + 255) / 256, 256, 0, s>>>(A, p, count, row0);
+    if (count > 0) k_halo_unpack_pos<<<(count + 255) / 256, 256, 0, s>>>(A, p, count, row0, w);
     return cudaGetLastError();
 }
 
@@ -191,8 +196,9 @@ __global__ void k_migrate_header(MigRow *out_lo, MigRow *out_hi, int cap, const 
 }
 
 __global__ void __launch_bounds__(256) k_migrate_unpack(StepArgs A, const MigRow *in_lo, const MigRow *in_hi, int cap, int use_lo, int use_hi,
-                                                        int32_t *free_list, int32_t *free_count, int32_t *cnt, int32_t *recv_row)
+                                                        int32_t *free_list, int32_t *free_count, int32_t *cnt, int32_t *recv_row, P2PWait w)
 {
+    p2p_block_wait(w.seq, w.flag_lo, w.flag_hi, A.counters);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= 2 * cap) return;
     if (recv_row) recv_row[k] = -1;                          // row given to arrival k (for k_migrate_extra_unpack); -1: none
@@ -231,11 +237,11 @@ cudaError_t launch_migrate_pack(const StepArgs &A, int own_cap, int axis, double
 }
 
 cudaError_t launch_migrate_unpack(const StepArgs &A, const void *in_lo, const void *in_hi, int cap, int use_lo, int use_hi,
-                                  int32_t *free_list, int32_t *free_count, int32_t *cnt, int32_t *recv_row, cudaStream_t s)
+                                  int32_t *free_list, int32_t *free_count, int32_t *cnt, int32_t *recv_row, cudaStream_t s, P2PWait w)
 {
     if (cap > 0)
         k_migrate_unpack<<<(2 * cap + 255) / 256, 256, 0, s>>>(A, (const MigRow *)in_lo, (const MigRow *)in_hi, cap, use_lo, use_hi, free_list,
-                                                              free_count, cnt, recv_row);
+                                                              free_count, cnt, recv_row, w);
     return cudaGetLastError();
 }
 

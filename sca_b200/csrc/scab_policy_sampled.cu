@@ -686,12 +686,10 @@ static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
         k_integrate<IS_ORCA><<<nb256, 256, 0, s>>>(A);
         return cudaGetLastError();
     }
-    cudaError_t e = cudaMemsetAsync(A.slow_count, 0, sizeof(int32_t), s);
+    cudaError_t e = cudaMemsetAsync(A.slow_count, 0, 2 * sizeof(int32_t), s);       // both work lists (slow_count2 == slow_count + 1)
     if (e != cudaSuccess) return e;
     const int need_f = (A.n + FG_WARPS * FG_PER_WARP - 1) / (FG_WARPS * FG_PER_WARP);
     const int grid_f = need_f < sms * per_sm_fast ? need_f : sms * per_sm_fast;
-    if (e == cudaSuccess) e = cudaMemsetAsync(A.slow_count2, 0, sizeof(int32_t), s);
-    if (e != cudaSuccess) return e;
     k_select_fast<POLICY, false><<<grid_f, FG_WARPS * 32, smem_fast, s>>>(A);
     // pass 2: the agents tier 1 did not pin (~1 %), eight lanes each again but examining EVERY candidate; what that cannot
     // handle either (no suitable velocity at all, > 63 surviving directions) goes on to the general kernel, one warp per

@@ -293,9 +293,11 @@ class ShardedSwarm:
         self.sw.h.p2p_signal(c + 8 * (8 + kind), lo, hi, self._stream())
 
     def _wait(self, kind):
+        """Folded into the unpack kernel that follows (no launch of its own): it waits until both neighbours' flags of this
+        exchange kind reach this rank's own sequence number (set by _signal just before)."""
         c = self.ctl.data_ptr()
-        self.sw.h.p2p_wait(c + 8 * (12 + kind), c + 8 * (2 * kind) if self.rank > 0 else 0,
-                           c + 8 * (2 * kind + 1) if self.rank < self.world - 1 else 0, self._stream())
+        self.sw.h.p2p_wait_next(c + 8 * (8 + kind), c + 8 * (2 * kind) if self.rank > 0 else 0,
+                                c + 8 * (2 * kind + 1) if self.rank < self.world - 1 else 0)
 
     # ------------------------------------------------------------------
     def _park_rows(self, r0, r1):
