@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
     RowTrim T;
     T.init(A.g, me, cx, cy, cz, lim);
     const float mx = (float)(me.x - A.g.ox), my = (float)(me.y - A.g.oy), mz = (float)(me.z - A.g.oz);
-    double range_used = DENSE ? 0.5 * A.nbr_dist_sq : A.nbr_dist_sq;
+    double range_used = A.nbr_dist_sq;
     float limf = prefilter_limit(range_used + 1e-4, mx, my, mz);
     // the (up to) nine x-rows of the block: all their cell_start bounds are fetched before any row is scanned
     int rbeg[9], rend[9];
@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
     for (int attempt = 0; attempt < (DENSE ? 5 : 1); attempt++) {
     nbuf = 0;
     overflow = false;
+    int nhit = 0;
 #pragma unroll
     for (int r = 0; r < 9; r++) {
         const int end = rend[r];
@@ -496,6 +497,7 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
                 m |= mq << j0;
             }
             if (n < 32) m &= (1u << n) - 1u;                      // the clamped tail loads repeat the last record
+            if (DENSE) nhit += __popc(m);
             while (m) {
                 const int b = __ffs(m) - 1;
                 m &= m - 1;
@@ -505,7 +507,9 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
         }
     }
     if (!DENSE || !overflow) break;
-    range_used *= 0.5;
+    // shrink the ball so that it holds ~36 of the nhit agents seen (count ~ r^3; a flatter crowd just takes another round)
+    const float sc = cbrtf(36.f / (float)nhit);
+    range_used *= (double)fminf(sc * sc, 0.8f);
     limf = prefilter_limit(range_used + 1e-4, mx, my, mz);
     }
     if (!DENSE && overflow) { A.slow_list[atomicAdd(A.slow_count, 1)] = s; return; }      // (the policy stage resets the list for its own use)
