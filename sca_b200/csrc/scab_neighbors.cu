@@ -119,7 +119,7 @@ __device__ __noinline__ void write_lists2(const StepArgs &A, int s, int id, cons
 
 // ------------------------------------------------------------------ KNN over the cell list
 #ifndef KNN_CAP
-#define KNN_CAP 48      // candidate slots per agent (in range + pre-filter guard); 128 threads x 48 x 4 B = 24 KB per CTA (64 measured 5 % slower: less L1)
+#define KNN_CAP 48      // candidate slots per agent of the tile variant (in range + pre-filter guard)
 #endif
 // The exact general path (obstacles, ties on the decimal-rounded distance, more than KNN_CAP raw candidates):
 // fp64 keys + the (distSq, obstacles-before-agents, id) comparator.
@@ -429,10 +429,12 @@ __global__ void __launch_bounds__(NT_THREADS, NT_MIN_CTAS) k_neighbors_tile(cons
 // nearest of a crowded neighbourhood are certainly inside a smaller ball).  Keeping the retry out of the first kernel keeps
 // a warp from re-scanning for one crowded lane (BASELINE config 4 has ~64 agents in range of each other; the uniform
 // workload gets there locally late in a rollout).
+// Candidates are recorded as 16-bit codes (row << 12 | offset in the row's range): 96 slots per agent in 24 KB per CTA.
+#define KND_CAP 96
 template <bool DENSE>
 __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const __grid_constant__ StepArgs A)
 {
-    __shared__ int buf[KNN_CAP][128];
+    __shared__ unsigned short buf[KND_CAP][128];
     const int t = blockIdx.x * blockDim.x + threadIdx.x, tid = threadIdx.x;
     const int n_work = DENSE ? min(*A.slow_count, A.n) : A.n;
     if (t >= n_work) return;
@@ -478,6 +480,7 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
 #pragma unroll
     for (int r = 0; r < 9; r++) {
         const int end = rend[r];
+        if (end - rbeg[r] > 4096) overflow = true;               // (a row the 12-bit offsets cannot address: exact path)
 #pragma unroll 1
         for (int c0 = rbeg[r]; c0 < end; c0 += 32) {
             const int n = min(32, end - c0);
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
             while (m) {
                 const int b = __ffs(m) - 1;
                 m &= m - 1;
-                if (nbuf < KNN_CAP) buf[nbuf++][tid] = c0 + b;
+                if (nbuf < KND_CAP) buf[nbuf++][tid] = (unsigned short)((r << 12) | ((c0 + b - rbeg[r]) & 4095));
                 else overflow = true;
             }
         }
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
     limf = prefilter_limit(range_used + 1e-4, mx, my, mz);
     }
     if (!DENSE && overflow) { A.slow_list[atomicAdd(A.slow_count, 1)] = s; return; }      // (the policy stage resets the list for its own use)
-    knn_phase2(A, s, id, me, nbuf, overflow, range_used, [&](int i) { return buf[i][tid]; });
+    knn_phase2(A, s, id, me, nbuf, overflow, range_used, [&](int i) { const unsigned c = buf[i][tid]; return rbeg[c >> 12] + (int)(c & 4095u); });
 }
 
 // the general path for every agent (obstacles in the merged list, SCAB_KNN_EXACT=1, neighbor_dist >= 12.9 m): thread per agent
