@@ -27,6 +27,8 @@
 #define LUT_B SCAB_POSTURE_LUT_B
 #define LIVE_CAP 136      // 2 * DIR_CAP + v_pref, rounded up
 #define VPREF_ENTRY 0x3ff
+#define LIST_EXTRA_DELTA 0.4f     // second pass: tier width 0.3 + 0.4
+#define LIST_MIN_AGENTS 3000      // second pass: shorter lists go straight to the general kernel
 #ifndef FG_MIN_CTAS
 #define FG_MIN_CTAS 5   // resident CTAs per SM the kernel is compiled for (96 registers): 1.39 -> 1.27 ms for the policy stage on B200; 6 spills
 #endif
@@ -104,11 +106,14 @@ __device__ __forceinline__ int posture_bin(float x, float y, float z)
     return iy * LUT_B + ix;
 }
 
-// LIST = false: every agent, tier 1 only.  LIST = true: the agents the first pass could not pin, every candidate.
+// LIST = false: every agent, tier 1 only.  LIST = true: the agents the first pass could not pin, with a wider tier
+// (tier_delta + LIST_EXTRA_DELTA); a short list skips this pass -- the general kernel finishes up to one wave of agents in
+// one warp's latency (~35 us), which a second 8-lane pass cannot beat.
 template <int POLICY, bool LIST>
 __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAMPLED) ? 4 : FG_MIN_CTAS) k_select_fast(const __grid_constant__ StepArgs A)
 {
-    const bool full_search = LIST || A.full_search != 0;
+    const bool full_search = A.full_search != 0;
+    const float tier_delta = A.tier_delta + (LIST ? LIST_EXTRA_DELTA : 0.f);
     constexpr bool IS_ORCA = (POLICY == SCAB_POLICY_ORCA_SAMPLED);
     constexpr bool SHUNT = (POLICY == SCAB_POLICY_SCA || POLICY == SCAB_POLICY_SRVO3D);
     typedef GroupSmemT<IS_ORCA> GroupSmem;
@@ -128,6 +133,11 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
     __syncthreads();
 
     const int n_work = LIST ? min(*A.slow_count, A.n) : A.n;
+    if (LIST && n_work < LIST_MIN_AGENTS) {      // hand the whole list on (uniform branch: every thread sees the same count)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x) A.slow_list2[i] = A.slow_list[i];
+        if (blockIdx.x == 0 && threadIdx.x == 0) *A.slow_count2 = n_work;
+        return;
+    }
     for (int wi = (blockIdx.x * FG_WARPS + wid) * FG_PER_WARP + g; wi < n_work; wi += groups_total) {
         const int s = LIST ? A.slow_list[wi] : wi;
         const float4 mv = A.s_vel[s];
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
                 }
                 kmin = sqrtf(__uint_as_float(__reduce_min_sync(gmask, __float_as_uint(kmin))));   // non-negative floats order as uints
             }
-            T1 = kmin + A.tier_delta;
+            T1 = kmin + tier_delta;
         }
         const float T1sq = T1 * T1;      // (+inf under full_search)
         // exact keys strictly below this are certainly smaller than any key outside tier 1 (fp32 key error <= 1e-3)
