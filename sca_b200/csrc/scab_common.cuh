@@ -98,6 +98,15 @@ struct StepArgs {
     double *dub_d0;                  // [capacity] this step's agent.neighbors[0][1] (-1: empty list), indexed by row
 };
 
+// ------------------------------------------------------------------ cache hints
+#ifdef __CUDACC__
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#else     // host builds of the device source (tests/hostsim)
+static inline void prefetch_l2(const void *) {}
+static inline void prefetch_l1(const void *) {}
+#endif
+
 // ------------------------------------------------------------------ rounding conventions
 // x / 1e5, correctly rounded, as one multiply and two FMAs (Markstein's division by a constant with y = RN(1/d)) instead
 // of the ~25-instruction IEEE division: every decimal rounding of the reference ends in this division.  Bit-identical to

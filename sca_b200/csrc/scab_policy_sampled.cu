@@ -97,14 +97,7 @@ __device__ __forceinline__ bool is_intersect64_fast(double ax, double ay, double
     return dt > 0.0 && df > 0.0;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void *p)
-{
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ void prefetch_l1(const void *p)
-{
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
+
 
 // lexicographic warp arg-min over (a, b); lanes without a value pass a = ~0ull
 __device__ __forceinline__ void warp_lexmin(unsigned long long &a, unsigned &b)
