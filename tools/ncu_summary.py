@@ -1,5 +1,5 @@
 """Compact text summary of one kernel capture (`ncu --set full --import-source on`):
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/rNN_kernel.txt
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [top] [kernel-name-regex] > profiles/rNN_kernel.txt
 Key raw metrics (duration, DRAM bytes, occupancy, issue/stall picture, divergence) + the hottest source lines."""
 import csv
 import io
@@ -7,16 +7,20 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+top = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 25
+ksel = [a for a in sys.argv[2:] if not a.isdigit()]            # optional: substring of the kernel name (a report may hold several kernels)
+ksub = ksel[0] if ksel else ''
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-h, units, v = rows[0], rows[1], rows[-1]
+h, units = rows[0], rows[1]
+cand = [r for r in rows[2:] if ksub in r[h.index('Kernel Name')]]
+v = cand[-1]
 WANT = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread', 'launch__occupancy_limit_registers',
         'launch__occupancy_limit_shared_mem', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_bytes.sum', 'l1tex__t_sector_hit_rate.pct',
         'lts__t_sector_hit_rate.pct', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
-        'smsp__inst_executed.sum', 'smsp__thread_inst_executed_per_inst_executed.ratio',
+        'smsp__inst_executed.sum', 'smsp__thread_inst_executed_per_inst_executed.ratio', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
@@ -36,10 +40,16 @@ src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-so
 from collections import defaultdict
 inst, samp, text = defaultdict(float), defaultdict(float), {}
 cur = hdr = None
+in_kernel = True
 fname = ''
 for r in csv.reader(io.StringIO(src)):
+    if len(r) >= 2 and r[0] == 'Function Name':
+        in_kernel = ksub in r[1].replace('(int)', '').replace('(bool)', '')
+        continue
     if len(r) >= 2 and r[0] in ('File Name', 'File Path'):
         fname = r[1].split('/')[-1]
+        continue
+    if not in_kernel:
         continue
     if len(r) > 4 and r[0] == 'Line No':
         hdr = r
