@@ -277,11 +277,18 @@ def run_ours(args):
                 traffic = json.load(f).get(dom if (dom != 'policy' or policy == 'sca') else 'policy_' + policy)   # ncu figures are per kernel
         except Exception:
             pass
+        counters = None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'kernel_counters.json')) as f:
+                counters = json.load(f).get(dom if (dom != 'policy' or policy == 'sca') else 'policy_' + policy)
+        except Exception:
+            pass
         roof = {'bound': 'hbm', 'kernel': {'grid': 'k_cell_count+k_scan_*+k_reorder', 'neighbors': 'k_neighbors_compat' if nbr_name == 'compat' else 'k_neighbors_direct',
                                            'policy': POLICY_KERNELS.get(policy, 'k_vpref+k_select_fast<%s>+k_select<%s>+k_integrate' % (policy.upper(), policy.upper())),
                                            'status': 'k_status'}[dom],
                 'achieved': round(achieved, 2), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 5),
-                'traffic': traffic, 'peak_source': how, 'algorithmic_bytes_per_agent_step': ALGO_BYTES[dom],
+                'traffic': traffic, 'traffic_source': 'profiles/dram_traffic.json (ncu --set full of this build at 10^6 agents; not measured in this run)',
+                'counters': counters, 'peak_source': how, 'algorithmic_bytes_per_agent_step': ALGO_BYTES[dom],
                 'units_per_launch': int(units), 'stage_ms': {k: round(v, 4) for k, v in stage_ms.items()},
                 'average_cost_ms_per_agent_step': average_cost,
                 'last_step_diag': {k: cdiag[k] for k in ('n_active', 'n_recheck', 'n_tier2', 'n_slow', 'n_collision')},

@@ -39,6 +39,7 @@ def main():
     hostsim_util.activate_streams(mp)
     mp.setattr(torch.cuda, 'Event', _Event)
     os.environ['SCAB_NO_GRAPH'] = '1'
+    os.environ['SCAB_TRANSPORT'] = 'nccl'          # separate processes without shared device memory: staged send / recv (gloo)
     src = open(os.path.join(ROOT, 'bench.py')).read()
     for old, new in (("device = 'cuda:%d' % local", "device = 'cpu'"),
                      ("dist.init_process_group('nccl', device_id=torch.device(device))", "dist.init_process_group('gloo')")):
