@@ -135,6 +135,68 @@ def make_config_swarm(cfg, device):
     return sw
 
 
+class _Agent(object):
+    """The attributes of mamp/agents/agent.py:9-77 that the policy interface reads and writes (the reference package is not on
+    the GPU box; the shims are duck-typed)."""
+
+    def __init__(self, start, goal, policy, i):
+        self.policy = policy()
+        self.initial_pos, self.goal_pos = np.array(start, 'float64'), np.array(goal, 'float64')
+        self.pos_global_frame, self.goal_global_frame = self.initial_pos[:3].copy(), self.goal_pos[:3].copy()
+        self.heading_global_frame = self.initial_pos[3:].copy()
+        self.vel_global_frame = np.zeros(3)
+        self.radius, self.pref_speed, self.id = 0.5, 1.0, i
+        self.neighbors, self.v_pref, self.path = [], np.zeros(3), []
+        self.total_time = self.total_dist = 0.0
+        self.step_num = 0
+        self.is_at_goal = self.is_collision = self.is_out_of_max_time = self.is_obstacle = False
+        self.max_run_dist = 3.0 * round(float(np.sqrt(((self.initial_pos[:3] - self.goal_pos[:3]) ** 2).sum())), 5)
+
+
+def shim_rate(cfg, policy, steps):
+    """agent-steps/s of the DROP-IN path (sca_b200.mamp_compat: GPUKDTree.buildAgentTree + find_next_action per agent, the two
+    calls MACAEnv._take_action makes, mampenv.py:28,40) on Agent objects, followed by the env's own per-agent Python update
+    (mampenv.py:83-105).  What a user of the unmodified reference gets after the one-line swap of INTEGRATION.md."""
+    import math
+    from sca_b200 import mamp_compat, scenarios
+    pos, goal, obs = cfg['gen'](scenarios)
+    cls = {'sca': mamp_compat.GPUSCAPolicy, 'orca_lp': mamp_compat.GPUORCA3DPolicyOfficial, 'rvo3d': mamp_compat.GPURVO3DPolicy,
+           'srvo3d': mamp_compat.GPUSRVO3DPolicy}[policy]
+    agents = [_Agent(pos[i], goal[i], cls, i) for i in range(len(pos))]
+
+    class _Obs(object):
+        def __init__(self, o, k):
+            self.pos_global_frame, self.radius, self.id, self.is_obstacle, self.is_at_goal = np.array(o[:3]), float(o[3]), k, True, True
+            self.vel_global_frame = np.zeros(3)
+    tree = mamp_compat.GPUKDTree(agents, [_Obs(o, k) for k, o in enumerate(obs)])
+    wrap = lambda a: (a + math.pi) % (2 * math.pi) - math.pi
+
+    def one():
+        tree.buildAgentTree()                                            # mampenv.py:28
+        n_act = 0
+        for a in agents:
+            if a.is_at_goal or a.is_collision or a.is_out_of_max_time:
+                continue
+            act = a.policy.find_next_action({}, a, tree)                 # mampenv.py:40
+            n_act += 1
+            al, be = wrap(a.heading_global_frame[0] + act[4]), wrap(a.heading_global_frame[1] + act[5])     # mampenv.py:83-105
+            d = act[3] * 0.1 * np.array([math.cos(be) * math.cos(al), math.cos(be) * math.sin(al), math.sin(be)])
+            a.pos_global_frame += d
+            a.total_dist += float(np.sqrt((d * d).sum()))
+            a.heading_global_frame = [al, be, 0.0]
+            a.vel_global_frame = np.array(act[:3])
+            a.step_num += 1
+        return n_act
+    for _ in range(3):
+        one()
+    t0 = time.perf_counter()
+    tot = sum(one() for _ in range(steps))
+    dt = time.perf_counter() - t0
+    return {'value': tot / dt, 'unit': 'agent-steps/s', 'ms_per_step': dt / steps * 1e3, 'steps': steps,
+            'what': 'unmodified-MACAEnv drop-in: GPUKDTree.buildAgentTree + GPU*Policy.find_next_action on Agent objects + the env\'s '
+                    'per-agent Python update; the reference\'s own policies run ~40 agent-steps/s on this scenario (BASELINE.md)'}
+
+
 def make_swarm(n_total, rank, world, device, seed=0):
     from sca_b200 import scenarios
     from sca_b200.swarm import Swarm
@@ -412,6 +474,8 @@ def run_ours(args):
             out['e2e'] = e2e
         if cpu:
             out['cpu_baseline'] = cpu
+        if cfg is not None and args.config in (1, 2) and not args.quick:
+            out['dropin_shim'] = shim_rate(cfg, policy, min(args.steps, 20))
         print(json.dumps(out))
     if world > 1:
         # captured graphs hold NCCL work: release them, then leave without the (blocking) group teardown
