@@ -195,6 +195,11 @@ int scab_neighbors(scab_handle *h, int mode, void *stream);
 /* Stage 3: v_pref, constraint construction, velocity selection, action, kinematic update
  * (replaces Policy.find_next_action + update_velocitie, mampenv.py:83-105). */
 int scab_policy_step(scab_handle *h, int policy, void *stream);
+/* Stage 3 for the state rows [row_begin, row_end) only.  The stage may be issued as several row ranges that together cover
+ * every row exactly once (any order): a caller whose state lives in host memory starts downloading the results of a range
+ * while the next one computes (sca_b200.Swarm.step_from_host).  The union of the ranges gives exactly what scab_policy_step
+ * gives.  Not available while the device Dubins tracker is enabled (its kernels run for every agent): SCAB_ERR_INVALID. */
+int scab_policy_step_rows(scab_handle *h, int policy, int64_t row_begin, int64_t row_end, void *stream);
 /* Stage 4: collision / timeout / goal flags and the done reduction (mampenv.py:51-80). */
 int scab_status_step(scab_handle *h, void *stream);
 /* Stages 1-4 back to back: one MACAEnv.step (mampenv.py:22-25). */

@@ -28,7 +28,7 @@ OVF_TEXT = {1: 'a halo face buffer overflowed (ghost records dropped)', 2: 'a mi
 
 SYMBOLS = ['scab_version', 'scab_default_params', 'scab_set_option', 'scab_set_max_radius', 'scab_set_motion_bound', 'scab_create', 'scab_destroy', 'scab_last_error', 'scab_set_grid',
            'scab_bind_state', 'scab_set_obstacles', 'scab_kdtree_build', 'scab_kdtree_get_perm', 'scab_build_grid',
-           'scab_neighbors', 'scab_policy_step', 'scab_status_step', 'scab_step', 'scab_read_counters',
+           'scab_neighbors', 'scab_policy_step', 'scab_policy_step_rows', 'scab_status_step', 'scab_step', 'scab_read_counters',
            'scab_reset_counters', 'scab_halo_pack', 'scab_halo_unpack', 'scab_halo_pack_pos', 'scab_halo_unpack_pos',
            'scab_halo_counts', 'scab_migrate_pack', 'scab_migrate_unpack', 'scab_migrate_extra_row_doubles', 'scab_migrate_extra_pack',
            'scab_migrate_extra_unpack', 'scab_p2p_alloc', 'scab_p2p_open', 'scab_p2p_signal', 'scab_p2p_wait', 'scab_p2p_wait_next', 'scab_dubins_enable', 'scab_dubins_state_size', 'scab_dubins_read']
@@ -99,6 +99,7 @@ def lib():
     L.scab_neighbors.argtypes = [vp, C.c_int, vp]
     L.scab_policy_step.argtypes = [vp, C.c_int, vp]
     L.scab_status_step.argtypes = [vp, vp]
+    L.scab_policy_step_rows.argtypes = [vp, C.c_int, i64, i64, vp]
     L.scab_step.argtypes = [vp, C.c_int, C.c_int, vp]
     L.scab_read_counters.argtypes = [vp, C.POINTER(Counters), vp]
     L.scab_reset_counters.argtypes = [vp, vp]
@@ -200,6 +201,9 @@ class Handle:
 
     def policy_step(self, policy, stream=0):
         self._ck(self._L.scab_policy_step(self._h, policy, stream))
+
+    def policy_step_rows(self, policy, row_begin, row_end, stream=0):
+        self._ck(self._L.scab_policy_step_rows(self._h, policy, int(row_begin), int(row_end), stream))
 
     def status_step(self, stream=0):
         self._ck(self._L.scab_status_step(self._h, stream))

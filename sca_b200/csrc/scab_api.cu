@@ -236,6 +236,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     A.max_speed = p->max_speed;
     A.near_goal = p->near_goal;
     A.tier_delta = TIER_DELTA_DEFAULT;
+    A.row_begin = 0; A.row_count = -1;
     // until scab_set_motion_bound: no agent moves more than 1.25 m per step (12.5 m/s at the reference's dt)
     A.move_bound = 1.25;
     {   // launch configuration of THIS handle: its device's SM count, the A/B switches as they are set right now
@@ -498,6 +499,20 @@ extern "C" int scab_policy_step(scab_handle *h, int policy, void *stream)
     if (policy < SCAB_POLICY_SCA || policy > SCAB_POLICY_ORCA_LP) return fail(h, SCAB_ERR_INVALID, "scab_policy_step: bad policy");
     if (policy == SCAB_POLICY_ORCA_LP) CK(launch_policy_lp(h->A, (cudaStream_t)stream));
     else CK(launch_policy_sampled(h->A, policy, (cudaStream_t)stream));
+    return SCAB_OK;
+}
+
+extern "C" int scab_policy_step_rows(scab_handle *h, int policy, int64_t row_begin, int64_t row_end, void *stream)
+{
+    int rc = check_ready(h, "scab_policy_step_rows");
+    if (rc) return rc;
+    if (policy < SCAB_POLICY_SCA || policy > SCAB_POLICY_ORCA_LP) return fail(h, SCAB_ERR_INVALID, "scab_policy_step_rows: bad policy");
+    if (row_begin < 0 || row_end < row_begin || row_end > h->A.n) return fail(h, SCAB_ERR_INVALID, "scab_policy_step_rows: bad row range");
+    StepArgs A = h->A;
+    A.row_begin = (int)row_begin; A.row_count = (int)(row_end - row_begin);
+    cudaError_t e = (policy == SCAB_POLICY_ORCA_LP) ? launch_policy_lp(A, (cudaStream_t)stream) : launch_policy_sampled(A, policy, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported) return fail(h, SCAB_ERR_INVALID, "scab_policy_step_rows: not available with the device Dubins tracker");
+    CK(e);
     return SCAB_OK;
 }
 

@@ -51,6 +51,9 @@ struct LaunchCfg {
 struct StepArgs {
     scab_state_ptrs st;
     int n;           // owned agents
+    // scab_policy_step_rows: the policy stage for the state rows [row_begin, row_begin + row_count) only (row_count < 0: every
+    // agent, in cell-sorted order).  Work item t of a per-agent kernel is then the agent of row row_begin + t.
+    int row_begin, row_count;
     int m;           // obstacles
     GridGeom g;      // agent grid
     GridGeom og;     // obstacle grid (static)
@@ -304,6 +307,10 @@ __device__ __forceinline__ void p2p_block_wait(const unsigned long long *seq, co
     }
     __syncthreads();
 }
+
+// number of per-agent work items of a policy kernel and the sorted index of item t (see StepArgs::row_count)
+__device__ __forceinline__ int policy_items(const StepArgs &A) { return A.row_count < 0 ? A.n : A.row_count; }
+__device__ __forceinline__ int policy_item(const StepArgs &A, int t) { return A.row_count < 0 ? t : A.rank[A.row_begin + t]; }
 
 // kernels' host-side launchers (one translation unit per stage)
 cudaError_t launch_grid_build(const StepArgs &A, cudaStream_t s);

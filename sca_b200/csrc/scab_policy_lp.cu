@@ -365,10 +365,10 @@ __global__ void __launch_bounds__((MODE & 1) ? LP_FAST_THREADS : LP_THREADS, (MO
     const int tid = threadIdx.x;
     unsigned long long ran = 0;
     constexpr bool LIST = (MODE == 2 || MODE == 4);
-    const int n_work = LIST ? min(*A.slow_count, A.n) : A.n;
-    if (LIST && blockIdx.x == 0 && tid == 0) A.counters[6] = (unsigned long long)n_work;
+    const int n_work = LIST ? min(*A.slow_count, A.n) : policy_items(A);
+    if (LIST && blockIdx.x == 0 && tid == 0) atomicAdd(&A.counters[6], (unsigned long long)n_work);
     for (int wi = blockIdx.x * blockDim.x + tid; wi < n_work; wi += gridDim.x * blockDim.x) {
-        const int s = LIST ? A.slow_list[wi] : wi;
+        const int s = LIST ? A.slow_list[wi] : policy_item(A, wi);
         const int id = A.s_id[s];
         const double4 me = A.s_posr[s];
         const float4 mv = A.s_vel[s];
@@ -489,7 +489,8 @@ __global__ void __launch_bounds__((MODE & 1) ? LP_FAST_THREADS : LP_THREADS, (MO
 #ifndef SCAB_HOSTSIM   // tests/hostsim compiles the device code above for the host (one thread at a time); no launcher there
 cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
 {
-    if (A.n <= 0) return cudaSuccess;
+    if (A.n <= 0 || A.row_count == 0) return cudaSuccess;
+    const int items = A.row_count < 0 ? A.n : A.row_count;
     LaunchCfg &cfg = *A.cfg;      // this handle's device and switches (slots 12, 13: the two list-pass kernels)
     int &per_sm = cfg.occ[12], &per_sm_c = cfg.occ[13];
     const int no_fast = cfg.no_fast, sms = cfg.sms, f64_only = cfg.lp_f64, compact = cfg.lp_compact, ctas8 = cfg.lp_ctas8;
@@ -504,14 +505,14 @@ cudaError_t launch_policy_lp(const StepArgs &A, cudaStream_t s)
         if (per_sm < 1) per_sm = 1;
         if (per_sm_c < 1) per_sm_c = 1;
     }
-    const int nb = (A.n + LP_THREADS - 1) / LP_THREADS;
+    const int nb = (items + LP_THREADS - 1) / LP_THREADS;
     if (no_fast) {
         k_policy_lp<0><<<nb, LP_THREADS, smem, s>>>(A);
         return cudaGetLastError();
     }
     cudaError_t e = cudaMemsetAsync(A.slow_count, 0, sizeof(int32_t), s);
     if (e != cudaSuccess) return e;
-    const int nbf = (A.n + LP_FAST_THREADS - 1) / LP_FAST_THREADS;
+    const int nbf = (items + LP_FAST_THREADS - 1) / LP_FAST_THREADS;
     if (f64_only) k_policy_lp<3><<<nbf, LP_FAST_THREADS, 0, s>>>(A);
     else if (ctas8) k_policy_lp<5><<<nbf, LP_FAST_THREADS, 0, s>>>(A);
     else k_policy_lp<1><<<nbf, LP_FAST_THREADS, 0, s>>>(A);

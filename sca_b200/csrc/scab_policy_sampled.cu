@@ -133,8 +133,9 @@ __device__ __forceinline__ void warp_min_key_c(unsigned long long &a, unsigned &
 template <bool USE_DISTANCE, bool ALLOW_EXT>
 __global__ void __launch_bounds__(256) k_vpref(StepArgs A)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= A.n) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= policy_items(A)) return;
+    const int s = policy_item(A, t);
     const float4 mv = A.s_vel[s];
     if (__float_as_int(mv.w) & FL_INACTIVE) return;
     const int id = A.s_id[s];
@@ -174,15 +175,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
     const int warps_total = gridDim.x * WARPS_PER_CTA;
     unsigned long long n_recheck = 0;
 
-    const int n_work = USE_LIST ? min(*A.slow_count2, A.n) : A.n;       // (the list the second fast pass leaves)
-    if (USE_LIST && blockIdx.x == 0 && threadIdx.x == 0) A.counters[6] = (unsigned long long)n_work;
+    const int n_work = USE_LIST ? min(*A.slow_count2, A.n) : policy_items(A);       // (the list the second fast pass leaves)
+    if (USE_LIST && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.counters[6], (unsigned long long)n_work);
     for (int wi = blockIdx.x * WARPS_PER_CTA + wid; wi < n_work; wi += warps_total) {
-        const int s = USE_LIST ? A.slow_list2[wi] : wi;
+        const int s = USE_LIST ? A.slow_list2[wi] : policy_item(A, wi);
         const float4 mv = A.s_vel[s];
         const int flags = __float_as_int(mv.w);
         if (flags & FL_INACTIVE) continue;
         const double4 vd = A.s_vdes[s];
-        if (!USE_LIST) {   // hide the two dependent global round trips of the NEXT agents behind this agent's arithmetic:
+        if (!USE_LIST && A.row_count < 0) {   // hide the two dependent global round trips of the NEXT agents behind this agent's arithmetic:
             // header lines two agents ahead -> L2; neighbour records one agent ahead -> L2 (their index list
             // was prefetched one iteration ago)
             const int s2 = s + 2 * warps_total, s1 = s + warps_total;
@@ -610,9 +611,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_select(StepArgs A)
 template <bool IS_ORCA>
 __global__ void __launch_bounds__(256) k_integrate(StepArgs A)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     bool ran = false;
-    if (s < A.n) {
+    if (t < policy_items(A)) {
+        const int s = policy_item(A, t);
         const int id = A.s_id[s];
         const double4 me = A.s_posr[s];
         const int flags = __float_as_int(A.s_vel[s].w);
@@ -654,7 +656,8 @@ template <int POLICY>
 static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
 {
     constexpr bool IS_ORCA = (POLICY == SCAB_POLICY_ORCA_SAMPLED);
-    const int nb256 = (A.n + 255) / 256;
+    const int items = A.row_count < 0 ? A.n : A.row_count;
+    const int nb256 = (items + 255) / 256;
     // resident CTAs per SM of the two persistent kernels on THIS handle's device (slots 2 * POLICY, 2 * POLICY + 1)
     LaunchCfg &cfg = *A.cfg;
     int &per_sm = cfg.occ[2 * POLICY], &per_sm_fast = cfg.occ[2 * POLICY + 1];
@@ -672,7 +675,7 @@ static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
         if (per_sm_fast < 1) per_sm_fast = 1;
     }
     // persistent kernels, exactly one resident wave each: grid = SMs x resident CTAs per SM
-    const int need = (A.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int need = (items + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const int grid = need < sms * per_sm ? need : sms * per_sm;
     if (no_fast) {
         k_select<POLICY, false><<<grid, WARPS_PER_CTA * 32, smem, s>>>(A);
@@ -681,7 +684,7 @@ static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
     }
     cudaError_t e = cudaMemsetAsync(A.slow_count, 0, 2 * sizeof(int32_t), s);       // both work lists (slow_count2 == slow_count + 1)
     if (e != cudaSuccess) return e;
-    const int need_f = (A.n + FG_WARPS * FG_PER_WARP - 1) / (FG_WARPS * FG_PER_WARP);
+    const int need_f = (items + FG_WARPS * FG_PER_WARP - 1) / (FG_WARPS * FG_PER_WARP);
     const int grid_f = need_f < sms * per_sm_fast ? need_f : sms * per_sm_fast;
     k_select_fast<POLICY, false><<<grid_f, FG_WARPS * 32, smem_fast, s>>>(A);
     // pass 2: the agents tier 1 did not pin (~1 %), eight lanes each again but examining EVERY candidate; what that cannot
@@ -695,9 +698,11 @@ static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
 
 cudaError_t launch_policy_sampled(const StepArgs &A, int policy, cudaStream_t s)
 {
-    if (A.n <= 0) return cudaSuccess;
+    if (A.n <= 0 || A.row_count == 0) return cudaSuccess;
     const int sms = A.cfg->sms;
-    const int nb = (A.n + 255) / 256;
+    const int nb = ((A.row_count < 0 ? A.n : A.row_count) + 255) / 256;
+    if (A.row_count >= 0 && A.dub_states && !A.st.vpref_ext && (policy == SCAB_POLICY_SCA || policy == SCAB_POLICY_RVO3D_DUBINS))
+        return cudaErrorNotSupported;       // the Dubins tracker kernels run for every agent
     const int grid = sms;   // launch_select multiplies by the resident CTAs per SM
     cudaError_t e;
     switch (policy) {

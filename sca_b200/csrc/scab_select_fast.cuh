@@ -132,17 +132,17 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
     for (int i = threadIdx.x; i < 128; i += blockDim.x) s_dir128[i] = A.dir128f[i];
     __syncthreads();
 
-    const int n_work = LIST ? min(*A.slow_count, A.n) : A.n;
+    const int n_work = LIST ? min(*A.slow_count, A.n) : policy_items(A);
     if (LIST && n_work < LIST_MIN_AGENTS) {      // hand the whole list on (uniform branch: every thread sees the same count)
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x) A.slow_list2[i] = A.slow_list[i];
         if (blockIdx.x == 0 && threadIdx.x == 0) *A.slow_count2 = n_work;
         return;
     }
     for (int wi = (blockIdx.x * FG_WARPS + wid) * FG_PER_WARP + g; wi < n_work; wi += groups_total) {
-        const int s = LIST ? A.slow_list[wi] : wi;
+        const int s = LIST ? A.slow_list[wi] : policy_item(A, wi);
         const float4 mv = A.s_vel[s];
         const int flags = __float_as_int(mv.w);
-        if (!LIST) {   // L2 prefetch of this group's next agent (header lines) and of its neighbour records
+        if (!LIST && A.row_count < 0) {   // L2 prefetch of this group's next agent (header lines) and of its neighbour records
             const int s1 = s + groups_total;
             if (s1 < A.n) {
                 if (l8 == 0) prefetch_l2(&A.s_vel[s1]);

@@ -216,7 +216,7 @@ class Swarm:
         host['action'] = torch.zeros((n, 7), dtype=_F4).pin_memory()
         return host
 
-    def step_from_host(self, host, policy, nbr_mode=capi.NBR_KNN, overlap=True, upload_vel=False):
+    def step_from_host(self, host, policy, nbr_mode=capi.NBR_KNN, overlap=True, upload_vel=False, chunks=4):
         """One MACAEnv.step for a caller whose state lives in HOST memory (what a mamp/envs drop-in pays per step): upload the
         step's inputs from the pinned buffers of host_buffers(), run the four stages, download the new state and the action
         matrix into the same buffers, and return once they are there.  Bytes per agent: 64 up (pos, heading, status,
@@ -224,7 +224,8 @@ class Swarm:
         upload_vel=True: update_velocitie sets it to action[:3] (mampenv.py:104) and the device did exactly that in the
         previous step, so its copy is current; host['vel'] is refreshed from the action rows on the host side lazily
         by host_velocity().  overlap=True hides the part of the upload the cell list does not read behind the cell list +
-        16-NN (second stream) and the download of everything k_status does not write behind k_status; the result is
+        16-NN (second stream), issues the policy stage as `chunks` row ranges (scab_policy_step_rows) so that the rows of a
+        range come down while the next range computes, and downloads what k_status writes behind it; the result is
         bit-identical to overlap=False (tests/test_gpu_step_from_host.py)."""
         pol = capi.POLICIES[policy] if isinstance(policy, str) else int(policy)
         n = self.n
@@ -248,7 +249,7 @@ class Swarm:
         if cs is None:
             cs = self._copy_stream = torch.cuda.Stream(device=self.device)
             self._ev = [torch.cuda.Event() for _ in range(3)]
-        ev_up, ev_in, ev_pol = self._ev
+        ev_up, ev_in, ev_pol = self._ev[:3]
         for k in first:
             t[k][:n].copy_(host[k], non_blocking=True)
         t['status'].bitwise_or_(self._zaxis)
@@ -263,12 +264,26 @@ class Swarm:
         self.h.build_grid(self._stream())
         self.h.neighbors(nbr_mode, self._stream())
         main_s.wait_event(ev_in)
-        self.h.policy_step(pol, self._stream())
-        ev_pol.record(main_s)
-        with torch.cuda.stream(cs):
-            cs.wait_event(ev_pol)
-            for k in early_down:
-                host[k].copy_(t[k][:n], non_blocking=True)
+        nch = max(1, min(int(chunks), n // 256)) if 'goal_heading' not in t or 'vpref_ext' in t or pol not in (0, 3) else 1
+        if nch <= 1:          # (also: the device Dubins tracker runs for every agent at once)
+            self.h.policy_step(pol, self._stream())
+            ev_pol.record(main_s)
+            with torch.cuda.stream(cs):
+                cs.wait_event(ev_pol)
+                for k in early_down:
+                    host[k].copy_(t[k][:n], non_blocking=True)
+        else:
+            while len(self._ev) < 3 + nch:
+                self._ev.append(torch.cuda.Event())
+            for c in range(nch):
+                a, b = c * n // nch, (c + 1) * n // nch
+                self.h.policy_step_rows(pol, a, b, self._stream())
+                ev_c = self._ev[3 + c]
+                ev_c.record(main_s)
+                with torch.cuda.stream(cs):
+                    cs.wait_event(ev_c)
+                    for k in early_down:
+                        host[k][a:b].copy_(t[k][a:b], non_blocking=True)
         self.h.status_step(self._stream())
         for k in late_down:
             host[k].copy_(t[k][:n], non_blocking=True)

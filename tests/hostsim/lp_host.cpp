@@ -22,6 +22,7 @@ extern "C" int hostsim_policy_lp(int mode, const scab_state_ptrs *st, int n, int
     A.st = *st;
     A.n = n; A.m = m;
     A.move_bound = 1e300;
+    A.row_count = -1;
     A.time_step = time_step; A.inv_time_step = 1.0 / time_step; A.inv_time_horizon = 1.0 / time_horizon; A.max_speed = max_speed;
     A.s_posr = (double4 *)posr; A.s_vel = (float4 *)vel4; A.s_id = ids; A.s_gid = ids;
     A.s_nbr = (int32_t *)nbr; A.s_nbr_cnt = (int32_t *)nbr_cnt; A.s_qcoll = (int32_t *)qcoll;

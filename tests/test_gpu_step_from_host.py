@@ -15,7 +15,7 @@ def test_step_from_host_equals_the_resident_step(request, monkeypatch, policy):
     if request.config.getoption('--hostsim'):
         import hostsim_util
         hostsim_util.activate_streams(monkeypatch)
-    n = 6000 if not request.config.getoption('--hostsim') else 1500
+    n = 20000 if not request.config.getoption('--hostsim') else 1500
     pos, goal, _ = scenarios.uniform_box_numpy(n, 4.0e6 / 560.0 ** 3, seed=9)
 
     def fresh():
@@ -28,17 +28,17 @@ def test_step_from_host_equals_the_resident_step(request, monkeypatch, policy):
         ref.step(policy, capi.NBR_KNN)
     torch.cuda.synchronize()
     want = ref.download()
-    for overlap in (False, True):
+    for overlap, chunks in ((False, 1), (True, 1), (True, 4), (True, 3)):
         sw = fresh()
         host = sw.host_buffers()
         for step in range(6):
-            sw.step_from_host(host, policy, overlap=overlap, upload_vel=(step == 0))
+            sw.step_from_host(host, policy, overlap=overlap, upload_vel=(step == 0), chunks=chunks)
             # a host-resident caller: wipe the device copies of everything the next step uploads
             for k in ('pos', 'heading', 'total_dist'):
                 sw.t[k].fill_(float('nan'))
             sw.t['status'].fill_(-1)
             sw.t['step_num'].fill_(-7)
         for k in ('pos', 'heading', 'status', 'total_dist', 'step_num', 'action'):
-            assert np.array_equal(host[k].numpy(), want[k]), (overlap, k)
+            assert np.array_equal(host[k].numpy(), want[k]), (overlap, chunks, k)
         assert np.array_equal(Swarm.host_velocity(host).numpy(), want['vel'])
         assert sw.counters()['n_active_total'] == ref.counters()['n_active_total']
