@@ -371,6 +371,7 @@ def run_ours(args):
         h2d, d2h = sw.H2D_BYTES_PER_AGENT * sw.n, sw.D2H_BYTES_PER_AGENT * sw.n
         steps_e = max(3, min(args.steps, 20))
         overlap = os.environ.get('SCAB_BENCH_E2E_OVERLAP', '1') == '1'
+        e2e_chunks = int(os.environ.get('SCAB_E2E_CHUNKS', '4'))        # row ranges of the policy stage (downloads overlap the next range)
         sw.step_from_host(host, policy, capi.NBR_KNN, overlap=overlap, upload_vel=True)
         a0 = sw.counters()['n_active_total']
         torch.cuda.synchronize()
@@ -381,7 +382,7 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         e2e = {'value': (sw.counters()['n_active_total'] - a0) / dt, 'unit': 'agent-steps/s',
                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'steps': steps_e,
-               'ms_per_step': round(dt / steps_e * 1e3, 3), 'api': 'Swarm.step_from_host',
+               'ms_per_step': round(dt / steps_e * 1e3, 3), 'api': 'Swarm.step_from_host', 'policy_row_ranges': e2e_chunks if overlap else 1,
                'copies': 'overlapped with the cell list / 16-NN / status kernels' if overlap else 'serial'}
 
     elif os.environ.get('SCAB_BENCH_E2E_SHARDED', '1') == '1':
