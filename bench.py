@@ -371,13 +371,13 @@ def run_ours(args):
         h2d, d2h = sw.H2D_BYTES_PER_AGENT * sw.n, sw.D2H_BYTES_PER_AGENT * sw.n
         steps_e = max(3, min(args.steps, 20))
         overlap = os.environ.get('SCAB_BENCH_E2E_OVERLAP', '1') == '1'
-        e2e_chunks = int(os.environ.get('SCAB_E2E_CHUNKS', '4'))        # row ranges of the policy stage (downloads overlap the next range)
-        sw.step_from_host(host, policy, capi.NBR_KNN, overlap=overlap, upload_vel=True)
+        e2e_chunks = int(os.environ.get('SCAB_E2E_CHUNKS', '8'))        # row ranges of the policy stage (downloads overlap the next range)
+        sw.step_from_host(host, policy, NBR, overlap=overlap, upload_vel=True, chunks=e2e_chunks)
         a0 = sw.counters()['n_active_total']
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(steps_e):
-            sw.step_from_host(host, policy, capi.NBR_KNN, overlap=overlap)
+            sw.step_from_host(host, policy, NBR, overlap=overlap, chunks=e2e_chunks)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         e2e = {'value': (sw.counters()['n_active_total'] - a0) / dt, 'unit': 'agent-steps/s',

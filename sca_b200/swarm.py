@@ -216,7 +216,7 @@ class Swarm:
         host['action'] = torch.zeros((n, 7), dtype=_F4).pin_memory()
         return host
 
-    def step_from_host(self, host, policy, nbr_mode=capi.NBR_KNN, overlap=True, upload_vel=False, chunks=4):
+    def step_from_host(self, host, policy, nbr_mode=capi.NBR_KNN, overlap=True, upload_vel=False, chunks=8):
         """One MACAEnv.step for a caller whose state lives in HOST memory (what a mamp/envs drop-in pays per step): upload the
         step's inputs from the pinned buffers of host_buffers(), run the four stages, download the new state and the action
         matrix into the same buffers, and return once they are there.  Bytes per agent: 64 up (pos, heading, status,
