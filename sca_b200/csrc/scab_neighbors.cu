@@ -435,6 +435,7 @@ template <bool DENSE>
 __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const __grid_constant__ StepArgs A)
 {
     __shared__ unsigned short buf[KND_CAP][128];
+    __shared__ int rowbase[9][128];          // first sorted index of each row's range, per thread (decodes the candidate codes)
     const int t = blockIdx.x * blockDim.x + threadIdx.x, tid = threadIdx.x;
     const int n_work = DENSE ? min(*A.slow_count, A.n) : A.n;
     if (t >= n_work) return;
@@ -468,6 +469,7 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
         const int rowi = (z * A.g.ny + y) * A.g.nx;
         rbeg[r] = ok ? A.cell_start[rowi + max(x0, 0)] : 0;
         rend[r] = ok ? A.cell_start[rowi + min(x1, A.g.nx - 1) + 1] : 0;
+        rowbase[r][tid] = rbeg[r];
     }
     // Per row, the hits of up to 32 consecutive records are collected as a bit mask (one instruction per record instead of
     // a predicated store sequence) and then drained into the thread's shared-memory column.  A neighbourhood too dense for
@@ -516,7 +518,7 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
     limf = prefilter_limit(range_used + 1e-4, mx, my, mz);
     }
     if (!DENSE && overflow) { A.slow_list[atomicAdd(A.slow_count, 1)] = s; return; }      // (the policy stage resets the list for its own use)
-    knn_phase2(A, s, id, me, nbuf, overflow, range_used, [&](int i) { const unsigned c = buf[i][tid]; return rbeg[c >> 12] + (int)(c & 4095u); });
+    knn_phase2(A, s, id, me, nbuf, overflow, range_used, [&](int i) { const unsigned c = buf[i][tid]; return rowbase[c >> 12][tid] + (int)(c & 4095u); });
 }
 
 // the general path for every agent (obstacles in the merged list, SCAB_KNN_EXACT=1, neighbor_dist >= 12.9 m): thread per agent

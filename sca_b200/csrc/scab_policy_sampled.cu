@@ -660,19 +660,22 @@ static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
     const int nb256 = (items + 255) / 256;
     // resident CTAs per SM of the two persistent kernels on THIS handle's device (slots 2 * POLICY, 2 * POLICY + 1)
     LaunchCfg &cfg = *A.cfg;
-    int &per_sm = cfg.occ[2 * POLICY], &per_sm_fast = cfg.occ[2 * POLICY + 1];
+    int &per_sm = cfg.occ[2 * POLICY], &per_sm_fast = cfg.occ[2 * POLICY + 1], &per_sm_list = cfg.occ[14 + POLICY];
     const int no_fast = cfg.no_fast;
-    const size_t smem = sizeof(WarpSmem) * WARPS_PER_CTA, smem_fast = sizeof(GroupSmemT<POLICY == SCAB_POLICY_ORCA_SAMPLED>) * FG_WARPS * FG_PER_WARP + 384 * sizeof(float4);
+    const size_t smem = sizeof(WarpSmem) * WARPS_PER_CTA, smem_list = sizeof(GroupSmemT<POLICY == SCAB_POLICY_ORCA_SAMPLED>) * FG_WARPS * FG_PER_WARP,
+                 smem_fast = smem_list + 384 * sizeof(float4);
     if (per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(k_select<POLICY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select<POLICY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select_fast<POLICY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select_fast<POLICY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select_fast<POLICY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_list);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_list, k_select_fast<POLICY, true>, FG_WARPS * 32, smem_list);
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_select<POLICY, true>, WARPS_PER_CTA * 32, smem);
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fast, k_select_fast<POLICY, false>, FG_WARPS * 32, smem_fast);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
         if (per_sm_fast < 1) per_sm_fast = 1;
+        if (per_sm_list < 1) per_sm_list = 1;
     }
     // persistent kernels, exactly one resident wave each: grid = SMs x resident CTAs per SM
     const int need = (items + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
@@ -690,7 +693,8 @@ static cudaError_t launch_select(const StepArgs &A, int sms, cudaStream_t s)
     // pass 2: the agents tier 1 did not pin (~1 %), eight lanes each again but examining EVERY candidate; what that cannot
     // handle either (no suitable velocity at all, > 63 surviving directions) goes on to the general kernel, one warp per
     // agent (usually nobody: the launch is then one warp's look at an empty list)
-    k_select_fast<POLICY, true><<<grid_f, FG_WARPS * 32, smem_fast, s>>>(A);
+    const int grid_l = need_f < sms * per_sm_list ? need_f : sms * per_sm_list;
+    k_select_fast<POLICY, true><<<grid_l, FG_WARPS * 32, smem_list, s>>>(A);
     k_select<POLICY, true><<<grid, WARPS_PER_CTA * 32, smem, s>>>(A);
     k_integrate<IS_ORCA><<<nb256, 256, 0, s>>>(A);
     return cudaGetLastError();

@@ -29,6 +29,9 @@
 #define VPREF_ENTRY 0x3ff
 #define LIST_EXTRA_DELTA 0.4f     // second pass: tier width 0.3 + 0.4
 #define LIST_MIN_AGENTS 3000      // second pass: shorter lists go straight to the general kernel
+#ifndef FG_LIST_CTAS
+#define FG_LIST_CTAS 6            // second pass: one more resident CTA (80 registers, direction tables read from global memory instead
+#endif                            // of shared): the pass is one agent's latency per group, so it wants every listed agent resident at once
 #ifndef FG_MIN_CTAS
 #define FG_MIN_CTAS 5   // resident CTAs per SM the kernel is compiled for (96 registers): 1.39 -> 1.27 ms for the policy stage on B200; 6 spills
 #endif
@@ -110,7 +113,7 @@ __device__ __forceinline__ int posture_bin(float x, float y, float z)
 // (tier_delta + LIST_EXTRA_DELTA); a short list skips this pass -- the general kernel finishes up to one wave of agents in
 // one warp's latency (~35 us), which a second 8-lane pass cannot beat.
 template <int POLICY, bool LIST>
-__global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAMPLED) ? 4 : FG_MIN_CTAS) k_select_fast(const __grid_constant__ StepArgs A)
+__global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAMPLED) ? 4 : (LIST ? FG_LIST_CTAS : FG_MIN_CTAS)) k_select_fast(const __grid_constant__ StepArgs A)
 {
     const bool full_search = A.full_search != 0;
     const float tier_delta = A.tier_delta + (LIST ? LIST_EXTRA_DELTA : 0.f);
@@ -126,11 +129,14 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
     const int groups_total = gridDim.x * FG_WARPS * FG_PER_WARP;
     unsigned long long n_recheck = 0, n_tier2 = 0;
     // fp32 direction tables, once per CTA (6 KB): conflict-free float4 reads in phases A and B
-    float4 *s_dir256 = reinterpret_cast<float4 *>(smem_raw + sizeof(GroupSmem) * FG_WARPS * FG_PER_WARP);
-    float4 *s_dir128 = s_dir256 + 256;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_dir256[i] = A.dir256f[i];
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_dir128[i] = A.dir128f[i];
-    __syncthreads();
+    const float4 *s_dir256 = A.dir256f, *s_dir128 = A.dir128f;       // (second pass: straight from global memory / L1)
+    if (!LIST) {
+        float4 *t256 = reinterpret_cast<float4 *>(smem_raw + sizeof(GroupSmem) * FG_WARPS * FG_PER_WARP);
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) t256[i] = A.dir256f[i];
+        for (int i = threadIdx.x; i < 128; i += blockDim.x) t256[256 + i] = A.dir128f[i];
+        s_dir256 = t256; s_dir128 = t256 + 256;
+        __syncthreads();
+    }
 
     const int n_work = LIST ? min(*A.slow_count, A.n) : policy_items(A);
     if (LIST && n_work < LIST_MIN_AGENTS) {      // hand the whole list on (uniform branch: every thread sees the same count)
