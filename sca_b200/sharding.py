@@ -143,7 +143,7 @@ class ShardedSwarm:
     """
 
     def __init__(self, pos6, goal6, rank, world, device, lo, hi, radius=0.5, pref_speed=1.0, migrate_every=8,
-                 halo_cap=None, debug=False, use_graph=True, mig_cap=4096, params=None, transport='nccl', own_slack=0.1):
+                 halo_cap=None, debug=False, use_graph=True, mig_cap=4096, params=None, transport='nccl', own_slack=0.2):
         """`transport`: how the halo / migration buffers reach the slab neighbours --
         'nccl'  pack -> torch.distributed send/recv -> unpack (any backend; gloo in the CPU tests);
         'p2p'   the pack kernels write straight into the neighbour's receive buffers over NVLink (CUDA IPC between the ranks of
