@@ -9,7 +9,7 @@ for p in (ROOT, os.path.join(ROOT, 'tests')):
         sys.path.insert(0, p)
 
 # -m gpu tests that need real hardware even under --hostsim (size, several devices, CUDA streams / graphs)
-HOSTSIM_SKIP = ('test_gpu_full_size', 'test_sharding_gpu', 'test_voxel_obstacle_field_at_scale')
+HOSTSIM_SKIP = ('test_gpu_full_size', 'test_sharding_gpu', 'test_voxel_obstacle_field_at_scale', 'config4_at_100000')
 
 
 def pytest_addoption(parser):
