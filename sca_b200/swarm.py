@@ -216,7 +216,7 @@ class Swarm:
         host['action'] = torch.zeros((n, 7), dtype=_F4).pin_memory()
         return host
 
-    def step_from_host(self, host, policy, nbr_mode=capi.NBR_KNN, overlap=True, upload_vel=False, chunks=8):
+    def step_from_host(self, host, policy, nbr_mode=capi.NBR_KNN, overlap=True, upload_vel=False, chunks=8, min_chunk_rows=65536):
         """One MACAEnv.step for a caller whose state lives in HOST memory (what a mamp/envs drop-in pays per step): upload the
         step's inputs from the pinned buffers of host_buffers(), run the four stages, download the new state and the action
         matrix into the same buffers, and return once they are there.  Bytes per agent: 64 up (pos, heading, status,
@@ -225,7 +225,8 @@ class Swarm:
         previous step, so its copy is current; host['vel'] is refreshed from the action rows on the host side lazily
         by host_velocity().  overlap=True hides the part of the upload the cell list does not read behind the cell list +
         16-NN (second stream), issues the policy stage as `chunks` row ranges (scab_policy_step_rows) so that the rows of a
-        range come down while the next range computes, and downloads what k_status writes behind it; the result is
+        range come down while the next range computes (ranges of at least `min_chunk_rows` rows: below that the extra launches
+        cost more than the overlap gives), and downloads what k_status writes behind it; the result is
         bit-identical to overlap=False (tests/test_gpu_step_from_host.py)."""
         pol = capi.POLICIES[policy] if isinstance(policy, str) else int(policy)
         n = self.n
@@ -264,7 +265,7 @@ class Swarm:
         self.h.build_grid(self._stream())
         self.h.neighbors(nbr_mode, self._stream())
         main_s.wait_event(ev_in)
-        nch = max(1, min(int(chunks), n // 256)) if 'goal_heading' not in t or 'vpref_ext' in t or pol not in (0, 3) else 1
+        nch = max(1, min(int(chunks), n // max(1, int(min_chunk_rows)))) if 'goal_heading' not in t or 'vpref_ext' in t or pol not in (0, 3) else 1
         if nch <= 1:          # (also: the device Dubins tracker runs for every agent at once)
             self.h.policy_step(pol, self._stream())
             ev_pol.record(main_s)

@@ -32,7 +32,7 @@ def test_step_from_host_equals_the_resident_step(request, monkeypatch, policy):
         sw = fresh()
         host = sw.host_buffers()
         for step in range(6):
-            sw.step_from_host(host, policy, overlap=overlap, upload_vel=(step == 0), chunks=chunks)
+            sw.step_from_host(host, policy, overlap=overlap, upload_vel=(step == 0), chunks=chunks, min_chunk_rows=256)
             # a host-resident caller: wipe the device copies of everything the next step uploads
             for k in ('pos', 'heading', 'total_dist'):
                 sw.t[k].fill_(float('nan'))
