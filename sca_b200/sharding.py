@@ -221,12 +221,15 @@ class ShardedSwarm:
         self.mig_cap = int(mig_cap)
         mk = lambda: torch.zeros((self.mig_cap + 1, 16), **f8)
         self.msend_lo, self.msend_hi = mk(), mk()
+        if self.transport != 'nccl' and not self._p2p_setup(dev):
+            # peer memory is not available between these ranks (every rank agrees on that): the staged transport instead
+            import warnings
+            warnings.warn('sca_b200: peer-to-peer buffers could not be shared between the ranks; falling back to transport=nccl')
+            self.transport = 'nccl'
         if self.transport == 'nccl':
             self.recv = torch.zeros((2 * self.cap, REC_DOUBLES), **f8)
             self.precv = torch.zeros((2 * self.cap, 3), **f8)
             self.mrecv_lo, self.mrecv_hi = mk(), mk()
-        else:
-            self._p2p_setup(dev)
         i4 = dict(dtype=torch.int32, device=dev)
         self.free_list = torch.zeros(self.own_cap, **i4)
         nfree = self.own_cap - self.n_own
@@ -260,7 +263,16 @@ class ShardedSwarm:
             total += (b + 255) // 256 * 256
         self._off = off
         ipc = self.transport == 'p2p'
-        self._arena, handle = self.sw.h.p2p_alloc(total, want_handle=ipc)
+        try:
+            self._arena, handle = self.sw.h.p2p_alloc(total, want_handle=ipc)
+        except capi.ScabError:
+            if not ipc:
+                raise
+            self._arena, handle = 0, None          # (still takes part in the collectives below)
+        if ipc:
+            peers = self._open_neighbours(handle)
+            if peers is None:
+                return False
         a = self._arena
         self.ctl = _view(a + off['ctl'], (32,), torch.int64, dev)
         self.recv = _view(a + off['recv'], (2 * cap, REC_DOUBLES), torch.float64, dev)
@@ -270,16 +282,24 @@ class ShardedSwarm:
         self._peer = {'lo': 0, 'hi': 0}          # base of the neighbours' arenas in THIS process's address space (0: none)
         self._xarena, self._xpeer = 0, {'lo': 0, 'hi': 0}
         if ipc:
-            lo_b, hi_b = self._open_neighbours(handle)
-            self._peer = {'lo': lo_b, 'hi': hi_b}
+            self._peer = {'lo': peers[0], 'hi': peers[1]}
+        return True
 
     def _open_neighbours(self, handle):
-        """Collective: every rank publishes the IPC handle of its arena and maps its slab neighbours'."""
+        """Collective: every rank publishes the IPC handle of its arena and maps its slab neighbours'.  Returns None -- on
+        EVERY rank -- if any rank could not allocate or map (no peer access between the devices, IPC disabled ...)."""
         handles = [None] * self.world
         torch.distributed.all_gather_object(handles, handle)
-        lo_b = self.sw.h.p2p_open(handles[self.rank - 1]) if self.rank > 0 else 0
-        hi_b = self.sw.h.p2p_open(handles[self.rank + 1]) if self.rank < self.world - 1 else 0
-        return lo_b, hi_b
+        ok, lo_b, hi_b = all(h is not None for h in handles), 0, 0
+        if ok:
+            try:
+                lo_b = self.sw.h.p2p_open(handles[self.rank - 1]) if self.rank > 0 else 0
+                hi_b = self.sw.h.p2p_open(handles[self.rank + 1]) if self.rank < self.world - 1 else 0
+            except capi.ScabError:
+                ok = False
+        oks = [None] * self.world
+        torch.distributed.all_gather_object(oks, bool(ok))
+        return (lo_b, hi_b) if all(oks) else None
 
     def _remote(self, side, offset, fallback):
         """Address of byte `offset` of the `side` ('lo' / 'hi') neighbour's arena; a local scratch tensor on a side without one."""
@@ -545,8 +565,10 @@ class ShardedSwarm:
                        'recv_lo': _view(self._xarena, (self.mig_cap, row), torch.float64, dev),
                        'recv_hi': _view(self._xarena + half, (self.mig_cap, row), torch.float64, dev)}
         if self.transport == 'p2p':
-            lo_b, hi_b = self._open_neighbours(handle)
-            self._xpeer = {'lo': lo_b, 'hi': hi_b}
+            peers = self._open_neighbours(handle)
+            if peers is None:
+                raise capi.ScabError('the extra migration buffers could not be shared between the ranks (the main ones could)')
+            self._xpeer = {'lo': peers[0], 'hi': peers[1]}
 
     def enable_dubins(self, goal_heading, policy='sca'):
         """SCA / RVO3D+Dubins on several GPUs: V_des from the device-side Dubins tracker (Swarm.enable_dubins); the tracker

@@ -47,3 +47,20 @@ def test_logical_shards_on_the_emulated_device(monkeypatch, policy, shards, n, s
     print(info)
     assert all(v == 0 for v in info['mismatches'].values()) and not info['counter_mismatches'], info
     assert info['migrations'] > 0
+
+
+def test_peer_to_peer_transport_falls_back_when_buffers_cannot_be_shared():
+    """transport='p2p' between processes needs CUDA IPC; where that is unavailable (here: the emulated devices are separate
+    host processes) every rank must agree to fall back to the staged transport -- and the run must still equal the single-device
+    run bit for bit."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'hostsim'))
+    import build as hostsim_build
+    hostsim_build.build()
+    env = dict(os.environ, SHARD_HOSTSIM='1', SHARD_TRANSPORT='p2p', SHARD_POLICY='rvo3d', SHARD_N='1400', SHARD_STEPS='6',
+               SHARD_WATCHDOG='300', OMP_NUM_THREADS='1')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+                        '127.0.0.1', '--master-port', str(29750 + os.getpid() % 100), os.path.join(ROOT, 'tests', 'sharding_check.py')],
+                       env=env, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-800:], r.stderr[-800:])
+    assert r.returncode == 0 and '-> OK' in r.stdout
+    assert 'falling back to transport=nccl' in r.stderr
