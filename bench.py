@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- agent-steps/s of the batched collision-avoidance step (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--agents A] [--policy P]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1..5] [--policy P] [--agents A]
+                    [--skip-steps S] [--quick] [--no-cpu]
 
-Workload (config.workload): BASELINE.json configs[4], "SCA synthetic uniform-random swarm, 1,000,000 UAVs"
+Default workload (config.workload): BASELINE.json configs[4], "SCA synthetic uniform-random swarm, 1,000,000 UAVs"
 (pos/goal ~ U(0, 560 m)^3, >= 1.1 m initial separation, r = 0.5, pref_speed = 1, straight-line v_pref --
 the Dubins provider is upstream of the path).  It fits one B200, so N = 1 runs all 10^6
 agents on one GPU; N > 1 shards the SAME 10^6 agents into spatial slabs with a halo exchange (strong scaling).
 
+`--config 1..4` run BASELINE configs[0..3] at their named sizes on one GPU (CONFIGS below; configs 1 and 2 with the
+reference's own neighbour semantics, REF_COMPAT).  KNN mode -- the true 16 nearest -- is what the default workload uses; it is
+NOT the reference's traversal-order neighbour list and the line says so.
+
 A "step" is one full MACAEnv.step for every agent: cell list -> 16-NN -> SCA candidate search ->
 kinematic update -> collision/goal status.  value = agent-steps/s with state resident in HBM;
-e2e = the same through host buffers (pinned H2D of the step's inputs + D2H of its results inside the timed
-region), which is what a mamp/envs drop-in pays per step.
+e2e = the same through host buffers and the repo's public API for that case, Swarm.step_from_host (pinned H2D of the step's
+inputs + D2H of its results inside the timed region), which is what a caller with host-resident state pays per step.
 `--impl reference` times the CPU oracle port of the reference (the reference is ~40 agent-steps/s of
 single-threaded Python and cannot run this workload) on a bounded sample with every host thread.
 """

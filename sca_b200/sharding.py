@@ -1,19 +1,23 @@
-"""Multi-GPU spatial sharding: one process per GPU, slabs along x, NCCL halo exchange.
+"""Multi-GPU spatial sharding: one process per GPU, slabs along x, halo exchange with the two slab neighbours.
 
 The reference is single-process; this is the only parallelism the new build adds.
 Per step and per rank (all asynchronous on the step's stream, fixed-size buffers, no host round trips):
 
-    halo_pack  ->  NCCL send/recv with the <= 2 slab neighbours  ->  halo_unpack   (ghost rows)
+    halo_pack  ->  exchange with the <= 2 slab neighbours  ->  halo_unpack          (ghost rows)
     cell list  ->  16-NN  ->  policy kernels (owned agents only)
-    halo_pack_pos -> NCCL send/recv -> halo_unpack_pos                               (ghosts' new positions)
+    halo_pack_pos -> exchange -> halo_unpack_pos                                     (ghosts' new positions)
     status kernel (owned agents only)
 
+The exchange is either fused into the pack kernels -- they write straight into the neighbour GPU's receive buffers over NVLink
+(CUDA IPC), a flag kernel publishes the data, the unpack kernel waits for it: transport='p2p', no communication library in the
+step -- or staged through torch.distributed send / recv (transport='nccl'; gloo in the CPU tests).  `LogicalShards` runs S slabs
+in ONE process on one device with the same kernels (transport='local').
 Every `migrate_every` steps agents that left their slab move to the neighbour rank (full state rows).
 Ties and the sequential collision-check order follow GLOBAL agent ids, so an S-shard run reproduces the
-1-GPU run of the same kernels bit for bit (tests/test_sharding_gpu.py).
+1-GPU run of the same kernels bit for bit (tests/test_gpu_logical_shards.py, tests/test_sharding_gpu.py).
 
-`SlabPlan` and the row packing are plain host logic (device agnostic) and are covered on CPU with a
-world_size-2 gloo test (tests/test_sharding_host.py).
+`SlabPlan` and the row packing are plain host logic (device agnostic) and are covered on CPU with
+world_size-2 gloo tests (tests/test_sharding_host.py, tests/test_sharding_hostsim.py).
 """
 import numpy as np
 import torch
