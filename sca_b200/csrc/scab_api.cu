@@ -261,7 +261,7 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
                  o_vdes = carve(cap * sizeof(double4)), o_vpost = carve(cap * sizeof(double4)),
                  o_vel = carve(cap * sizeof(float4)), o_posf = carve(cap * sizeof(float4)), o_id = carve(cap * 4), o_rank = carve(cap * 4),
                  o_cid = carve(cap * 4), o_cloc = carve(cap * 4), o_nbr = carve(cap * 4 * KNBR),
-                 o_ncnt = carve(cap * 4), o_qc = carve(cap * 4), o_kdp = carve(cap * 4),
+                 o_ncnt = carve(cap * 4), o_qc = carve(cap * 4), o_r16 = carve(cap * 4), o_kdp = carve(cap * 4),
                  o_slo = carve(cap * 4), o_shi = carve(cap * 4), o_hcnt = carve(64),
                  o_slow = carve(cap * 4), o_slowc = carve(64), o_slow2 = carve(cap * 4), o_srow = carve(cap * 4), o_rrow = carve(cap * 4),
                  o_kdn = carve((2 * cap) * sizeof(KdNodeDev));
@@ -276,6 +276,8 @@ extern "C" int scab_create(scab_handle **out, const scab_params *p, int device, 
     A.s_nbr = (int32_t *)(b + o_nbr); A.s_nbr_cnt = (int32_t *)(b + o_ncnt); A.s_qcoll = (int32_t *)(b + o_qc);
     h->d_kd_agent_perm = (int32_t *)(b + o_kdp); h->d_kd_agent = (KdNodeDev *)(b + o_kdn);
     A.slow_list = (int32_t *)(b + o_slow); A.slow_count = (int32_t *)(b + o_slowc);
+    A.r16_prev = (float *)(b + o_r16);
+    cudaMemset(A.r16_prev, 0x7f, cap * 4);        // 3.4e38: no previous query
     A.slow_list2 = (int32_t *)(b + o_slow2); A.slow_count2 = A.slow_count + 1;      // adjacent: one memset resets both
     h->d_mig_sent_row = (int32_t *)(b + o_srow); h->d_mig_recv_row = (int32_t *)(b + o_rrow);
     h->d_sent_lo = (int32_t *)(b + o_slo); h->d_sent_hi = (int32_t *)(b + o_shi); h->d_halo_cnt = (int32_t *)(b + o_hcnt);
@@ -335,6 +337,7 @@ extern "C" int scab_bind_state(scab_handle *h, const scab_state_ptrs *s, int64_t
         return fail(h, SCAB_ERR_INVALID, "scab_bind_state: a required state pointer is NULL");
     h->A.st = *s;
     h->A.n = (int)n;
+    cudaMemset(h->A.r16_prev, 0x7f, (size_t)h->capacity * 4);      // the rows may hold other agents now
     h->A.obst_base = (int)(s->n_global > 0 ? s->n_global : n);
     h->bound = true;
     h->kd_valid = false;

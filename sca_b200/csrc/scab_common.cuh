@@ -73,6 +73,8 @@ struct StepArgs {
     int32_t *s_nbr;     // [n,16] sorted idx, or n + sorted obstacle idx
     int32_t *s_nbr_cnt; // [n]
     int32_t *s_qcoll;   // [n] collision flag raised by the neighbour query (agent.py:83-85)
+    float *r16_prev;    // [capacity], by ROW: distance of the 16th neighbour found by the previous query (huge: unknown) -- the
+                        // next query only looks that far plus two steps of motion, and falls back if that was not enough
     int32_t *slow_list; // [n] agents the 8-lane fast selection kernel hands to the general kernel
     int32_t *slow_count;
     int32_t *slow_list2, *slow_count2;   // agents the second (every-candidate) fast pass hands to the general kernel

@@ -184,6 +184,7 @@ __device__ __noinline__ void knn_exact(const StepArgs &A, int s, int id, const d
         }
     }
     write_lists2(A, s, id, L, coll ? 1 : 0);
+    A.r16_prev[id] = 3.0e38f;
 }
 
 
@@ -200,8 +201,10 @@ __device__ __noinline__ void knn_exact(const StepArgs &A, int s, int id, const d
 // `rangeSq`: the squared query radius the candidates were collected for -- neighbor_dist^2, or less when a dense
 // neighbourhood overflowed the candidate column and the scan was repeated with a smaller ball (the 16 nearest are then
 // certainly inside it, provided it still holds 16 agents: checked here).
+// Returns 0 when the lists were written, 1 when the agent needs the exact path (tie, full column), 2 when the reduced ball
+// held fewer than 16 agents (the caller retries with the full radius).
 template <class GetJ>
-__device__ __forceinline__ void knn_phase2(const StepArgs &A, int s, int id, const double4 me, int nbuf, bool overflow, double rangeSq, GetJ getj)
+__device__ __forceinline__ int knn_phase2(const StepArgs &A, int s, int id, const double4 me, int nbuf, bool overflow, double rangeSq, GetJ getj)
 {
     unsigned L[KNBR];
 #pragma unroll
@@ -243,10 +246,13 @@ __device__ __forceinline__ void knn_phase2(const StepArgs &A, int s, int id, con
         }
     }
     const int n_in = min(cnt, KNBR);
-    bool tie = overflow || (cnt > KNBR && (rej_min >> 8) == (L[KNBR - 1] >> 8)) || (rangeSq < A.nbr_dist_sq && !coll && cnt < KNBR);
+    if (!overflow && rangeSq < A.nbr_dist_sq && !coll && cnt < KNBR) return 2;
+    bool tie = overflow || (cnt > KNBR && (rej_min >> 8) == (L[KNBR - 1] >> 8));
 #pragma unroll
     for (int k = 1; k < KNBR; k++) tie |= (k < n_in) && ((L[k] >> 8) == (L[k - 1] >> 8));
-    if (tie) { knn_exact(A, s, id, me); return; }
+    if (tie) return 1;
+    // how far the next query has to look: the 16th neighbour's distance (a shorter or colliders-only list says nothing)
+    A.r16_prev[id] = (n_in == KNBR && !coll) ? (float)sqrt(div1e5((double)(L[KNBR - 1] >> 8))) * 1.000001f : 3.0e38f;
     int sx[KNBR];
 #pragma unroll
     for (int k = 0; k < KNBR; k++) sx[k] = (k < n_in) ? getj((int)(L[k] & 0xffu)) : -1;
@@ -265,6 +271,7 @@ __device__ __forceinline__ void knn_phase2(const StepArgs &A, int s, int id, con
 #pragma unroll
         for (int k = 0; k < KNBR; k++) A.st.nbr_dsq[(size_t)id * KNBR + k] = (k < n_in) ? div1e5((double)(L[k] >> 8)) : 0.0;
     }
+    return 0;
 }
 
 // The trimmed x-range of one of the nine x-rows around cell (cx, cy, cz) for a query ball of squared radius `limt`:
@@ -419,7 +426,8 @@ __global__ void __launch_bounds__(NT_THREADS, NT_MIN_CTAS) k_neighbors_tile(cons
                 }
             }
         }
-        knn_phase2(A, s, id, me, nbuf, overflow, A.nbr_dist_sq, [&](int i) { const unsigned c = buf[i][tid]; return cs[c >> 11][0] + (int)(c & 2047u); });
+        if (knn_phase2(A, s, id, me, nbuf, overflow, A.nbr_dist_sq, [&](int i) { const unsigned c = buf[i][tid]; return cs[c >> 11][0] + (int)(c & 2047u); }))
+            knn_exact(A, s, id, me);
     }
 }
 
@@ -457,7 +465,14 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
     RowTrim T;
     T.init(A.g, me, cx, cy, cz, lim);
     const float mx = (float)(me.x - A.g.ox), my = (float)(me.y - A.g.oy), mz = (float)(me.z - A.g.oz);
+    // Temporal coherence: neither this agent nor its neighbours move more than move_bound per step, so the 16th neighbour is
+    // at most 2 move_bound farther away than it was at the previous query.  (If the state was changed from outside in
+    // between, the ball may hold fewer than 16 agents: phase 2 notices and the agent is redone with the full radius.)
     double range_used = A.nbr_dist_sq;
+    if (!DENSE) {
+        const double r = (double)A.r16_prev[id] + 2.0 * A.move_bound + 1e-3;
+        if (r * r < range_used) range_used = r * r;
+    }
     float limf = prefilter_limit(range_used + 1e-4, mx, my, mz);
     // the (up to) nine x-rows of the block: all their cell_start bounds are fetched before any row is scanned
     int rbeg[9], rend[9];
@@ -518,7 +533,9 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
     limf = prefilter_limit(range_used + 1e-4, mx, my, mz);
     }
     if (!DENSE && overflow) { A.slow_list[atomicAdd(A.slow_count, 1)] = s; return; }      // (the policy stage resets the list for its own use)
-    knn_phase2(A, s, id, me, nbuf, overflow, range_used, [&](int i) { const unsigned c = buf[i][tid]; return rowbase[c >> 12][tid] + (int)(c & 4095u); });
+    const int rc = knn_phase2(A, s, id, me, nbuf, overflow, range_used, [&](int i) { const unsigned c = buf[i][tid]; return rowbase[c >> 12][tid] + (int)(c & 4095u); });
+    if (rc == 2 && !DENSE) { A.slow_list[atomicAdd(A.slow_count, 1)] = s; return; }        // the reduced ball was too small: second pass, full radius
+    if (rc) knn_exact(A, s, id, me);
 }
 
 // the general path for every agent (obstacles in the merged list, SCAB_KNN_EXACT=1, neighbor_dist >= 12.9 m): thread per agent
