@@ -461,9 +461,6 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
     bool overflow = false;
     int cx, cy, cz;
     cell_of(A.g, me.x, me.y, me.z, cx, cy, cz);
-    const double lim = A.nbr_dist_sq + 1e-4;
-    RowTrim T;
-    T.init(A.g, me, cx, cy, cz, lim);
     const float mx = (float)(me.x - A.g.ox), my = (float)(me.y - A.g.oy), mz = (float)(me.z - A.g.oz);
     // Temporal coherence: neither this agent nor its neighbours move more than move_bound per step, so the 16th neighbour is
     // at most 2 move_bound farther away than it was at the previous query.  (If the state was changed from outside in
@@ -473,6 +470,8 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
         const double r = (double)A.r16_prev[id] + 2.0 * A.move_bound + 1e-3;
         if (r * r < range_used) range_used = r * r;
     }
+    RowTrim T;          // (the smaller ball also reaches fewer cells)
+    T.init(A.g, me, cx, cy, cz, range_used + 1e-4);
     float limf = prefilter_limit(range_used + 1e-4, mx, my, mz);
     // the (up to) nine x-rows of the block: all their cell_start bounds are fetched before any row is scanned
     int rbeg[9], rend[9];
