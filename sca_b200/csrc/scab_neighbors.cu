@@ -465,9 +465,11 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
     // Temporal coherence: neither this agent nor its neighbours move more than move_bound per step, so the 16th neighbour is
     // at most 2 move_bound farther away than it was at the previous query.  (If the state was changed from outside in
     // between, the ball may hold fewer than 16 agents: phase 2 notices and the agent is redone with the full radius.)
+    // A collider displaces every non-collider from the list (agent.py:82-92) however far it is, so the ball also has to hold
+    // every possible collider: r_i + the largest radius (scab_set_max_radius; unknown -> no reduced ball).
     double range_used = A.nbr_dist_sq;
-    if (!DENSE) {
-        const double r = (double)A.r16_prev[id] + 2.0 * A.move_bound + 1e-3;
+    if (!DENSE && A.max_radius > 0.0) {
+        const double r = fmax((double)A.r16_prev[id] + 2.0 * A.move_bound, me.w + A.max_radius) + 1e-3;
         if (r * r < range_used) range_used = r * r;
     }
     RowTrim T;          // (the smaller ball also reaches fewer cells)

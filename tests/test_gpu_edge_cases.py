@@ -124,6 +124,48 @@ def test_knn_integer_key_path_equals_exact_path_and_oracle():
     assert (w.nbr_cnt == 16).mean() > 0.5
 
 
+def test_knn_reduced_ball_never_hides_a_collider():
+    """The 16-NN query starts from last step's 16th-neighbour distance plus two steps of motion.  From the first collider
+    on the reference keeps colliders only (agent.py:82-92), and a collider of large radius can sit OUTSIDE that ball while
+    16 small agents sit inside it: the ball must never be smaller than r_i + r_max.  Stage-wise calls (no status stage in
+    between, which would retire the colliding agents) reach the case; the lists are compared with the oracle's."""
+    import torch
+    from oracle import oracle as orc
+    from sca_b200 import capi
+    rng = np.random.default_rng(5)
+    small = []
+    while len(small) < 24:                   # 24 small agents within 3 m of agent 0, >= 0.4 m apart
+        p = rng.normal(0, 1.0, 3)
+        p *= rng.uniform(0.5, 3.0) / np.linalg.norm(p)
+        if all(np.linalg.norm(p - q) >= 0.4 for q in small + [np.zeros(3)]):
+            small.append(p)
+    c = np.array([60.0, 60.0, 60.0])
+    pos = np.vstack([c, c + np.array(small), c + [0.0, 5.0 + 0.05 + 0.16, 0.0]])
+    n = len(pos)
+    goal = pos + [0.0, 40.0, 0.0]
+    goal[-1] = pos[-1] - [0.0, 40.0, 0.0]    # the big agent flies at the cluster: 0.2 m closer per step
+    radius = np.full(n, 0.05)
+    radius[-1] = 5.0
+    vel = (0.5 * (goal - pos) / np.linalg.norm(goal - pos, axis=1)[:, None]).astype(np.float32)   # (a zero velocity skips the query)
+    sw = _swarm(pos, goal, radius=radius, vel=vel)
+    seen = []
+    for t in range(4):
+        sw.stage_grid(); sw.stage_neighbors(capi.NBR_KNN)
+        torch.cuda.synchronize()
+        d = sw.download(('pos', 'vel'))
+        w = orc.World(d['pos'][:n, :3], goal, radius=radius, vel=d['vel'][:n, :3])
+        w.status[:] = sw.status.cpu().numpy()[:n] & 15       # (a query that saw a collider retires the agent, agent.py:83-85)
+        w.policy_step('srvo3d', orc.NBR_KNN)
+        cnt, ids = sw.nbr_cnt.cpu().numpy()[:n], sw.nbr_ids.cpu().numpy()[:n]
+        assert np.array_equal(cnt, w.nbr_cnt), (t, cnt, w.nbr_cnt)
+        for i in np.nonzero(cnt >= 0)[0]:
+            assert np.array_equal(ids[i, :cnt[i]], w.nbr_ids[i, :cnt[i]]), (t, i)
+        seen.append((int(cnt[0]), int(ids[0, 0])))
+        sw.stage_policy('srvo3d')
+    assert seen[0][0] == 16, 'agent 0 starts with a full list of small neighbours'
+    assert (1, n - 1) in seen[1:3], 'then sees the big collider only, and is retired (%r)' % (seen,)
+
+
 def test_boundary_errors_are_reported_not_swallowed():
     from sca_b200 import capi
     from sca_b200.swarm import Swarm
