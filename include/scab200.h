@@ -162,7 +162,9 @@ const char *scab_last_error(const scab_handle *h);
 int scab_set_option(scab_handle *h, int option, int value);
 
 /* Largest agent radius in the swarm (0 = unknown).  When known, the status stage reuses the step's neighbour
- * lists instead of re-scanning the cell list wherever those lists provably hold every possible collision partner. */
+ * lists instead of re-scanning the cell list wherever those lists provably hold every possible collision partner,
+ * and the 16-NN query may look inside a ball smaller than neighbor_dist (never smaller than r_i + r_max: a collider
+ * displaces every other neighbour from the reference's list, agent.py:82-92).  Unknown: full-radius queries only. */
 int scab_set_max_radius(scab_handle *h, double r_max);
 
 /* Largest speed any agent can be commanded (max of max_speed, every pref_speed, 0.5 = the inner candidate shell, and the

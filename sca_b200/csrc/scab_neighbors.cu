@@ -528,9 +528,12 @@ __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const
         }
     }
     if (!DENSE || !overflow) break;
-    // shrink the ball so that it holds ~36 of the nhit agents seen (count ~ r^3; a flatter crowd just takes another round)
+    // shrink the ball so that it holds ~36 of the nhit agents seen (count ~ r^3; a flatter crowd just takes another round),
+    // but never below the reach of a collider (see above); a ball that cannot shrink leaves the agent to knn_exact
+    const double floor_r = me.w + A.max_radius + 1e-3;
+    if (!(A.max_radius > 0.0) || range_used <= floor_r * floor_r) break;
     const float sc = cbrtf(36.f / (float)nhit);
-    range_used *= (double)fminf(sc * sc, 0.8f);
+    range_used = fmax(range_used * (double)fminf(sc * sc, 0.8f), floor_r * floor_r);
     limf = prefilter_limit(range_used + 1e-4, mx, my, mz);
     }
     if (!DENSE && overflow) { A.slow_list[atomicAdd(A.slow_count, 1)] = s; return; }      // (the policy stage resets the list for its own use)

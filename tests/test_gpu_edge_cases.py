@@ -166,6 +166,38 @@ def test_knn_reduced_ball_never_hides_a_collider():
     assert (1, n - 1) in seen[1:3], 'then sees the big collider only, and is retired (%r)' % (seen,)
 
 
+def test_knn_crowded_pass_never_hides_a_collider():
+    """Same rule for the crowded-neighbourhood pass, which shrinks the ball from the hit count when more than 96 agents are
+    in range: 150 small agents within 3 m and a collider of radius 5 m at 4.9 m."""
+    import torch
+    from oracle import oracle as orc
+    from sca_b200 import capi
+    rng = np.random.default_rng(6)
+    small = []
+    while len(small) < 150:
+        p = rng.normal(0, 1.0, 3)
+        p *= 3.0 * rng.uniform(0.05, 1.0) ** (1 / 3) / np.linalg.norm(p)
+        if all(np.linalg.norm(p - q) >= 0.25 for q in small + [np.zeros(3)]):
+            small.append(p)
+    c = np.array([60.0, 60.0, 60.0])
+    pos = np.vstack([c, c + np.array(small), c + [0.0, 4.9, 0.0]])
+    n = len(pos)
+    goal = pos + [0.0, 40.0, 0.0]
+    radius = np.full(n, 0.02)
+    radius[-1] = 5.0
+    vel = np.tile(np.float32([0.0, 0.5, 0.0]), (n, 1))
+    w = orc.World(pos, goal, radius=radius, vel=vel)
+    w.policy_step('srvo3d', orc.NBR_KNN)
+    sw = _swarm(pos, goal, radius=radius, vel=vel)
+    sw.stage_grid(); sw.stage_neighbors(capi.NBR_KNN)
+    torch.cuda.synchronize()
+    cnt, ids = sw.nbr_cnt.cpu().numpy()[:n], sw.nbr_ids.cpu().numpy()[:n]
+    assert np.array_equal(cnt, w.nbr_cnt)
+    for i in range(n):
+        assert np.array_equal(ids[i, :cnt[i]], w.nbr_ids[i, :cnt[i]]), i
+    assert cnt[0] == 1 and ids[0, 0] == n - 1 and (cnt == 16).sum() > 20
+
+
 def test_boundary_errors_are_reported_not_swallowed():
     from sca_b200 import capi
     from sca_b200.swarm import Swarm
