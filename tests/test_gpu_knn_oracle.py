@@ -6,7 +6,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _compare(pos6, goal6, obstacles, policy, steps, lo=None, hi=None, full_search=True):
+def _compare(pos6, goal6, obstacles, policy, steps, lo=None, hi=None, full_search=True, radius=0.5, pref_speed=1.0):
     import torch
     from oracle import oracle as orc
     from sca_b200 import capi
@@ -15,11 +15,12 @@ def _compare(pos6, goal6, obstacles, policy, steps, lo=None, hi=None, full_searc
     n = len(pos6)
     import os
     orc.set_threads(max(8, min(32, os.cpu_count() or 8)))
-    w = orc.World(pos6[:, :3], goal6[:, :3], heading=pos6[:, 3:6], obstacles=obstacles, initial_pos=pos6, goal_pos=goal6)
+    w = orc.World(pos6[:, :3], goal6[:, :3], heading=pos6[:, 3:6], obstacles=obstacles, initial_pos=pos6, goal_pos=goal6,
+                  radius=radius, pref_speed=pref_speed)
     sw = Swarm(n, debug=True)
     sw.h.set_option(capi.OPT_FULL_SEARCH, 1 if full_search else 0)
     sw.set_state(pos6[:, :3], goal6[:, :3], heading=pos6[:, 3:6], initial_pos=pos6, goal_pos=goal6,
-                 max_run_dist=w.max_run_dist)
+                 max_run_dist=w.max_run_dist, radius=radius, pref_speed=pref_speed)
     sw.set_obstacles(obstacles)
     lo = np.minimum(pos6[:, :3].min(0), goal6[:, :3].min(0)) - 15 if lo is None else lo
     hi = np.maximum(pos6[:, :3].max(0), goal6[:, :3].max(0)) + 15 if hi is None else hi
@@ -63,6 +64,24 @@ def test_uniform_swarm_config5_density(policy, full_search):
     tot = _compare(pos, goal, obs, policy, steps=5, full_search=full_search)
     print(policy, tot)
     assert tot['agents'] > 20000
+    for k in ('nbr', 'tag', 'nsuit', 'vel', 'status', 'planes'):
+        assert tot[k] == 0, (policy, tot)
+
+
+@pytest.mark.parametrize('full_search', [True, False], ids=['full', 'lazy'])
+@pytest.mark.parametrize('policy', ['sca', 'rvo3d', 'orca_lp'])
+def test_mixed_radii_and_speeds_without_obstacles(policy, full_search):
+    """Radii from 0.1 to 2.5 m and preferred speeds from 0.5 to 2 m/s in one swarm, no obstacles -- so the 16-NN runs on its
+    scale path (reduced query ball, crowded pass) and the status stage on its list shortcut, whose bounds all depend on the
+    largest radius and the fastest agent; colliders of large radius displace nearer small agents from the lists."""
+    from sca_b200 import scenarios
+    pos, goal, _ = scenarios.uniform_box_numpy(4000, 3.0 * 1.0e6 / 560.0 ** 3, seed=17)
+    rng = np.random.default_rng(9)
+    radius = np.exp(rng.uniform(np.log(0.1), np.log(2.5), len(pos)))
+    pref = rng.uniform(0.5, 2.0, len(pos))
+    tot = _compare(pos, goal, None, policy, steps=8, full_search=full_search, radius=radius, pref_speed=pref)
+    print(policy, tot)
+    assert tot['agents'] > 15000
     for k in ('nbr', 'tag', 'nsuit', 'vel', 'status', 'planes'):
         assert tot[k] == 0, (policy, tot)
 
