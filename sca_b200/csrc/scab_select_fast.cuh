@@ -27,7 +27,11 @@
 #define LUT_B SCAB_POSTURE_LUT_B
 #define LIVE_CAP 136      // 2 * DIR_CAP + v_pref, rounded up
 #define VPREF_ENTRY 0x3ff
-#define LIST_EXTRA_DELTA 0.4f     // second pass: tier width 0.3 + 0.4
+#ifndef LIST_EXTRA_DELTA
+#define LIST_EXTRA_DELTA 0.15f    // second pass: tier width 0.3 + 0.15 (measured on B200, policy stage at 10^6 agents: +0.05 1.259 ms,
+                                  // +0.1 1.245, +0.15 1.244, +0.25 1.247, +0.4 1.262, +0.55 1.269 -- a narrower second tier leaves more
+                                  // agents to the general kernel, whose first wave of 2960 costs the same 20-36 us however full it is)
+#endif
 #define LIST_MIN_AGENTS 3000      // second pass: shorter lists go straight to the general kernel
 #ifndef FG_LIST_CTAS
 #define FG_LIST_CTAS 6            // second pass: one more resident CTA (80 registers, direction tables read from global memory instead
