@@ -10,7 +10,8 @@
 #include <string>
 #include <vector>
 
-#define TIER_DELTA_DEFAULT 0.3f   // measured on B200: 0.12 -> 5.0 ms, 0.18 -> 4.1, 0.25 -> 3.0, 0.4 -> 3.0, 0.55 -> 3.6, 0.75 -> 4.9 (policy stage, 1M SCA)
+#define TIER_DELTA_DEFAULT 0.28f  // round 2, with the second pass at + 0.15 (policy stage, 1M SCA): 0.24 -> 1.244 ms, 0.26 -> 1.233, 0.28 -> 1.239 (best whole
+                                  // step), 0.30 -> 1.244, 0.31 -> 1.288, 0.33 -> 1.41 (one more round of cone tests for most agents).  Round 1: 0.12 -> 5.0 ms, 0.18 -> 4.1, 0.25 -> 3.0, 0.4 -> 3.0, 0.55 -> 3.6, 0.75 -> 4.9 (policy stage, 1M SCA)
 
 struct scab_handle {
     int device = 0;

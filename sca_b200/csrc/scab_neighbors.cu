@@ -315,8 +315,8 @@ __device__ __forceinline__ float prefilter_limit(double lim, float mx, float my,
 #define KNN_UNROLL 4       // records loaded per inner iteration of the direct scan (must divide 32)
 #endif
 #ifndef KNN_DIRECT_CTAS
-#define KNN_DIRECT_CTAS 5
-#endif
+#define KNN_DIRECT_CTAS 6    // resident CTAs per SM the direct kernel is compiled for (80 registers, no spills); measured on B200 at 10^6
+#endif                       // agents: 5 -> 0.398 ms, 6 -> 0.372, 7 (72 registers, spills) -> 0.387, 8 -> 0.424; KNN_UNROLL 8: +0.004
 
 // ---- variant 0: one CTA per WORK ITEM = NT_W consecutive cells of one x-row of the grid.  Its agents are a contiguous range
 // of the cell-sorted snapshot, and everything they can see lies in nine contiguous ranges (the 3 x 3 neighbouring x-rows,
@@ -438,7 +438,9 @@ __global__ void __launch_bounds__(NT_THREADS, NT_MIN_CTAS) k_neighbors_tile(cons
 // a warp from re-scanning for one crowded lane (BASELINE config 4 has ~64 agents in range of each other; the uniform
 // workload gets there locally late in a rollout).
 // Candidates are recorded as 16-bit codes (row << 12 | offset in the row's range): 96 slots per agent in 24 KB per CTA.
+#ifndef KND_CAP
 #define KND_CAP 96
+#endif
 template <bool DENSE>
 __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const __grid_constant__ StepArgs A)
 {

@@ -28,10 +28,12 @@
 #define LIVE_CAP 136      // 2 * DIR_CAP + v_pref, rounded up
 #define VPREF_ENTRY 0x3ff
 #ifndef LIST_EXTRA_DELTA
-#define LIST_EXTRA_DELTA 0.15f    // second pass: tier width 0.3 + 0.15 (measured on B200, policy stage at 10^6 agents: +0.05 1.259 ms,
+#define LIST_EXTRA_DELTA 0.15f    // second pass: tier width + 0.15 (measured on B200, policy stage at 10^6 agents: +0.05 1.259 ms,
                                   // +0.1 1.245, +0.15 1.244, +0.25 1.247, +0.4 1.262, +0.55 1.269 -- a narrower second tier leaves more
                                   // agents to the general kernel, whose first wave of 2960 costs the same 20-36 us however full it is)
 #endif
+#define LIST_EXTRA_DELTA_WIDE 0.4f // ... unless the list is long (a dense scene: BASELINE config 4 lists 93 % of its agents and the narrow tier
+#define LIST_NARROW_MAX 24000     // would pass 90 % of them on): beyond ~8 waves' worth of leftovers the second pass examines tier + 0.4
 #define LIST_MIN_AGENTS 3000      // second pass: shorter lists go straight to the general kernel
 #ifndef FG_LIST_CTAS
 #define FG_LIST_CTAS 6            // second pass: one more resident CTA (80 registers, direction tables read from global memory instead
@@ -39,7 +41,7 @@
 #ifndef FG_MIN_CTAS
 #define FG_MIN_CTAS 5   // resident CTAs per SM the kernel is compiled for (96 registers): 1.39 -> 1.27 ms for the policy stage on B200; 6 spills
 #endif
-// tier 1 = candidates within StepArgs::tier_delta (default 0.3, SCAB_TIER_DELTA) of the one closest to v_pref
+// tier 1 = candidates within StepArgs::tier_delta (default 0.28, SCAB_TIER_DELTA) of the one closest to v_pref
 
 // fp64 copies of the constraints for the guard-band recheck.  Only the ORCA planes keep them in shared memory;
 // a cone is cheap to rebuild from the neighbour record (recheck_cone64), and without these 896 bytes a fifth CTA
@@ -120,7 +122,6 @@ template <int POLICY, bool LIST>
 __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAMPLED) ? 4 : (LIST ? FG_LIST_CTAS : FG_MIN_CTAS)) k_select_fast(const __grid_constant__ StepArgs A)
 {
     const bool full_search = A.full_search != 0;
-    const float tier_delta = A.tier_delta + (LIST ? LIST_EXTRA_DELTA : 0.f);
     constexpr bool IS_ORCA = (POLICY == SCAB_POLICY_ORCA_SAMPLED);
     constexpr bool SHUNT = (POLICY == SCAB_POLICY_SCA || POLICY == SCAB_POLICY_SRVO3D);
     typedef GroupSmemT<IS_ORCA> GroupSmem;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, (POLICY == SCAB_POLICY_ORCA_SAM
     }
 
     const int n_work = LIST ? min(*A.slow_count, A.n) : policy_items(A);
+    const float tier_delta = A.tier_delta + (LIST ? (n_work <= LIST_NARROW_MAX ? LIST_EXTRA_DELTA : LIST_EXTRA_DELTA_WIDE) : 0.f);
     if (LIST && n_work < LIST_MIN_AGENTS) {      // hand the whole list on (uniform branch: every thread sees the same count)
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x) A.slow_list2[i] = A.slow_list[i];
         if (blockIdx.x == 0 && threadIdx.x == 0) *A.slow_count2 = n_work;
