@@ -89,6 +89,17 @@ class ClockSampler:
     def __init__(self, index):
         self.rows = []
         self.p = None
+        self.nvml = None
+        self._stop = False
+        try:        # NVML directly: a reading every 2 ms from the first moment on (a sharded timed region lasts ~20 ms, less than
+            import pynvml                      # nvidia-smi needs to print its first line)
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(int(index)))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.p = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '50',
                                        '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -97,18 +108,43 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def _poll(self):
+        nv, h = self.nvml
+        bits = ((0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'), (0x20, 'sw_thermal_slowdown'), (0x4, 'sw_power_cap'))
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = ''
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                f = ['Active' if r & b else 'Not Active' for b, _ in bits]
+                self.rows.append((time.time(), '%s, %s, , %s' % (sm, mx, ', '.join(f))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.p.stdout:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
-        if self.p is None:
+        if self.p is None and self.nvml is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        time.sleep(0.12)
-        self.p.terminate()
+        if self.nvml is not None:
+            self._stop = True
+            self.t.join(0.5)
+        else:
+            time.sleep(0.12)
+            self.p.terminate()
         sm, mx, reasons = [], None, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.1] or [r for (_, r) in self.rows[-3:]]
+        pad = (0.0, 0.0) if self.nvml is not None else (0.05, 0.1)        # (nvidia-smi's 50 ms period needs the slack)
+        rows = [r for (t, r) in self.rows if t0 - pad[0] <= t <= t1 + pad[1]] or [r for (_, r) in self.rows[-3:]]
         for r in rows:
             f = [x.strip() for x in r.split(',')]
             try:
