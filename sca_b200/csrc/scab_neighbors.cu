@@ -437,10 +437,10 @@ __global__ void __launch_bounds__(NT_THREADS, NT_MIN_CTAS) k_neighbors_tile(cons
 // nearest of a crowded neighbourhood are certainly inside a smaller ball).  Keeping the retry out of the first kernel keeps
 // a warp from re-scanning for one crowded lane (BASELINE config 4 has ~64 agents in range of each other; the uniform
 // workload gets there locally late in a rollout).
-// Candidates are recorded as 16-bit codes (row << 12 | offset in the row's range): 96 slots per agent in 24 KB per CTA.
+// Candidates are recorded as 16-bit codes (row << 12 | offset in the row's range): 80 slots per agent in 20 KB per CTA.
 #ifndef KND_CAP
-#define KND_CAP 96
-#endif
+#define KND_CAP 80      // measured at 6 resident CTAs (10^6 uniform / late rollout / config 4): 64 -> 0.363 / 0.409 / 0.653 ms,
+#endif                  // 80 -> 0.366 / 0.413 / 0.221, 96 -> 0.371 / 0.419 / 0.226, 112 -> 0.386 / 0.440 / 0.304
 template <bool DENSE>
 __global__ void __launch_bounds__(128, KNN_DIRECT_CTAS) k_neighbors_direct(const __grid_constant__ StepArgs A)
 {

@@ -36,8 +36,8 @@
 #define LIST_NARROW_MAX 24000     // would pass 90 % of them on): beyond ~8 waves' worth of leftovers the second pass examines tier + 0.4
 #define LIST_MIN_AGENTS 3000      // second pass: shorter lists go straight to the general kernel
 #ifndef FG_LIST_CTAS
-#define FG_LIST_CTAS 6            // second pass: one more resident CTA (80 registers, direction tables read from global memory instead
-#endif                            // of shared): the pass is one agent's latency per group, so it wants every listed agent resident at once
+#define FG_LIST_CTAS 5            // second pass: resident CTAs per SM it is compiled for.  6 (80 registers, a few spills) paid off while the
+#endif                            // pass was one long wave at tier + 0.4; with the narrow tier 5 (96 registers, no spills) is 0.6 % faster
 #ifndef FG_MIN_CTAS
 #define FG_MIN_CTAS 5   // resident CTAs per SM the kernel is compiled for (96 registers): 1.39 -> 1.27 ms for the policy stage on B200; 6 spills
 #endif

@@ -167,7 +167,7 @@ def test_knn_reduced_ball_never_hides_a_collider():
 
 
 def test_knn_crowded_pass_never_hides_a_collider():
-    """Same rule for the crowded-neighbourhood pass, which shrinks the ball from the hit count when more than 96 agents are
+    """Same rule for the crowded-neighbourhood pass, which shrinks the ball from the hit count when more than 80 agents are
     in range: 150 small agents within 3 m and a collider of radius 5 m at 4.9 m."""
     import torch
     from oracle import oracle as orc
