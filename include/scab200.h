@@ -139,12 +139,14 @@ typedef struct {
     int64_t overflow;      /* STICKY bit mask (cleared only by scab_reset_counters); non-zero = results may be wrong:
                               1 a halo face buffer was too small (records dropped), 2 a migration buffer was full (an agent
                               stayed outside its slab), 4 an arriving agent found no free row (lost), 8 an agent moved farther
-                              in one step than scab_set_motion_bound allows (the collision stage's reach assumes the bound) */
+                              in one step than scab_set_motion_bound allows (the collision stage's reach assumes the bound),
+                              16 a peer-to-peer halo wait timed out, 32 an agent's radius exceeds scab_set_max_radius */
 } scab_counters;
 #define SCAB_OVF_HALO 1
 #define SCAB_OVF_MIGRATION_DEFERRED 2
 #define SCAB_OVF_MIGRATION_LOST 4
 #define SCAB_OVF_MOTION 8
+#define SCAB_OVF_RADIUS 32
 
 const char *scab_version(void);
 void scab_default_params(scab_params *p);
@@ -164,7 +166,8 @@ int scab_set_option(scab_handle *h, int option, int value);
 /* Largest agent radius in the swarm (0 = unknown).  When known, the status stage reuses the step's neighbour
  * lists instead of re-scanning the cell list wherever those lists provably hold every possible collision partner,
  * and the 16-NN query may look inside a ball smaller than neighbor_dist (never smaller than r_i + r_max: a collider
- * displaces every other neighbour from the reference's list, agent.py:82-92).  Unknown: full-radius queries only. */
+ * displaces every other neighbour from the reference's list, agent.py:82-92).  Unknown: full-radius queries only.
+ * A radius above a declared bound raises SCAB_OVF_RADIUS in scab_counters.overflow at the next cell-list build. */
 int scab_set_max_radius(scab_handle *h, double r_max);
 
 /* Largest speed any agent can be commanded (max of max_speed, every pref_speed, 0.5 = the inner candidate shell, and the

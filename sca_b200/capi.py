@@ -19,12 +19,13 @@ TAG_FIRST, TAG_SUITABLE, TAG_FALLBACK, TAG_LP3_OK, TAG_LP4 = 1, 2, 4, 8, 16
 # every symbol include/scab200.h declares (tests/test_capi_symbols.py checks the header against this)
 OPT_FULL_SEARCH = 1
 
-OVF_HALO, OVF_MIGRATION_DEFERRED, OVF_MIGRATION_LOST, OVF_MOTION, OVF_P2P_TIMEOUT = 1, 2, 4, 8, 16
+OVF_HALO, OVF_MIGRATION_DEFERRED, OVF_MIGRATION_LOST, OVF_MOTION, OVF_P2P_TIMEOUT, OVF_RADIUS = 1, 2, 4, 8, 16, 32
 IPC_HANDLE_BYTES = 64
 OVF_TEXT = {1: 'a halo face buffer overflowed (ghost records dropped)', 2: 'a migration buffer was full (an agent stayed outside its slab)',
             4: 'an arriving agent found no free row (agent lost)',
             8: 'an agent moved farther in one step than the motion bound the collision stage relies on (scab_set_motion_bound)',
-            16: 'a peer-to-peer halo wait timed out (the neighbour rank never published its data)'}
+            16: 'a peer-to-peer halo wait timed out (the neighbour rank never published its data)',
+            32: 'an agent has a larger radius than scab_set_max_radius declared (the 16-NN query ball and the status shortcut rely on it)'}
 
 SYMBOLS = ['scab_version', 'scab_default_params', 'scab_set_option', 'scab_set_max_radius', 'scab_set_motion_bound', 'scab_create', 'scab_destroy', 'scab_last_error', 'scab_set_grid',
            'scab_bind_state', 'scab_set_obstacles', 'scab_kdtree_build', 'scab_kdtree_get_perm', 'scab_build_grid',

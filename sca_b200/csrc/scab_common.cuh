@@ -46,6 +46,7 @@ struct LaunchCfg {
 #define OVF_MIG_LOST 4ull    // k_migrate_unpack found no free row for an arrival: the agent is gone
 #define OVF_MOTION 8ull      // an agent moved farther in one step than the bound the collision stage relies on
 #define OVF_P2P_TIMEOUT 16ull // a peer-to-peer halo wait gave up after ~2 s (the neighbour rank never published its data)
+#define OVF_RADIUS 32ull      // an agent's radius exceeds scab_set_max_radius (the 16-NN ball and the status shortcut rely on it)
 
 // Everything a kernel needs; passed by value.
 struct StepArgs {

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(256) k_reorder(StepArgs A)
     double4 p;
     p.x = A.st.pos[3 * i]; p.y = A.st.pos[3 * i + 1]; p.z = A.st.pos[3 * i + 2];
     p.w = A.st.radius[i];
+    if (A.max_radius > 0.0 && p.w > A.max_radius) atomicOr(&A.counters[7], OVF_RADIUS);   // a declared bound must hold: be loud
     float4 v;
     v.x = A.st.vel[3 * i]; v.y = A.st.vel[3 * i + 1]; v.z = A.st.vel[3 * i + 2];
     v.w = __int_as_float(A.st.status[i]);

@@ -635,7 +635,7 @@ class ShardedSwarm:
         overflow masks are OR-ed (as a per-bit sum), and every rank raises together if any rank's is set."""
         c = self.counters(check=False)
         keys = sorted(k for k, v in c.items() if isinstance(v, (int, np.integer)) and k != 'overflow')
-        ovf = [(int(c['overflow']) >> b) & 1 for b in range(5)]
+        ovf = [(int(c['overflow']) >> b) & 1 for b in range(6)]
         if self.world > 1:
             t = torch.tensor([int(c[k]) for k in keys] + ovf, dtype=torch.int64, device=self.sw.device)
             torch.distributed.all_reduce(t)
@@ -643,7 +643,7 @@ class ShardedSwarm:
         else:
             vals = [int(c[k]) for k in keys] + ovf
         out = {k: int(v) for k, v in zip(keys, vals)}
-        out['overflow'] = sum((1 << b) for b in range(5) if vals[len(keys) + b])
+        out['overflow'] = sum((1 << b) for b in range(6) if vals[len(keys) + b])
         if out['overflow']:
             raise capi.ScabError('sharded run overflow flags %d: %s' % (out['overflow'], '; '.join(
                 t for b, t in capi.OVF_TEXT.items() if out['overflow'] & b)))

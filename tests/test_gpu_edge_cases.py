@@ -296,6 +296,23 @@ def test_a_move_beyond_the_motion_bound_is_loud():
     assert sw.counters()['overflow'] == 0
 
 
+def test_a_radius_above_the_declared_bound_is_loud():
+    """scab_set_max_radius is a promise the 16-NN query ball and the status shortcut rely on; a larger radius in the state
+    raises the sticky overflow flag at the next cell-list build instead of silently dropping a collider."""
+    from sca_b200 import capi
+    rng = np.random.default_rng(3)
+    pos = rng.uniform(0, 40, (200, 3)) + [0, 0, 20]
+    goal = pos + [30.0, 0, 0]
+    sw = _swarm(pos, goal, radius=np.where(np.arange(200) == 17, 1.5, 0.5))
+    sw.step('rvo3d', capi.NBR_KNN)
+    sw.counters()                            # Swarm.set_state declared max(radius) = 1.5: fine
+    sw.h.set_max_radius(1.0)
+    sw.step('rvo3d', capi.NBR_KNN)
+    with pytest.raises(capi.ScabError, match='radius'):
+        sw.counters()
+    assert sw.counters(check=False)['overflow'] & capi.OVF_RADIUS
+
+
 def test_status_stage_refuses_a_reach_beyond_the_cell_size():
     from sca_b200 import capi
     pos = np.array([[0.0, 0.0, 20.0], [8.0, 0.0, 20.0]])
