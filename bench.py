@@ -36,10 +36,12 @@ import numpy as np  # noqa: E402
 
 DENSITY = 1.0e6 / 560.0 ** 3          # agents per m^3 of BASELINE config 5
 ALGO_BYTES = {'grid': 168, 'neighbors': 116, 'policy': 660, 'status': 144}   # SURVEY.md 8(d), per agent-step
-# kernels launched per step: k_cell_count, k_scan_tile_sums, k_scan_tiles, k_scan_apply, k_reorder, k_neighbors_direct,
-# then k_vpref, k_select_fast, k_select, k_integrate (sampled policies) or k_policy_lp<1>, k_policy_lp<2> (ORCA LP), then k_status
-KERNELS_PER_STEP = {'orca_lp': 9}
-KERNELS_PER_STEP_SAMPLED = 11
+# this library's kernels launched per step (profiles/r2_launches_{sca,lp}.csv): k_cell_count, k_scan_tile_sums, k_scan_tiles,
+# k_scan_apply, k_reorder, k_neighbors_direct<pass 1>, <pass 2>, then k_vpref, k_select_fast<pass 1>, <pass 2>, k_select,
+# k_integrate (sampled policies) or k_policy_lp<5>, k_policy_lp<4> (ORCA LP), then k_status; a sharded step adds the halo pack /
+# signal / unpack kernels of its two exchanges (6; the migration kernels of every 8th step are not counted)
+KERNELS_PER_STEP = {'orca_lp': 10}
+KERNELS_PER_STEP_SAMPLED = 13
 POLICY_KERNELS = {'orca_lp': 'k_policy_lp'}
 METRIC = 'agent-steps/sec (SCA, 1M UAVs)'      # --policy other than sca: the same workload under that policy (named in config)
 
@@ -509,7 +511,7 @@ def run_ours(args):
                'data': 'synthetic',
                'config': conf,
                # + 5 halo kernels per step when sharded: k_halo_fill, k_halo_pack, k_halo_unpack, k_halo_pack_pos, k_halo_unpack_pos
-               'gpu_launches': (KERNELS_PER_STEP.get(policy, KERNELS_PER_STEP_SAMPLED) + (5 if world > 1 else 0)) * args.steps, 'clocks': clocks}
+               'gpu_launches': (KERNELS_PER_STEP.get(policy, KERNELS_PER_STEP_SAMPLED) + (6 if world > 1 else 0)) * args.steps, 'clocks': clocks}
         if roof:
             out['roofline'] = roof
         if e2e:
